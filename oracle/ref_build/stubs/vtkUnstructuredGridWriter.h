@@ -1,0 +1,1 @@
+// empty VTK stub (oracle/_ref build only); see vtkUnstructuredGrid.h

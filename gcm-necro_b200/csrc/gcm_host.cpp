@@ -1,0 +1,424 @@
+// gcm_host.cpp -- see gcm_host.h.  Compiled with  g++ -O2 -ffp-contract=off -fopenmp.
+#include "gcm_host.h"
+#include "gcm_math.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace gcmh {
+
+using gcm::Vec3;
+
+void GlibcRand::seed(unsigned s)
+{
+	if(s == 0) s = 1;
+	r[0] = s;
+	long word = (long)(int32_t)s;
+	for(int i = 1; i < 31; i++) {
+		long hi = word / 127773;
+		long lo = word % 127773;
+		word = 16807 * lo - 2836 * hi;
+		if(word < 0) word += 2147483647;
+		r[i] = (uint32_t)word;
+	}
+	f = 3; b = 0;
+	for(int i = 0; i < 310; i++) (void)next();
+}
+
+static inline Vec3 P(const std::vector<float>& c, int i)
+{
+	Vec3 v; v.x = c[3*(size_t)i]; v.y = c[3*(size_t)i+1]; v.z = c[3*(size_t)i+2];
+	return v;
+}
+
+void HostMesh::translate(float dx, float dy, float dz)
+{
+	// TetrMesh::translate, gcm/meshtypes/TetrMesh.cpp:29-45
+	for(int i = 0; i < N; i++) {
+		coords[3*(size_t)i] += dx; coords[3*(size_t)i+1] += dy; coords[3*(size_t)i+2] += dz;
+	}
+	for(int k = 0; k < 3; k++) { outline_min[k] += (k == 0 ? dx : k == 1 ? dy : dz); outline_max[k] += (k == 0 ? dx : k == 1 ? dy : dz); }
+}
+
+// quick_math::solid_angle, gcm/system/quick_math.cpp:70-82 (atanf of the host libm, as the reference)
+static float solid_angle(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3)
+{
+	static const float PI = atanf(1) * 4;
+	float det = fabsf( gcm::determinant(x1, y1, z1, x2, y2, z2, x3, y3, z3) );
+	float norm_v1 = sqrtf( x1*x1 + y1*y1 + z1*z1 );
+	float norm_v2 = sqrtf( x2*x2 + y2*y2 + z2*z2 );
+	float norm_v3 = sqrtf( x3*x3 + y3*y3 + z3*z3 );
+	float div = norm_v1 * norm_v2 * norm_v3 + (x1*x2 + y1*y2 + z1*z2) * norm_v3
+					+ (x1*x3 + y1*y3 + z1*z3) * norm_v2 + (x2*x3 + y2*y3 + z2*z3) * norm_v1;
+	float at = atanf( det / div );
+	if (at < 0) { at += PI; }
+	return 2 * at;
+}
+
+// find_border_elem_normal, gcm/meshtypes/TetrMesh_1stOrder.cpp:333-370
+static void elem_normal(const Vec3& p1, const Vec3& p2, const Vec3& p3, float n[3])
+{
+	float v0x = p2.x - p1.x, v0y = p2.y - p1.y, v0z = p2.z - p1.z;
+	float v1x = p3.x - p1.x, v1y = p3.y - p1.y, v1z = p3.z - p1.z;
+	n[0] = v0y * v1z - v0z * v1y;
+	n[1] = v0z * v1x - v0x * v1z;
+	n[2] = v0x * v1y - v0y * v1x;
+	float l = sqrtf( n[0] * n[0] + n[1] * n[1] + n[2] * n[2] );
+	n[0] /= l;
+	n[1] /= l;
+	n[2] /= l;
+}
+
+int HostMesh::find_owner_tetr(int base, const float node_pos[3], float dx, float dy, float dz) const
+{
+	const Vec3 X = P(coords, base);
+	const float R2 = dx * dx + dy * dy + dz * dz;
+	const float delta = sqrtf(R2);
+	std::vector<int> checked, checking, tmp;
+	for(int e = n2t_off[base]; e < n2t_off[base+1]; e++) checking.push_back(n2t[e]);
+	bool inside_R = true;
+	while(inside_R) {
+		inside_R = false;
+		for(size_t i = 0; i < checking.size(); i++) {
+			const int t = checking[i];
+			const int* tv = &tets[4*(size_t)t];
+			Vec3 p[4] = { P(coords, tv[0]), P(coords, tv[1]), P(coords, tv[2]), P(coords, tv[3]) };
+			float h, vol;
+			if(!tet_hv.empty()) { h = tet_hv[2*(size_t)t]; vol = tet_hv[2*(size_t)t+1]; }
+			else { h = gcm::tetr_h(p[0], p[1], p[2], p[3]); vol = gcm::tet_signed_volume(p[0], p[1], p[2], p[3]); }
+			if(h < 0) throw HostError{MESH_EXCEPTION, "Tetr volume is zero"};
+			if(gcm::point_in_tetr(X, dx, dy, dz, delta, p[0], p[1], p[2], p[3], h, vol))
+				return t;
+			if(!inside_R) {
+				for(int j = 0; j < 4; j++) {
+					if(tv[j] == base) break;
+					float lx = p[j].x, ly = p[j].y, lz = p[j].z;
+					if( ( (node_pos[0] - lx) * (node_pos[0] - lx)
+						+ (node_pos[1] - ly) * (node_pos[1] - ly)
+						+ (node_pos[2] - lz) * (node_pos[2] - lz) ) < R2 )
+						inside_R = true;
+				}
+			}
+		}
+		if(!inside_R) return -1;
+		checked.insert(checked.end(), checking.begin(), checking.end());
+		tmp.clear();
+		for(size_t i = 0; i < checking.size(); i++)
+			for(int j = 0; j < 4; j++) {
+				int v = tets[4*(size_t)checking[i] + j];
+				for(int e = n2t_off[v]; e < n2t_off[v+1]; e++) tmp.push_back(n2t[e]);
+			}
+		std::sort(tmp.begin(), tmp.end());
+		tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+		std::vector<int> sorted_checked(checked);
+		std::sort(sorted_checked.begin(), sorted_checked.end());
+		checking.clear();
+		for(size_t i = 0; i < tmp.size(); i++)
+			if(!std::binary_search(sorted_checked.begin(), sorted_checked.end(), tmp[i]))
+				checking.push_back(tmp[i]);
+	}
+	return -1;
+}
+
+void HostMesh::find_border_node_normal(int node, float h, float out[3]) const
+{
+	float fn[3] = {0, 0, 0};
+	float cur[3];
+	const int f0 = n2f_off[node], f1 = n2f_off[node+1];
+	const int count = f1 - f0;
+	for(int e = f0; e < f1; e++) {
+		const int* fv = &faces[3*(size_t)n2f[e]];
+		elem_normal(P(coords, fv[0]), P(coords, fv[1]), P(coords, fv[2]), cur);
+		fn[0] += cur[0]; fn[1] += cur[1]; fn[2] += cur[2];
+	}
+	fn[0] /= count; fn[1] /= count; fn[2] /= count;
+	float l = sqrtf( fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2] );
+	fn[0] /= l; fn[1] /= l; fn[2] /= l;
+	out[0] = fn[0]; out[1] = fn[1]; out[2] = fn[2];
+	const float* X = &coords[3*(size_t)node];
+	if(find_owner_tetr(node, X, - h * fn[0], - h * fn[1], - h * fn[2]) != -1)
+		return;
+
+	// last chance option (:414-439): direction from the centre of elements[0]
+	{
+		const int* tv = &tets[4*(size_t)n2t[n2t_off[node]]];
+		for(int i = 0; i < 3; i++) {
+			float ve = 0;
+			for(int j = 0; j < 4; j++) ve += coords[3*(size_t)tv[j] + i];
+			ve /= 4;
+			fn[i] = X[i] - ve;
+		}
+	}
+	l = sqrtf( fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2] );
+	fn[0] /= l; fn[1] /= l; fn[2] /= l;
+	out[0] = fn[0]; out[1] = fn[1]; out[2] = fn[2];
+	if(find_owner_tetr(node, X, - h * fn[0], - h * fn[1], - h * fn[2]) != -1)
+		return;
+
+	// failback option (:441-478): min + max of the incident face normals
+	float mn[3], mx[3];
+	{
+		const int* fv = &faces[3*(size_t)n2f[f0]];
+		elem_normal(P(coords, fv[0]), P(coords, fv[1]), P(coords, fv[2]), cur);
+		for(int i = 0; i < 3; i++) { mn[i] = cur[i]; mx[i] = cur[i]; }
+	}
+	for(int e = f0 + 1; e < f1; e++) {
+		const int* fv = &faces[3*(size_t)n2f[e]];
+		elem_normal(P(coords, fv[0]), P(coords, fv[1]), P(coords, fv[2]), cur);
+		for(int i = 0; i < 3; i++) {
+			if(mx[i] < cur[i]) mx[i] = cur[i];
+			if(mn[i] > cur[i]) mn[i] = cur[i];
+		}
+	}
+	for(int i = 0; i < 3; i++) fn[i] = mn[i] + mx[i];
+	l = sqrtf( fn[0] * fn[0] + fn[1] * fn[1] + fn[2] * fn[2] );
+	fn[0] /= l; fn[1] /= l; fn[2] /= l;
+	out[0] = fn[0]; out[1] = fn[1]; out[2] = fn[2];
+	if(find_owner_tetr(node, X, - h * fn[0], - h * fn[1], - h * fn[2]) == -1)
+		throw HostError{MESH_EXCEPTION, "Can not create reasonable normal for node - is the border too sharp?"};
+}
+
+void HostMesh::pre_process_mesh()
+{
+	faces.clear();
+	tet_hv.assign(2*(size_t)T, 0.f);
+
+	// node numbering checks of :86-102 are implicit (index == local_num by construction)
+	for(size_t k = 0; k < tets.size(); k++)
+		if(tets[k] < 0 || tets[k] >= N) throw HostError{MESH_EXCEPTION, "Invalid node numbering"};
+
+	// ---- per-tet statics + get_max_h() over ALL tets (every node is still `used`, :81) -----
+	int bad = 0;
+	float mx_h = -1;
+	#pragma omp parallel for schedule(static) reduction(max:mx_h) reduction(+:bad)
+	for(int t = 0; t < T; t++) {
+		const int* tv = &tets[4*(size_t)t];
+		Vec3 p0 = P(coords, tv[0]), p1 = P(coords, tv[1]), p2 = P(coords, tv[2]), p3 = P(coords, tv[3]);
+		float h = gcm::tetr_h(p0, p1, p2, p3);
+		tet_hv[2*(size_t)t] = h;
+		tet_hv[2*(size_t)t+1] = gcm::tet_signed_volume(p0, p1, p2, p3);
+		if(h < 0) bad++;
+		if(h > mx_h) mx_h = h;
+	}
+	if(bad) throw HostError{MESH_EXCEPTION, "Tetr volume is zero"};
+	max_h = mx_h;
+	const float step_h = max_h / 4;
+
+	// ---- volume reverse lookups (:104-118) ------------------------------------------------
+	n2t_off.assign((size_t)N + 1, 0);
+	for(size_t k = 0; k < tets.size(); k++) n2t_off[tets[k] + 1]++;
+	for(int i = 0; i < N; i++) n2t_off[i+1] += n2t_off[i];
+	n2t.resize(tets.size());
+	{
+		std::vector<int> pos(n2t_off.begin(), n2t_off.end() - 1);
+		for(int t = 0; t < T; t++)
+			for(int j = 0; j < 4; j++)
+				n2t[pos[tets[4*(size_t)t + j]]++] = t;
+	}
+
+	// ---- unused nodes (:120-152) ----------------------------------------------------------
+	for(int i = 0; i < N; i++)
+		if(n2t_off[i+1] == n2t_off[i]) flags[i] &= ~4;
+	{
+		std::vector<char> drop(N, 0);
+		#pragma omp parallel for schedule(static)
+		for(int i = 0; i < N; i++) {
+			if(!is_remote(i)) continue;
+			int count = 0;
+			for(int e = n2t_off[i]; e < n2t_off[i+1] && !count; e++)
+				for(int k = 0; k < 4; k++)
+					if(is_local(tets[4*(size_t)n2t[e] + k])) { count++; break; }
+			if(count == 0) drop[i] = 1;
+		}
+		for(int i = 0; i < N; i++) if(drop[i]) flags[i] &= ~4;
+	}
+
+	// ---- border nodes by solid angle (:156-180) -------------------------------------------
+	static const float PI = atanf(1) * 4;
+	#pragma omp parallel for schedule(static)
+	for(int i = 0; i < N; i++) {
+		if(!is_local(i)) continue;
+		float sa = 0;
+		const Vec3 X = P(coords, i);
+		for(int e = n2t_off[i]; e < n2t_off[i+1]; e++) {
+			const int* tv = &tets[4*(size_t)n2t[e]];
+			int vert[3], c = 0;
+			for(int k = 0; k < 4; k++) if(tv[k] != i) { if(c < 3) vert[c] = tv[k]; c++; }
+			if(c != 3) continue;   // degenerate tet: the reference aborts preprocessing here
+			Vec3 a = P(coords, vert[0]), b = P(coords, vert[1]), d = P(coords, vert[2]);
+			sa += solid_angle(a.x - X.x, a.y - X.y, a.z - X.z, b.x - X.x, b.y - X.y, b.z - X.z,
+			                  d.x - X.x, d.y - X.y, d.z - X.z);
+		}
+		if( (4 * PI - sa) > PI / 100 ) flags[i] |= 8;
+	}
+
+	// ---- border triangles (:182-191, check_triangle_to_be_border :261-325) ------------------
+	// The test of each (tet, face) is independent; the list order is tet-major, face-minor.
+	static const int FV[4][4] = {{0,1,2,3},{0,1,3,2},{0,2,3,1},{1,2,3,0}};
+	std::vector<int> cand;   // tet*4+face for faces whose three vertices are local border nodes
+	for(int t = 0; t < T; t++) {
+		const int* tv = &tets[4*(size_t)t];
+		int nb = 0;
+		for(int k = 0; k < 4; k++) nb += (is_border(tv[k]) && is_local(tv[k])) ? 1 : 0;
+		if(nb < 3) continue;
+		for(int f = 0; f < 4; f++) {
+			int a = tv[FV[f][0]], b = tv[FV[f][1]], c = tv[FV[f][2]];
+			if(is_border(a) && is_border(b) && is_border(c) && is_local(a) && is_local(b) && is_local(c))
+				cand.push_back(t*4 + f);
+		}
+	}
+	std::vector<int> cand_face(3*cand.size(), -1);
+	std::vector<char> cand_ok(cand.size(), 0);
+	std::string err;
+	#pragma omp parallel for schedule(dynamic, 256)
+	for(long ci = 0; ci < (long)cand.size(); ci++) {
+		const int t = cand[ci] / 4, f = cand[ci] % 4;
+		const int* tv = &tets[4*(size_t)t];
+		int v1 = tv[FV[f][0]], v2 = tv[FV[f][1]], v3 = tv[FV[f][2]], tetr_vert = tv[FV[f][3]];
+		float normal[3], dx[3], tri_center[3], dir[3], plane_move[3];
+		elem_normal(P(coords, v1), P(coords, v2), P(coords, v3), normal);
+		for(int i = 0; i < 3; i++)
+			tri_center[i] = (coords[3*(size_t)v1+i] + coords[3*(size_t)v2+i] + coords[3*(size_t)v3+i]) / 3;
+		for(int i = 0; i < 3; i++)
+			dir[i] = coords[3*(size_t)tetr_vert+i] - tri_center[i];
+		if(normal[0] * dir[0] + normal[1] * dir[1] + normal[2] * dir[2] > 0) {
+			for(int i = 0; i < 3; i++) normal[i] = -normal[i];
+			int s = v2; v2 = v3; v3 = s;
+		}
+		for(int i = 0; i < 3; i++) dx[i] = step_h * normal[i];
+		for(int i = 0; i < 3; i++) plane_move[i] = tri_center[i] - coords[3*(size_t)v1+i];
+		try {
+			if(find_owner_tetr(v1, &coords[3*(size_t)v1], dx[0] + plane_move[0], dx[1] + plane_move[1], dx[2] + plane_move[2]) == -1) {
+				cand_ok[ci] = 1;
+				cand_face[3*ci] = v1; cand_face[3*ci+1] = v2; cand_face[3*ci+2] = v3;
+			}
+		} catch(HostError& e) {
+			#pragma omp critical
+			err = e.msg;
+		}
+	}
+	if(!err.empty()) throw HostError{MESH_EXCEPTION, err};
+	for(size_t ci = 0; ci < cand.size(); ci++)
+		if(cand_ok[ci]) { faces.push_back(cand_face[3*ci]); faces.push_back(cand_face[3*ci+1]); faces.push_back(cand_face[3*ci+2]); }
+
+	// ---- surface reverse lookups (:192-200) ------------------------------------------------
+	const int F = (int)(faces.size() / 3);
+	n2f_off.assign((size_t)N + 1, 0);
+	for(size_t k = 0; k < faces.size(); k++) n2f_off[faces[k] + 1]++;
+	for(int i = 0; i < N; i++) n2f_off[i+1] += n2f_off[i];
+	n2f.resize(faces.size());
+	{
+		std::vector<int> pos(n2f_off.begin(), n2f_off.end() - 1);
+		for(int f = 0; f < F; f++)
+			for(int j = 0; j < 3; j++)
+				n2f[pos[faces[3*(size_t)f + j]]++] = f;
+	}
+
+	// ---- node lists -------------------------------------------------------------------------
+	border_nodes.clear(); inner_nodes.clear();
+	border_slot.assign(N, -1);
+	for(int i = 0; i < N; i++) {
+		if(!is_local(i)) continue;
+		if(is_border(i)) { border_slot[i] = (int)border_nodes.size(); border_nodes.push_back(i); }
+		else inner_nodes.push_back(i);
+	}
+	const int NB = (int)border_nodes.size();
+
+	// ---- outer-normal check of :202-234 (only its exceptions are observable) ---------------
+	#pragma omp parallel for schedule(dynamic, 256)
+	for(int s = 0; s < NB; s++) {
+		float n[3];
+		try { find_border_node_normal(border_nodes[s], step_h, n); }
+		catch(HostError& e) {
+			#pragma omp critical
+			err = e.msg;
+		}
+	}
+	if(!err.empty()) throw HostError{MESH_EXCEPTION, err};
+
+	// ---- outline (:238-254) -------------------------------------------------------------------
+	if(N) {
+		for(int j = 0; j < 3; j++) outline_min[j] = outline_max[j] = coords[j];
+		for(int i = 0; i < N; i++)
+			for(int j = 0; j < 3; j++) {
+				float c = coords[3*(size_t)i + j];
+				if(c > outline_max[j]) outline_max[j] = c;
+				if(c < outline_min[j]) outline_min[j] = c;
+			}
+	}
+
+	// ---- get_min_h() over tets whose vertices are all used (:1040-1065) ----------------------
+	float mn_h = -1;
+	for(int t = 0; t < T; t++) {
+		const int* tv = &tets[4*(size_t)t];
+		if(!is_used(tv[0]) || !is_used(tv[1]) || !is_used(tv[2]) || !is_used(tv[3])) continue;
+		float h = tet_hv[2*(size_t)t];
+		if(mn_h < 0) mn_h = h;
+		if(h < mn_h) mn_h = h;
+	}
+	min_h = mn_h;
+
+	// ---- static node normals: find_border_node_normal(i) == (i, get_min_h()) (:377-380) -------
+	normals.assign(3*(size_t)NB, 0.f);
+	#pragma omp parallel for schedule(dynamic, 256)
+	for(int s = 0; s < NB; s++) {
+		try { find_border_node_normal(border_nodes[s], min_h, &normals[3*(size_t)s]); }
+		catch(HostError& e) {
+			#pragma omp critical
+			err = e.msg;
+		}
+	}
+	if(!err.empty()) throw HostError{MESH_EXCEPTION, err};
+	basis.assign(9*(size_t)NB, 0.f);
+	cond_id.assign(NB, -1);
+	preprocessed = true;
+}
+
+// create_rotation_matrix_with_normal + the rand() bookkeeping of create_random_axis,
+// gcm/methods/TetrMethod_Plastic_1stOrder.cpp:697-748, :843-901.
+void HostMesh::create_random_axes(GlibcRand& rng)
+{
+	const double PI = atan(1) * 4;
+	for(int i = 0; i < N; i++) {
+		if(!is_local(i)) continue;
+		if(!is_border(i)) {
+			(void)rng.next(); (void)rng.next(); (void)rng.next();   // phi, psi, teta; basis := E
+			continue;
+		}
+		const int s = border_slot[i];
+		const float x = normals[3*(size_t)s], y = normals[3*(size_t)s+1], z = normals[3*(size_t)s+2];
+		float teta = (rng.next() % 360) * 2 * PI / 360;
+		float a[3][3];
+		a[0][0] = x; a[0][1] = y; a[0][2] = z;
+		if( (fabsf(x) >= fabsf(y)) && (fabsf(x) >= fabsf(z)) ) { a[1][0] = y; a[1][1] = -x; a[1][2] = 0; }
+		else if( (fabsf(y) >= fabsf(x)) && (fabsf(y) >= fabsf(z)) ) { a[1][0] = y; a[1][1] = -x; a[1][2] = 0; }
+		else { a[1][0] = 0; a[1][1] = -z; a[1][2] = y; }
+		float modul = sqrtf( a[1][0] * a[1][0] + a[1][1] * a[1][1] + a[1][2] * a[1][2] );
+		a[1][0] /= modul; a[1][1] /= modul; a[1][2] /= modul;
+		a[2][0] = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+		a[2][1] = a[0][2] * a[1][0] - a[0][0] * a[1][2];
+		a[2][2] = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+		const float ct = cosf(teta), st = sinf(teta);
+		float rot[3][3];
+		rot[0][0] = ct + x * x * (1 - ct);
+		rot[0][1] = y * x * (1 - ct) + z * st;
+		rot[0][2] = z * x * (1 - ct) - y * st;
+		rot[1][0] = y * x * (1 - ct) - z * st;
+		rot[1][1] = ct + y * y * (1 - ct);
+		rot[1][2] = y * z * (1 - ct) + x * st;
+		rot[2][0] = x * z * (1 - ct) + y * st;
+		rot[2][1] = y * z * (1 - ct) - x * st;
+		rot[2][2] = ct + z * z * (1 - ct);
+		float* out = &basis[9*(size_t)s];
+		for(int r = 0; r < 3; r++)
+			for(int c = 0; c < 3; c++) {
+				float v = 0;
+				for(int k = 0; k < 3; k++)
+					v += rot[k][c] * a[r][k];
+				out[3*r + c] = v;
+			}
+	}
+}
+
+} // namespace gcmh

@@ -1,0 +1,80 @@
+// gcm_host.h -- host-side (C++) half of the GCM step: the mesh container and everything the
+// reference keeps on the CPU around the hot loop -- reverse lookups, border detection,
+// border faces, node normals (gcm/meshtypes/TetrMesh_1stOrder.cpp:66-479), the per-step
+// random local bases (gcm/methods/TetrMethod_Plastic_1stOrder.cpp:697-919) and the libc
+// rand() stream they consume.  Nothing here does the per-node update: that is CUDA only.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace gcmh {
+
+// GCMException codes, gcm/system/GCMException.h:19-29
+enum ExcCode { MPI_EXCEPTION = 0, SYNC_EXCEPTION = 1, CONFIG_EXCEPTION = 2, METHOD_EXCEPTION = 3,
+               MESH_EXCEPTION = 4, SNAP_EXCEPTION = 5, COLLISION_EXCEPTION = 6, MATH_EXCEPTION = 7,
+               UNIMPLEMENTED_EXCEPTION = 8, INPUT_EXCEPTION = 9 };
+
+struct HostError { int code; std::string msg; };
+
+// glibc rand()/srand() (random_r TYPE_3: additive feedback, degree 31, separation 3).
+// glibc is a platform dependency of the reference, not under /root/reference; the algorithm
+// is restated from its published description so that `srand(seed)` streams match bit for bit
+// (checked against the C library in tests/test_host_logic.py).
+struct GlibcRand {
+	uint32_t r[34];
+	int f, b;   // front / rear positions
+	void seed(unsigned s);
+	inline int next()
+	{
+		uint32_t v = (r[f] += r[b]);
+		if(++f >= 31) f = 0;
+		if(++b >= 31) b = 0;
+		return (int)(v >> 1);
+	}
+};
+
+struct HostMesh {
+	int zone = -1;
+	int N = 0, T = 0;
+	std::vector<float> coords;        // [N][3]
+	std::vector<int> flags;           // node_flags bits (Node.h:4-27)
+	std::vector<int> remote_zone, remote_num;
+	std::vector<float> mat;           // [N][4] la, mu, rho, yield_limit
+	std::vector<float> values;        // [N][9] host mirror (load / snapshot time only)
+	std::vector<int> tets;            // [T][4]
+
+	// built by pre_process_mesh
+	std::vector<int> n2t_off, n2t;    // node -> tets (`elements`), ascending
+	std::vector<int> faces;           // [F][3] border triangles, outward oriented
+	std::vector<int> n2f_off, n2f;    // node -> border faces (`border_elements`)
+	std::vector<float> tet_hv;        // [T][2] tetr_h, signed volume
+	std::vector<int> border_nodes;    // local border nodes, ascending
+	std::vector<int> border_slot;     // [N] index into border_nodes or -1
+	std::vector<int> inner_nodes;     // local inner nodes, ascending
+	std::vector<float> normals;       // [n_border][3] find_border_node_normal(min_h)
+	std::vector<float> basis;         // [n_border][9] local basis of the current step
+	std::vector<int> cond_id;         // [n_border] border condition id or -1 (default)
+	float min_h = -1, max_h = -1;
+	float outline_min[3] = {0, 0, 0}, outline_max[3] = {0, 0, 0};
+	float current_time = 0;
+	bool preprocessed = false;
+
+	bool is_used(int i) const { return (flags[i] & 4) != 0; }
+	bool is_local(int i) const { return (flags[i] & 6) == 6; }
+	bool is_remote(int i) const { return (flags[i] & 6) == 4; }
+	bool is_border(int i) const { return (flags[i] & 8) != 0; }
+
+	// TetrMesh_1stOrder::pre_process_mesh (:66-259). Throws HostError.
+	void pre_process_mesh();
+	// TetrMesh_1stOrder::find_owner_tetr (:1468-1602), all rings. Returns tet id or -1.
+	int find_owner_tetr(int base, const float node_pos[3], float dx, float dy, float dz) const;
+	// TetrMesh_1stOrder::find_border_node_normal (:382-479). Throws HostError.
+	void find_border_node_normal(int node, float h, float n[3]) const;
+	// GCM_..._Rotate_Axis::create_random_axis over all local nodes in index order, as driven
+	// by TetrMesh_1stOrder::get_max_possible_tau (:1882-1900). Fills `basis`.
+	void create_random_axes(GlibcRand& rng);
+	void translate(float dx, float dy, float dz);
+};
+
+} // namespace gcmh

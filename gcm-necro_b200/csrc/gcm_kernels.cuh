@@ -1,0 +1,95 @@
+// gcm_kernels.cuh -- sm_100a kernels of the GCM stage.  Included by gcm_capi.cu only.
+#pragma once
+#include <cuda_runtime.h>
+#include "gcm_step.cuh"
+
+namespace gcm {
+
+// err[0] = StepError (0 = none), err[1] = zone, err[2] = node, err[3] = stage; first error wins.
+__device__ __forceinline__ void report_error(int* err, int code, int zone, int node, int stage)
+{
+	if(atomicCAS(&err[0], 0, code) == 0) { err[1] = zone; err[2] = node; err[3] = stage; }
+}
+
+// One thread per listed node, one axis stage: TetrMesh_1stOrder::do_next_part_step's two
+// node loops (gcm/meshtypes/TetrMesh_1stOrder.cpp:1906-1923); the copy-back loop (:1925-1932)
+// is the caller's buffer swap.
+__global__ void __launch_bounds__(128)
+stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
+                     int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
+{
+	int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	int node = list[idx];
+	float out[9];
+	StageTap t;
+	int e = node_stage_nocontact(m, node, stage, out, tap ? &t : nullptr);
+	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
+	if(e) { report_error(err, e, zone, node, stage); return; }
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		un[(size_t)k * m.stride + node] = out[k];
+}
+
+// Stage 3: the plastic corrector drop_deviator (TetrMethod_Plastic_1stOrder.cpp:51-71,192-199),
+// in place on the current layer for every local node.
+__global__ void __launch_bounds__(256)
+plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* __restrict__ flags,
+               int n_nodes, size_t stride, int* err, int zone)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n_nodes) return;
+	if((flags[i] & (NF_LOCAL | NF_USED)) != (NF_LOCAL | NF_USED)) return;
+	float v[9];
+	bool bad = false;
+	#pragma unroll
+	for(int k = 0; k < 9; k++) {
+		v[k] = u[(size_t)k * stride + i];
+		bad |= (isnan(v[k]) || isinf(v[k]));
+	}
+	if(bad) { report_error(err, ERR_NAN, zone, i, 3); return; }
+	float yield_limit = mat[3 * stride + i];
+	if(drop_deviator(v, yield_limit)) {
+		#pragma unroll
+		for(int k = 3; k < 9; k++)
+			u[(size_t)k * stride + i] = v[k];
+	}
+}
+
+// DataBus::sync_nodes, same-process branch (gcm/system/DataBus.cpp:64-79): halo node values
+// of one zone copied from the owner zone's nodes.  Only the 9 evolving values move per stage.
+__global__ void halo_copy_kernel(float* __restrict__ dst_u, size_t dst_stride, const int* __restrict__ dst_idx,
+                                 const float* __restrict__ src_u, size_t src_stride, const int* __restrict__ src_idx, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	int d = dst_idx[i], s = src_idx[i];
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		dst_u[(size_t)k * dst_stride + d] = src_u[(size_t)k * src_stride + s];
+}
+
+// Cross-process halo: gather into / scatter from a plane-major [9][n] exchange buffer.
+__global__ void halo_pack_kernel(float* __restrict__ buf, const float* __restrict__ u, size_t stride,
+                                 const int* __restrict__ idx, int n, int n_total, int offset)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	int s = idx[i];
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		buf[(size_t)k * n_total + offset + i] = u[(size_t)k * stride + s];
+}
+
+__global__ void halo_unpack_kernel(float* __restrict__ u, size_t stride, const float* __restrict__ buf,
+                                   const int* __restrict__ idx, int n, int n_total, int offset)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	int d = idx[i];
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		u[(size_t)k * stride + d] = buf[(size_t)k * n_total + offset + i];
+}
+
+} // namespace gcm

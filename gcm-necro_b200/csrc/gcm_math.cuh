@@ -1,0 +1,383 @@
+// gcm_math.cuh -- scalar building blocks of the grid-characteristic step.
+//
+// Every function restates, operation by operation and in the reference's float/double mix,
+// one routine of avasyukov/gcm-necro (cited per function as gcm/<file>:<lines>).  The
+// reference is built for x86-64 without FMA contraction, so this translation unit MUST be
+// compiled with  nvcc -fmad=false -prec-div=true -prec-sqrt=true -ftz=false  (device) or
+// g++ -ffp-contract=off (the CPU emulation used by tests/ only).  Where a fused multiply-add
+// is wanted on purpose (conservative pre-filters) it is spelled __fmaf_rn explicitly.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define GCM_HD __host__ __device__ __forceinline__
+#define GCM_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define GCM_HD inline
+#define GCM_HD_NOINLINE
+#endif
+
+namespace gcm {
+
+// ---- error codes written by kernels (first error wins) ------------------------------------
+// Mapped by the host wrapper to the reference's GCMException codes (gcm/system/GCMException.h:19-29).
+enum StepError {
+	ERR_NONE = 0,
+	ERR_NAN = 1,              // "NAN or INF detected. Instability?"  TetrMethod_Plastic_1stOrder.cpp:192-194
+	ERR_OUTER_COUNT = 2,      // "Illegal number of outer characteristics"  :234-239
+	ERR_NOT_BORDER = 3,       // "Border node is not marked as border"  :268-272
+	ERR_BOTH_CONTACT = 4,     // "Both direction of contact are marked as contact"  :280-284
+	ERR_INTERP_SUM = 5,       // "Sum of factors is greater than 1.0"  TetrMesh_1stOrder.cpp:1855
+	ERR_INNER_NO_OWNER = 6,   // inner node without owner: find_border_cross path (:619-643), not built
+	ERR_RING_OVERFLOW = 7,    // owner search ring expansion exceeded the device scratch
+	ERR_BAD_RHEOLOGY = 8,     // "Bad rheology" ElasticMatrix3D.cpp:28-29
+	ERR_VIRT_OUTER_COUNT = 9, // virt node outer count != 3  TetrMethod_Plastic_1stOrder.cpp:348-356
+	ERR_BAD_Q = 10,           // "Bad vector q" ElasticMatrix3D.cpp:31-32
+	ERR_ZERO_VOLUME = 11,     // "Tetr volume is zero" / "Tri area is zero" TetrMesh_1stOrder.cpp:1010-1015
+	ERR_FOOT_PATTERN = 12     // characteristic dedupe did not give the 5-point pattern (0,1,2,3,2,3,4,4,4)
+};
+
+// gcm/system/quick_math.cpp:26-29
+GCM_HD float determinant(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3)
+{
+	return (x1*(y2*z3-y3*z2) - x2*(y1*z3-y3*z1) + x3*(y1*z2-y2*z1));
+}
+
+// gcm/system/quick_math.cpp:7-10
+GCM_HD float tetr_volume(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3)
+{
+	return determinant(x1, y1, z1, x2, y2, z2, x3, y3, z3) / 6;
+}
+
+// gcm/system/quick_math.cpp:13-23
+GCM_HD float tri_area(float x1, float y1, float z1, float x2, float y2, float z2)
+{
+	float a2 = x1*x1 + y1*y1 + z1*z1;
+	float b2 = x2*x2 + y2*y2 + z2*z2;
+	float ab = x1*x2 + y1*y2 + z1*z2;
+	float diff = a2*b2 - ab*ab;
+	if(diff < 0)
+		return 0;
+	return sqrtf(diff) / 2;
+}
+
+struct Vec3 { float x, y, z; };
+
+// Signed volume of the tetrahedron on (v1-v0, v2-v0, v3-v0); the `Vol` of
+// gcm/meshtypes/TetrMesh_1stOrder.cpp:1330-1340 (after fabs) and :1766-1776 (signed).
+GCM_HD float tet_signed_volume(const Vec3& v0, const Vec3& v1, const Vec3& v2, const Vec3& v3)
+{
+	return tetr_volume(v1.x - v0.x, v1.y - v0.y, v1.z - v0.z,
+	                   v2.x - v0.x, v2.y - v0.y, v2.z - v0.z,
+	                   v3.x - v0.x, v3.y - v0.y, v3.z - v0.z);
+}
+
+// gcm/meshtypes/TetrMesh_1stOrder.cpp:951-1029.  Returns < 0 when the reference would throw
+// (zero volume or a zero-area face).
+GCM_HD float tetr_h(const Vec3& v0, const Vec3& v1, const Vec3& v2, const Vec3& v3)
+{
+	float ax = v1.x - v0.x, ay = v1.y - v0.y, az = v1.z - v0.z;
+	float bx = v2.x - v0.x, by = v2.y - v0.y, bz = v2.z - v0.z;
+	float cx = v3.x - v0.x, cy = v3.y - v0.y, cz = v3.z - v0.z;
+	float vol = tetr_volume(ax, ay, az, bx, by, bz, cx, cy, cz);
+	float area[4];
+	area[0] = tri_area(ax, ay, az, bx, by, bz);
+	area[1] = tri_area(ax, ay, az, cx, cy, cz);
+	area[2] = tri_area(bx, by, bz, cx, cy, cz);
+	area[3] = tri_area(v2.x - v1.x, v2.y - v1.y, v2.z - v1.z, v3.x - v1.x, v3.y - v1.y, v3.z - v1.z);
+	if(vol == 0) return -1.f;
+	for(int j = 0; j < 4; j++)
+		if(area[j] == 0) return -1.f;
+	float min_h = fabsf(3*vol/area[0]);
+	for(int j = 1; j < 4; j++) {
+		float h = fabsf(3*vol/area[j]);
+		if(h < min_h) min_h = h;
+	}
+	return min_h;
+}
+
+// The four sub-volumes of point P against the faces of (v0,v1,v2,v3), in the vertex orderings
+// of gcm/meshtypes/TetrMesh_1stOrder.cpp:1348-1394 (point_in_tetr) == :1780-1826 (interpolate).
+GCM_HD void sub_volumes(const Vec3& v0, const Vec3& v1, const Vec3& v2, const Vec3& v3,
+                        float x, float y, float z, float s[4])
+{
+	float a0x = v0.x - x, a0y = v0.y - y, a0z = v0.z - z;
+	float a1x = v1.x - x, a1y = v1.y - y, a1z = v1.z - z;
+	float a2x = v2.x - x, a2y = v2.y - y, a2z = v2.z - z;
+	float a3x = v3.x - x, a3y = v3.y - y, a3z = v3.z - z;
+	s[0] = tetr_volume(a1x, a1y, a1z, a2x, a2y, a2z, a3x, a3y, a3z);
+	s[1] = tetr_volume(a0x, a0y, a0z, a2x, a2y, a2z, a3x, a3y, a3z);
+	s[2] = tetr_volume(a1x, a1y, a1z, a0x, a0y, a0z, a3x, a3y, a3z);
+	s[3] = tetr_volume(a1x, a1y, a1z, a2x, a2y, a2z, a0x, a0y, a0z);
+}
+
+// gcm/meshtypes/TetrMesh_1stOrder.cpp:1295-1402 with the per-tet statics hoisted:
+// min_h = tetr_h(tet) and vol = signed Vol(tet) are functions of the (static) coordinates only.
+// base = coordinates of the base node, (dx,dy,dz) the raw displacement, delta = sqrtf(dx^2+dy^2+dz^2)
+// (the same for every candidate, so the caller computes it once).
+GCM_HD bool point_in_tetr(const Vec3& base, float _dx, float _dy, float _dz, float delta,
+                          const Vec3& v0, const Vec3& v1, const Vec3& v2, const Vec3& v3,
+                          float min_h, float vol)
+{
+	float dx, dy, dz;
+	if( (delta > 0) && ((double)delta < (double)min_h * 0.99) ) {
+		dx = (float)( (double)(_dx * min_h) * 0.99 / (double)delta );
+		dy = (float)( (double)(_dy * min_h) * 0.99 / (double)delta );
+		dz = (float)( (double)(_dz * min_h) * 0.99 / (double)delta );
+	} else {
+		dx = _dx; dy = _dy; dz = _dz;
+	}
+	float Vol = fabsf(vol);
+	float x = base.x + dx;
+	float y = base.y + dy;
+	float z = base.z + dz;
+	float s[4];
+	sub_volumes(v0, v1, v2, v3, x, y, z, s);
+	return (double)(fabsf(s[0]) + fabsf(s[1]) + fabsf(s[2]) + fabsf(s[3])) < (double)Vol * 1.001;
+}
+
+// Barycentric factors of gcm/meshtypes/TetrMesh_1stOrder.cpp:1764-1857.  (x,y,z) = foot
+// coordinates, vol = signed Vol(tet).  Returns false when the reference throws (sum >= 1.25).
+GCM_HD bool interp_factors(const Vec3& v0, const Vec3& v1, const Vec3& v2, const Vec3& v3,
+                           float x, float y, float z, float vol, float f[4])
+{
+	float s[4];
+	sub_volumes(v0, v1, v2, v3, x, y, z, s);
+	f[0] = fabsf(s[0] / vol);
+	f[1] = fabsf(s[1] / vol);
+	f[2] = fabsf(s[2] / vol);
+	f[3] = fabsf(s[3] / vol);
+	float sum = f[0] + f[1] + f[2] + f[3];
+	if((double)sum > 1.0) {
+		if((double)sum < 1.25) {
+			for(int i = 0; i < 4; i++)
+				f[i] = (float)( (double)f[i] * 0.995 / (double)sum );
+		} else {
+			return false;
+		}
+	}
+	return true;
+}
+
+// One interpolated quantity, gcm/meshtypes/TetrMesh_1stOrder.cpp:1864-1877.
+GCM_HD float interp4(float a0, float a1, float a2, float a3, const float f[4])
+{
+	return (a0*f[0] + a1*f[1] + a2*f[2] + a3*f[3]);
+}
+
+// ---- elastic eigensystem -----------------------------------------------------------------
+// gcm/datatypes/ElasticMatrix3D.cpp:522-530
+GCM_HD void create_matrix_N(const float n[3][3], int i, int j, float res[6])
+{
+	res[0] = (n[i][0]*n[j][0] + n[j][0]*n[i][0])/2;
+	res[1] = (n[i][0]*n[j][1] + n[j][0]*n[i][1])/2;
+	res[2] = (n[i][0]*n[j][2] + n[j][0]*n[i][2])/2;
+	res[3] = (n[i][1]*n[j][1] + n[j][1]*n[i][1])/2;
+	res[4] = (n[i][1]*n[j][2] + n[j][1]*n[i][2])/2;
+	res[5] = (n[i][2]*n[j][2] + n[j][2]*n[i][2])/2;
+}
+
+// Direction triple (n0 = q/|q|, n1, n2) of gcm/datatypes/ElasticMatrix3D.cpp:284-339.
+GCM_HD void elastic_axes(float qjx, float qjy, float qjz, float n[3][3], float* l_out)
+{
+	float l = sqrtf(qjx*qjx + qjy*qjy + qjz*qjz);
+	n[0][0] = qjx/l;
+	n[0][1] = qjy/l;
+	n[0][2] = qjz/l;
+	if(fabsf(n[0][0]) <= fabsf(n[0][1])) {
+		if(fabsf(n[0][0]) <= fabsf(n[0][2])) {
+			n[1][0] = 0;         n[1][1] = -n[0][2]; n[1][2] = n[0][1];
+		} else {
+			n[1][0] = -n[0][1];  n[1][1] = n[0][0];  n[1][2] = 0;
+		}
+	} else {
+		if(fabsf(n[0][1]) <= fabsf(n[0][2])) {
+			n[1][0] = -n[0][2];  n[1][1] = 0;        n[1][2] = n[0][0];
+		} else {
+			n[1][0] = -n[0][1];  n[1][1] = n[0][0];  n[1][2] = 0;
+		}
+	}
+	float dtmp = sqrtf(n[1][0]*n[1][0] + n[1][1]*n[1][1] + n[1][2]*n[1][2]);
+	n[1][0] /= dtmp;
+	n[1][1] /= dtmp;
+	n[1][2] /= dtmp;
+	n[2][0] = n[0][1]*n[1][2] - n[0][2]*n[1][1];
+	n[2][1] = n[0][2]*n[1][0] - n[0][0]*n[1][2];
+	n[2][2] = n[0][0]*n[1][1] - n[0][1]*n[1][0];
+	*l_out = l;
+}
+
+// Lambda (diagonal), Omega (U) and Omega^-1 (U1) of
+// gcm/datatypes/ElasticMatrix3D.cpp:243-519 (CreateGeneralizedMatrix); A is never read by
+// the step and is not built.  U/U1 are row-major 9x9.  Returns a StepError.
+GCM_HD int elastic_matrix(float la, float mu, float ro, float qjx, float qjy, float qjz,
+                          float L[9], float* U, float* U1)
+{
+	if((la <= 0) || (mu <= 0) || (ro <= 0))
+		return ERR_BAD_RHEOLOGY;
+	if( qjx*qjx + qjy*qjy + qjz*qjz <= 0 )
+		return ERR_BAD_Q;
+	float n[3][3];
+	float l;
+	elastic_axes(qjx, qjy, qjz, n, &l);
+
+	float c1 = sqrtf((la+2*mu)/ro);
+	float c2 = sqrtf(mu/ro);
+	float c3 = sqrtf(la*la/(ro*(la+2*mu)));
+
+	L[0] = c1 * l;  L[1] = -c1 * l;
+	L[2] = c2 * l;  L[3] = -c2 * l;
+	L[4] = c2 * l;  L[5] = -c2 * l;
+	L[6] = 0; L[7] = 0; L[8] = 0;
+
+	float I[6] = {1, 0, 0, 1, 0, 1};
+	float N00[6], N01[6], N02[6], N11[6], N12[6], N22[6];
+	create_matrix_N(n, 0, 0, N00);
+	create_matrix_N(n, 0, 1, N01);
+	create_matrix_N(n, 0, 2, N02);
+	create_matrix_N(n, 1, 1, N11);
+	create_matrix_N(n, 1, 2, N12);
+	create_matrix_N(n, 2, 2, N22);
+
+	if(U1) {
+#define GCM_U1(i,j) U1[(i)*9+(j)]
+		for(int k = 0; k < 3; k++) {
+			GCM_U1(k,0) = n[0][k]; GCM_U1(k,1) = n[0][k];
+			GCM_U1(k,2) = n[1][k]; GCM_U1(k,3) = n[1][k];
+			GCM_U1(k,4) = n[2][k]; GCM_U1(k,5) = n[2][k];
+			GCM_U1(k,6) = 0; GCM_U1(k,7) = 0; GCM_U1(k,8) = 0;
+		}
+		for(int i = 0; i < 6; i++) {
+			GCM_U1(3+i,0) = -ro*((c1-c3)*N00[i] + c3*I[i]);
+			GCM_U1(3+i,1) = ro*((c1-c3)*N00[i] + c3*I[i]);
+			GCM_U1(3+i,2) = -2*ro*c2*N01[i];
+			GCM_U1(3+i,3) = 2*ro*c2*N01[i];
+			GCM_U1(3+i,4) = -2*ro*c2*N02[i];
+			GCM_U1(3+i,5) = 2*ro*c2*N02[i];
+			GCM_U1(3+i,6) = 4*N12[i];
+			GCM_U1(3+i,7) = N11[i] - N22[i];
+			GCM_U1(3+i,8) = I[i] - N00[i];
+		}
+		for(int i = 0; i < 81; i++)
+			U1[i] /= 2;
+#undef GCM_U1
+	}
+	if(U) {
+#define GCM_U(i,j) U[(i)*9+(j)]
+		const float w[6] = {1, 2, 2, 1, 2, 1};
+		for(int k = 0; k < 3; k++) {
+			GCM_U(0,k) = n[0][k]; GCM_U(1,k) = n[0][k];
+			GCM_U(2,k) = n[1][k]; GCM_U(3,k) = n[1][k];
+			GCM_U(4,k) = n[2][k]; GCM_U(5,k) = n[2][k];
+			GCM_U(6,k) = 0; GCM_U(7,k) = 0; GCM_U(8,k) = 0;
+		}
+		// the reference writes  -N/(c*ro)  for w==1 and  -2*N/(c*ro)  for w==2; 1*N == N exactly
+		for(int i = 0; i < 6; i++) {
+			GCM_U(0,3+i) = -w[i]*N00[i]/(c1*ro);
+			GCM_U(1,3+i) = w[i]*N00[i]/(c1*ro);
+			GCM_U(2,3+i) = -w[i]*N01[i]/(c2*ro);
+			GCM_U(3,3+i) = w[i]*N01[i]/(c2*ro);
+			GCM_U(4,3+i) = -w[i]*N02[i]/(c2*ro);
+			GCM_U(5,3+i) = w[i]*N02[i]/(c2*ro);
+			GCM_U(6,3+i) = w[i]*N12[i];
+			GCM_U(7,3+i) = w[i]*(N11[i]-N22[i]);
+			GCM_U(8,3+i) = w[i]*(N11[i]+N22[i]-2*la*N00[i]/(la+2*mu));
+		}
+#undef GCM_U
+	}
+	return ERR_NONE;
+}
+
+// gcm/methods/TetrMethod_Plastic_1stOrder.cpp:51-71 (drop_deviator).  In place: s = values[3..8]
+// (sxx,sxy,sxz,syy,syz,szz); writes only when yielding, exactly as the reference.
+GCM_HD bool drop_deviator(float v[9], float yield_limit)
+{
+	float J2 = sqrtf( ( (v[3] - v[6]) * (v[3] - v[6])
+			+ (v[6] - v[8]) * (v[6] - v[8])
+			+ (v[3] - v[8]) * (v[3] - v[8])
+			+ 6 * ( (v[4]) * (v[4]) + (v[5]) * (v[5])
+				+ (v[7]) * (v[7])) ) / 6 );
+	float p = (v[3] + v[6] + v[8]) / 3;
+	if (yield_limit < J2)
+	{
+		float n3 = ((v[3] - p) * yield_limit / J2) + p;
+		float n4 = v[4] * yield_limit / J2;
+		float n5 = v[5] * yield_limit / J2;
+		float n6 = ((v[6] - p) * yield_limit / J2) + p;
+		float n7 = v[7] * yield_limit / J2;
+		float n8 = ((v[8] - p) * yield_limit / J2) + p;
+		v[3] = n3; v[4] = n4; v[5] = n5; v[6] = n6; v[7] = n7; v[8] = n8;
+		return true;
+	}
+	return false;
+}
+
+// ---- dense LU in double (GSL gsl_linalg_LU_decomp / gsl_linalg_LU_solve semantics) --------
+// GSL is a third-party dependency of the reference, absent from /root/reference and unpinned
+// (gcm/CMakeLists.txt:88).  Published GSL 1.x algorithm: Gaussian elimination with partial
+// pivoting, pivot = first row of maximal |a_ij| (strict >), multipliers stored in place,
+// rank-1 update; solve = permute, unit-lower forward substitution, upper back substitution.
+// A is row-major NxN and is destroyed; b is overwritten by x.
+template<int N>
+GCM_HD void lu_solve(double* A, double* b)
+{
+	int perm[N];
+	for(int i = 0; i < N; i++) perm[i] = i;
+	for(int j = 0; j + 1 < N; j++) {
+		double mx = fabs(A[j*N+j]);
+		int ip = j;
+		for(int i = j + 1; i < N; i++) {
+			double a = fabs(A[i*N+j]);
+			if(a > mx) { mx = a; ip = i; }
+		}
+		if(ip != j) {
+			for(int k = 0; k < N; k++) { double t = A[j*N+k]; A[j*N+k] = A[ip*N+k]; A[ip*N+k] = t; }
+			int t = perm[j]; perm[j] = perm[ip]; perm[ip] = t;
+		}
+		double ajj = A[j*N+j];
+		if(ajj != 0.0) {
+			for(int i = j + 1; i < N; i++) {
+				double aij = A[i*N+j] / ajj;
+				A[i*N+j] = aij;
+				for(int k = j + 1; k < N; k++)
+					A[i*N+k] = A[i*N+k] - aij * A[j*N+k];
+			}
+		}
+	}
+	double x[N];
+	for(int i = 0; i < N; i++) x[i] = b[perm[i]];
+	for(int i = 0; i < N; i++) {
+		double t = x[i];
+		for(int j = 0; j < i; j++) t -= A[i*N+j] * x[j];
+		x[i] = t;
+	}
+	for(int i = N - 1; i >= 0; i--) {
+		double t = x[i];
+		for(int j = i + 1; j < N; j++) t -= A[i*N+j] * x[j];
+		x[i] = t / A[i*N+i];
+	}
+	for(int i = 0; i < N; i++) b[i] = x[i];
+}
+
+// gcm/system/quick_math.cpp:85-115 (create_local_basis)
+GCM_HD void create_local_basis(const float n[3], float n1[3], float n2[3])
+{
+	if(fabsf(n[0]) <= fabsf(n[1])) {
+		if(fabsf(n[0]) <= fabsf(n[2])) { n1[0] = 0; n1[1] = -n[2]; n1[2] = n[1]; }
+		else { n1[0] = -n[1]; n1[1] = n[0]; n1[2] = 0; }
+	} else {
+		if(fabsf(n[1]) <= fabsf(n[2])) { n1[0] = -n[2]; n1[1] = 0; n1[2] = n[0]; }
+		else { n1[0] = -n[1]; n1[1] = n[0]; n1[2] = 0; }
+	}
+	float dtmp = sqrtf(n1[0]*n1[0] + n1[1]*n1[1] + n1[2]*n1[2]);
+	n1[0] /= dtmp;
+	n1[1] /= dtmp;
+	n1[2] /= dtmp;
+	// vector_product, quick_math.cpp:38-43
+	n2[0] = n[1] * n1[2] - n1[1] * n[2];
+	n2[1] = n1[0] * n[2] - n[0] * n1[2];
+	n2[2] = n[0] * n1[1] - n1[0] * n[1];
+}
+
+} // namespace gcm

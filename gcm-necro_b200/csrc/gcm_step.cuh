@@ -1,0 +1,443 @@
+// gcm_step.cuh -- one node, one stage of the grid-characteristic method, as straight-line
+// __host__ __device__ code over an SoA mesh view.
+//
+// Follows gcm/methods/TetrMethod_Plastic_1stOrder.cpp:190-423 (do_next_part_step),
+// :78-111 (prepare_node), :430-681 (find_nodes_on_previous_time_layer) and
+// gcm/meshtypes/TetrMesh_1stOrder.cpp:1468-1602 (find_owner_tetr), :1764-1880 (interpolate).
+// The kernels in gcm_kernels.cu call these per thread; tests/ compile the same header with
+// g++ to single-step the logic on the CPU (debug aid only -- not part of the product library).
+#pragma once
+#include "gcm_math.cuh"
+
+namespace gcm {
+
+// node_flags bits, gcm/datatypes/Node.h:4-27
+enum NodeFlags { NF_IN_CONTACT = 1, NF_LOCAL = 2, NF_USED = 4, NF_BORDER = 8, NF_GCM = 16, NF_SPH = 32 };
+
+// Border calculators (gcm/methods/border/*.cpp) as device-side condition ids.
+enum BorderCalcType { BC_FREE = 0, BC_FIXED = 1, BC_EXT_FORCE = 2, BC_EXT_VELOCITY = 3, BC_EXT_VALUES = 4 };
+// Contact calculators (gcm/methods/contact/*.cpp).
+enum ContactCalcType { CC_ADHESION = 0, CC_FRICTION = 1 };
+
+// One BorderCondition = calculator + its parameters + the pulse form evaluated for this step
+// (gcm/system/BorderCondition.cpp:3-6, gcm/system/forms/StepPulseForm.cpp:5-14).
+struct BorderCond {
+	int type;            // BorderCalcType
+	float p_normal;      // normal_stress / normal_v
+	float p_tangential;  // tangential_stress / tangential_v
+	float dir[3];        // tangential_direction, already normalised (set_parameters)
+	int vars_index[3];   // ExternalValuesCalculator
+	float vars_values[3];
+	float scale;         // form->calcMagnitudeNorm(t) for the current step
+	int active;          // form->isActive(t); inactive -> default condition (check_stresses)
+};
+
+#define GCM_MAX_BORDER_CONDS 16
+
+// Read-only view of one zone mesh in device (or, in the test emulation, host) memory.
+struct MeshView {
+	int n_nodes, n_tets;
+	size_t stride;           // plane stride of the SoA arrays (floats)
+	const float* xyz;        // [3][stride]
+	const float* u;          // [9][stride]  current layer (vx,vy,vz,sxx,sxy,sxz,syy,syz,szz)
+	const float* mat;        // [4][stride]  la, mu, rho, yield_limit
+	const int* flags;        // [n_nodes]
+	const int* n2t_off;      // [n_nodes+1]  node -> incident tets (ascending ids), CSR
+	const int* n2t;
+	const int* tets;         // [n_tets][4]
+	const float* tet_hv;     // [n_tets][2]  (tetr_h, signed volume) -- static geometry
+	const int* border_slot;  // [n_nodes]    index into the border arrays or -1
+	const float* basis;      // [n_border][9] local basis ksi[3][3] of this step (border nodes)
+	const int* cond_id;      // [n_border]   index into conds[] or -1 = default
+	const int* contact;      // [n_border][6] axis_plus[3], axis_minus[3] (virt node ids) or NULL
+	float tau;
+	float time;
+	float min_h;
+	BorderCond conds[GCM_MAX_BORDER_CONDS];
+	int n_conds;
+};
+
+GCM_HD Vec3 load_xyz(const MeshView& m, int i)
+{
+	Vec3 v; v.x = m.xyz[i]; v.y = m.xyz[m.stride + i]; v.z = m.xyz[2*m.stride + i];
+	return v;
+}
+
+struct TetGeom { int v[4]; Vec3 p[4]; float h, vol; };
+
+GCM_HD void load_tet(const MeshView& m, int t, TetGeom& g)
+{
+#if defined(__CUDA_ARCH__)
+	int4 q = reinterpret_cast<const int4*>(m.tets)[t];
+	g.v[0] = q.x; g.v[1] = q.y; g.v[2] = q.z; g.v[3] = q.w;
+	float2 hv = reinterpret_cast<const float2*>(m.tet_hv)[t];
+	g.h = hv.x; g.vol = hv.y;
+#else
+	for(int k = 0; k < 4; k++) g.v[k] = m.tets[4*(size_t)t + k];
+	g.h = m.tet_hv[2*(size_t)t]; g.vol = m.tet_hv[2*(size_t)t + 1];
+#endif
+	for(int k = 0; k < 4; k++) g.p[k] = load_xyz(m, g.v[k]);
+}
+
+// First ring of gcm/meshtypes/TetrMesh_1stOrder.cpp:1468-1602: the candidates are the base
+// node's incident tets in stored order, the first one passing point_in_tetr wins.
+//   base      = index whose `elements` list and stored coordinates are used (nodes[base_node])
+//   node_pos  = node->coords (differs from the stored coordinates only for virtual nodes)
+// Returns the tet id, -1 for "not found and the search would stop" (NULL), and sets *expand
+// when the reference would go on to the next ring (some candidate vertex closer than |dx|).
+GCM_HD int find_owner_first_ring(const MeshView& m, int base, const Vec3& node_pos,
+                                 float dx, float dy, float dz, TetGeom& g, bool* expand)
+{
+	Vec3 X = load_xyz(m, base);
+	float R2 = dx * dx + dy * dy + dz * dz;
+	float delta = sqrtf(R2);
+	bool inside_R = false;
+	int e0 = m.n2t_off[base], e1 = m.n2t_off[base + 1];
+	for(int e = e0; e < e1; e++) {
+		int t = m.n2t[e];
+		load_tet(m, t, g);
+		if(point_in_tetr(X, dx, dy, dz, delta, g.p[0], g.p[1], g.p[2], g.p[3], g.h, g.vol))
+			return t;
+		if(!inside_R) {
+			for(int j = 0; j < 4; j++) {
+				if(g.v[j] == base) break;   // the reference `break`s (not `continue`s) here, :1544-1545
+				float lx = g.p[j].x, ly = g.p[j].y, lz = g.p[j].z;
+				if( ( (node_pos.x - lx) * (node_pos.x - lx)
+					+ (node_pos.y - ly) * (node_pos.y - ly)
+					+ (node_pos.z - lz) * (node_pos.z - lz) ) < R2 )
+					inside_R = true;
+			}
+		}
+	}
+	*expand = inside_R;
+	return -1;
+}
+
+// Interpolated state at a foot (gcm/meshtypes/TetrMesh_1stOrder.cpp:1764-1880).
+// out[0..8] = values, out[9..11] = la, mu, rho (only virtual nodes read those).
+GCM_HD int interpolate_foot(const MeshView& m, const TetGeom& g, float x, float y, float z,
+                            float out[12], bool with_material)
+{
+	float f[4];
+	if(!interp_factors(g.p[0], g.p[1], g.p[2], g.p[3], x, y, z, g.vol, f))
+		return ERR_INTERP_SUM;
+	for(int k = 0; k < 9; k++) {
+		const float* pl = m.u + (size_t)k * m.stride;
+		out[k] = interp4(pl[g.v[0]], pl[g.v[1]], pl[g.v[2]], pl[g.v[3]], f);
+	}
+	if(with_material) {
+		for(int k = 0; k < 3; k++) {
+			const float* pl = m.mat + (size_t)k * m.stride;
+			out[9 + k] = interp4(pl[g.v[0]], pl[g.v[1]], pl[g.v[2]], pl[g.v[3]], f);
+		}
+	}
+	return ERR_NONE;
+}
+
+// The node being advanced: a mesh node, or a virtual (contact) node borrowing the element
+// list and local_num of a mesh node (gcm/system/TetrMeshSet.cpp:236-271).
+struct CurNode {
+	int base;          // local_num: index into the mesh arrays
+	Vec3 pos;          // cur_node->coords
+	float val[9];      // cur_node->values[0..8]
+	float la, mu, rho;
+	bool is_border;
+	int axis_plus[3], axis_minus[3];  // contact_data (all -1 when none)
+	bool has_contact_data;
+};
+
+struct FeetOut {
+	float val[5][12];  // previous_nodes[count].values (+ la, mu, rho)
+	bool inner[9];
+	int ppoint[9];
+	int owner[5];      // owner tet per distinct point (-1 = none); debug/parity tap
+	int n_points;
+};
+
+// gcm/methods/TetrMethod_Plastic_1stOrder.cpp:430-681.  ksi = random_axis[basis_num].ksi[stage].
+// Returns the outer count, or -(StepError) on a condition the reference throws on.
+GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& cur, int stage,
+	float alpha, const float dksi[9], const float ksi[3], FeetOut& out, bool with_material)
+{
+	Vec3 X = load_xyz(m, cur.base);
+	float Xc[3] = {X.x, X.y, X.z};
+	float curc[3] = {cur.pos.x, cur.pos.y, cur.pos.z};
+	float safe_direction[3];
+	for(int j = 0; j < 3; j++)
+		safe_direction[j] = - ( curc[j] - Xc[j] );
+
+	float tetr_center[3];
+	{
+		int tetr_num = m.n2t[m.n2t_off[cur.base]];
+		const int* tv = m.tets + 4*(size_t)tetr_num;
+		Vec3 a = load_xyz(m, tv[0]), b = load_xyz(m, tv[1]), c = load_xyz(m, tv[2]), d = load_xyz(m, tv[3]);
+		tetr_center[0] = ( a.x + b.x + c.x + d.x ) / 4;
+		tetr_center[1] = ( a.y + b.y + c.y + d.y ) / 4;
+		tetr_center[2] = ( a.z + b.z + c.z + d.z ) / 4;
+	}
+	if(alpha > 1.0)
+		alpha = 1.0;
+
+	int count = 0;
+	float dx[3], dx_ksi[3];
+	const bool contact_axis = cur.has_contact_data
+		&& ( (cur.axis_plus[stage] != -1) || (cur.axis_minus[stage] != -1) );
+
+	for(int i = 0; i < 9; i++)
+	{
+		bool already_found = false;
+		for(int j = 0; j < i; j++) {
+			if( (double)fabsf(dksi[i] - dksi[j]) <= 0.01 * (double)fabsf(dksi[i] + dksi[j]) ) {
+				already_found = true;
+				out.ppoint[i] = out.ppoint[j];
+				out.inner[i] = out.inner[j];
+			}
+		}
+		if(already_found) continue;
+		if(count >= 5) return -ERR_FOOT_PATTERN;
+		out.ppoint[i] = count;
+		// previous_nodes[count] = *cur_node
+		for(int k = 0; k < 9; k++) out.val[count][k] = cur.val[k];
+		out.val[count][9] = cur.la; out.val[count][10] = cur.mu; out.val[count][11] = cur.rho;
+
+		for(int j = 0; j < 3; j++)
+			dx_ksi[j] = dksi[i] * ksi[j];
+		float safe_direction_projection_modul = 1;
+		float fc[3];
+		for(int j = 0; j < 3; j++) {
+			bool bend;
+			if(contact_axis) {
+				if(cur.axis_plus[stage] != -1) bend = !(dksi[i] >= 0);
+				else bend = !(dksi[i] <= 0);
+			} else {
+				bend = !(dksi[i] >= 0);
+			}
+			if(!bend) {
+				dx[j] = dx_ksi[j];
+			} else {
+				float sdp = safe_direction_projection_modul * safe_direction[j];
+				dx[j] = dx_ksi[j] * (1 - alpha) + sdp * alpha;
+			}
+			dx[j] += ( curc[j] - Xc[j] );
+			fc[j] = Xc[j] + dx[j];
+		}
+		if((double)alpha > 0.95) {
+			if( ! ( cur.is_border && (stage == 0) && (dksi[i] > 0) ) )
+				for(int z = 0; z < 3; z++) {
+					dx[z] = tetr_center[z] - Xc[z];
+					fc[z] = Xc[z] + dx[z];
+				}
+		}
+
+		TetGeom g;
+		bool expand = false;
+		int owner = find_owner_first_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
+		if(owner < 0 && expand)
+			return -ERR_RING_OVERFLOW;
+		out.owner[count] = owner;
+
+		if( cur.has_contact_data && (cur.axis_plus[stage] != -1) && (dksi[i] > 0) ) {
+			out.inner[i] = false;
+		} else if( cur.has_contact_data && (cur.axis_minus[stage] != -1) && (dksi[i] < 0) ) {
+			out.inner[i] = false;
+		} else if(owner >= 0) {
+			int e = interpolate_foot(m, g, fc[0], fc[1], fc[2], out.val[count], with_material);
+			if(e) return -e;
+			out.inner[i] = true;
+		} else if(dksi[i] == 0) {
+			out.inner[i] = true;   // previous_nodes[count] = *cur_node (already copied)
+		} else if(!cur.is_border) {
+			return -ERR_INNER_NO_OWNER;
+		} else {
+			out.inner[i] = false;
+		}
+		count++;
+	}
+	out.n_points = count;
+	int outer_count = 0;
+	for(int i = 0; i < 9; i++)
+		if(!out.inner[i]) outer_count++;
+	return outer_count;
+}
+
+// gcm/methods/TetrMethod_Plastic_1stOrder.cpp:78-111 (prepare_node): eigensystem for axis
+// `stage` of basis `ksi3x3`, dksi, and the alpha-retry loop.  *tries = number of searches run.
+GCM_HD int prepare_node(const MeshView& m, const CurNode& cur, int stage, const float* ksi3x3,
+                        float L[9], float* U, float* U1, FeetOut& feet, bool with_material, int* tries)
+{
+	// prepare_part_step: q = column `stage` of basis^-1 = row `stage` of the basis (:40-49, :903-919)
+	const float* ksi = ksi3x3 + 3*stage;
+	int e = elastic_matrix(cur.la, cur.mu, cur.rho, ksi[0], ksi[1], ksi[2], L, U, U1);
+	if(e) return -e;
+	float dksi[9];
+	for(int i = 0; i < 9; i++)
+		dksi[i] = - L[i] * m.tau;
+	float alpha = 0;
+	int outer_count;
+	int n = 0;
+	do {
+		outer_count = find_nodes_on_previous_time_layer(m, cur, stage, alpha, dksi, ksi, feet, with_material);
+		n++;
+		if(outer_count < 0) break;
+		alpha = (float)((double)alpha + 0.1);
+	} while( (outer_count != 0) && (outer_count != 3) && ((double)alpha < 1.01) );
+	*tries = n;
+	return outer_count;
+}
+
+// omega_i = sum_j U(i,j) * u^{p(i)}_j  (the inner rows of every calculator)
+GCM_HD float omega_row(const float* U, int i, const float* vals)
+{
+	float om = 0;
+	for(int j = 0; j < 9; j++)
+		om += U[i*9+j] * vals[j];
+	return om;
+}
+
+// gcm/methods/volume/SimpleVolumeCalculator.cpp:7-32
+GCM_HD void volume_calc(const float* U, const float* U1, const FeetOut& feet, float out[9])
+{
+	float omega[9];
+	for(int i = 0; i < 9; i++)
+		omega[i] = omega_row(U, i, feet.val[feet.ppoint[i]]);
+	for(int i = 0; i < 9; i++) {
+		float v = 0;
+		for(int j = 0; j < 9; j++)
+			v += U1[i*9+j] * omega[j];
+		out[i] = v;
+	}
+}
+
+// The five border calculators of gcm/methods/border/*.cpp behind one switch:
+// inner rows = Omega rows, the three outer rows (in index order) = condition rows.
+// outer_normal = basis.ksi[stage] (TetrMethod_Plastic_1stOrder.cpp:289-297).
+GCM_HD void border_calc(const BorderCond& bc, const float* U, const FeetOut& feet,
+                        const float outer_normal[3], float out[9])
+{
+	double A[81];
+	double b[9];
+	float local_n[3][3];
+	local_n[0][0] = outer_normal[0]; local_n[0][1] = outer_normal[1]; local_n[0][2] = outer_normal[2];
+	if(bc.type == BC_EXT_FORCE || bc.type == BC_EXT_VELOCITY)
+		create_local_basis(local_n[0], local_n[1], local_n[2]);
+	const float scale = bc.scale;
+	int outer_count = 3;
+	for(int i = 0; i < 9; i++) {
+		if(feet.inner[i]) {
+			b[i] = (double)omega_row(U, i, feet.val[feet.ppoint[i]]);
+			for(int j = 0; j < 9; j++) A[i*9+j] = (double)U[i*9+j];
+			continue;
+		}
+		b[i] = 0;
+		for(int j = 0; j < 9; j++) A[i*9+j] = 0;
+		const int k = 3 - outer_count;   // 0, 1, 2: which condition row
+		if(outer_count <= 0) continue;
+		outer_count--;
+		switch(bc.type) {
+		case BC_FREE: {
+			// FreeBorderCalculator.cpp:59-74
+			const int c[3][3] = {{3,4,5},{4,6,7},{5,7,8}};
+			A[i*9+c[k][0]] = (double)outer_normal[0];
+			A[i*9+c[k][1]] = (double)outer_normal[1];
+			A[i*9+c[k][2]] = (double)outer_normal[2];
+		} break;
+		case BC_FIXED:
+			// FixedBorderCalculator.cpp:52-58
+			A[i*9+k] = 1;
+			break;
+		case BC_EXT_FORCE: {
+			// ExternalForceCalculator.cpp:76-110
+			const float* n0 = local_n[0];
+			if(k == 0) {
+				A[i*9+3] = (double)(n0[0] * n0[0]);
+				A[i*9+4] = (double)(2 * n0[1] * n0[0]);
+				A[i*9+5] = (double)(2 * n0[2] * n0[0]);
+				A[i*9+6] = (double)(n0[1] * n0[1]);
+				A[i*9+7] = (double)(2 * n0[2] * n0[1]);
+				A[i*9+8] = (double)(n0[2] * n0[2]);
+				b[i] = (double)(scale * bc.p_normal);
+			} else {
+				const float* t = local_n[k];
+				A[i*9+3] = (double)(n0[0] * t[0]);
+				A[i*9+4] = (double)(n0[1] * t[0] + n0[0] * t[1]);
+				A[i*9+5] = (double)(n0[2] * t[0] + n0[0] * t[2]);
+				A[i*9+6] = (double)(n0[1] * t[1]);
+				A[i*9+7] = (double)(n0[2] * t[1] + n0[1] * t[2]);
+				A[i*9+8] = (double)(n0[2] * t[2]);
+				b[i] = (double)(scale * bc.p_tangential * (t[0]*bc.dir[0] + t[1]*bc.dir[1] + t[2]*bc.dir[2]));
+			}
+		} break;
+		case BC_EXT_VELOCITY: {
+			// ExternalVelocityCalculator.cpp:70-98
+			const float* t = local_n[k];
+			A[i*9+0] = (double)t[0];
+			A[i*9+1] = (double)t[1];
+			A[i*9+2] = (double)t[2];
+			if(k == 0) b[i] = (double)(scale * bc.p_normal);
+			else b[i] = (double)(scale * bc.p_tangential * (t[0]*bc.dir[0] + t[1]*bc.dir[1] + t[2]*bc.dir[2]));
+		} break;
+		case BC_EXT_VALUES:
+			// ExternalValuesCalculator.cpp:63-78
+			A[i*9+bc.vars_index[k]] = 1;
+			b[i] = (double)bc.vars_values[k];
+			break;
+		}
+	}
+	lu_solve<9>(A, b);
+	for(int j = 0; j < 9; j++)
+		out[j] = (float)b[j];
+}
+
+// Debug/parity tap of one node-stage: owner per distinct point of the LAST alpha try.
+struct StageTap { int owner[5]; int outer_count; int tries; };
+
+// One mesh node, one axis stage (stage 0..2), without contact:
+// gcm/methods/TetrMethod_Plastic_1stOrder.cpp:190-297.  Writes out[9]; returns a StepError.
+GCM_HD int node_stage_nocontact(const MeshView& m, int node, int stage, float out[9], StageTap* tap)
+{
+	CurNode cur;
+	cur.base = node;
+	cur.pos = load_xyz(m, node);
+	for(int k = 0; k < 9; k++) {
+		float v = m.u[(size_t)k * m.stride + node];
+		if(isnan(v) || isinf(v)) return ERR_NAN;
+		cur.val[k] = v;
+	}
+	cur.la = m.mat[node]; cur.mu = m.mat[m.stride + node]; cur.rho = m.mat[2*m.stride + node];
+	cur.is_border = (m.flags[node] & NF_BORDER) != 0;
+	cur.has_contact_data = cur.is_border;
+	for(int k = 0; k < 3; k++) { cur.axis_plus[k] = -1; cur.axis_minus[k] = -1; }
+
+	const float E[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+	const float* basis = E;
+	int slot = -1;
+	if(cur.is_border) {
+		slot = m.border_slot[node];
+		basis = m.basis + 9*(size_t)slot;
+	}
+	float L[9], U[81], U1[81];
+	FeetOut feet;
+	int tries = 0;
+	int outer_count = prepare_node(m, cur, stage, basis, L, U, U1, feet, false, &tries);
+	if(tap) {
+		for(int k = 0; k < 5; k++) tap->owner[k] = (outer_count >= 0 && k < feet.n_points) ? feet.owner[k] : -2;
+		tap->outer_count = outer_count; tap->tries = tries;
+	}
+	if(outer_count < 0) return -outer_count;
+	if(outer_count == 0) {
+		volume_calc(U, U1, feet, out);
+		return ERR_NONE;
+	}
+	if(outer_count != 3) return ERR_OUTER_COUNT;
+	if(!cur.is_border) return ERR_NOT_BORDER;
+	// default condition: FreeBorderCalculator with an always-on form (TetrMeshSet.cpp:11-21)
+	BorderCond def;
+	def.type = BC_FREE; def.scale = 1; def.active = 1;
+	const BorderCond* bc = &def;
+	int cid = m.cond_id ? m.cond_id[slot] : -1;
+	if(cid >= 0 && m.conds[cid].active) bc = &m.conds[cid];
+	border_calc(*bc, U, feet, basis + 3*stage, out);
+	return ERR_NONE;
+}
+
+} // namespace gcm

@@ -1,0 +1,224 @@
+// emul_main.cpp -- TEST-ONLY debugging aid (never part of libgcm_b200.so, never shipped).
+//
+// Single-steps the `__host__ __device__` per-node logic of gcm-necro_b200/csrc/gcm_step.cuh on
+// the CPU so that the restatement can be compared with oracle/_ref in a container that has no
+// GPU.  Takes the same files and flags as oracle/ref_build/driver.cpp and writes the same
+// outputs (<out>.z<k>.values.f32, .flags.i32, .faces.i32, .bases.f32, .tap.i32).
+// The product has no CPU path: kernels are validated on the B200 by tests/ -m gpu.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <memory>
+
+#include "../../gcm-necro_b200/csrc/gcm_host.h"
+#include "../../gcm-necro_b200/csrc/gcm_step.cuh"
+
+using gcmh::HostMesh;
+using std::string;
+using std::vector;
+
+static void die(const string& m) { fprintf(stderr, "gcm_emul: %s\n", m.c_str()); exit(2); }
+template<class T> static void read_vec(FILE* f, vector<T>& v, size_t n) { v.resize(n); if(n && fread(v.data(), sizeof(T), n, f) != n) die("short read"); }
+template<class T> static void write_file(const string& name, const vector<T>& v)
+{
+	FILE* f = fopen(name.c_str(), "wb"); if(!f) die("cannot open " + name);
+	if(v.size()) fwrite(v.data(), sizeof(T), v.size(), f);
+	fclose(f);
+}
+
+struct Z {
+	HostMesh hm;
+	size_t stride;
+	vector<float> xyz, u[2], mat;
+	int cur = 0;
+};
+struct Cond { gcm::BorderCond bc; float start, dur, box[6]; };
+
+int main(int argc, char** argv)
+{
+	vector<string> mesh_files, state_files;
+	vector<Cond> conds;
+	float la = 7e9f, mu = 1e9f, rho = 7.8e6f, yield = 1e16f;
+	int steps = 1, seed = 12345, tap_step = -1;
+	string out;
+	for(int a = 1; a < argc; a++) {
+		string s = argv[a];
+		if(s == "--mesh") { while(a + 1 < argc && argv[a+1][0] != '-') mesh_files.push_back(argv[++a]); }
+		else if(s == "--state") { while(a + 1 < argc && argv[a+1][0] != '-') state_files.push_back(argv[++a]); }
+		else if(s == "--la") la = atof(argv[++a]);
+		else if(s == "--mu") mu = atof(argv[++a]);
+		else if(s == "--rho") rho = atof(argv[++a]);
+		else if(s == "--yield") yield = atof(argv[++a]);
+		else if(s == "--steps") steps = atoi(argv[++a]);
+		else if(s == "--seed") seed = atoi(argv[++a]);
+		else if(s == "--out") out = argv[++a];
+		else if(s == "--tap-step") tap_step = atoi(argv[++a]);
+		else if(s == "--border") {
+			Cond c; memset(&c, 0, sizeof c);
+			string t = argv[++a];
+			float p[5]; for(int k = 0; k < 5; k++) p[k] = atof(argv[++a]);
+			c.start = atof(argv[++a]); c.dur = atof(argv[++a]);
+			for(int k = 0; k < 6; k++) c.box[k] = atof(argv[++a]);
+			c.bc.type = t == "free" ? 0 : t == "fixed" ? 1 : t == "extforce" ? 2 : t == "extvel" ? 3 : -1;
+			if(c.bc.type < 0) die("unknown border calculator");
+			c.bc.p_normal = p[0]; c.bc.p_tangential = p[1];
+			float d = sqrtf(p[2]*p[2] + p[3]*p[3] + p[4]*p[4]);
+			c.bc.dir[0] = p[2] / d; c.bc.dir[1] = p[3] / d; c.bc.dir[2] = p[4] / d;
+			conds.push_back(c);
+		}
+		else die("unknown argument " + s);
+	}
+	const int NZ = (int)mesh_files.size();
+	vector<std::unique_ptr<Z>> zs;
+	for(int z = 0; z < NZ; z++) {
+		FILE* f = fopen(mesh_files[z].c_str(), "rb"); if(!f) die("cannot open mesh");
+		int hdr[5]; if(fread(hdr, 4, 5, f) != 5 || hdr[0] != 0x424D4347) die("bad mesh header");
+		int N = hdr[3], T = hdr[4];
+		vector<int> placement;
+		zs.emplace_back(new Z()); HostMesh& hm = zs.back()->hm;
+		hm.zone = z; hm.N = N; hm.T = T;
+		read_vec(f, placement, N); read_vec(f, hm.coords, 3*(size_t)N);
+		read_vec(f, hm.remote_zone, N); read_vec(f, hm.remote_num, N); read_vec(f, hm.tets, 4*(size_t)T);
+		fclose(f);
+		hm.flags.resize(N); hm.mat.resize(4*(size_t)N); hm.values.assign(9*(size_t)N, 0.f);
+		for(int i = 0; i < N; i++) {
+			hm.flags[i] = 16 | 4 | (placement[i] ? 2 : 0);
+			if(!placement[i]) for(int k = 0; k < 3; k++) hm.coords[3*(size_t)i+k] = 0;
+			hm.mat[4*(size_t)i] = la; hm.mat[4*(size_t)i+1] = mu; hm.mat[4*(size_t)i+2] = rho; hm.mat[4*(size_t)i+3] = yield;
+		}
+	}
+	auto host_sync = [&](bool with_coords) {
+		for(auto& zp : zs) {
+			HostMesh& d = zp->hm;
+			for(int i = 0; i < d.N; i++) {
+				if(d.flags[i] & 2) continue;
+				HostMesh& o = zs[d.remote_zone[i]]->hm;
+				int si = d.remote_num[i];
+				if(with_coords) {
+					memcpy(&d.coords[3*(size_t)i], &o.coords[3*(size_t)si], 12);
+					memcpy(&d.mat[4*(size_t)i], &o.mat[4*(size_t)si], 16);
+				}
+				memcpy(&d.values[9*(size_t)i], &o.values[9*(size_t)si], 36);
+			}
+		}
+	};
+	try {
+		host_sync(true);
+		for(auto& zp : zs) zp->hm.pre_process_mesh();
+	} catch(gcmh::HostError& e) { die("preprocess: " + e.msg); }
+	for(size_t c = 0; c < conds.size(); c++)
+		for(auto& zp : zs) {
+			HostMesh& hm = zp->hm;
+			for(size_t b = 0; b < hm.border_nodes.size(); b++) {
+				const float* x = &hm.coords[3*(size_t)hm.border_nodes[b]]; const float* box = conds[c].box;
+				if(x[0] < box[1] && x[0] > box[0] && x[1] < box[3] && x[1] > box[2] && x[2] < box[5] && x[2] > box[4]) hm.cond_id[b] = (int)c;
+			}
+		}
+	for(int z = 0; z < NZ && z < (int)state_files.size(); z++) {
+		HostMesh& hm = zs[z]->hm;
+		FILE* f = fopen(state_files[z].c_str(), "rb"); if(!f) die("cannot open state");
+		vector<float> st; read_vec(f, st, 9*(size_t)hm.N); fclose(f);
+		for(int i = 0; i < hm.N; i++) if(hm.is_local(i)) memcpy(&hm.values[9*(size_t)i], &st[9*(size_t)i], 36);
+	}
+	// SoA
+	for(auto& zp : zs) {
+		Z& z = *zp; HostMesh& hm = z.hm;
+		z.stride = (hm.N + 31) / 32 * 32;
+		z.xyz.assign(3*z.stride, 0); z.mat.assign(4*z.stride, 0); z.u[0].assign(9*z.stride, 0);
+		for(int i = 0; i < hm.N; i++) {
+			for(int k = 0; k < 3; k++) z.xyz[k*z.stride+i] = hm.coords[3*(size_t)i+k];
+			for(int k = 0; k < 4; k++) z.mat[k*z.stride+i] = hm.mat[4*(size_t)i+k];
+			for(int k = 0; k < 9; k++) z.u[0][k*z.stride+i] = hm.values[9*(size_t)i+k];
+		}
+		z.u[1] = z.u[0];
+	}
+	gcmh::GlibcRand rng; rng.seed(seed);
+	vector<int> tap;   // records: zone node stage owner[5] outer tries
+	int rc = 0;
+	const float tau = 0.002f;
+	for(int step = 0; step < steps && !rc; step++) {
+		for(auto& zp : zs) zp->hm.create_random_axes(rng);
+		for(int stage = 0; stage < 4 && !rc; stage++) {
+			// sync_nodes on the SoA layers
+			for(auto& zp : zs) {
+				Z& d = *zp;
+				for(int i = 0; i < d.hm.N; i++) {
+					if(d.hm.flags[i] & 2) continue;
+					Z& o = *zs[d.hm.remote_zone[i]]; int si = d.hm.remote_num[i];
+					for(int k = 0; k < 9; k++) d.u[d.cur][k*d.stride+i] = o.u[o.cur][k*o.stride+si];
+				}
+			}
+			for(int zi = 0; zi < NZ && !rc; zi++) {
+				Z& z = *zs[zi]; HostMesh& hm = z.hm;
+				float* ucur = z.u[z.cur].data(); float* un = z.u[z.cur^1].data();
+				if(stage == 3) {
+					for(int i = 0; i < hm.N; i++) {
+						if(!hm.is_local(i)) continue;
+						float v[9]; for(int k = 0; k < 9; k++) v[k] = ucur[k*z.stride+i];
+						if(gcm::drop_deviator(v, z.mat[3*z.stride+i])) for(int k = 3; k < 9; k++) ucur[k*z.stride+i] = v[k];
+					}
+					continue;
+				}
+				gcm::MeshView m; memset(&m, 0, sizeof m);
+				m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
+				m.xyz = z.xyz.data(); m.u = ucur; m.mat = z.mat.data(); m.flags = hm.flags.data();
+				m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
+				m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
+				m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
+				m.n_conds = (int)conds.size();
+				for(size_t c = 0; c < conds.size(); c++) {
+					m.conds[c] = conds[c].bc;
+					float t = hm.current_time;
+					m.conds[c].active = (conds[c].dur < 0) ? 1 : !(t > conds[c].start + conds[c].dur);
+					m.conds[c].scale = t < conds[c].start ? 0.f : conds[c].dur < 0 ? 1.f : (t <= conds[c].start + conds[c].dur ? 1.f : 0.f);
+				}
+				int err = 0;
+				#pragma omp parallel for schedule(dynamic, 1024)
+				for(int i = 0; i < hm.N; i++) {
+					if(!hm.is_local(i)) continue;
+					float o[9]; gcm::StageTap t;
+					int e = gcm::node_stage_nocontact(m, i, stage, o, &t);
+					if(e) {
+						#pragma omp critical
+						{ if(!err) { err = e; fprintf(stderr, "gcm_emul: error %d zone %d node %d stage %d\n", e, zi, i, stage); } }
+						continue;
+					}
+					for(int k = 0; k < 9; k++) un[k*z.stride+i] = o[k];
+					if(step == tap_step) {
+						#pragma omp critical
+						{ tap.push_back(zi); tap.push_back(i); tap.push_back(stage); for(int k = 0; k < 5; k++) tap.push_back(t.owner[k]); tap.push_back(t.outer_count); tap.push_back(t.tries); }
+					}
+				}
+				if(err) rc = 10 + err;
+				z.cur ^= 1;
+			}
+		}
+		for(auto& zp : zs) zp->hm.current_time += tau;
+	}
+	if(out.size()) {
+		for(int zi = 0; zi < NZ; zi++) {
+			Z& z = *zs[zi]; HostMesh& hm = z.hm;
+			vector<float> vals(9*(size_t)hm.N), bases(9*(size_t)hm.N, 0.f);
+			for(int i = 0; i < hm.N; i++) {
+				for(int k = 0; k < 9; k++) vals[9*(size_t)i+k] = z.u[z.cur][k*z.stride+i];
+				if(hm.is_local(i)) {
+					int b = hm.border_slot[i];
+					const float E[9] = {1,0,0,0,1,0,0,0,1};
+					memcpy(&bases[9*(size_t)i], b >= 0 ? &hm.basis[9*(size_t)b] : E, 36);
+				}
+			}
+			vector<int> fl(hm.N);
+			for(int i = 0; i < hm.N; i++) fl[i] = hm.flags[i] & 15;
+			char zs_[32]; snprintf(zs_, sizeof zs_, ".z%d", zi);
+			write_file(out + zs_ + ".values.f32", vals);
+			write_file(out + zs_ + ".flags.i32", fl);
+			write_file(out + zs_ + ".faces.i32", hm.faces);
+			write_file(out + zs_ + ".bases.f32", bases);
+		}
+		if(tap_step >= 0) write_file(out + ".tap.i32", tap);
+	}
+	printf("{\"impl\": \"emul\", \"steps\": %d, \"rc\": %d}\n", steps, rc);
+	return rc;
+}

@@ -1,0 +1,243 @@
+"""Shared helpers of the parity tests: case definitions, oracle/_ref and emulation runners,
+tap decoding and the runner for the product (C ABI on the GPU).
+
+A *case* is a dict: zones (list of meshgen.ZoneMesh), states (list of [N,9] arrays), material
+(la, mu, rho, yield), steps, seed, borders (list of oracle-driver --border tuples).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "gcm-necro_b200"))
+from gcm_b200 import meshgen  # noqa: E402
+
+ORACLE_TAP = os.path.join(ROOT, "oracle", "_ref", "gcm3d_ref_tap")
+ORACLE = os.path.join(ROOT, "oracle", "_ref", "gcm3d_ref")
+EMUL = os.path.join(ROOT, "tests", "emul", "_build", "gcm_emul")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+LA, MU, RHO = 7e9, 1e9, 7.8e6   # tasks/friction-test.xml:15
+
+TAP_DT = np.dtype([("step", "i4"), ("zone", "i4"), ("node", "i4"), ("is_virt", "i4"), ("stage", "i4"),
+                   ("ch", "i4"), ("count", "i4"), ("owner", "i4"), ("alpha", "f4"), ("dx", "f4", 3)])
+
+BORDER_TYPES = {"free": 0, "fixed": 1, "extforce": 2, "extvel": 3}
+
+
+def make_case(name):
+    """The small parity cases (also the golden fixtures). Deterministic."""
+    c = dict(name=name, material=(LA, MU, RHO, 1e16), steps=3, seed=12345, borders=[], tap_step=0)
+    if name == "cube8":
+        z = meshgen.make_cube(8)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=1)]
+    elif name == "cube8_pwave":
+        z = meshgen.make_cube(8)
+        c["zones"] = [z]
+        c["states"] = [meshgen.pwave_state(z.coords, LA, MU, RHO, width=1.5)]
+    elif name == "jitter8":
+        z = meshgen.make_cube(8, jitter=0.2, seed=3)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=2)]
+    elif name == "jitter8_border":
+        z = meshgen.make_cube(8, jitter=0.15, jitter_border=True, seed=5)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=4)]
+    elif name == "zones2":
+        zs = meshgen.make_box_zones(6, 6, 8, 2)
+        c["zones"] = zs
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=7) for z in zs]
+    elif name == "zones3_jitter":
+        zs = meshgen.make_box_zones(5, 5, 9, 3, jitter=0.2, seed=11)
+        c["zones"] = zs
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=8) for z in zs]
+    elif name == "plastic8":
+        z = meshgen.make_cube(8)
+        c["zones"] = [z]
+        c["states"] = [meshgen.pwave_state(z.coords, LA, MU, RHO, width=1.5)]
+        c["material"] = (LA, MU, RHO, 1e7)    # J2 of the pulse peak ~3.4e7 -> yields
+    elif name == "extforce8":
+        z = meshgen.make_cube(8, spacing=(1.0, 1.0, 0.5))
+        c["zones"] = [z]
+        c["states"] = [np.zeros((z.n_nodes, 9), np.float32)]
+        # ExternalForceCalculator on the top face for the first 2 steps, then it expires
+        c["borders"] = [("extforce", (-1e8, 3e7, 1.0, 0.5, 0.0), 0.0, 0.003, (-1, 8, -1, 8, 3.4, 3.6))]
+        c["steps"] = 4
+    elif name == "fixed_extvel8":
+        z = meshgen.make_cube(8)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=9)]
+        c["borders"] = [("fixed", (0, 0, 0, 0, 1), -1.0, -1.0, (-1, 8, -1, 8, -0.5, 0.5)),
+                        ("extvel", (2.0, 1.0, 0.0, 1.0, 0.0), -1.0, -1.0, (-1, 8, -1, 8, 6.5, 7.5))]
+    else:
+        raise KeyError(name)
+    return c
+
+
+CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zones3_jitter", "plastic8",
+              "extforce8", "fixed_extvel8"]
+
+
+def _write_inputs(case, d):
+    meshes, states = [], []
+    for k, (z, st) in enumerate(zip(case["zones"], case["states"])):
+        mp = os.path.join(d, "z%d.gcmb" % k)
+        sp = os.path.join(d, "z%d.state" % k)
+        meshgen.write_gcmb(mp, z)
+        np.ascontiguousarray(st, np.float32).tofile(sp)
+        meshes.append(mp)
+        states.append(sp)
+    return meshes, states
+
+
+def _cli(case, meshes, states, out):
+    la, mu, rho, yl = case["material"]
+    a = ["--mesh"] + meshes + ["--state"] + states + ["--la", repr(la), "--mu", repr(mu), "--rho", repr(rho),
+                                                       "--yield", repr(yl), "--steps", str(case["steps"]),
+                                                       "--seed", str(case["seed"]), "--out", out,
+                                                       "--tap-step", str(case["tap_step"])]
+    for (t, p, start, dur, box) in case["borders"]:
+        a += ["--border", t] + [repr(float(x)) for x in p] + [repr(float(start)), repr(float(dur))] + [repr(float(x)) for x in box]
+    return a
+
+
+def decode_oracle_tap(path, n_nodes_per_zone):
+    """Last-try owner per (zone, stage, node, point) and tries per (zone, stage, node)."""
+    t = np.fromfile(path, TAP_DT)
+    t = t[t["is_virt"] == 0]
+    owners = [np.full((3, n, 5), -2, np.int32) for n in n_nodes_per_zone]
+    tries = [np.zeros((3, n), np.int32) for n in n_nodes_per_zone]
+    for z in range(len(n_nodes_per_zone)):
+        tz = t[t["zone"] == z]
+        # records are in program order: a later try overwrites an earlier one
+        owners[z][tz["stage"], tz["node"], tz["count"]] = tz["owner"]
+        first = tz[tz["count"] == 0]
+        np.add.at(tries[z], (first["stage"], first["node"]), 1)
+    return owners, tries
+
+
+def run_oracle(case, tap=True):
+    """Run oracle/_ref on the case; returns per-zone dict of arrays."""
+    exe = ORACLE_TAP if tap else ORACLE
+    with tempfile.TemporaryDirectory() as d:
+        meshes, states = _write_inputs(case, d)
+        out = os.path.join(d, "o")
+        r = subprocess.run([exe] + _cli(case, meshes, states, out), capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("oracle failed: %s %s" % (r.stdout, r.stderr))
+        res = []
+        ns = [z.n_nodes for z in case["zones"]]
+        owners, tries = decode_oracle_tap(out + ".tap.bin", ns) if tap else (None, None)
+        for k, n in enumerate(ns):
+            pre = "%s.z%d." % (out, k)
+            res.append(dict(values=np.fromfile(pre + "values.f32", np.float32).reshape(n, 9),
+                            flags=np.fromfile(pre + "flags.i32", np.int32),
+                            faces=np.fromfile(pre + "faces.i32", np.int32).reshape(-1, 3),
+                            bases=np.fromfile(pre + "bases.f32", np.float32).reshape(n, 9),
+                            owners=owners[k] if tap else None, tries=tries[k] if tap else None))
+        return res
+
+
+def run_emul(case):
+    """Run the CPU emulation of gcm_step.cuh (tests/emul) on the case."""
+    with tempfile.TemporaryDirectory() as d:
+        meshes, states = _write_inputs(case, d)
+        out = os.path.join(d, "e")
+        r = subprocess.run([EMUL] + _cli(case, meshes, states, out), capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("emul failed: %s %s" % (r.stdout, r.stderr))
+        ns = [z.n_nodes for z in case["zones"]]
+        tap = np.fromfile(out + ".tap.i32", np.int32).reshape(-1, 10)
+        res = []
+        for k, n in enumerate(ns):
+            pre = "%s.z%d." % (out, k)
+            tz = tap[tap[:, 0] == k]
+            owners = np.full((3, n, 5), -2, np.int32)
+            tries = np.zeros((3, n), np.int32)
+            owners[tz[:, 2], tz[:, 1]] = tz[:, 3:8]
+            tries[tz[:, 2], tz[:, 1]] = tz[:, 9]
+            res.append(dict(values=np.fromfile(pre + "values.f32", np.float32).reshape(n, 9),
+                            flags=np.fromfile(pre + "flags.i32", np.int32),
+                            faces=np.fromfile(pre + "faces.i32", np.int32).reshape(-1, 3),
+                            bases=np.fromfile(pre + "bases.f32", np.float32).reshape(n, 9),
+                            owners=owners, tries=tries))
+        return res
+
+
+def run_product(case, device=0):
+    """Run the case through the C ABI (libgcm_b200.so) on the GPU."""
+    import gcm_b200
+    la, mu, rho, yl = case["material"]
+    ms = gcm_b200.TetrMeshSet(n_zones=len(case["zones"]), device=device)
+    try:
+        ms.srand(case["seed"])
+        for k, z in enumerate(case["zones"]):
+            ms.get_mesh_by_zone_num(k).load(z, la=la, mu=mu, rho=rho, yield_limit=yl)
+        ms.pre_process_meshes()
+        for (t, p, start, dur, box) in case["borders"]:
+            ms.add_border_condition(BORDER_TYPES[t], box, params=p, start=start, duration=dur)
+        for k, st in enumerate(case["states"]):
+            ms.get_mesh_by_zone_num(k).set_values(st)
+        res = [dict() for _ in case["zones"]]
+        for step in range(case["steps"]):
+            ms.enable_tap(step == case["tap_step"])
+            ms.do_next_step()
+            ms.synchronize()
+            if step == case["tap_step"]:
+                for k in range(len(case["zones"])):
+                    o, outer, tr = ms.get_mesh_by_zone_num(k).get_tap()
+                    res[k].update(owners=o, tries=tr, outer=outer)
+        for k in range(len(case["zones"])):
+            m = ms.get_mesh_by_zone_num(k)
+            res[k].update(values=m.get_values(), flags=m.get_flags() & 15, faces=m.get_faces(), bases=m.get_bases())
+        return res
+    finally:
+        ms.close()
+
+
+def local_mask(flags):
+    return (flags & 6) == 6
+
+
+def compare(ref, got, what=("flags", "faces", "bases", "owners", "tries", "values")):
+    """Bit-exact comparison of a run against the reference run; returns list of mismatch strings."""
+    bad = []
+    for k, (r, g) in enumerate(zip(ref, got)):
+        loc = local_mask(r["flags"])
+        for w in what:
+            a, b = r[w], g[w]
+            if a is None or b is None:
+                continue
+            if w in ("values", "bases"):
+                a, b = a[loc], b[loc]
+                same = a.shape == b.shape and np.array_equal(a.view(np.uint32) & 0x7fffffff == 0, b.view(np.uint32) & 0x7fffffff == 0) \
+                    and np.array_equal(a, b)
+            elif w in ("owners", "tries"):
+                a, b = a[:, loc], b[:, loc]
+                if w == "owners":
+                    # slots past the number of distinct points are unspecified (-2 in both decoders)
+                    pass
+                same = a.shape == b.shape and np.array_equal(a, b)
+            else:
+                same = a.shape == b.shape and np.array_equal(a, b)
+            if not same:
+                n = int((a != b).sum()) if a.shape == b.shape else -1
+                bad.append("zone %d %s: %d mismatches" % (k, w, n))
+    return bad
+
+
+def golden_path(name):
+    return os.path.join(GOLDEN, name + ".npz")
+
+
+def load_golden(name):
+    g = np.load(golden_path(name))
+    nz = int(g["n_zones"])
+    return [dict(values=g["values%d" % k], flags=g["flags%d" % k], faces=g["faces%d" % k], bases=g["bases%d" % k],
+                 owners=g["owners%d" % k], tries=g["tries%d" % k]) for k in range(nz)]

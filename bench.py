@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- tet node-updates/s of the grid-characteristic step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): elastic cube of
+216^3 = 10 077 696 nodes / 59 630 250 tets (create_cube.c semantics, 6 tets per hex), split into
+8 z-slab zones with one halo layer, material la=7e9 mu=1e9 rho=7.8e6, plane P-wave initial state,
+tau = 0.002, srand(12345).  One *step* = TetrMeshSet::do_next_step = 3 axis stages + plastic
+stage on every local node, with the halo exchange before each stage.  Strong scaling: the 8 zones
+are dealt to the N ranks (8/N zones per GPU); the cross-rank halo goes over NCCL send/recv.
+One JSON line is printed by rank 0 (see the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "gcm-necro_b200"))
+
+LA, MU, RHO, YIELD = 7e9, 1e9, 7.8e6, 1e16
+B_STAGE = 292          # algorithmic bytes per node per axis stage (SURVEY 8d / DESIGN.md)
+B_PLASTIC = 52
+B_STEP = 3 * B_STAGE + B_PLASTIC   # 928 B per node-update
+ORACLE = os.path.join(ROOT, "oracle", "_ref", "gcm3d_ref")
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (profiling recipe's line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                sm.append(float(c[1])); mx.append(float(c[2]))
+                for k, nm in enumerate(names):
+                    if c[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def zone_owner(n_zones, world):
+    return [z * world // n_zones for z in range(n_zones)]
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation (oracle/_ref = its sources compiled here), timed on
+    the box's host cores on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from gcm_b200 import meshgen
+    size, nz = args.ref_size, args.zones
+    if not os.path.exists(ORACLE):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/gcm3d_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
+        return
+    zones = meshgen.make_box_zones(size, size, size, nz)
+    with tempfile.TemporaryDirectory() as d:
+        meshes, states = [], []
+        for k, z in enumerate(zones):
+            mp, sp = os.path.join(d, "z%d.gcmb" % k), os.path.join(d, "z%d.state" % k)
+            meshgen.write_gcmb(mp, z)
+            meshgen.pwave_state(z.coords, LA, MU, RHO, z_c=size / 2.0).tofile(sp)
+            meshes.append(mp); states.append(sp)
+        cmd = [ORACLE, "--mesh"] + meshes + ["--state"] + states + ["--steps", str(args.steps + args.warmup),
+                                                                      "--warmup", str(args.warmup), "--seed", "12345"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle run failed: " + r.stderr[-200:].replace("\n", " ")}))
+        return
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    n_nodes = j["local_nodes"]
+    v = n_nodes * j["timed_steps"] / j["seconds"]
+    sample = "%d^3 = %d-node cube in %d zones on one rank, %d steps (same mesh family / material / IC as the 216^3 workload)" % (size, n_nodes, nz, j["timed_steps"])
+    line = {"impl": "reference", "metric": "tet node-updates/sec", "value": v, "unit": "node-updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * j["seconds"] / j["timed_steps"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "elastic cube 216^3 nodes in 8 zones (BASELINE configs[2]); reference timed on a bounded sample", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "node-updates/s", "cores": 1, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "node-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def cpu_baseline(args):
+    """Bounded CPU sample for the b200 arm's line (rank 0, N=1)."""
+    from gcm_b200 import meshgen
+    if not os.path.exists(ORACLE):
+        return {"value": None, "unit": "node-updates/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
+    size = args.cpu_size
+    z = meshgen.make_cube(size)
+    with tempfile.TemporaryDirectory() as d:
+        mp, sp = os.path.join(d, "m.gcmb"), os.path.join(d, "m.state")
+        meshgen.write_gcmb(mp, z)
+        meshgen.pwave_state(z.coords, LA, MU, RHO).tofile(sp)
+        r = subprocess.run([ORACLE, "--mesh", mp, "--state", sp, "--steps", "3", "--warmup", "1", "--seed", "12345"],
+                           capture_output=True, text=True)
+    if r.returncode != 0:
+        return {"value": None, "unit": "node-updates/s", "cores": 1, "kind": "reference", "sample": "oracle run failed"}
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    return {"value": j["local_nodes"] * j["timed_steps"] / j["seconds"], "unit": "node-updates/s", "cores": 1,
+            "kind": "reference",
+            "sample": "%d^3 = %d-node single-zone cube, %d timed steps of the reference's do_next_step (its sources, g++ -O3, single thread as the reference is)" % (size, j["local_nodes"], j["timed_steps"])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=216, help="cube side in nodes (216 -> 10 077 696 nodes)")
+    ap.add_argument("--zones", type=int, default=8)
+    ap.add_argument("--ref-size", type=int, default=48, help="cube side of the bounded sample of --impl reference")
+    ap.add_argument("--cpu-size", type=int, default=64, help="cube side of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--yield-limit", type=float, default=YIELD, help="1e7 = BASELINE configs[3] (plastic corrector fires)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import gcm_b200
+    from gcm_b200 import meshgen
+    from gcm_b200.distributed import DataBus
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    size, nz = args.size, args.zones
+    owner = zone_owner(nz, world)
+    mine = [z for z in range(nz) if owner[z] == rank]
+    t0 = time.time()
+    zones = meshgen.make_box_zones(size, size, size, nz, only=set(mine))
+    ms = gcm_b200.TetrMeshSet(n_zones=nz, zone_rank=owner, my_rank=rank, device=local_rank)
+    ms.srand(12345)
+    for z in mine:
+        ms.get_mesh_by_zone_num(z).load(zones[z], la=LA, mu=MU, rho=RHO, yield_limit=args.yield_limit)
+    bus = None
+    if world > 1:
+        bus = DataBus(ms)
+        bus.create_custom_types()
+        bus.sync_nodes_startup()
+    ms.pre_process_meshes()
+    n_local = 0
+    host = {}
+    for z in mine:
+        m = ms.get_mesh_by_zone_num(z)
+        st = meshgen.pwave_state(zones[z].coords, LA, MU, RHO, z_c=size / 2.0)
+        m.set_values(st)
+        n_local += m.counts()["local_nodes"]
+        host[z] = torch.from_numpy(st.copy()).pin_memory()
+    zones = None
+    t_setup = time.time() - t0
+    stream = torch.cuda.ExternalStream(ms.stream())
+
+    def step():
+        if bus is None:
+            ms.do_next_step()
+        else:
+            bus.do_next_step()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        ms.synchronize()
+        barrier()
+        ms_ = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms_, op=dist.ReduceOp.MAX)
+        return float(ms_.item())
+
+    for _ in range(args.warmup):
+        step()
+    ms.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ms.launch_count()
+    total_ms = timed(step, args.steps)
+    launches = ms.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    n_total = torch.tensor([n_local], device="cuda", dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(n_total)
+    n_total = int(n_total.item())
+    value = n_total * args.steps / (total_ms * 1e-3)
+
+    # ---- per-kernel timing for the roofline (same steps, events around each launch) ----------
+    ms.profile(True)
+    for _ in range(min(args.steps, 5)):
+        step()
+    ms.synchronize()
+    prof = {k: ms.profile_read(i) for i, k in enumerate(["inner_stage", "border_stage", "plastic", "halo_copy"])}
+    ms.profile(False)
+    peak, peak_src = measured_peak_gbs()
+    in_ms, in_launches, in_units = prof["inner_stage"]
+    achieved = (B_STAGE * in_units) / (in_ms * 1e-3) / 1e9 if in_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "inner-node axis stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "algorithmic_bytes_per_node_stage": B_STAGE, "avg_launch_ms": in_ms / max(in_launches, 1),
+                "nodes_per_launch": in_units / max(in_launches, 1),
+                "step_frac": value / world * B_STEP / 1e9 / peak,
+                "kernel_ms_share": {k: v[0] for k, v in prof.items()}}
+
+    # ---- end to end through the C ABI with HOST buffers ---------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            for z in mine:
+                ms.get_mesh_by_zone_num(z).upload_values_async(host[z].data_ptr())
+            step()
+            for z in mine:
+                ms.get_mesh_by_zone_num(z).download_values_async(host[z].data_ptr())
+            ms.synchronize()
+        e2e_step()
+        k2 = max(1, min(args.steps, 5))
+        e_ms = timed(e2e_step, k2)
+        bytes_io = sum(int(host[z].numel()) * 4 for z in mine)
+        e2e = {"value": n_total * k2 / (e_ms * 1e-3), "unit": "node-updates/s", "steps": k2,
+               "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
+               "note": "per rank: pinned host values[9N] -> device (H2D + transpose), do_next_step, device -> pinned host"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args)
+
+    if rank == 0:
+        line = {"metric": "tet node-updates/sec", "value": value, "unit": "node-updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "elastic cube %d^3 = %d nodes, 6 tets/hex, %d z-slab zones (BASELINE configs[2]%s)"
+                                       % (size, n_total, nz, "; yield 1e7 = configs[3]" if args.yield_limit < 1e15 else ""),
+                           "zones_per_gpu": nz // world if nz % world == 0 else [owner.count(r) for r in range(world)],
+                           "tau": 0.002, "material": [LA, MU, RHO, args.yield_limit], "seed": 12345,
+                           "l2": "inputs larger than L2 (state %.0f MB + mesh > 126 MB per GPU)" % (n_total / world * 72 / 1e6),
+                           "setup_s": t_setup},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ms.close()
+
+
+if __name__ == "__main__":
+    main()

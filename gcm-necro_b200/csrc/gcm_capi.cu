@@ -66,7 +66,7 @@ struct Zone {
 	HostMesh hm;
 	bool loaded = false;
 	size_t stride = 0;
-	DevBuf<float> xyz, u0, u1, mat, tet_hv, basis;
+	DevBuf<float> xyz, u0, u1, mat, tet_hv, basis, aos;
 	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, border_nodes, inner_nodes, cond_id;
 	DevBuf<gcm::StageTap> tap;
 	int cur = 0;
@@ -103,6 +103,12 @@ struct gcm_b200_set {
 	long long launches = 0;
 	float time_step = 0.002f;
 	bool in_step = false;
+	// per-kernel CUDA-event profile (gcm_b200_set_profile): 0 inner stage, 1 border stage, 2 plastic, 3 halo
+	bool profile = false;
+	struct ProfRec { int which; long long units; cudaEvent_t a, b; };
+	std::vector<ProfRec> prof;
+	double prof_ms[4] = {0, 0, 0, 0};
+	long long prof_launches[4] = {0, 0, 0, 0}, prof_units[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -157,15 +163,16 @@ void host_sync_nodes(gcm_b200_set* s)
 	}
 }
 
+// Host node-major values -> both device layers (start-up; includes halo slots).
 void upload_values(gcm_b200_set* s, Zone& z)
 {
 	const HostMesh& hm = z.hm;
-	std::vector<float> soa(9 * z.stride, 0.f);
-	for(int i = 0; i < hm.N; i++)
-		for(int k = 0; k < 9; k++)
-			soa[k * z.stride + i] = hm.values[9*(size_t)i + k];
-	CK(cudaMemcpyAsync(z.u0.p, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-	CK(cudaMemcpyAsync(z.u1.p, soa.data(), soa.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	const int n = hm.N;
+	if(!n) return;
+	if(!z.aos.p) z.aos.alloc(9 * (size_t)n);
+	CK(cudaMemcpyAsync(z.aos.p, hm.values.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	gcm::aos_to_soa_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z.u0.p, z.u1.p, z.stride, z.aos.p, z.flags.p, n, 0);
+	s->launches++;
 	CK(cudaStreamSynchronize(s->stream));
 	z.cur = 0;
 }
@@ -186,6 +193,8 @@ void upload_zone(gcm_b200_set* s, Zone& z)
 	z.mat.upload(soa, s->stream);
 	CK(cudaStreamSynchronize(s->stream));
 	z.u0.alloc(9 * z.stride); z.u1.alloc(9 * z.stride);
+	CK(cudaMemsetAsync(z.u0.p, 0, 9 * z.stride * sizeof(float), s->stream));
+	CK(cudaMemsetAsync(z.u1.p, 0, 9 * z.stride * sizeof(float), s->stream));
 	z.flags.upload(hm.flags, s->stream);
 	z.n2t_off.upload(hm.n2t_off, s->stream);
 	z.n2t.upload(hm.n2t, s->stream);
@@ -232,6 +241,32 @@ gcm::MeshView make_view(gcm_b200_set* s, Zone& z)
 	return m;
 }
 
+struct ProfScope {
+	gcm_b200_set* s; int which; long long units; cudaEvent_t a = nullptr, b = nullptr;
+	ProfScope(gcm_b200_set* s_, int w, long long u) : s(s_), which(w), units(u) {
+		if(!s->profile) return;
+		CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+		CK(cudaEventRecord(a, s->stream));
+	}
+	~ProfScope() {
+		if(!a) return;
+		cudaEventRecord(b, s->stream);
+		s->prof.push_back({which, units, a, b});
+	}
+};
+
+void prof_drain(gcm_b200_set* s)
+{
+	for(auto& r : s->prof) {
+		float ms = 0;
+		cudaEventSynchronize(r.b);
+		cudaEventElapsedTime(&ms, r.a, r.b);
+		s->prof_ms[r.which] += ms; s->prof_launches[r.which]++; s->prof_units[r.which] += r.units;
+		cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+	}
+	s->prof.clear();
+}
+
 void begin_step(gcm_b200_set* s)
 {
 	// get_max_possible_tau(): only its side effect survives: new local bases,
@@ -259,7 +294,10 @@ void sync_nodes_device(gcm_b200_set* s)
 		int n = (int)gp->h_dst.size();
 		if(!n) continue;
 		if(!gp->dst.p) { gp->dst.upload(gp->h_dst, s->stream); gp->src.upload(gp->h_src, s->stream); }
-		gcm::halo_copy_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(d.ucur(), d.stride, gp->dst.p, o.ucur(), o.stride, gp->src.p, n);
+		{
+			ProfScope ps(s, 3, n);
+			gcm::halo_copy_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(d.ucur(), d.stride, gp->dst.p, o.ucur(), o.stride, gp->src.p, n);
+		}
 		s->launches++;
 	}
 }
@@ -270,6 +308,7 @@ void zone_stage(gcm_b200_set* s, int zi, float tau, int stage)
 	if(stage == 3) {
 		int n = z.hm.N;
 		if(n) {
+			ProfScope ps(s, 2, (long long)(z.hm.border_nodes.size() + z.hm.inner_nodes.size()));
 			gcm::plastic_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z.ucur(), z.mat.p, z.flags.p, n, z.stride, s->d_err, zi);
 			s->launches++;
 		}
@@ -280,10 +319,12 @@ void zone_stage(gcm_b200_set* s, int zi, float tau, int stage)
 	gcm::StageTap* tap = s->tap_on ? z.tap.p : nullptr;
 	int nb = (int)z.hm.border_nodes.size(), ni = (int)z.hm.inner_nodes.size();
 	if(nb) {
+		ProfScope ps(s, 1, nb);
 		gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, s->stream>>>(m, z.border_nodes.p, nb, stage, z.unext(), s->d_err, zi, tap);
 		s->launches++;
 	}
 	if(ni) {
+		ProfScope ps(s, 0, ni);
 		gcm::stage_generic_kernel<<<(ni + 127) / 128, 128, 0, s->stream>>>(m, z.inner_nodes.p, ni, stage, z.unext(), s->d_err, zi, tap);
 		s->launches++;
 	}
@@ -338,22 +379,26 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 {
 	GUARD_BEGIN
 	if(!out || n_zones <= 0) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
-	int ndev = 0;
-	if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-		return fail(gcmh::CONFIG_EXCEPTION, "no CUDA device: libgcm_b200 has no CPU execution path");
-	if(device < 0 || device >= ndev) return fail(gcmh::CONFIG_EXCEPTION, "bad device ordinal");
-	CK(cudaSetDevice(device));
 	std::unique_ptr<gcm_b200_set> s(new gcm_b200_set());
+	if(device >= 0) {
+		int ndev = 0;
+		if(cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+			return fail(gcmh::CONFIG_EXCEPTION, "no CUDA device: libgcm_b200 has no CPU execution path");
+		if(device >= ndev) return fail(gcmh::CONFIG_EXCEPTION, "bad device ordinal");
+		CK(cudaSetDevice(device));
+	}
 	s->device = device; s->n_zones = n_zones; s->my_rank = my_rank;
 	s->zone_rank.assign(n_zones, my_rank);
 	if(zone_rank) s->zone_rank.assign(zone_rank, zone_rank + n_zones);
 	s->zones.resize(n_zones);
 	for(int z = 0; z < n_zones; z++)
 		if(s->zone_rank[z] == my_rank) { s->zones[z].reset(new Zone()); s->local_zones.push_back(z); }
-	CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-	CK(cudaMalloc(&s->d_err, 4 * sizeof(int)));
-	CK(cudaMemset(s->d_err, 0, 4 * sizeof(int)));
-	CK(cudaMallocHost(&s->h_err, 4 * sizeof(int)));
+	if(device >= 0) {
+		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		CK(cudaMalloc(&s->d_err, 4 * sizeof(int)));
+		CK(cudaMemset(s->d_err, 0, 4 * sizeof(int)));
+		CK(cudaMallocHost(&s->h_err, 4 * sizeof(int)));
+	}
 	s->rng.seed(1);   // libc default when srand() was never called
 	*out = s.release();
 	return 0;
@@ -363,7 +408,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 int gcm_b200_set_destroy(gcm_b200_set* s)
 {
 	if(!s) return 0;
-	cudaSetDevice(s->device);
+	if(s->device >= 0) cudaSetDevice(s->device);
 	if(s->stream) { cudaStreamSynchronize(s->stream); }
 	s->zones.clear();
 	s->halo_groups.clear();
@@ -458,14 +503,49 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values)
 	HostMesh& hm = z->hm;
 	if(z->on_device) {
 		CK(cudaSetDevice(s->device));
-		std::vector<float> soa(9 * z->stride);
-		CK(cudaMemcpyAsync(soa.data(), z->ucur(), soa.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-		CK(cudaStreamSynchronize(s->stream));
-		for(int i = 0; i < hm.N; i++)
-			for(int k = 0; k < 9; k++)
-				hm.values[9*(size_t)i + k] = soa[k * z->stride + i];
+		const int n = hm.N;
+		if(n) {
+			if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
+			gcm::soa_to_aos_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), z->stride, n);
+			s->launches++;
+			CK(cudaMemcpyAsync(hm.values.data(), z->aos.p, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+			CK(cudaStreamSynchronize(s->stream));
+		}
 	}
 	memcpy(values, hm.values.data(), 9*(size_t)hm.N * sizeof(float));
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* host_values)
+{
+	GUARD_BEGIN
+	Zone* z = get_zone(s, zone);
+	if(!z || !z->on_device || !host_values) return fail(gcmh::CONFIG_EXCEPTION, "zone is not on the device");
+	CK(cudaSetDevice(s->device));
+	const int n = z->hm.N;
+	if(!n) return 0;
+	if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
+	CK(cudaMemcpyAsync(z->aos.p, host_values, 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	gcm::aos_to_soa_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->ucur(), nullptr, z->stride, z->aos.p, z->flags.p, n, 1);
+	s->launches++;
+	CK(cudaGetLastError());
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_values)
+{
+	GUARD_BEGIN
+	Zone* z = get_zone(s, zone);
+	if(!z || !z->on_device || !host_values) return fail(gcmh::CONFIG_EXCEPTION, "zone is not on the device");
+	CK(cudaSetDevice(s->device));
+	const int n = z->hm.N;
+	if(!n) return 0;
+	if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
+	gcm::soa_to_aos_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), z->stride, n);
+	s->launches++;
+	CK(cudaMemcpyAsync(host_values, z->aos.p, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 	return 0;
 	GUARD_END
 }
@@ -499,7 +579,7 @@ int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const floa
 	memcpy(cs.box, box, 6 * sizeof(float));
 	int id = (int)s->conds.size();
 	s->conds.push_back(cs);
-	CK(cudaSetDevice(s->device));
+	if(s->device >= 0) CK(cudaSetDevice(s->device));
 	// BoxArea::isInArea (areas/BoxArea.cpp:15-26) over every node of every local mesh; a later
 	// condition overrides an earlier one (TaskPreparator.cpp:432-438)
 	for(int zi : s->local_zones) {
@@ -510,8 +590,10 @@ int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const floa
 			if(c[0] < box[1] && c[0] > box[0] && c[1] < box[3] && c[1] > box[2] && c[2] < box[5] && c[2] > box[4])
 				hm.cond_id[b] = id;
 		}
-		z.cond_id.upload(hm.cond_id, s->stream);
-		CK(cudaStreamSynchronize(s->stream));
+		if(z.on_device) {
+			z.cond_id.upload(hm.cond_id, s->stream);
+			CK(cudaStreamSynchronize(s->stream));
+		}
 	}
 	return 0;
 	GUARD_END
@@ -523,11 +605,13 @@ int gcm_b200_set_preprocess(gcm_b200_set* s)
 	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
 	for(int zi : s->local_zones)
 		if(!s->zones[zi]->loaded) return fail(gcmh::CONFIG_EXCEPTION, "a local zone was not loaded");
-	CK(cudaSetDevice(s->device));
 	build_halo_plan(s);
 	host_sync_nodes(s);
 	for(int zi : s->local_zones) s->zones[zi]->hm.pre_process_mesh();
-	for(int zi : s->local_zones) upload_zone(s, *s->zones[zi]);
+	if(s->device >= 0) {
+		CK(cudaSetDevice(s->device));
+		for(int zi : s->local_zones) upload_zone(s, *s->zones[zi]);
+	}
 	s->preprocessed = true;
 	return 0;
 	GUARD_END
@@ -537,6 +621,7 @@ int gcm_b200_set_begin_step(gcm_b200_set* s)
 {
 	GUARD_BEGIN
 	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
+	if(s->device < 0) return fail(gcmh::CONFIG_EXCEPTION, "host-only set (device -1): there is no CPU execution path for the step");
 	CK(cudaSetDevice(s->device));
 	s->time_step = 0.002f;   // TetrMeshSet.cpp:105-106
 	begin_step(s);
@@ -844,6 +929,27 @@ int gcm_b200_zone_get_tap(gcm_b200_set* s, int zone, int* owners, int* outer, in
 }
 
 long long gcm_b200_set_launch_count(gcm_b200_set* s) { return s ? s->launches : 0; }
+
+int gcm_b200_set_profile(gcm_b200_set* s, int on)
+{
+	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	cudaSetDevice(s->device);
+	prof_drain(s);
+	s->profile = on != 0;
+	if(on) for(int k = 0; k < 4; k++) { s->prof_ms[k] = 0; s->prof_launches[k] = 0; s->prof_units[k] = 0; }
+	return 0;
+}
+
+int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long long* launches, long long* units)
+{
+	if(!s || which < 0 || which > 3) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
+	cudaSetDevice(s->device);
+	prof_drain(s);
+	if(total_ms) *total_ms = s->prof_ms[which];
+	if(launches) *launches = s->prof_launches[which];
+	if(units) *units = s->prof_units[which];
+	return 0;
+}
 int gcm_b200_set_virt_count(gcm_b200_set* s) { (void)s; return 0; }
 
 } // extern "C"

@@ -92,4 +92,30 @@ __global__ void halo_unpack_kernel(float* __restrict__ u, size_t stride, const f
 		u[(size_t)k * stride + d] = buf[(size_t)k * n_total + offset + i];
 }
 
+// Host-facing state layout is the reference's node-major values[9] (ElasticNode.h:28-44); the
+// device keeps plane-major SoA.  These two kernels are the transposes on either side of a
+// pinned-memory copy.  aos_to_soa writes local nodes only (halo slots belong to sync_nodes).
+__global__ void aos_to_soa_kernel(float* __restrict__ u0, float* __restrict__ u1, size_t stride,
+                                  const float* __restrict__ aos, const int* __restrict__ flags, int n, int local_only)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	if(local_only && !(flags[i] & NF_LOCAL)) return;
+	#pragma unroll
+	for(int k = 0; k < 9; k++) {
+		float v = aos[9 * (size_t)i + k];
+		u0[(size_t)k * stride + i] = v;
+		if(u1) u1[(size_t)k * stride + i] = v;
+	}
+}
+
+__global__ void soa_to_aos_kernel(float* __restrict__ aos, const float* __restrict__ u, size_t stride, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		aos[9 * (size_t)i + k] = u[(size_t)k * stride + i];
+}
+
 } // namespace gcm

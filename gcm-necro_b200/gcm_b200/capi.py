@@ -59,6 +59,8 @@ SIGNATURES = {
     "gcm_b200_zone_translate": (_i, [_p, _i, _f, _f, _f]),
     "gcm_b200_zone_set_values": (_i, [_p, _i, _fp]),
     "gcm_b200_zone_get_values": (_i, [_p, _i, _fp]),
+    "gcm_b200_zone_upload_values_async": (_i, [_p, _i, _p]),
+    "gcm_b200_zone_download_values_async": (_i, [_p, _i, _p]),
     "gcm_b200_set_add_border_condition": (_i, [_p, _i, _fp, _ip, _fp, _f, _f, _fp]),
     "gcm_b200_set_preprocess": (_i, [_p]),
     "gcm_b200_set_do_next_step": (_i, [_p]),
@@ -86,6 +88,8 @@ SIGNATURES = {
     "gcm_b200_zone_get_tap": (_i, [_p, _i, _ip, _ip, _ip]),
     "gcm_b200_set_launch_count": (C.c_longlong, [_p]),
     "gcm_b200_set_virt_count": (_i, [_p]),
+    "gcm_b200_set_profile": (_i, [_p, _i]),
+    "gcm_b200_set_profile_read": (_i, [_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
 }
 
 
@@ -156,6 +160,12 @@ class TetrMesh_1stOrder:
         v = np.empty((self._n_nodes, 9), np.float32)
         self._ck(self.mesh_set.lib.gcm_b200_zone_get_values(self.mesh_set.h, self.zone_num, _fptr(v)))
         return v
+
+    def upload_values_async(self, host_ptr):
+        self._ck(self.mesh_set.lib.gcm_b200_zone_upload_values_async(self.mesh_set.h, self.zone_num, C.c_void_p(host_ptr)))
+
+    def download_values_async(self, host_ptr):
+        self._ck(self.mesh_set.lib.gcm_b200_zone_download_values_async(self.mesh_set.h, self.zone_num, C.c_void_p(host_ptr)))
 
     def do_next_part_step(self, tau, stage):
         self._ck(self.mesh_set.lib.gcm_b200_zone_do_next_part_step(self.mesh_set.h, self.zone_num, tau, stage))
@@ -279,6 +289,14 @@ class TetrMeshSet:
 
     def launch_count(self):
         return self.lib.gcm_b200_set_launch_count(self.h)
+
+    def profile(self, on=True):
+        self._ck(self.lib.gcm_b200_set_profile(self.h, int(on)))
+
+    def profile_read(self, which):
+        ms, n, u = C.c_double(), C.c_longlong(), C.c_longlong()
+        self._ck(self.lib.gcm_b200_set_profile_read(self.h, which, C.byref(ms), C.byref(n), C.byref(u)))
+        return ms.value, n.value, u.value
 
     # ---- cross-process halo (DataBus role) ------------------------------------------------
     def halo_counts(self, peer):

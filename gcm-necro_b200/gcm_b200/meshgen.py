@@ -59,13 +59,15 @@ def _slab_tets(nx: int, ny: int, nlayers: int) -> np.ndarray:
 
 def make_box_zones(nx: int, ny: int, nz: int, n_zones: int = 1, spacing=(1.0, 1.0, 1.0),
                    origin=(0.0, 0.0, 0.0), jitter: float = 0.0, jitter_border: bool = False,
-                   seed: int = 0) -> list[ZoneMesh]:
+                   seed: int = 0, only=None) -> list[ZoneMesh]:
     """nx x ny x nz node box split into n_zones z-slabs, create_cube.c semantics.
 
     With nx == ny == nz == N*M and n_zones == N this is exactly ``create_cube`` with
     Nnum=N, Mnum=M.  ``jitter`` displaces nodes by a uniform random offset of up to
     +-jitter (in units of the spacing) so that owner searches are not all axis-aligned ties;
     the offset is a function of the GLOBAL node id, so every zone sees the same coordinates.
+    ``only`` = iterable of zone numbers to build (others are returned as None): a rank of a
+    multi-process run builds only the zones it owns.
     """
     if nz % n_zones:
         raise ValueError("nz must be divisible by n_zones")
@@ -85,6 +87,9 @@ def make_box_zones(nx: int, ny: int, nz: int, n_zones: int = 1, spacing=(1.0, 1.
     layer = nx * ny
     zones = []
     for n in range(n_zones):
+        if only is not None and n not in only:
+            zones.append(None)
+            continue
         k_lo = n * m - (1 if n > 0 else 0)
         k_hi = (n + 1) * m + (1 if n < n_zones - 1 else 0)   # exclusive
         nl = k_hi - k_lo

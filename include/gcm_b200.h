@@ -57,6 +57,11 @@ int gcm_b200_zone_translate(gcm_b200_set* s, int zone, float dx, float dy, float
 /* Initial state, written straight into nodes[i].values[0..8]; values[9N] node-major. */
 int gcm_b200_zone_set_values(gcm_b200_set* s, int zone, const float* values);
 int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values);
+/* Stream-ordered variants for callers that keep the state in (pinned) host memory between
+ * steps: H2D copy + transpose into the current layer (local nodes only) / transpose + D2H copy.
+ * They return before the copy is done; gcm_b200_set_synchronize() waits. */
+int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* host_values);
+int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_values);
 /* A BorderCondition (calculator + StepPulseForm + BoxArea), TaskPreparator.cpp:388-441 and
  * gcm/methods/border/*.cpp.  calc_type: 0 Free, 1 Fixed, 2 ExternalForce, 3 ExternalVelocity,
  * 4 ExternalValues.  params[5] = set_parameters(normal, tangential, dir x,y,z) for 2/3;
@@ -117,6 +122,11 @@ int gcm_b200_set_enable_tap(gcm_b200_set* s, int on);
 int gcm_b200_zone_get_tap(gcm_b200_set* s, int zone, int* owners, int* outer, int* tries);
 /* Kernel launches issued so far by this set (bench.py's gpu_launches). */
 long long gcm_b200_set_launch_count(gcm_b200_set* s);
+/* Per-kernel CUDA-event timing for roofline accounting (bench.py): while on, every launch of
+ * kernel class `which` (0 inner-node stage, 1 border-node stage, 2 plastic corrector, 3 halo copy)
+ * is bracketed by events on the set's stream; read returns summed ms, launches and nodes. */
+int gcm_b200_set_profile(gcm_b200_set* s, int on);
+int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long long* launches, long long* units);
 /* Virtual (contact) nodes of the last collision pass: n and [16] floats each (coords, values). */
 int gcm_b200_set_virt_count(gcm_b200_set* s);
 

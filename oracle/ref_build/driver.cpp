@@ -84,7 +84,7 @@ int main(int argc, char** argv)
 	vector<CondSpec> conds;
 	vector< vector<float> > translates; // zone dx dy dz
 	float la = 7e9f, mu = 1e9f, rho = 7.8e6f, yield = 1e16f;
-	int steps = 1, seed = 12345;
+	int steps = 1, seed = 12345, warmup = 0;
 	string detector = "void", out, contact_calc = "adhesion";
 	bool detector_static = false;
 
@@ -99,6 +99,7 @@ int main(int argc, char** argv)
 		else if(s == "--yield") yield = atof(argv[++a]);
 		else if(s == "--steps") steps = atoi(argv[++a]);
 		else if(s == "--seed") seed = atoi(argv[++a]);
+		else if(s == "--warmup") warmup = atoi(argv[++a]);   // untimed leading steps (bench.py)
 		else if(s == "--detector") detector = argv[++a];
 		else if(s == "--static") detector_static = true;
 		else if(s == "--contact-calc") contact_calc = argv[++a];
@@ -245,8 +246,10 @@ int main(int argc, char** argv)
 
 		struct timespec t0, t1;
 		clock_gettime(CLOCK_MONOTONIC, &t0);
-		for(g_cur_step = 0; g_cur_step < steps; g_cur_step++)
+		for(g_cur_step = 0; g_cur_step < steps; g_cur_step++) {
+			if(g_cur_step == warmup) clock_gettime(CLOCK_MONOTONIC, &t0);
 			if(ms->do_next_step() < 0) { rc = 3; break; }
+		}
 		clock_gettime(CLOCK_MONOTONIC, &t1);
 		seconds = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 	} catch(GCMException& e) {
@@ -286,7 +289,7 @@ int main(int argc, char** argv)
 		write_file(out + ".virt.f32", virt);
 		if(g_tap_step >= 0) write_file(out + ".tap.bin", g_tap);
 	}
-	printf("{\"impl\": \"reference\", \"steps\": %d, \"seconds\": %.6f, \"local_nodes\": %ld, \"virt_nodes\": %ld, \"rc\": %d}\n",
-		steps, seconds, local_nodes, (long)ms->virt_nodes.size(), rc);
+	printf("{\"impl\": \"reference\", \"steps\": %d, \"timed_steps\": %d, \"seconds\": %.6f, \"local_nodes\": %ld, \"virt_nodes\": %ld, \"rc\": %d}\n",
+		steps, steps - warmup, seconds, local_nodes, (long)ms->virt_nodes.size(), rc);
 	return rc;
 }

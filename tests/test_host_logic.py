@@ -1,0 +1,51 @@
+"""Host-side logic that needs no GPU: the libc rand() stream restatement, mesh generator."""
+import ctypes
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+import util_parity as up
+from gcm_b200 import meshgen
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+RAND_SRC = r'''
+#include <cstdio>
+#include <cstdlib>
+#include "gcm_host.h"
+int main() {
+    unsigned seeds[] = {1u, 12345u, 0u, 2147483647u, 4000000000u};
+    for(unsigned s : seeds) {
+        srand(s); gcmh::GlibcRand r; r.seed(s);
+        for(int i = 0; i < 100000; i++) { int a = rand(), b = r.next(); if(a != b) { printf("MISMATCH seed %u i %d %d %d\n", s, i, a, b); return 1; } }
+    }
+    printf("OK\n"); return 0;
+}
+'''
+
+
+def test_glibc_rand_restatement(built):
+    """GlibcRand (gcm_host.h) reproduces srand()/rand() of the C library bit for bit."""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "r.cpp")
+        open(src, "w").write(RAND_SRC)
+        exe = os.path.join(d, "r")
+        csrc = os.path.join(ROOT, "gcm-necro_b200", "csrc")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-I", csrc, src, os.path.join(csrc, "gcm_host.cpp"), "-o", exe], check=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
+def test_create_cube_counts():
+    """create_cube.c semantics: 100^3 would give 5 821 794 tets; check the formula on 10^3."""
+    z = meshgen.make_cube(10)
+    assert z.n_nodes == 1000 and z.n_tets == 6 * 9 ** 3
+    zs = meshgen.make_box_zones(6, 6, 8, 2)
+    assert [x.n_local for x in zs] == [144, 144]
+    assert [x.n_nodes for x in zs] == [180, 180]
+    # halo of zone 0 = first local layer of zone 1
+    h = np.nonzero(zs[0].placement == 0)[0]
+    assert np.array_equal(zs[0].coords[h], zs[1].coords[zs[0].remote_num[h]])
+    assert np.all(zs[1].placement[zs[0].remote_num[h]] == 1)

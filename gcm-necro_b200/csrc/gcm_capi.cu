@@ -66,7 +66,8 @@ struct Zone {
 	HostMesh hm;
 	bool loaded = false;
 	size_t stride = 0;
-	DevBuf<float> xyz, u0, u1, mat, tet_hv, basis, aos;
+	DevBuf<float> xyz, u0, u1, mat, tet_hv, basis, aos, normals;
+	int slot_offset = 0;                       // first global border slot of this zone (device RNG)
 	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, border_nodes, inner_nodes, cond_id;
 	DevBuf<gcm::StageTap> tap;
 	int cur = 0;
@@ -103,12 +104,22 @@ struct gcm_b200_set {
 	long long launches = 0;
 	float time_step = 0.002f;
 	bool in_step = false;
+	// device-side rand() stream + bases (rng_chunk_kernel / basis_kernel)
+	bool basis_on_device = true;
+	bool rng_ready = false;
+	long long rng_draws_per_step = 0;
+	int rng_chunks = 0;
+	uint32_t rng_jump[961];
+	DevBuf<uint32_t> d_chunk_state, d_jump, d_slot_pos;
+	DevBuf<int> d_chunk_first_slot;
+	DevBuf<unsigned short> d_teta_idx;
+	DevBuf<float> d_cos, d_sin;
 	// per-kernel CUDA-event profile (gcm_b200_set_profile): 0 inner stage, 1 border stage, 2 plastic, 3 halo
 	bool profile = false;
 	struct ProfRec { int which; long long units; cudaEvent_t a, b; };
 	std::vector<ProfRec> prof;
-	double prof_ms[4] = {0, 0, 0, 0};
-	long long prof_launches[4] = {0, 0, 0, 0}, prof_units[4] = {0, 0, 0, 0};
+	double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+	long long prof_launches[6] = {0, 0, 0, 0, 0, 0}, prof_units[6] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -267,10 +278,89 @@ void prof_drain(gcm_b200_set* s)
 	s->prof.clear();
 }
 
+// Lay the step's rand() stream out for the device: draw positions of the border nodes, chunk
+// start windows from the current host generator state, the one-step jump matrix.
+void rng_device_init(gcm_b200_set* s)
+{
+	std::vector<uint32_t> slot_pos;
+	unsigned long long pos = 0;
+	int slot_total = 0;
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		const HostMesh& hm = z.hm;
+		z.slot_offset = slot_total;
+		for(int i = 0; i < hm.N; i++) {
+			if(!hm.is_local(i)) continue;
+			if(hm.is_border(i)) { slot_pos.push_back((uint32_t)pos); pos += 1; }
+			else pos += 3;
+		}
+		slot_total += (int)hm.border_nodes.size();
+	}
+	if(pos >= 0xffffffffull) throw HostError{gcmh::CONFIG_EXCEPTION, "too many rand() draws per step for the device generator"};
+	s->rng_draws_per_step = (long long)pos;
+	s->rng_chunks = (int)((pos + GCM_RNG_CHUNK - 1) / GCM_RNG_CHUNK);
+	const int nc = s->rng_chunks;
+	std::vector<uint32_t> st((size_t)31 * nc);
+	std::vector<int> first(nc + 1, 0);
+	{
+		gcmh::GlibcRand g = s->rng;
+		size_t sl = 0;
+		for(int c = 0; c < nc; c++) {
+			uint32_t w[31];
+			g.get_window(w);
+			for(int i = 0; i < 31; i++) st[(size_t)i * nc + c] = w[i];
+			while(sl < slot_pos.size() && slot_pos[sl] < (uint32_t)c * GCM_RNG_CHUNK) sl++;
+			first[c] = (int)sl;
+			if(c + 1 < nc) for(int k = 0; k < GCM_RNG_CHUNK; k++) (void)g.next();
+		}
+		first[nc] = (int)slot_pos.size();
+	}
+	gcmh::rng_jump_matrix((unsigned long long)pos, s->rng_jump);
+	std::vector<uint32_t> jm(s->rng_jump, s->rng_jump + 961);
+	float ct[360], sn[360];
+	gcmh::rng_teta_tables(ct, sn);
+	s->d_chunk_state.upload(st, s->stream);
+	s->d_jump.upload(jm, s->stream);
+	s->d_slot_pos.upload(slot_pos, s->stream);
+	s->d_chunk_first_slot.upload(first, s->stream);
+	s->d_teta_idx.alloc(slot_pos.size() + 1);
+	s->d_cos.upload(std::vector<float>(ct, ct + 360), s->stream);
+	s->d_sin.upload(std::vector<float>(sn, sn + 360), s->stream);
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		if(!z.normals.p) z.normals.upload(z.hm.normals, s->stream);
+	}
+	CK(cudaStreamSynchronize(s->stream));
+	s->rng_ready = true;
+}
+
 void begin_step(gcm_b200_set* s)
 {
 	// get_max_possible_tau(): only its side effect survives: new local bases,
 	// meshes in local_meshes order, nodes in index order, one libc rand() stream.
+	if(s->basis_on_device) {
+		if(!s->rng_ready) rng_device_init(s);
+		if(s->rng_chunks) {
+			ProfScope ps(s, 4, s->rng_draws_per_step);
+			gcm::rng_chunk_kernel<<<(s->rng_chunks + 127) / 128, 128, 0, s->stream>>>(s->d_chunk_state.p, s->rng_chunks,
+				s->d_jump.p, s->d_slot_pos.p, s->d_chunk_first_slot.p, s->d_teta_idx.p);
+			s->launches++;
+			for(int zi : s->local_zones) {
+				Zone& z = *s->zones[zi];
+				int nb = (int)z.hm.border_nodes.size();
+				if(!nb) continue;
+				gcm::basis_kernel<<<(nb + 127) / 128, 128, 0, s->stream>>>(z.basis.p, z.normals.p, s->d_teta_idx.p, z.slot_offset, nb, s->d_cos.p, s->d_sin.p);
+				s->launches++;
+			}
+		}
+		// keep the host generator in step with the device one
+		uint32_t w[31];
+		s->rng.get_window(w);
+		gcmh::rng_apply_jump(s->rng_jump, w);
+		s->rng.set_window(w);
+		s->in_step = true;
+		return;
+	}
 	for(int zi : s->local_zones) {
 		Zone& z = *s->zones[zi];
 		z.hm.create_random_axes(s->rng);
@@ -420,7 +510,21 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 	return 0;
 }
 
-int gcm_b200_set_seed(gcm_b200_set* s, unsigned seed) { if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set"); s->rng.seed(seed); return 0; }
+int gcm_b200_set_seed(gcm_b200_set* s, unsigned seed)
+{
+	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	s->rng.seed(seed);
+	s->rng_ready = false;
+	return 0;
+}
+
+int gcm_b200_set_basis_mode(gcm_b200_set* s, int on_device)
+{
+	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	s->basis_on_device = on_device != 0;
+	s->rng_ready = false;
+	return 0;
+}
 
 int gcm_b200_set_collision_detector(gcm_b200_set* s, int type, int is_static, float threshold)
 {
@@ -888,6 +992,12 @@ int gcm_b200_zone_get_bases(gcm_b200_set* s, int zone, float* bases)
 	Zone* z = get_zone(s, zone);
 	if(!z || !z->hm.preprocessed || !bases) return fail(gcmh::CONFIG_EXCEPTION, "zone not preprocessed");
 	HostMesh& hm = z->hm;
+	if(z->on_device && s->basis_on_device && !hm.basis.empty()) {
+		cudaSetDevice(s->device);
+		if(cudaMemcpyAsync(hm.basis.data(), z->basis.p, hm.basis.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess
+		   || cudaStreamSynchronize(s->stream) != cudaSuccess)
+			return fail(gcmh::CONFIG_EXCEPTION, "CUDA: reading the bases failed");
+	}
 	static const float E[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 	for(int i = 0; i < hm.N; i++) {
 		float* o = bases + 9*(size_t)i;
@@ -936,13 +1046,13 @@ int gcm_b200_set_profile(gcm_b200_set* s, int on)
 	cudaSetDevice(s->device);
 	prof_drain(s);
 	s->profile = on != 0;
-	if(on) for(int k = 0; k < 4; k++) { s->prof_ms[k] = 0; s->prof_launches[k] = 0; s->prof_units[k] = 0; }
+	if(on) for(int k = 0; k < 6; k++) { s->prof_ms[k] = 0; s->prof_launches[k] = 0; s->prof_units[k] = 0; }
 	return 0;
 }
 
 int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long long* launches, long long* units)
 {
-	if(!s || which < 0 || which > 3) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
+	if(!s || which < 0 || which > 5) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
 	cudaSetDevice(s->device);
 	prof_drain(s);
 	if(total_ms) *total_ms = s->prof_ms[which];

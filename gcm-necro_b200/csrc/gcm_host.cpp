@@ -389,35 +389,58 @@ void HostMesh::create_random_axes(GlibcRand& rng)
 		const int s = border_slot[i];
 		const float x = normals[3*(size_t)s], y = normals[3*(size_t)s+1], z = normals[3*(size_t)s+2];
 		float teta = (rng.next() % 360) * 2 * PI / 360;
-		float a[3][3];
-		a[0][0] = x; a[0][1] = y; a[0][2] = z;
-		if( (fabsf(x) >= fabsf(y)) && (fabsf(x) >= fabsf(z)) ) { a[1][0] = y; a[1][1] = -x; a[1][2] = 0; }
-		else if( (fabsf(y) >= fabsf(x)) && (fabsf(y) >= fabsf(z)) ) { a[1][0] = y; a[1][1] = -x; a[1][2] = 0; }
-		else { a[1][0] = 0; a[1][1] = -z; a[1][2] = y; }
-		float modul = sqrtf( a[1][0] * a[1][0] + a[1][1] * a[1][1] + a[1][2] * a[1][2] );
-		a[1][0] /= modul; a[1][1] /= modul; a[1][2] /= modul;
-		a[2][0] = a[0][1] * a[1][2] - a[0][2] * a[1][1];
-		a[2][1] = a[0][2] * a[1][0] - a[0][0] * a[1][2];
-		a[2][2] = a[0][0] * a[1][1] - a[0][1] * a[1][0];
-		const float ct = cosf(teta), st = sinf(teta);
-		float rot[3][3];
-		rot[0][0] = ct + x * x * (1 - ct);
-		rot[0][1] = y * x * (1 - ct) + z * st;
-		rot[0][2] = z * x * (1 - ct) - y * st;
-		rot[1][0] = y * x * (1 - ct) - z * st;
-		rot[1][1] = ct + y * y * (1 - ct);
-		rot[1][2] = y * z * (1 - ct) + x * st;
-		rot[2][0] = x * z * (1 - ct) + y * st;
-		rot[2][1] = y * z * (1 - ct) - x * st;
-		rot[2][2] = ct + z * z * (1 - ct);
-		float* out = &basis[9*(size_t)s];
-		for(int r = 0; r < 3; r++)
-			for(int c = 0; c < 3; c++) {
-				float v = 0;
-				for(int k = 0; k < 3; k++)
-					v += rot[k][c] * a[r][k];
-				out[3*r + c] = v;
-			}
+		gcm::rotation_basis_with_normal(x, y, z, cosf(teta), sinf(teta), &basis[9*(size_t)s]);
+	}
+}
+
+// ---- the rand() stream as a linear recurrence ----------------------------------------------
+// o[n] = o[n-31] + o[n-3] (mod 2^32), rand() = o[n] >> 1.  State in stream order
+// W = (o[n-31] .. o[n-1]); one call maps W -> (W[1] .. W[30], W[0] + W[28]).
+void GlibcRand::get_window(uint32_t w[31]) const { for(int i = 0; i < 31; i++) w[i] = r[(f + i) % 31]; }
+void GlibcRand::set_window(const uint32_t w[31]) { for(int i = 0; i < 31; i++) r[i] = w[i]; f = 0; b = 28; }
+
+static void mat_mul(const uint32_t* a, const uint32_t* b, uint32_t* c)
+{
+	for(int i = 0; i < 31; i++)
+		for(int j = 0; j < 31; j++) {
+			uint32_t acc = 0;
+			for(int k = 0; k < 31; k++) acc += a[i*31+k] * b[k*31+j];
+			c[i*31+j] = acc;
+		}
+}
+
+void rng_jump_matrix(unsigned long long k, uint32_t out[961])
+{
+	std::vector<uint32_t> base(961, 0), res(961, 0), tmp(961);
+	for(int i = 0; i < 30; i++) base[i*31 + i + 1] = 1;
+	base[30*31 + 0] = 1; base[30*31 + 28] = 1;
+	for(int i = 0; i < 31; i++) res[i*31+i] = 1;
+	while(k) {
+		if(k & 1) { mat_mul(base.data(), res.data(), tmp.data()); res = tmp; }
+		mat_mul(base.data(), base.data(), tmp.data()); base = tmp;
+		k >>= 1;
+	}
+	memcpy(out, res.data(), 961 * sizeof(uint32_t));
+}
+
+void rng_apply_jump(const uint32_t m[961], uint32_t w[31])
+{
+	uint32_t n[31];
+	for(int i = 0; i < 31; i++) {
+		uint32_t acc = 0;
+		for(int j = 0; j < 31; j++) acc += m[i*31+j] * w[j];
+		n[i] = acc;
+	}
+	memcpy(w, n, sizeof n);
+}
+
+void rng_teta_tables(float cos_t[360], float sin_t[360])
+{
+	const double PI = atan(1) * 4;
+	for(int k = 0; k < 360; k++) {
+		float teta = k * 2 * PI / 360;   // (rand() % 360) * 2 * PI / 360, TetrMethod_Plastic_1stOrder.cpp:729
+		cos_t[k] = cosf(teta);
+		sin_t[k] = sinf(teta);
 	}
 }
 

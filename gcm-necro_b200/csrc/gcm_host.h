@@ -32,7 +32,17 @@ struct GlibcRand {
 		if(++b >= 31) b = 0;
 		return (int)(v >> 1);
 	}
+	void get_window(uint32_t w[31]) const;   // state in stream order (o[n-31] .. o[n-1])
+	void set_window(const uint32_t w[31]);
 };
+
+// Jump-ahead for the rand() recurrence: out = A^k (31x31 over Z/2^32, row-major), and its
+// application to a stream-order window.  Lets the GPU produce a whole step's draws in parallel
+// chunks (gcm_kernels.cuh: rng_chunk_kernel) instead of 3 host rand() calls per inner node.
+void rng_jump_matrix(unsigned long long k, uint32_t out[961]);
+void rng_apply_jump(const uint32_t m[961], uint32_t w[31]);
+// cosf/sinf of the 360 angles create_random_axis can draw, from the host libm.
+void rng_teta_tables(float cos_t[360], float sin_t[360]);
 
 struct HostMesh {
 	int zone = -1;

@@ -92,6 +92,71 @@ __global__ void halo_unpack_kernel(float* __restrict__ u, size_t stride, const f
 		u[(size_t)k * stride + d] = buf[(size_t)k * n_total + offset + i];
 }
 
+// ---- the per-step random local bases, generated on the device ------------------------------
+// create_random_axis (gcm/methods/TetrMethod_Plastic_1stOrder.cpp:697-748) consumes libc rand():
+// 3 draws per inner node (discarded: basis := E) and 1 per border node, nodes in index order.
+// rand() is the linear recurrence o[n] = o[n-31] + o[n-3] (mod 2^32), value o[n] >> 1, so a
+// step's stream is cut into chunks of GCM_RNG_CHUNK draws; one thread owns one chunk, keeps the
+// 31-word window at the chunk start, (a) jumps it by one whole step (31x31 matrix A^C over
+// Z/2^32, built by the host) for the next call and (b) walks its chunk, storing
+// (draw % 360) for the draws that belong to border nodes.
+#define GCM_RNG_CHUNK (31 * 32)
+
+__global__ void __launch_bounds__(128)
+rng_chunk_kernel(uint32_t* __restrict__ chunk_state, int n_chunks, const uint32_t* __restrict__ jump,
+                 const uint32_t* __restrict__ slot_pos, const int* __restrict__ chunk_first_slot,
+                 unsigned short* __restrict__ teta_idx)
+{
+	__shared__ uint32_t J[961];
+	for(int i = threadIdx.x; i < 961; i += blockDim.x) J[i] = jump[i];
+	__syncthreads();
+	int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= n_chunks) return;
+	uint32_t w[31];
+	#pragma unroll
+	for(int i = 0; i < 31; i++) w[i] = chunk_state[(size_t)i * n_chunks + c];
+	#pragma unroll
+	for(int i = 0; i < 31; i++) {
+		uint32_t acc = 0;
+		#pragma unroll
+		for(int j = 0; j < 31; j++) acc += J[i * 31 + j] * w[j];
+		chunk_state[(size_t)i * n_chunks + c] = acc;
+	}
+	int slot = chunk_first_slot[c];
+	const int slot_end = chunk_first_slot[c + 1];
+	if(slot == slot_end) return;
+	const uint32_t base = (uint32_t)c * GCM_RNG_CHUNK;
+	uint32_t next = slot_pos[slot] - base;
+	for(int blk = 0; blk < GCM_RNG_CHUNK / 31; blk++) {
+		#pragma unroll
+		for(int i = 0; i < 31; i++) {
+			w[i] += w[(i + 28) % 31];
+			if((uint32_t)(blk * 31 + i) == next) {
+				teta_idx[slot] = (unsigned short)((w[i] >> 1) % 360u);
+				slot++;
+				next = slot < slot_end ? slot_pos[slot] - base : 0xffffffffu;
+			}
+		}
+		if(slot >= slot_end) break;
+	}
+}
+
+// create_rotation_matrix_with_normal for every border node of a zone (:843-901), from the static
+// node normal and the drawn angle index; cos/sin of the 360 possible angles come from the host.
+__global__ void basis_kernel(float* __restrict__ basis, const float* __restrict__ normals,
+                             const unsigned short* __restrict__ teta_idx, int slot_offset, int nb,
+                             const float* __restrict__ cos_t, const float* __restrict__ sin_t)
+{
+	int s = blockIdx.x * blockDim.x + threadIdx.x;
+	if(s >= nb) return;
+	int k = teta_idx[slot_offset + s];
+	float out[9];
+	rotation_basis_with_normal(normals[3 * (size_t)s], normals[3 * (size_t)s + 1], normals[3 * (size_t)s + 2],
+	                           cos_t[k], sin_t[k], out);
+	#pragma unroll
+	for(int q = 0; q < 9; q++) basis[9 * (size_t)s + q] = out[q];
+}
+
 // Host-facing state layout is the reference's node-major values[9] (ElasticNode.h:28-44); the
 // device keeps plane-major SoA.  These two kernels are the transposes on either side of a
 // pinned-memory copy.  aos_to_soa writes local nodes only (halo slots belong to sync_nodes).

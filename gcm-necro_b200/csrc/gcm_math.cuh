@@ -380,4 +380,39 @@ GCM_HD void create_local_basis(const float n[3], float n1[3], float n2[3])
 	n2[2] = n[0] * n1[1] - n1[0] * n[1];
 }
 
+// create_rotation_matrix_with_normal, gcm/methods/TetrMethod_Plastic_1stOrder.cpp:843-901:
+// local basis of a border node = (normal, a perpendicular, their cross product) rotated about
+// the normal by teta.  ct/st = cos(teta)/sin(teta) as the host libm gives them for the float
+// angle (the reference calls cos/sin on a float; 360 distinct angles, tabulated by the host).
+GCM_HD void rotation_basis_with_normal(float x, float y, float z, float ct, float st, float out[9])
+{
+	float a[3][3];
+	a[0][0] = x; a[0][1] = y; a[0][2] = z;
+	if( (fabsf(x) >= fabsf(y)) && (fabsf(x) >= fabsf(z)) ) { a[1][0] = y; a[1][1] = -x; a[1][2] = 0; }
+	else if( (fabsf(y) >= fabsf(x)) && (fabsf(y) >= fabsf(z)) ) { a[1][0] = y; a[1][1] = -x; a[1][2] = 0; }
+	else { a[1][0] = 0; a[1][1] = -z; a[1][2] = y; }
+	float modul = sqrtf( a[1][0] * a[1][0] + a[1][1] * a[1][1] + a[1][2] * a[1][2] );
+	a[1][0] /= modul; a[1][1] /= modul; a[1][2] /= modul;
+	a[2][0] = a[0][1] * a[1][2] - a[0][2] * a[1][1];
+	a[2][1] = a[0][2] * a[1][0] - a[0][0] * a[1][2];
+	a[2][2] = a[0][0] * a[1][1] - a[0][1] * a[1][0];
+	float rot[3][3];
+	rot[0][0] = ct + x * x * (1 - ct);
+	rot[0][1] = y * x * (1 - ct) + z * st;
+	rot[0][2] = z * x * (1 - ct) - y * st;
+	rot[1][0] = y * x * (1 - ct) - z * st;
+	rot[1][1] = ct + y * y * (1 - ct);
+	rot[1][2] = y * z * (1 - ct) + x * st;
+	rot[2][0] = x * z * (1 - ct) + y * st;
+	rot[2][1] = y * z * (1 - ct) - x * st;
+	rot[2][2] = ct + z * z * (1 - ct);
+	for(int r = 0; r < 3; r++)
+		for(int c = 0; c < 3; c++) {
+			float v = 0;
+			for(int k = 0; k < 3; k++)
+				v += rot[k][c] * a[r][k];
+			out[3*r + c] = v;
+		}
+}
+
 } // namespace gcm

@@ -39,6 +39,10 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 int gcm_b200_set_destroy(gcm_b200_set* s);
 /* srand(seed) of gcm/main.cpp:26 -- the stream consumed by create_random_axis. */
 int gcm_b200_set_seed(gcm_b200_set* s, unsigned seed);
+/* Where create_random_axis runs: 1 (default) = on the device (the rand() recurrence jumped and
+ * walked in parallel chunks, bit-identical to libc for the given seed); 0 = on the host with the
+ * restated libc generator, bases uploaded every step. */
+int gcm_b200_set_basis_mode(gcm_b200_set* s, int on_device);
 /* CollisionDetector selection, TaskPreparator.cpp:225-254: type 0 = Void, 1 = Bruteforce;
  * is_static as <collision_detector static="true">; threshold as set_treshold(). */
 int gcm_b200_set_collision_detector(gcm_b200_set* s, int type, int is_static, float threshold);

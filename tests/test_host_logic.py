@@ -38,6 +38,39 @@ def test_glibc_rand_restatement(built):
         assert r.returncode == 0 and "OK" in r.stdout, r.stdout
 
 
+JUMP_SRC = r'''
+#include <cstdio>
+#include <cstring>
+#include "gcm_host.h"
+int main() {
+    unsigned long long ks[] = {1ull, 3ull, 31ull, 992ull, 100003ull, 30233088ull};
+    for(unsigned long long k : ks) {
+        gcmh::GlibcRand a; a.seed(12345); gcmh::GlibcRand b = a;
+        for(unsigned long long i = 0; i < k; i++) (void)a.next();
+        uint32_t m[961], w[31], wa[31];
+        gcmh::rng_jump_matrix(k, m);
+        b.get_window(w); gcmh::rng_apply_jump(m, w); b.set_window(w);
+        a.get_window(wa);
+        if(memcmp(w, wa, sizeof w)) { printf("MISMATCH window k=%llu\n", k); return 1; }
+        for(int i = 0; i < 1000; i++) if(a.next() != b.next()) { printf("MISMATCH stream k=%llu\n", k); return 1; }
+    }
+    printf("OK\n"); return 0;
+}
+'''
+
+
+def test_rand_jump_ahead(built):
+    """A^k applied to the 31-word window == k calls of rand() (the device generator's host half)."""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "j.cpp")
+        open(src, "w").write(JUMP_SRC)
+        exe = os.path.join(d, "j")
+        csrc = os.path.join(ROOT, "gcm-necro_b200", "csrc")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fopenmp", "-I", csrc, src, os.path.join(csrc, "gcm_host.cpp"), "-o", exe], check=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
 def test_create_cube_counts():
     """create_cube.c semantics: 100^3 would give 5 821 794 tets; check the formula on 10^3."""
     z = meshgen.make_cube(10)

@@ -263,7 +263,7 @@ def main():
     for _ in range(min(args.steps, 5)):
         step()
     ms.synchronize()
-    prof = {k: ms.profile_read(i) for i, k in enumerate(["inner_stage", "border_stage", "plastic", "halo_copy", "rng_bases"])}
+    prof = {k: ms.profile_read(i) for i, k in enumerate(["inner_stage", "border_stage", "plastic", "halo_copy", "rng_bases", "inner_generic"])}
     ms.profile(False)
     peak, peak_src = measured_peak_gbs()
     in_ms, in_launches, in_units = prof["inner_stage"]

@@ -68,7 +68,9 @@ struct Zone {
 	size_t stride = 0;
 	DevBuf<float> xyz, u0, u1, mat, tet_hv, basis, aos, normals;
 	int slot_offset = 0;                       // first global border slot of this zone (device RNG)
-	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, border_nodes, inner_nodes, cond_id;
+	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, border_nodes, inner_nodes, cond_id, inner_fast, inner_generic;
+	DevBuf<float> w0, mat_tab;
+	DevBuf<unsigned char> mat_id;
 	DevBuf<gcm::StageTap> tap;
 	int cur = 0;
 	float* h_basis[2] = {nullptr, nullptr};   // pinned staging, double buffered
@@ -105,6 +107,7 @@ struct gcm_b200_set {
 	float time_step = 0.002f;
 	bool in_step = false;
 	// device-side rand() stream + bases (rng_chunk_kernel / basis_kernel)
+	bool fast_inner = true;   // specialised inner-node kernel (gcm_inner.cuh); false = generic kernel for every node
 	bool basis_on_device = true;
 	bool rng_ready = false;
 	long long rng_draws_per_step = 0;
@@ -214,6 +217,11 @@ void upload_zone(gcm_b200_set* s, Zone& z)
 	z.border_slot.upload(hm.border_slot, s->stream);
 	z.border_nodes.upload(hm.border_nodes, s->stream);
 	z.inner_nodes.upload(hm.inner_nodes, s->stream);
+	z.inner_fast.upload(hm.inner_fast, s->stream);
+	z.inner_generic.upload(hm.inner_generic, s->stream);
+	z.w0.upload(hm.w0, s->stream);
+	z.mat_tab.upload(hm.mat_table, s->stream);
+	z.mat_id.upload(hm.mat_id, s->stream);
 	z.cond_id.upload(hm.cond_id, s->stream);
 	z.basis.alloc(hm.basis.size());
 	CK(cudaStreamSynchronize(s->stream));
@@ -413,14 +421,33 @@ void zone_stage(gcm_b200_set* s, int zi, float tau, int stage)
 		gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, s->stream>>>(m, z.border_nodes.p, nb, stage, z.unext(), s->d_err, zi, tap);
 		s->launches++;
 	}
-	if(ni) {
-		ProfScope ps(s, 0, ni);
-		gcm::stage_generic_kernel<<<(ni + 127) / 128, 128, 0, s->stream>>>(m, z.inner_nodes.p, ni, stage, z.unext(), s->d_err, zi, tap);
-		s->launches++;
+	if(!s->fast_inner) {
+		if(ni) {
+			ProfScope ps(s, 0, ni);
+			gcm::stage_generic_kernel<<<(ni + 127) / 128, 128, 0, s->stream>>>(m, z.inner_nodes.p, ni, stage, z.unext(), s->d_err, zi, tap);
+			s->launches++;
+		}
+	} else {
+		const int ng = (int)z.hm.inner_generic.size(), nf = (int)z.hm.inner_fast.size();
+		if(ng) {
+			ProfScope ps(s, 5, ng);
+			gcm::stage_generic_kernel<<<(ng + 127) / 128, 128, 0, s->stream>>>(m, z.inner_generic.p, ng, stage, z.unext(), s->d_err, zi, tap);
+			s->launches++;
+		}
+		if(nf) {
+			ProfScope ps(s, 0, nf);
+			const int n_mat = (int)(z.hm.materials.size() / 3);
+			const unsigned char* mid = n_mat > 1 ? z.mat_id.p : nullptr;
+			const gcm::MatTab* tab = reinterpret_cast<const gcm::MatTab*>(z.mat_tab.p);
+			const dim3 grid((nf + 127) / 128), block(128);
+			if(stage == 0) gcm::stage_inner_kernel<0><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p);
+			else if(stage == 1) gcm::stage_inner_kernel<1><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p);
+			else gcm::stage_inner_kernel<2><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p);
+			s->launches++;
+		}
 	}
-	// copy-back loop of TetrMesh_1stOrder.cpp:1925-1932 == buffer swap; halo slots of the new
-	// current layer are refreshed by the sync_nodes that precedes every stage, but non-local
-	// slots must hold defined values: keep them by copying the halo of the old layer lazily.
+	// copy-back loop of TetrMesh_1stOrder.cpp:1925-1932 == buffer swap: the halo slots of the new
+	// current layer are refreshed by the sync_nodes that precedes every stage
 	z.cur ^= 1;
 }
 
@@ -515,6 +542,13 @@ int gcm_b200_set_seed(gcm_b200_set* s, unsigned seed)
 	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
 	s->rng.seed(seed);
 	s->rng_ready = false;
+	return 0;
+}
+
+int gcm_b200_set_kernel_mode(gcm_b200_set* s, int fast_inner)
+{
+	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	s->fast_inner = fast_inner != 0;
 	return 0;
 }
 

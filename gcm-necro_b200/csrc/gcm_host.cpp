@@ -1,6 +1,7 @@
 // gcm_host.cpp -- see gcm_host.h.  Compiled with  g++ -O2 -ffp-contract=off -fopenmp.
 #include "gcm_host.h"
 #include "gcm_math.cuh"
+#include "gcm_inner.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -197,7 +198,21 @@ void HostMesh::pre_process_mesh()
 		Vec3 p0 = P(coords, tv[0]), p1 = P(coords, tv[1]), p2 = P(coords, tv[2]), p3 = P(coords, tv[3]);
 		float h = gcm::tetr_h(p0, p1, p2, p3);
 		tet_hv[2*(size_t)t] = h;
-		tet_hv[2*(size_t)t+1] = gcm::tet_signed_volume(p0, p1, p2, p3);
+		// Both uses of Vol are sign-blind (fabs(Vol) in point_in_tetr, fabs(s/Vol) in interpolate), so
+		// |Vol| is stored and its sign bit carries a shape flag for the inner kernel's pre-filter:
+		// positive = well shaped (6|Vol| > 0.02 * longest edge^3), negative = use the exact test only.
+		{
+			float vol = fabsf(gcm::tet_signed_volume(p0, p1, p2, p3));
+			const Vec3 pp[4] = {p0, p1, p2, p3};
+			float l2 = 0;
+			for(int a = 0; a < 4; a++) for(int b = a + 1; b < 4; b++) {
+				float dx = pp[a].x - pp[b].x, dy = pp[a].y - pp[b].y, dz = pp[a].z - pp[b].z;
+				float d2 = dx*dx + dy*dy + dz*dz;
+				if(d2 > l2) l2 = d2;
+			}
+			float l3 = l2 * sqrtf(l2);
+			tet_hv[2*(size_t)t+1] = (6 * vol > 0.02f * l3) ? vol : -vol;
+		}
 		if(h < 0) bad++;
 		if(h > mx_h) mx_h = h;
 	}
@@ -372,7 +387,83 @@ void HostMesh::pre_process_mesh()
 	if(!err.empty()) throw HostError{MESH_EXCEPTION, err};
 	basis.assign(9*(size_t)NB, 0.f);
 	cond_id.assign(NB, -1);
+	build_fast_path_tables();
 	preprocessed = true;
+}
+
+// Static inputs of gcm_inner.cuh.  Everything here is computed with the general routines, so
+// the specialised kernel reproduces them by construction; whatever does not fit its
+// assumptions is routed to the generic kernel (inner_generic).
+void HostMesh::build_fast_path_tables()
+{
+	// ---- distinct materials of local nodes and their identity-basis eigensystems -----------
+	materials.clear(); mat_table.clear();
+	mat_id.assign(N, 255);
+	std::vector<char> mat_ok;
+	for(int i = 0; i < N; i++) {
+		if(!is_local(i)) continue;
+		const float* mt = &mat[4*(size_t)i];
+		int id = -1;
+		for(size_t k = 0; k < materials.size() / 3; k++)
+			if(memcmp(&materials[3*k], mt, 3 * sizeof(float)) == 0) { id = (int)k; break; }
+		if(id < 0) {
+			if(materials.size() / 3 >= GCM_MAX_MATERIALS) continue;   // not tabulated -> generic kernel
+			id = (int)(materials.size() / 3);
+			materials.insert(materials.end(), mt, mt + 3);
+			bool ok = true;
+			for(int st = 0; st < 3; st++) {
+				float L[9], U[81], U1[81];
+				float q[3] = {0, 0, 0}; q[st] = 1;
+				if(gcm::elastic_matrix(mt[0], mt[1], mt[2], q[0], q[1], q[2], L, U, U1) != 0) ok = false;
+				for(int r = 0; r < 9; r++)
+					for(int c = 0; c < 9; c++) {
+						if(!((gcm::u_pattern(st, r) >> c) & 1) && U[r*9+c] != 0) ok = false;
+						if(!((gcm::u1_pattern(st, r) >> c) & 1) && U1[r*9+c] != 0) ok = false;
+					}
+				// the five-point pattern (0,1,2,3,2,3,4,4,4) of the characteristic dedupe (:479-490)
+				float dksi[9]; int pp[9], count = 0;
+				for(int r = 0; r < 9; r++) dksi[r] = - L[r] * 0.002f;
+				for(int r = 0; r < 9; r++) {
+					bool found = false;
+					for(int c = 0; c < r; c++)
+						if( (double)fabsf(dksi[r] - dksi[c]) <= 0.01 * (double)fabsf(dksi[r] + dksi[c]) ) { found = true; pp[r] = pp[c]; }
+					if(!found) pp[r] = count++;
+				}
+				static const int want[9] = {0, 1, 2, 3, 2, 3, 4, 4, 4};
+				if(count != 5 || memcmp(pp, want, sizeof want) != 0 || L[2] != L[4] || L[3] != L[5] || L[6] != 0) ok = false;
+				mat_table.insert(mat_table.end(), L, L + 9);
+				mat_table.insert(mat_table.end(), U, U + 81);
+				mat_table.insert(mat_table.end(), U1, U1 + 81);
+			}
+			mat_ok.push_back(ok ? 1 : 0);
+		}
+		mat_id[i] = mat_ok[id] ? (unsigned char)id : 255;
+	}
+
+	// ---- zero-speed foot: owner must be elements[0], all weight on the node itself ------------
+	w0.assign(N, 0.f);
+	std::vector<char> fast(N, 0);
+	const int NI = (int)inner_nodes.size();
+	#pragma omp parallel for schedule(static)
+	for(int q = 0; q < NI; q++) {
+		const int i = inner_nodes[q];
+		if(mat_id[i] == 255 || n2t_off[i+1] == n2t_off[i]) continue;
+		const Vec3 X = P(coords, i);
+		const int t = n2t[n2t_off[i]];
+		const int* tv = &tets[4*(size_t)t];
+		const Vec3 p[4] = { P(coords, tv[0]), P(coords, tv[1]), P(coords, tv[2]), P(coords, tv[3]) };
+		const float h = tet_hv[2*(size_t)t], vol = tet_hv[2*(size_t)t+1];
+		if(!gcm::point_in_tetr(X, 0.f, 0.f, 0.f, 0.f, p[0], p[1], p[2], p[3], h, vol)) continue;
+		float f[4];
+		if(!gcm::interp_factors(p[0], p[1], p[2], p[3], X.x, X.y, X.z, vol, f)) continue;
+		int k = -1; bool ok = true;
+		for(int j = 0; j < 4; j++) { if(tv[j] == i) k = j; else if(f[j] != 0) ok = false; }
+		if(k < 0 || !ok) continue;
+		w0[i] = f[k];
+		fast[i] = 1;
+	}
+	inner_fast.clear(); inner_generic.clear();
+	for(int q = 0; q < NI; q++) (fast[inner_nodes[q]] ? inner_fast : inner_generic).push_back(inner_nodes[q]);
 }
 
 // create_rotation_matrix_with_normal + the rand() bookkeeping of create_random_axis,

@@ -65,6 +65,14 @@ struct HostMesh {
 	std::vector<float> normals;       // [n_border][3] find_border_node_normal(min_h)
 	std::vector<float> basis;         // [n_border][9] local basis of the current step
 	std::vector<int> cond_id;         // [n_border] border condition id or -1 (default)
+	// static inputs of the specialised inner-node kernel (gcm_inner.cuh), built by
+	// build_fast_path_tables(): nodes it may take, their zero-foot weight, the material table
+	std::vector<int> inner_fast, inner_generic;   // partition of inner_nodes
+	std::vector<float> w0;                        // [N] own-vertex factor of the zero-speed foot
+	std::vector<unsigned char> mat_id;            // [N] index into materials (255 = not tabulated)
+	std::vector<float> materials;                 // [n_mat][3] distinct (la, mu, rho)
+	std::vector<float> mat_table;                 // [n_mat][3 stages][9 + 81 + 81] L, U, U1 for q = e_stage
+	void build_fast_path_tables();
 	float min_h = -1, max_h = -1;
 	float outline_min[3] = {0, 0, 0}, outline_max[3] = {0, 0, 0};
 	float current_time = 0;

@@ -11,6 +11,10 @@ __device__ __forceinline__ void report_error(int* err, int code, int zone, int n
 	if(atomicCAS(&err[0], 0, code) == 0) { err[1] = zone; err[2] = node; err[3] = stage; }
 }
 
+} // namespace gcm
+#include "gcm_inner.cuh"
+namespace gcm {
+
 // One thread per listed node, one axis stage: TetrMesh_1stOrder::do_next_part_step's two
 // node loops (gcm/meshtypes/TetrMesh_1stOrder.cpp:1906-1923); the copy-back loop (:1925-1932)
 // is the caller's buffer swap.

@@ -54,6 +54,7 @@ SIGNATURES = {
     "gcm_b200_set_destroy": (_i, [_p]),
     "gcm_b200_set_seed": (_i, [_p, C.c_uint]),
     "gcm_b200_set_basis_mode": (_i, [_p, _i]),
+    "gcm_b200_set_kernel_mode": (_i, [_p, _i]),
     "gcm_b200_set_collision_detector": (_i, [_p, _i, _i, _f]),
     "gcm_b200_set_contact_calculator": (_i, [_p, _i]),
     "gcm_b200_zone_load": (_i, [_p, _i, _i, _i, _fp, _ip, _ip, _ip, _ip, _fp]),
@@ -242,6 +243,9 @@ class TetrMeshSet:
 
     def srand(self, seed):
         self._ck(self.lib.gcm_b200_set_seed(self.h, seed))
+
+    def set_kernel_mode(self, fast_inner=True):
+        self._ck(self.lib.gcm_b200_set_kernel_mode(self.h, int(fast_inner)))
 
     def set_basis_mode(self, on_device=True):
         self._ck(self.lib.gcm_b200_set_basis_mode(self.h, int(on_device)))

@@ -43,6 +43,10 @@ int gcm_b200_set_seed(gcm_b200_set* s, unsigned seed);
  * walked in parallel chunks, bit-identical to libc for the given seed); 0 = on the host with the
  * restated libc generator, bases uploaded every step. */
 int gcm_b200_set_basis_mode(gcm_b200_set* s, int on_device);
+/* 1 (default): inner nodes go through the specialised kernel (identity basis, tabulated
+ * eigensystems, pre-filtered owner search); 0: every node through the generic per-node routine
+ * (the literal restatement of the reference).  Results are bit-identical; 0 exists for A/B tests. */
+int gcm_b200_set_kernel_mode(gcm_b200_set* s, int fast_inner);
 /* CollisionDetector selection, TaskPreparator.cpp:225-254: type 0 = Void, 1 = Bruteforce;
  * is_static as <collision_detector static="true">; threshold as set_treshold(). */
 int gcm_b200_set_collision_detector(gcm_b200_set* s, int type, int is_static, float threshold);

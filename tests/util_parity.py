@@ -170,13 +170,14 @@ def run_emul(case):
         return res
 
 
-def run_product(case, device=0):
+def run_product(case, device=0, fast_inner=True):
     """Run the case through the C ABI (libgcm_b200.so) on the GPU."""
     import gcm_b200
     la, mu, rho, yl = case["material"]
     ms = gcm_b200.TetrMeshSet(n_zones=len(case["zones"]), device=device)
     try:
         ms.srand(case["seed"])
+        ms.set_kernel_mode(fast_inner)
         for k, z in enumerate(case["zones"]):
             ms.get_mesh_by_zone_num(k).load(z, la=la, mu=mu, rho=rho, yield_limit=yl)
         ms.pre_process_meshes()

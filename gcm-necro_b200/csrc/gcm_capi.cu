@@ -185,7 +185,7 @@ void upload_values(gcm_b200_set* s, Zone& z)
 	if(!n) return;
 	if(!z.aos.p) z.aos.alloc(9 * (size_t)n);
 	CK(cudaMemcpyAsync(z.aos.p, hm.values.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-	gcm::aos_to_soa_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z.u0.p, z.u1.p, z.stride, z.aos.p, z.flags.p, n, 0);
+	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z.u0.p, z.u1.p, z.aos.p, z.flags.p, n, 0);
 	s->launches++;
 	CK(cudaStreamSynchronize(s->stream));
 	z.cur = 0;
@@ -196,19 +196,19 @@ void upload_zone(gcm_b200_set* s, Zone& z)
 	HostMesh& hm = z.hm;
 	const size_t N = hm.N;
 	z.stride = (N + 31) / 32 * 32;
-	std::vector<float> soa(3 * z.stride, 0.f);
-	for(size_t i = 0; i < N; i++)
-		for(int k = 0; k < 3; k++) soa[k * z.stride + i] = hm.coords[3*i + k];
-	z.xyz.upload(soa, s->stream);
-	CK(cudaStreamSynchronize(s->stream));
-	soa.assign(4 * z.stride, 0.f);
+	z.xyz.upload(hm.coords, s->stream);   // node-major staging; lives on in the records
+	std::vector<float> soa(4 * z.stride, 0.f);
 	for(size_t i = 0; i < N; i++)
 		for(int k = 0; k < 4; k++) soa[k * z.stride + i] = hm.mat[4*i + k];
 	z.mat.upload(soa, s->stream);
 	CK(cudaStreamSynchronize(s->stream));
-	z.u0.alloc(9 * z.stride); z.u1.alloc(9 * z.stride);
-	CK(cudaMemsetAsync(z.u0.p, 0, 9 * z.stride * sizeof(float), s->stream));
-	CK(cudaMemsetAsync(z.u1.p, 0, 9 * z.stride * sizeof(float), s->stream));
+	z.u0.alloc(GCM_REC * (N + 1)); z.u1.alloc(GCM_REC * (N + 1));
+	CK(cudaMemsetAsync(z.u0.p, 0, GCM_REC * (N + 1) * sizeof(float), s->stream));
+	CK(cudaMemsetAsync(z.u1.p, 0, GCM_REC * (N + 1) * sizeof(float), s->stream));
+	if(N) {
+		gcm::coords_to_records_kernel<<<(int)((N + 255) / 256), 256, 0, s->stream>>>(z.u0.p, z.u1.p, z.xyz.p, (int)N);
+		s->launches++;
+	}
 	z.flags.upload(hm.flags, s->stream);
 	z.n2t_off.upload(hm.n2t_off, s->stream);
 	z.n2t.upload(hm.n2t, s->stream);
@@ -238,7 +238,7 @@ gcm::MeshView make_view(gcm_b200_set* s, Zone& z)
 	gcm::MeshView m;
 	memset(&m, 0, sizeof(m));
 	m.n_nodes = z.hm.N; m.n_tets = z.hm.T; m.stride = z.stride;
-	m.xyz = z.xyz.p; m.u = z.ucur(); m.mat = z.mat.p; m.flags = z.flags.p;
+	m.u = z.ucur(); m.mat = z.mat.p; m.flags = z.flags.p;
 	m.n2t_off = z.n2t_off.p; m.n2t = z.n2t.p; m.tets = z.tets.p; m.tet_hv = z.tet_hv.p;
 	m.border_slot = z.border_slot.p; m.basis = z.basis.p; m.cond_id = z.cond_id.p; m.contact = nullptr;
 	m.tau = s->time_step; m.time = z.hm.current_time; m.min_h = z.hm.min_h;
@@ -394,7 +394,7 @@ void sync_nodes_device(gcm_b200_set* s)
 		if(!gp->dst.p) { gp->dst.upload(gp->h_dst, s->stream); gp->src.upload(gp->h_src, s->stream); }
 		{
 			ProfScope ps(s, 3, n);
-			gcm::halo_copy_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(d.ucur(), d.stride, gp->dst.p, o.ucur(), o.stride, gp->src.p, n);
+			gcm::halo_copy_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(d.ucur(), gp->dst.p, o.ucur(), gp->src.p, n);
 		}
 		s->launches++;
 	}
@@ -644,7 +644,7 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values)
 		const int n = hm.N;
 		if(n) {
 			if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
-			gcm::soa_to_aos_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), z->stride, n);
+			gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), n);
 			s->launches++;
 			CK(cudaMemcpyAsync(hm.values.data(), z->aos.p, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 			CK(cudaStreamSynchronize(s->stream));
@@ -665,7 +665,7 @@ int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* ho
 	if(!n) return 0;
 	if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
 	CK(cudaMemcpyAsync(z->aos.p, host_values, 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-	gcm::aos_to_soa_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->ucur(), nullptr, z->stride, z->aos.p, z->flags.p, n, 1);
+	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->ucur(), nullptr, z->aos.p, z->flags.p, n, 1);
 	s->launches++;
 	CK(cudaGetLastError());
 	return 0;
@@ -681,7 +681,7 @@ int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_v
 	const int n = z->hm.N;
 	if(!n) return 0;
 	if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
-	gcm::soa_to_aos_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), z->stride, n);
+	gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), n);
 	s->launches++;
 	CK(cudaMemcpyAsync(host_values, z->aos.p, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 	return 0;
@@ -962,7 +962,7 @@ int gcm_b200_halo_pack(gcm_b200_set* s, int peer_rank, float* dev_buf)
 	int total = (int)p.send_node.size();
 	for(auto& sg : p.send_segs) {
 		Zone& z = *s->zones[sg->zone];
-		gcm::halo_pack_kernel<<<(sg->n + 255) / 256, 256, 0, s->stream>>>(dev_buf, z.ucur(), z.stride, sg->idx.p, sg->n, total, sg->offset);
+		gcm::halo_pack_kernel<<<(sg->n + 255) / 256, 256, 0, s->stream>>>(dev_buf, z.ucur(), sg->idx.p, sg->n, total, sg->offset);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
@@ -982,7 +982,7 @@ int gcm_b200_halo_unpack(gcm_b200_set* s, int peer_rank, const float* dev_buf)
 	int total = (int)p.recv_node.size();
 	for(auto& sg : p.recv_segs) {
 		Zone& z = *s->zones[sg->zone];
-		gcm::halo_unpack_kernel<<<(sg->n + 255) / 256, 256, 0, s->stream>>>(z.ucur(), z.stride, dev_buf, sg->idx.p, sg->n, total, sg->offset);
+		gcm::halo_unpack_kernel<<<(sg->n + 255) / 256, 256, 0, s->stream>>>(z.ucur(), dev_buf, sg->idx.p, sg->n, total, sg->offset);
 		s->launches++;
 	}
 	CK(cudaGetLastError());

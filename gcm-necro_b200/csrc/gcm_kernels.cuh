@@ -32,14 +32,14 @@ stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 	if(e) { report_error(err, e, zone, node, stage); return; }
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		un[(size_t)k * m.stride + node] = out[k];
+		un[(size_t)node * GCM_REC + k] = out[k];
 }
 
 // Stage 3: the plastic corrector drop_deviator (TetrMethod_Plastic_1stOrder.cpp:51-71,192-199),
 // in place on the current layer for every local node.
 __global__ void __launch_bounds__(256)
 plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* __restrict__ flags,
-               int n_nodes, size_t stride, int* err, int zone)
+               int n_nodes, size_t stride, int* err, int zone)   // u: node records, mat: planes
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n_nodes) return;
@@ -48,7 +48,7 @@ plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* 
 	bool bad = false;
 	#pragma unroll
 	for(int k = 0; k < 9; k++) {
-		v[k] = u[(size_t)k * stride + i];
+		v[k] = u[(size_t)i * GCM_REC + k];
 		bad |= (isnan(v[k]) || isinf(v[k]));
 	}
 	if(bad) { report_error(err, ERR_NAN, zone, i, 3); return; }
@@ -56,25 +56,25 @@ plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* 
 	if(drop_deviator(v, yield_limit)) {
 		#pragma unroll
 		for(int k = 3; k < 9; k++)
-			u[(size_t)k * stride + i] = v[k];
+			u[(size_t)i * GCM_REC + k] = v[k];
 	}
 }
 
 // DataBus::sync_nodes, same-process branch (gcm/system/DataBus.cpp:64-79): halo node values
 // of one zone copied from the owner zone's nodes.  Only the 9 evolving values move per stage.
-__global__ void halo_copy_kernel(float* __restrict__ dst_u, size_t dst_stride, const int* __restrict__ dst_idx,
-                                 const float* __restrict__ src_u, size_t src_stride, const int* __restrict__ src_idx, int n)
+__global__ void halo_copy_kernel(float* __restrict__ dst_u, const int* __restrict__ dst_idx,
+                                 const float* __restrict__ src_u, const int* __restrict__ src_idx, int n)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n) return;
 	int d = dst_idx[i], s = src_idx[i];
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		dst_u[(size_t)k * dst_stride + d] = src_u[(size_t)k * src_stride + s];
+		dst_u[(size_t)d * GCM_REC + k] = src_u[(size_t)s * GCM_REC + k];
 }
 
 // Cross-process halo: gather into / scatter from a plane-major [9][n] exchange buffer.
-__global__ void halo_pack_kernel(float* __restrict__ buf, const float* __restrict__ u, size_t stride,
+__global__ void halo_pack_kernel(float* __restrict__ buf, const float* __restrict__ u,
                                  const int* __restrict__ idx, int n, int n_total, int offset)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,10 +82,10 @@ __global__ void halo_pack_kernel(float* __restrict__ buf, const float* __restric
 	int s = idx[i];
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		buf[(size_t)k * n_total + offset + i] = u[(size_t)k * stride + s];
+		buf[(size_t)k * n_total + offset + i] = u[(size_t)s * GCM_REC + k];
 }
 
-__global__ void halo_unpack_kernel(float* __restrict__ u, size_t stride, const float* __restrict__ buf,
+__global__ void halo_unpack_kernel(float* __restrict__ u, const float* __restrict__ buf,
                                    const int* __restrict__ idx, int n, int n_total, int offset)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,7 +93,7 @@ __global__ void halo_unpack_kernel(float* __restrict__ u, size_t stride, const f
 	int d = idx[i];
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		u[(size_t)k * stride + d] = buf[(size_t)k * n_total + offset + i];
+		u[(size_t)d * GCM_REC + k] = buf[(size_t)k * n_total + offset + i];
 }
 
 // ---- the per-step random local bases, generated on the device ------------------------------
@@ -162,10 +162,10 @@ __global__ void basis_kernel(float* __restrict__ basis, const float* __restrict_
 }
 
 // Host-facing state layout is the reference's node-major values[9] (ElasticNode.h:28-44); the
-// device keeps plane-major SoA.  These two kernels are the transposes on either side of a
-// pinned-memory copy.  aos_to_soa writes local nodes only (halo slots belong to sync_nodes).
-__global__ void aos_to_soa_kernel(float* __restrict__ u0, float* __restrict__ u1, size_t stride,
-                                  const float* __restrict__ aos, const int* __restrict__ flags, int n, int local_only)
+// device keeps 12-float node records.  These kernels sit on either side of a pinned-memory copy;
+// values_to_records with local_only writes local nodes only (halo slots belong to sync_nodes).
+__global__ void values_to_records_kernel(float* __restrict__ u0, float* __restrict__ u1,
+                                         const float* __restrict__ aos, const int* __restrict__ flags, int n, int local_only)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n) return;
@@ -173,18 +173,31 @@ __global__ void aos_to_soa_kernel(float* __restrict__ u0, float* __restrict__ u1
 	#pragma unroll
 	for(int k = 0; k < 9; k++) {
 		float v = aos[9 * (size_t)i + k];
-		u0[(size_t)k * stride + i] = v;
-		if(u1) u1[(size_t)k * stride + i] = v;
+		u0[(size_t)i * GCM_REC + k] = v;
+		if(u1) u1[(size_t)i * GCM_REC + k] = v;
 	}
 }
 
-__global__ void soa_to_aos_kernel(float* __restrict__ aos, const float* __restrict__ u, size_t stride, int n)
+__global__ void records_to_values_kernel(float* __restrict__ aos, const float* __restrict__ u, int n)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n) return;
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		aos[9 * (size_t)i + k] = u[(size_t)k * stride + i];
+		aos[9 * (size_t)i + k] = u[(size_t)i * GCM_REC + k];
+}
+
+// Static coordinates into the xyz slots of both layers' records (once, at upload).
+__global__ void coords_to_records_kernel(float* __restrict__ u0, float* __restrict__ u1, const float* __restrict__ xyz, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	#pragma unroll
+	for(int k = 0; k < 3; k++) {
+		float v = xyz[3 * (size_t)i + k];
+		u0[(size_t)i * GCM_REC + 9 + k] = v;
+		u1[(size_t)i * GCM_REC + 9 + k] = v;
+	}
 }
 
 } // namespace gcm

@@ -37,9 +37,9 @@ struct BorderCond {
 // Read-only view of one zone mesh in device (or, in the test emulation, host) memory.
 struct MeshView {
 	int n_nodes, n_tets;
-	size_t stride;           // plane stride of the SoA arrays (floats)
-	const float* xyz;        // [3][stride]
-	const float* u;          // [9][stride]  current layer (vx,vy,vz,sxx,sxy,sxz,syy,syz,szz)
+	size_t stride;           // plane stride of the material planes (floats)
+	const float* u;          // [n_nodes][GCM_REC] current layer: one 48-byte record per node =
+	                         //   vx,vy,vz,sxx | sxy,sxz,syy,syz | szz,x,y,z   (three float4)
 	const float* mat;        // [4][stride]  la, mu, rho, yield_limit
 	const int* flags;        // [n_nodes]
 	const int* n2t_off;      // [n_nodes+1]  node -> incident tets (ascending ids), CSR
@@ -57,9 +57,14 @@ struct MeshView {
 	int n_conds;
 };
 
+// Node record: the 9 evolving values and the (static) coordinates share three float4 so that a
+// gather of one vertex is 3 x LDG.128 instead of 12 x LDG.32 (the kernels are load-issue bound).
+#define GCM_REC 12
+
 GCM_HD Vec3 load_xyz(const MeshView& m, int i)
 {
-	Vec3 v; v.x = m.xyz[i]; v.y = m.xyz[m.stride + i]; v.z = m.xyz[2*m.stride + i];
+	const float* r = m.u + (size_t)i * GCM_REC;
+	Vec3 v; v.x = r[9]; v.y = r[10]; v.z = r[11];
 	return v;
 }
 
@@ -121,10 +126,12 @@ GCM_HD int interpolate_foot(const MeshView& m, const TetGeom& g, float x, float 
 	float f[4];
 	if(!interp_factors(g.p[0], g.p[1], g.p[2], g.p[3], x, y, z, g.vol, f))
 		return ERR_INTERP_SUM;
-	for(int k = 0; k < 9; k++) {
-		const float* pl = m.u + (size_t)k * m.stride;
-		out[k] = interp4(pl[g.v[0]], pl[g.v[1]], pl[g.v[2]], pl[g.v[3]], f);
-	}
+	const float* r0 = m.u + (size_t)g.v[0] * GCM_REC;
+	const float* r1 = m.u + (size_t)g.v[1] * GCM_REC;
+	const float* r2 = m.u + (size_t)g.v[2] * GCM_REC;
+	const float* r3 = m.u + (size_t)g.v[3] * GCM_REC;
+	for(int k = 0; k < 9; k++)
+		out[k] = interp4(r0[k], r1[k], r2[k], r3[k], f);
 	if(with_material) {
 		for(int k = 0; k < 3; k++) {
 			const float* pl = m.mat + (size_t)k * m.stride;
@@ -399,7 +406,7 @@ GCM_HD int node_stage_nocontact(const MeshView& m, int node, int stage, float ou
 	cur.base = node;
 	cur.pos = load_xyz(m, node);
 	for(int k = 0; k < 9; k++) {
-		float v = m.u[(size_t)k * m.stride + node];
+		float v = m.u[(size_t)node * GCM_REC + k];
 		if(isnan(v) || isinf(v)) return ERR_NAN;
 		cur.val[k] = v;
 	}

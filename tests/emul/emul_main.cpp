@@ -126,11 +126,11 @@ int main(int argc, char** argv)
 	for(auto& zp : zs) {
 		Z& z = *zp; HostMesh& hm = z.hm;
 		z.stride = (hm.N + 31) / 32 * 32;
-		z.xyz.assign(3*z.stride, 0); z.mat.assign(4*z.stride, 0); z.u[0].assign(9*z.stride, 0);
+		z.mat.assign(4*z.stride, 0); z.u[0].assign(GCM_REC*(size_t)hm.N, 0);
 		for(int i = 0; i < hm.N; i++) {
-			for(int k = 0; k < 3; k++) z.xyz[k*z.stride+i] = hm.coords[3*(size_t)i+k];
+			for(int k = 0; k < 3; k++) z.u[0][GCM_REC*(size_t)i+9+k] = hm.coords[3*(size_t)i+k];
 			for(int k = 0; k < 4; k++) z.mat[k*z.stride+i] = hm.mat[4*(size_t)i+k];
-			for(int k = 0; k < 9; k++) z.u[0][k*z.stride+i] = hm.values[9*(size_t)i+k];
+			for(int k = 0; k < 9; k++) z.u[0][GCM_REC*(size_t)i+k] = hm.values[9*(size_t)i+k];
 		}
 		z.u[1] = z.u[0];
 	}
@@ -147,7 +147,7 @@ int main(int argc, char** argv)
 				for(int i = 0; i < d.hm.N; i++) {
 					if(d.hm.flags[i] & 2) continue;
 					Z& o = *zs[d.hm.remote_zone[i]]; int si = d.hm.remote_num[i];
-					for(int k = 0; k < 9; k++) d.u[d.cur][k*d.stride+i] = o.u[o.cur][k*o.stride+si];
+					for(int k = 0; k < 9; k++) d.u[d.cur][GCM_REC*(size_t)i+k] = o.u[o.cur][GCM_REC*(size_t)si+k];
 				}
 			}
 			for(int zi = 0; zi < NZ && !rc; zi++) {
@@ -156,14 +156,14 @@ int main(int argc, char** argv)
 				if(stage == 3) {
 					for(int i = 0; i < hm.N; i++) {
 						if(!hm.is_local(i)) continue;
-						float v[9]; for(int k = 0; k < 9; k++) v[k] = ucur[k*z.stride+i];
-						if(gcm::drop_deviator(v, z.mat[3*z.stride+i])) for(int k = 3; k < 9; k++) ucur[k*z.stride+i] = v[k];
+						float v[9]; for(int k = 0; k < 9; k++) v[k] = ucur[GCM_REC*(size_t)i+k];
+						if(gcm::drop_deviator(v, z.mat[3*z.stride+i])) for(int k = 3; k < 9; k++) ucur[GCM_REC*(size_t)i+k] = v[k];
 					}
 					continue;
 				}
 				gcm::MeshView m; memset(&m, 0, sizeof m);
 				m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
-				m.xyz = z.xyz.data(); m.u = ucur; m.mat = z.mat.data(); m.flags = hm.flags.data();
+				m.u = ucur; m.mat = z.mat.data(); m.flags = hm.flags.data();
 				m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 				m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 				m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
@@ -185,7 +185,7 @@ int main(int argc, char** argv)
 						{ if(!err) { err = e; fprintf(stderr, "gcm_emul: error %d zone %d node %d stage %d\n", e, zi, i, stage); } }
 						continue;
 					}
-					for(int k = 0; k < 9; k++) un[k*z.stride+i] = o[k];
+					for(int k = 0; k < 9; k++) un[GCM_REC*(size_t)i+k] = o[k];
 					if(step == tap_step) {
 						#pragma omp critical
 						{ tap.push_back(zi); tap.push_back(i); tap.push_back(stage); for(int k = 0; k < 5; k++) tap.push_back(t.owner[k]); tap.push_back(t.outer_count); tap.push_back(t.tries); }
@@ -202,7 +202,7 @@ int main(int argc, char** argv)
 			Z& z = *zs[zi]; HostMesh& hm = z.hm;
 			vector<float> vals(9*(size_t)hm.N), bases(9*(size_t)hm.N, 0.f);
 			for(int i = 0; i < hm.N; i++) {
-				for(int k = 0; k < 9; k++) vals[9*(size_t)i+k] = z.u[z.cur][k*z.stride+i];
+				for(int k = 0; k < 9; k++) vals[9*(size_t)i+k] = z.u[z.cur][GCM_REC*(size_t)i+k];
 				if(hm.is_local(i)) {
 					int b = hm.border_slot[i];
 					const float E[9] = {1,0,0,0,1,0,0,0,1};

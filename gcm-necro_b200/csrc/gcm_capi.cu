@@ -70,6 +70,7 @@ struct Zone {
 	int slot_offset = 0;                       // first global border slot of this zone (device RNG)
 	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, border_nodes, inner_nodes, cond_id, inner_fast, inner_generic;
 	DevBuf<float> w0, mat_tab;
+	DevBuf<int> n2x;
 	DevBuf<unsigned char> mat_id;
 	DevBuf<gcm::StageTap> tap;
 	int cur = 0;
@@ -222,6 +223,7 @@ void upload_zone(gcm_b200_set* s, Zone& z)
 	z.w0.upload(hm.w0, s->stream);
 	z.mat_tab.upload(hm.mat_table, s->stream);
 	z.mat_id.upload(hm.mat_id, s->stream);
+	z.n2x.upload(hm.n2x, s->stream);
 	z.cond_id.upload(hm.cond_id, s->stream);
 	z.basis.alloc(hm.basis.size());
 	CK(cudaStreamSynchronize(s->stream));
@@ -440,9 +442,9 @@ void zone_stage(gcm_b200_set* s, int zi, float tau, int stage)
 			const unsigned char* mid = n_mat > 1 ? z.mat_id.p : nullptr;
 			const gcm::MatTab* tab = reinterpret_cast<const gcm::MatTab*>(z.mat_tab.p);
 			const dim3 grid((nf + 127) / 128), block(128);
-			if(stage == 0) gcm::stage_inner_kernel<0><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p);
-			else if(stage == 1) gcm::stage_inner_kernel<1><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p);
-			else gcm::stage_inner_kernel<2><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p);
+			if(stage == 0) gcm::stage_inner_kernel<0><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p, reinterpret_cast<const int4*>(z.n2x.p));
+			else if(stage == 1) gcm::stage_inner_kernel<1><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p, reinterpret_cast<const int4*>(z.n2x.p));
+			else gcm::stage_inner_kernel<2><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p, reinterpret_cast<const int4*>(z.n2x.p));
 			s->launches++;
 		}
 	}

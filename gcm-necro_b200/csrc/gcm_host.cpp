@@ -464,6 +464,22 @@ void HostMesh::build_fast_path_tables()
 	}
 	inner_fast.clear(); inner_generic.clear();
 	for(int q = 0; q < NI; q++) (fast[inner_nodes[q]] ? inner_fast : inner_generic).push_back(inner_nodes[q]);
+
+	// ---- node -> tet CSR expanded with the other three vertices (removes the tets[t] hop) ------
+	if(T >= (1 << 30)) throw HostError{CONFIG_EXCEPTION, "too many tetrahedrons for the packed candidate table"};
+	n2x.assign(4 * n2t.size(), 0);
+	#pragma omp parallel for schedule(static)
+	for(int i = 0; i < N; i++)
+		for(int e = n2t_off[i]; e < n2t_off[i+1]; e++) {
+			const int t = n2t[e];
+			const int* tv = &tets[4*(size_t)t];
+			int k = -1, o[3], c = 0;
+			for(int j = 0; j < 4; j++) { if(tv[j] == i && k < 0) k = j; else if(c < 3) o[c++] = tv[j]; }
+			if(k < 0) k = 3;
+			while(c < 3) o[c++] = i;
+			n2x[4*(size_t)e] = o[0]; n2x[4*(size_t)e+1] = o[1]; n2x[4*(size_t)e+2] = o[2];
+			n2x[4*(size_t)e+3] = (int)((unsigned)t | ((unsigned)k << 30));
+		}
 }
 
 // create_rotation_matrix_with_normal + the rand() bookkeeping of create_random_axis,

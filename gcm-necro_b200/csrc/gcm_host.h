@@ -72,6 +72,7 @@ struct HostMesh {
 	std::vector<unsigned char> mat_id;            // [N] index into materials (255 = not tabulated)
 	std::vector<float> materials;                 // [n_mat][3] distinct (la, mu, rho)
 	std::vector<float> mat_table;                 // [n_mat][3 stages][9 + 81 + 81] L, U, U1 for q = e_stage
+	std::vector<int> n2x;                         // [len(n2t)][4] CSR entry -> (other vertices a, b, c in tet order, tet | k << 30)
 	void build_fast_path_tables();
 	float min_h = -1, max_h = -1;
 	float outline_min[3] = {0, 0, 0}, outline_max[3] = {0, 0, 0};

@@ -10,13 +10,15 @@
 //     table built with the general routine elastic_matrix() (bit-identical by construction);
 //   * never more than one alpha try (all nine characteristics are inner), never a border solve;
 //   * the zero-speed characteristics interpolate at the node itself, inside elements[0]: that
-//     weight is static geometry (w0, computed once with the general routines).
+//     weight is static geometry (w0, computed once with the general routines);
+//   * point_in_tetr rescales every short displacement to 0.99 h(tet) (TetrMesh_1stOrder.cpp:
+//     1304-1307), so the tested point depends on the DIRECTION of the foot only (up to rounding):
+//     the -c1 and -c2 feet share one candidate scan, and so do the +c1 and +c2 feet.
 // Owner search = the reference's first-passing-candidate rule, but each candidate first goes
-// through a conservative barycentric pre-filter (plain float, FMA allowed) that can only answer
-// "certainly fails" / "certainly passes" / "don't know"; "don't know" (e.g. feet lying exactly
-// on mesh edges, the norm on 6-tet-per-hex meshes) falls to the reference's own volume-sum
-// predicate, evaluated division-free when the answer is clear of the 1.001 threshold by > 1e-5
-// and literally (point_in_tetr) otherwise.  Owners and values stay bit-identical to the
+// through a conservative barycentric pre-filter (plain float) that can only answer "certainly
+// fails" / "certainly passes" / "don't know"; "don't know" falls to the reference's own
+// volume-sum predicate, evaluated division-free when the answer is clear of the 1.001 threshold
+// by > 1e-5 and literally (point_in_tetr) otherwise.  Owners and values stay bit-identical to the
 // reference; tests/test_gpu_parity.py checks that on every case.
 #pragma once
 #include "gcm_step.cuh"
@@ -35,8 +37,8 @@ struct MatTab { float L[9]; float U[81]; float U1[81]; };
 
 // Structural non-zeros of Omega (U) and Omega^-1 (U1) rows for q = e_stage (bit j = column j).
 // Derived by evaluating elastic_matrix() for several materials; re-verified against the actual
-// table entries at upload time (gcm_capi.cu: build_material_table) -- a material whose table
-// has a non-zero outside the pattern is routed to the generic kernel.
+// table entries at preprocessing time (gcm_host.cpp: build_fast_path_tables) -- a material whose
+// table has a non-zero outside the pattern is routed to the generic kernel.
 GCM_CONSTEXPR_HD unsigned short u_pattern(int stage, int row)
 {
 	constexpr unsigned short P[3][9] = {
@@ -58,6 +60,7 @@ GCM_CONSTEXPR_HD unsigned short u1_pattern(int stage, int row)
 
 struct F3 { float x, y, z; };
 __device__ __forceinline__ F3 sel3(bool c, const F3& a, const F3& b) { F3 r; r.x = c ? a.x : b.x; r.y = c ? a.y : b.y; r.z = c ? a.z : b.z; return r; }
+__device__ __forceinline__ Vec3 to_vec3(const F3& a) { Vec3 v; v.x = a.x; v.y = a.y; v.z = a.z; return v; }
 template<int S> __device__ __forceinline__ float comp(const F3& v) { return S == 0 ? v.x : (S == 1 ? v.y : v.z); }
 // cross(a, b)[S]
 template<int S> __device__ __forceinline__ float cross_comp(const F3& a, const F3& b)
@@ -67,11 +70,159 @@ template<int S> __device__ __forceinline__ float cross_comp(const F3& a, const F
 	return a.x * b.y - a.y * b.x;
 }
 
-// One candidate tetrahedron as seen from inner node X: the three other vertices (A, B, C in
-// tet order), their third record quad (szz, x, y, z) and the position k of X in the tet.
+// One candidate tetrahedron as seen from inner node X.  The node->tet CSR is expanded for this
+// kernel into n2x[e] = (ia, ib, ic, t | k << 30): the three OTHER vertices in tet order and the
+// position k of the node in the tet, so that the vertex gathers do not wait for a tets[t] lookup.
 struct Cand {
-	int t; int4 tv; float h, vol; int k; int ia, ib, ic; float4 qa, qb, qc;
+	int t, k, ia, ib, ic;
+	float h, vol;
+	float4 qa, qb, qc;      // third record quad of A, B, C: (szz, x, y, z)
 };
+
+__device__ __forceinline__ void tet_order(const Cand& c, const F3& X, F3& p0, F3& p1, F3& p2, F3& p3)
+{
+	F3 A, B, C;
+	A.x = c.qa.y; A.y = c.qa.z; A.z = c.qa.w;
+	B.x = c.qb.y; B.y = c.qb.z; B.z = c.qb.w;
+	C.x = c.qc.y; C.y = c.qc.z; C.z = c.qc.w;
+	p0 = sel3(c.k == 0, X, A);
+	p1 = sel3(c.k == 0, A, sel3(c.k == 1, X, B));
+	p2 = sel3(c.k <= 1, B, sel3(c.k == 2, X, C));
+	p3 = sel3(c.k == 3, X, C);
+}
+
+// The reference's predicate (TetrMesh_1stOrder.cpp:1295-1402) for a displacement dks along axis
+// S; only coordinate S of the tested point moves.  Division-free unless within 1e-5 of 1.001.
+template<int S>
+__device__ __noinline__ bool exact_in_tetr(const Cand& c, const F3& X, float dks, float delta)
+{
+	const bool rescale = (delta > 0) && ((double)delta < (double)c.h * 0.99);
+	float d_s = dks;
+	if(rescale) d_s = (float)( (double)(dks * c.h) * 0.99 / (double)delta );
+	F3 P = X;
+	if(S == 0) P.x = X.x + d_s; else if(S == 1) P.y = X.y + d_s; else P.z = X.z + d_s;
+	F3 p0, p1, p2, p3;
+	tet_order(c, X, p0, p1, p2, p3);
+	const float a0x = p0.x - P.x, a0y = p0.y - P.y, a0z = p0.z - P.z;
+	const float a1x = p1.x - P.x, a1y = p1.y - P.y, a1z = p1.z - P.z;
+	const float a2x = p2.x - P.x, a2y = p2.y - P.y, a2z = p2.z - P.z;
+	const float a3x = p3.x - P.x, a3y = p3.y - P.y, a3z = p3.z - P.z;
+	const float d0 = determinant(a1x, a1y, a1z, a2x, a2y, a2z, a3x, a3y, a3z);
+	const float d1 = determinant(a0x, a0y, a0z, a2x, a2y, a2z, a3x, a3y, a3z);
+	const float d2 = determinant(a1x, a1y, a1z, a0x, a0y, a0z, a3x, a3y, a3z);
+	const float d3 = determinant(a1x, a1y, a1z, a2x, a2y, a2z, a0x, a0y, a0z);
+	const float S6 = fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
+	const float av = fabsf(c.vol);
+	if(S6 < av * 6.0059f) return true;
+	if(S6 > av * 6.0061f) return false;
+	const float z0 = dks * 0.0f;
+	return point_in_tetr(to_vec3(X), S == 0 ? dks : z0, S == 1 ? dks : z0, S == 2 ? dks : z0, delta,
+	                     to_vec3(p0), to_vec3(p1), to_vec3(p2), to_vec3(p3), c.h, c.vol);
+}
+
+// Pre-filter: barycentric coordinates (Cramer) of P = X + 0.99 h sgn e_S w.r.t. A, B, C and X.
+// Returns -1 when some coordinate is below -1e-3 (then sum|s| > 1.0019 Vol: the predicate
+// fails), +1 when all are above -1e-4 (sum|s| < 1.0007 Vol: it passes), 0 otherwise.  Only for
+// well-shaped tets (stored |Vol| > 0) whose displacement is rescaled (delta < 0.99 h).
+template<int S>
+__device__ __forceinline__ int prefilter(const Cand& c, const F3& X, float sgn)
+{
+	F3 ea, eb, ec;
+	ea.x = c.qa.y - X.x; ea.y = c.qa.z - X.y; ea.z = c.qa.w - X.z;
+	eb.x = c.qb.y - X.x; eb.y = c.qb.z - X.y; eb.z = c.qb.w - X.z;
+	ec.x = c.qc.y - X.x; ec.y = c.qc.z - X.y; ec.z = c.qc.w - X.z;
+	F3 cbc;
+	cbc.x = eb.y * ec.z - eb.z * ec.y;
+	cbc.y = eb.z * ec.x - eb.x * ec.z;
+	cbc.z = eb.x * ec.y - eb.y * ec.x;
+	const float D = ea.x * cbc.x + ea.y * cbc.y + ea.z * cbc.z;
+	const float mD = sgn * 0.99f * c.h * D;
+	// lambda_j = n_j / D  ->  compare n_j * D with multiples of D^2
+	const float la_ = mD * comp<S>(cbc);
+	const float lb_ = mD * cross_comp<S>(ec, ea);
+	const float lc_ = mD * cross_comp<S>(ea, eb);
+	const float D2 = D * D;
+	const float lx_ = D2 - (la_ + lb_ + lc_);
+	const float lo = -1e-3f * D2, ok = -1e-4f * D2;
+	const float mn = fminf(fminf(la_, lb_), fminf(lc_, lx_));
+	return mn < lo ? -1 : (mn > ok ? 1 : 0);
+}
+
+template<int S>
+__device__ __forceinline__ void load_cand(Cand& c, const int4 x, const float4* __restrict__ rec, const float2* __restrict__ hv2)
+{
+	c.ia = x.x; c.ib = x.y; c.ic = x.z;
+	c.t = x.w & 0x3fffffff; c.k = (unsigned)x.w >> 30;
+	c.qa = __ldg(rec + 3 * (size_t)c.ia + 2);
+	c.qb = __ldg(rec + 3 * (size_t)c.ib + 2);
+	c.qc = __ldg(rec + 3 * (size_t)c.ic + 2);
+	const float2 hv = __ldg(hv2 + c.t);
+	c.h = hv.x; c.vol = hv.y;
+}
+
+// First passing candidate for ONE foot (cold path: used when the two feet of a direction
+// disagree, and to classify a failed search).  *expand as in find_owner_first_ring.
+template<int S>
+__device__ __noinline__ int search_one(const int4* __restrict__ n2x, int e0, int e1, const float4* __restrict__ rec,
+                                       const float2* __restrict__ hv2, const F3& X, float dks, Cand& c, bool* expand)
+{
+	const float R2 = dks * dks;
+	const float delta = sqrtf(R2);
+	bool inside_R = false;
+	for(int e = e0; e < e1; e++) {
+		load_cand<S>(c, __ldg(n2x + e), rec, hv2);
+		if(exact_in_tetr<S>(c, X, dks, delta)) return c.t;
+		if(!inside_R) {
+			// vertices in tet order up to (not including) the node itself, :1541-1555
+			const float ax = X.x - c.qa.y, ay = X.y - c.qa.z, az = X.z - c.qa.w;
+			const float bx = X.x - c.qb.y, by = X.y - c.qb.z, bz = X.z - c.qb.w;
+			const float cx = X.x - c.qc.y, cy = X.y - c.qc.z, cz = X.z - c.qc.w;
+			if(c.k >= 1 && ax * ax + ay * ay + az * az < R2) inside_R = true;
+			if(c.k >= 2 && bx * bx + by * by + bz * bz < R2) inside_R = true;
+			if(c.k >= 3 && cx * cx + cy * cy + cz * cz < R2) inside_R = true;
+		}
+	}
+	*expand = inside_R;
+	return -1;
+}
+
+// Interpolated state at the foot X + dks e_S inside candidate c (TetrMesh_1stOrder.cpp:1764-1880).
+// va/vb/vc = the 9 values of A, B, C; own = the node's.  Returns false when the reference throws.
+template<int S>
+__device__ __forceinline__ bool interp_axis(const Cand& c, const F3& X, float dks, const float own[9],
+                                            const float va[9], const float vb[9], const float vc[9], float v[9])
+{
+	F3 Fp = X;
+	if(S == 0) Fp.x = X.x + dks; else if(S == 1) Fp.y = X.y + dks; else Fp.z = X.z + dks;
+	F3 p0, p1, p2, p3;
+	tet_order(c, X, p0, p1, p2, p3);
+	float f[4];
+	if(!interp_factors(to_vec3(p0), to_vec3(p1), to_vec3(p2), to_vec3(p3), Fp.x, Fp.y, Fp.z, c.vol, f))
+		return false;
+	const float fX = c.k == 0 ? f[0] : (c.k == 1 ? f[1] : (c.k == 2 ? f[2] : f[3]));
+	const float fA = c.k == 0 ? f[1] : f[0];
+	const float fB = c.k <= 1 ? f[2] : f[1];
+	const float fC = c.k == 3 ? f[2] : f[3];
+	// ((v0 f0 + v1 f1) + v2 f2) + v3 f3 in tet order; a + b == b + a, so k = 0 and k = 1 coincide
+	#pragma unroll
+	for(int q = 0; q < 9; q++) {
+		const float tA = va[q] * fA, tB = vb[q] * fB, tC = vc[q] * fC, tX = own[q] * fX;
+		const float s1 = tA + (c.k <= 1 ? tX : tB);
+		const float s2 = s1 + (c.k <= 1 ? tB : (c.k == 2 ? tX : tC));
+		v[q] = s2 + (c.k == 3 ? tX : tC);
+	}
+	return true;
+}
+
+__device__ __forceinline__ void load_values(const Cand& c, const float4* __restrict__ rec, float va[9], float vb[9], float vc[9])
+{
+	const float4 a0 = __ldg(rec + 3 * (size_t)c.ia), a1 = __ldg(rec + 3 * (size_t)c.ia + 1);
+	const float4 b0 = __ldg(rec + 3 * (size_t)c.ib), b1 = __ldg(rec + 3 * (size_t)c.ib + 1);
+	const float4 c0 = __ldg(rec + 3 * (size_t)c.ic), c1 = __ldg(rec + 3 * (size_t)c.ic + 1);
+	va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w; va[8] = c.qa.x;
+	vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w; vb[8] = c.qb.x;
+	vc[0] = c0.x; vc[1] = c0.y; vc[2] = c0.z; vc[3] = c0.w; vc[4] = c1.x; vc[5] = c1.y; vc[6] = c1.z; vc[7] = c1.w; vc[8] = c.qc.x;
+}
 
 // One thread per listed inner node, axis stage S.  mat_id == nullptr: single material (id 0).
 template<int S>
@@ -79,7 +230,7 @@ __global__ void __launch_bounds__(128)
 stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
                    float* __restrict__ un, int* err, int zone, StageTap* tap,
                    const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
-                   const float* __restrict__ w0)
+                   const float* __restrict__ w0, const int4* __restrict__ n2x)
 {
 	__shared__ float sU[GCM_MAX_MATERIALS][81];
 	__shared__ float sU1[GCM_MAX_MATERIALS][81];
@@ -97,6 +248,7 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	const int node = list[idx];
 	const int mid = mat_id ? mat_id[node] : 0;
 	const float4* __restrict__ rec = reinterpret_cast<const float4*>(m.u);
+	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(m.tet_hv);
 	const float4 o0 = rec[3 * (size_t)node], o1 = rec[3 * (size_t)node + 1], o2 = rec[3 * (size_t)node + 2];
 	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
 	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
@@ -106,164 +258,77 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
 
 	const int e0 = m.n2t_off[node], e1 = m.n2t_off[node + 1];
-	const int4* __restrict__ tets4 = reinterpret_cast<const int4*>(m.tets);
-	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(m.tet_hv);
 	const float* U = sU[mid];
 	const float* U1 = sU1[mid];
 	float omega[9];
 	StageTap tp;
-	#pragma unroll 1
-	for(int p = 0; p < 4; p++) {
-		const float dks = - sL[mid][p] * m.tau;      // dksi[i] = - L(i,i) * time_step
-		// displacement dks * ksi[S][j]: +-0 off-axis, so R2 == dks*dks and delta == sqrtf(R2)
-		const float R2 = dks * dks;
-		const float delta = sqrtf(R2);
-		const float sgn = dks < 0 ? -1.0f : 1.0f;
-		bool inside_R = false;
-		int owner = -1;
-		Cand c;
-		F3 A, B, C;
-		for(int e = e0; e < e1; e++) {
-			c.t = __ldg(m.n2t + e);
-			c.tv = __ldg(tets4 + c.t);
-			const float2 hv = __ldg(hv2 + c.t);
-			c.h = hv.x; c.vol = hv.y;
-			c.k = (c.tv.x == node) ? 0 : (c.tv.y == node) ? 1 : (c.tv.z == node) ? 2 : 3;
-			c.ia = (c.k == 0) ? c.tv.y : c.tv.x;
-			c.ib = (c.k <= 1) ? c.tv.z : c.tv.y;
-			c.ic = (c.k == 3) ? c.tv.z : c.tv.w;
-			c.qa = __ldg(rec + 3 * (size_t)c.ia + 2);
-			c.qb = __ldg(rec + 3 * (size_t)c.ib + 2);
-			c.qc = __ldg(rec + 3 * (size_t)c.ic + 2);
-			A.x = c.qa.y; A.y = c.qa.z; A.z = c.qa.w;
-			B.x = c.qb.y; B.y = c.qb.z; B.z = c.qb.w;
-			C.x = c.qc.y; C.y = c.qc.z; C.z = c.qc.w;
 
-			const bool rescale = (delta > 0) && ((double)delta < (double)c.h * 0.99);
-			int verdict = 0;   // 0 unknown, 1 certainly in, -1 certainly out
-			if(rescale && c.vol > 0) {   // vol > 0: well-shaped tet (sign bit of the stored |Vol| is the flag)
-				// barycentric coordinates of P = X + 0.99 h sgn e_S w.r.t. A, B, C (Cramer)
-				F3 ea, eb, ec;
-				ea.x = A.x - X.x; ea.y = A.y - X.y; ea.z = A.z - X.z;
-				eb.x = B.x - X.x; eb.y = B.y - X.y; eb.z = B.z - X.z;
-				ec.x = C.x - X.x; ec.y = C.y - X.y; ec.z = C.z - X.z;
-				F3 cbc;
-				cbc.x = eb.y * ec.z - eb.z * ec.y;
-				cbc.y = eb.z * ec.x - eb.x * ec.z;
-				cbc.z = eb.x * ec.y - eb.y * ec.x;
-				const float D = ea.x * cbc.x + ea.y * cbc.y + ea.z * cbc.z;
-				const float mm = sgn * 0.99f * c.h;
-				// lambda_j = n_j / D  ->  compare n_j * D with multiples of D^2
-				const float la_ = mm * comp<S>(cbc) * D;
-				const float lb_ = mm * cross_comp<S>(ec, ea) * D;
-				const float lc_ = mm * cross_comp<S>(ea, eb) * D;
-				const float D2 = D * D;
-				const float lx_ = D2 - (la_ + lb_ + lc_);
-				const float lo = -1e-3f * D2, ok = -1e-4f * D2;
-				// any coordinate below -1e-3: sum|s| > 1.0019 Vol, fails; all above -1e-4: sum|s| < 1.0007 Vol, passes
-				if(la_ < lo || lb_ < lo || lc_ < lo || lx_ < lo) verdict = -1;
-				else if(la_ > ok && lb_ > ok && lc_ > ok && lx_ > ok) verdict = 1;
+	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
+	#pragma unroll
+	for(int dir = 0; dir < 2; dir++) {
+		const float dk1 = - sL[mid][dir] * m.tau;        // dksi[i] = - L(i,i) * time_step
+		const float dk2 = - sL[mid][2 + dir] * m.tau;
+		const float sgn = dir == 0 ? -1.0f : 1.0f;
+		const float de1 = sqrtf(dk1 * dk1), de2 = sqrtf(dk2 * dk2);   // delta; off-axis components are +-0
+		Cand c, c2;
+		int own1 = -1, own2 = -1;
+		bool split = false;
+		int4 xn = __ldg(n2x + e0);
+		for(int e = e0; e < e1; e++) {
+			const int4 x = xn;
+			if(e + 1 < e1) xn = __ldg(n2x + e + 1);
+			load_cand<S>(c, x, rec, hv2);
+			const double h99 = (double)c.h * 0.99;
+			int v1, v2;
+			if(c.vol > 0 && de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99) {
+				v1 = prefilter<S>(c, X, sgn);
+				if(v1 == 0) {
+					v1 = exact_in_tetr<S>(c, X, dk1, de1) ? 1 : -1;
+					v2 = exact_in_tetr<S>(c, X, dk2, de2) ? 1 : -1;
+				} else v2 = v1;
+			} else {
+				v1 = exact_in_tetr<S>(c, X, dk1, de1) ? 1 : -1;
+				v2 = exact_in_tetr<S>(c, X, dk2, de2) ? 1 : -1;
 			}
-			if(verdict == 0) {
-				// the reference's predicate (TetrMesh_1stOrder.cpp:1295-1402); only coordinate S of P moves
-				float d_s = dks;
-				if(rescale) d_s = (float)( (double)(dks * c.h) * 0.99 / (double)delta );
-				F3 P = X;
-				if(S == 0) P.x = X.x + d_s; else if(S == 1) P.y = X.y + d_s; else P.z = X.z + d_s;
-				const F3 p0 = sel3(c.k == 0, X, A);
-				const F3 p1 = sel3(c.k == 0, A, sel3(c.k == 1, X, B));
-				const F3 p2 = sel3(c.k <= 1, B, sel3(c.k == 2, X, C));
-				const F3 p3 = sel3(c.k == 3, X, C);
-				const float a0x = p0.x - P.x, a0y = p0.y - P.y, a0z = p0.z - P.z;
-				const float a1x = p1.x - P.x, a1y = p1.y - P.y, a1z = p1.z - P.z;
-				const float a2x = p2.x - P.x, a2y = p2.y - P.y, a2z = p2.z - P.z;
-				const float a3x = p3.x - P.x, a3y = p3.y - P.y, a3z = p3.z - P.z;
-				const float d0 = determinant(a1x, a1y, a1z, a2x, a2y, a2z, a3x, a3y, a3z);
-				const float d1 = determinant(a0x, a0y, a0z, a2x, a2y, a2z, a3x, a3y, a3z);
-				const float d2 = determinant(a1x, a1y, a1z, a0x, a0y, a0z, a3x, a3y, a3z);
-				const float d3 = determinant(a1x, a1y, a1z, a2x, a2y, a2z, a0x, a0y, a0z);
-				const float S6 = fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
-				const float av = fabsf(c.vol);
-				if(S6 < av * 6.0059f) verdict = 1;
-				else if(S6 > av * 6.0061f) verdict = -1;
-				else {
-					Vec3 q0, q1, q2, q3, XX;
-					q0.x = p0.x; q0.y = p0.y; q0.z = p0.z; q1.x = p1.x; q1.y = p1.y; q1.z = p1.z;
-					q2.x = p2.x; q2.y = p2.y; q2.z = p2.z; q3.x = p3.x; q3.y = p3.y; q3.z = p3.z;
-					XX.x = X.x; XX.y = X.y; XX.z = X.z;
-					const float z0 = dks * 0.0f;
-					verdict = point_in_tetr(XX, S == 0 ? dks : z0, S == 1 ? dks : z0, S == 2 ? dks : z0, delta,
-					                        q0, q1, q2, q3, c.h, c.vol) ? 1 : -1;
-				}
+			if(v1 != v2) { split = true; break; }
+			if(v1 > 0) { own1 = own2 = c.t; break; }
+		}
+		if(split || own1 < 0) {
+			// cold path: each foot on its own, literally
+			bool ex1 = false, ex2 = false;
+			own1 = search_one<S>(n2x, e0, e1, rec, hv2, X, dk1, c, &ex1);
+			own2 = search_one<S>(n2x, e0, e1, rec, hv2, X, dk2, c2, &ex2);
+			if(own1 < 0 || own2 < 0) {
+				report_error(err, (own1 < 0 ? ex1 : ex2) ? ERR_RING_OVERFLOW : ERR_INNER_NO_OWNER, zone, node, S);
+				return;
 			}
-			if(verdict > 0) { owner = c.t; break; }
-			if(!inside_R) {
-				// vertices in tet order up to (not including) the node itself, :1541-1555
-				const float da = (X.x - A.x) * (X.x - A.x) + (X.y - A.y) * (X.y - A.y) + (X.z - A.z) * (X.z - A.z);
-				const float db = (X.x - B.x) * (X.x - B.x) + (X.y - B.y) * (X.y - B.y) + (X.z - B.z) * (X.z - B.z);
-				const float dc = (X.x - C.x) * (X.x - C.x) + (X.y - C.y) * (X.y - C.y) + (X.z - C.z) * (X.z - C.z);
-				if(c.k >= 1 && da < R2) inside_R = true;
-				if(c.k >= 2 && db < R2) inside_R = true;
-				if(c.k >= 3 && dc < R2) inside_R = true;
+		} else c2 = c;
+		tp.owner[dir] = own1;
+		tp.owner[2 + dir] = own2;
+
+		float va[9], vb[9], vc[9], v[9];
+		load_values(c, rec, va, vb, vc);
+		if(!interp_axis<S>(c, X, dk1, own, va, vb, vc, v)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
+		// omega_i = Omega(i,:) . u(foot of i)  (SimpleVolumeCalculator.cpp:14-23); ppoint_num = (0,1,2,3,2,3,4,4,4)
+		{
+			float om = 0;
+			#pragma unroll
+			for(int j = 0; j < 9; j++)
+				if((u_pattern(S, dir) >> j) & 1) om += U[dir * 9 + j] * v[j];
+			omega[dir] = om;
+		}
+		if(own2 != own1) load_values(c2, rec, va, vb, vc);
+		if(!interp_axis<S>(c2, X, dk2, own, va, vb, vc, v)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
+		{
+			float om = 0, om4 = 0;
+			#pragma unroll
+			for(int j = 0; j < 9; j++) {
+				if((u_pattern(S, 2 + dir) >> j) & 1) om += U[(2 + dir) * 9 + j] * v[j];
+				if((u_pattern(S, 4 + dir) >> j) & 1) om4 += U[(4 + dir) * 9 + j] * v[j];
 			}
+			omega[2 + dir] = om;
+			omega[4 + dir] = om4;
 		}
-		if(p == 0) tp.owner[0] = owner;
-		if(p == 1) tp.owner[1] = owner;
-		if(p == 2) tp.owner[2] = owner;
-		if(p == 3) tp.owner[3] = owner;
-		if(owner < 0) {
-			report_error(err, inside_R ? ERR_RING_OVERFLOW : ERR_INNER_NO_OWNER, zone, node, S);
-			return;
-		}
-		// interpolation at the foot = stored coordinates + dx (TetrMesh_1stOrder.cpp:1764-1880)
-		F3 Fp = X;
-		if(S == 0) Fp.x = X.x + dks; else if(S == 1) Fp.y = X.y + dks; else Fp.z = X.z + dks;
-		const F3 p0 = sel3(c.k == 0, X, A);
-		const F3 p1 = sel3(c.k == 0, A, sel3(c.k == 1, X, B));
-		const F3 p2 = sel3(c.k <= 1, B, sel3(c.k == 2, X, C));
-		const F3 p3 = sel3(c.k == 3, X, C);
-		Vec3 q0, q1, q2, q3;
-		q0.x = p0.x; q0.y = p0.y; q0.z = p0.z; q1.x = p1.x; q1.y = p1.y; q1.z = p1.z;
-		q2.x = p2.x; q2.y = p2.y; q2.z = p2.z; q3.x = p3.x; q3.y = p3.y; q3.z = p3.z;
-		float f[4];
-		if(!interp_factors(q0, q1, q2, q3, Fp.x, Fp.y, Fp.z, c.vol, f)) {
-			report_error(err, ERR_INTERP_SUM, zone, node, S);
-			return;
-		}
-		// factors of A, B, C and of the node itself
-		const float fX = c.k == 0 ? f[0] : (c.k == 1 ? f[1] : (c.k == 2 ? f[2] : f[3]));
-		const float fA = c.k == 0 ? f[1] : f[0];
-		const float fB = c.k <= 1 ? f[2] : f[1];
-		const float fC = c.k == 3 ? f[2] : f[3];
-		const float4 a0 = __ldg(rec + 3 * (size_t)c.ia), a1 = __ldg(rec + 3 * (size_t)c.ia + 1);
-		const float4 b0 = __ldg(rec + 3 * (size_t)c.ib), b1 = __ldg(rec + 3 * (size_t)c.ib + 1);
-		const float4 c0 = __ldg(rec + 3 * (size_t)c.ic), c1 = __ldg(rec + 3 * (size_t)c.ic + 1);
-		const float va[9] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, c.qa.x};
-		const float vb[9] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, c.qb.x};
-		const float vc[9] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c.qc.x};
-		// ((v0 f0 + v1 f1) + v2 f2) + v3 f3 in tet order; a + b == b + a, so k = 0 and k = 1 coincide
-		float v[9];
-		#pragma unroll
-		for(int q = 0; q < 9; q++) {
-			const float tA = va[q] * fA, tB = vb[q] * fB, tC = vc[q] * fC, tX = own[q] * fX;
-			const float s1 = tA + (c.k <= 1 ? tX : tB);
-			const float s2 = s1 + (c.k <= 1 ? tB : (c.k == 2 ? tX : tC));
-			v[q] = s2 + (c.k == 3 ? tX : tC);
-		}
-		// omega_i = Omega(i,:) . u(foot of i)  (SimpleVolumeCalculator.cpp:14-23): foot p feeds row p
-		// and, for p = 2, 3, row p + 2 (ppoint_num = 0,1,2,3,2,3,4,4,4).  Rows 0-3 are summed over the
-		// union of the row-0/1 and row-2/3 patterns: the extra entries are exact zeros of Omega, as in
-		// the reference's dense loop.
-		float oa = 0, ob = 0;
-		#pragma unroll
-		for(int j = 0; j < 9; j++) {
-			if(((u_pattern(S, 0) | u_pattern(S, 2)) >> j) & 1) oa += U[p * 9 + j] * v[j];
-			if((u_pattern(S, 4) >> j) & 1) ob += U[(p + 2) * 9 + j] * v[j];
-		}
-		if(p == 0) omega[0] = oa;
-		if(p == 1) omega[1] = oa;
-		if(p == 2) { omega[2] = oa; omega[4] = ob; }
-		if(p == 3) { omega[3] = oa; omega[5] = ob; }
 	}
 	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every
 	// factor but the node's own is exactly 0, the own one is the static weight w0
@@ -276,9 +341,6 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		tp.outer_count = 0; tp.tries = 1;
 		tap[(size_t)S * m.n_nodes + node] = tp;
 	}
-
-	// rows 6-8 read the zero-speed foot; then u' = Omega^-1 * omega (SimpleVolumeCalculator.cpp:24-31),
-	// skipping the structural zeros
 	#pragma unroll
 	for(int i = 6; i < 9; i++) {
 		float om = 0;
@@ -287,6 +349,7 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 			if((u_pattern(S, i) >> j) & 1) om += U[i * 9 + j] * vz[j];
 		omega[i] = om;
 	}
+	// u' = Omega^-1 * omega (SimpleVolumeCalculator.cpp:24-31), skipping the structural zeros
 	float res[9];
 	#pragma unroll
 	for(int i = 0; i < 9; i++) {

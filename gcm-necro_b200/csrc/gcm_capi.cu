@@ -1,6 +1,12 @@
-// gcm_capi.cu -- the C ABI of include/gcm_b200.h: TetrMeshSet-level orchestration of the
-// device-resident zones (gcm/system/TetrMeshSet.cpp:101-184) over the kernels of
-// gcm_kernels.cuh and the host-side mesh logic of gcm_host.cpp.
+// gcm_capi.cu -- the C ABI of include/gcm_b200.h: TetrMeshSet-level orchestration
+// (gcm/system/TetrMeshSet.cpp:101-184) over the kernels of gcm_kernels.cuh / gcm_inner.cuh and
+// the host-side mesh logic of gcm_host.cpp.
+//
+// Device layout: the zones a process owns are concatenated into ONE device mesh (node, tet,
+// CSR-entry and border-slot indices shifted by per-zone offsets).  Within a stage the zones are
+// independent (Jacobi; TetrMeshSet.cpp:148-167 syncs the halo before the per-mesh loop), so one
+// launch per kernel class covers all of them; the halo between two zones of the same process is
+// an index-to-index copy inside the merged arrays (DataBus.cpp:64-79).
 #include "../../include/gcm_b200.h"
 #include "gcm_host.h"
 #include "gcm_kernels.cuh"
@@ -32,9 +38,12 @@ struct CudaError { std::string msg; };
 template<class T> struct DevBuf {
 	T* p = nullptr; size_t n = 0;
 	void alloc(size_t count) { free(); n = count; if(count) CK(cudaMalloc(&p, count * sizeof(T))); }
-	void upload(const std::vector<T>& h, cudaStream_t st) {
-		alloc(h.size());
-		if(h.size()) CK(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+	void upload(const std::vector<T>& h, cudaStream_t st) { alloc(h.size()); put(h, 0, st); }
+	// copy h into [offset, offset + h.size()) and wait (h may be a temporary)
+	void put(const std::vector<T>& h, size_t offset, cudaStream_t st) {
+		if(h.empty()) return;
+		CK(cudaMemcpyAsync(p + offset, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+		CK(cudaStreamSynchronize(st));
 	}
 	void free() { if(p) cudaFree(p); p = nullptr; n = 0; }
 	~DevBuf() { free(); }
@@ -46,44 +55,41 @@ struct CondSpec {   // one BorderCondition: calculator + StepPulseForm + BoxArea
 	float box[6];
 };
 
-struct HaloGroup {  // nodes of dst zone copied from src zone (same process)
-	int dst_zone, src_zone;
-	std::vector<int> h_dst, h_src;
-	DevBuf<int> dst, src;
-};
-
 struct PeerPlan {   // exchange with one other process
 	std::vector<int> recv_zone, recv_node;       // my halo slots, in request order
 	std::vector<int> req_pairs;                  // (owner zone, owner node) per slot
 	std::vector<int> send_zone, send_node;       // my nodes the peer asked for
-	// per zone segments for the device kernels
-	struct Seg { int zone, offset, n; DevBuf<int> idx; };
-	std::vector<std::unique_ptr<Seg>> recv_segs, send_segs;
+	DevBuf<int> d_recv, d_send;                  // merged-mesh indices
 	bool dev_ready = false;
 };
 
 struct Zone {
 	HostMesh hm;
 	bool loaded = false;
-	size_t stride = 0;
-	DevBuf<float> xyz, u0, u1, mat, tet_hv, basis, aos, normals;
-	int slot_offset = 0;                       // first global border slot of this zone (device RNG)
-	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, border_nodes, inner_nodes, cond_id, inner_fast, inner_generic;
-	DevBuf<float> w0, mat_tab;
-	DevBuf<int> n2x;
+	size_t node_off = 0, tet_off = 0, entry_off = 0, slot_off = 0;
+	size_t fast_off = 0, generic_off = 0, inner_off = 0;   // ranges of this zone in the merged node lists
+	bool stage_done = false;
+};
+
+// The merged device mesh of every local zone.
+struct DeviceMesh {
+	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0;
+	size_t n_fast = 0, n_generic = 0, n_inner = 0;
+	DevBuf<float> u0, u1, mat, tet_hv, basis, normals, w0, aos, mat_tab;
+	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x;
+	DevBuf<int> border_list, fast_list, generic_list, inner_list;
 	DevBuf<unsigned char> mat_id;
 	DevBuf<gcm::StageTap> tap;
+	DevBuf<int> halo_dst, halo_src;
+	size_t n_halo = 0;
+	int n_mat = 0;
 	int cur = 0;
-	float* h_basis[2] = {nullptr, nullptr};   // pinned staging, double buffered
-	cudaEvent_t basis_ev[2] = {nullptr, nullptr};
-	int basis_flip = 0;
-	bool on_device = false;
+	bool ready = false;
 	float* ucur() { return cur ? u1.p : u0.p; }
 	float* unext() { return cur ? u0.p : u1.p; }
-	~Zone() {
-		for(int k = 0; k < 2; k++) { if(h_basis[k]) cudaFreeHost(h_basis[k]); if(basis_ev[k]) cudaEventDestroy(basis_ev[k]); }
-	}
 };
+
+enum ProfClass { PROF_INNER = 0, PROF_BORDER = 1, PROF_PLASTIC = 2, PROF_HALO = 3, PROF_RNG = 4, PROF_INNER_GENERIC = 5, PROF_N = 6 };
 
 } // namespace
 
@@ -93,11 +99,14 @@ struct gcm_b200_set {
 	std::vector<std::unique_ptr<Zone>> zones;   // indexed by zone number; null when remote
 	std::vector<int> local_zones;               // TetrMeshSet::local_meshes order
 	gcmh::GlibcRand rng;
-	cudaStream_t stream = nullptr;
+	gcmh::MaterialRegistry materials;
+	DeviceMesh dm;
+	cudaStream_t stream = nullptr, aux = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	int* d_err = nullptr;
 	int* h_err = nullptr;
 	std::vector<CondSpec> conds;
-	std::vector<std::unique_ptr<HaloGroup>> halo_groups;
+	std::vector<int> halo_dst, halo_src;        // same-process halo, merged indices
 	std::map<int, PeerPlan> peers;
 	bool plan_built = false;
 	bool preprocessed = false;
@@ -106,9 +115,9 @@ struct gcm_b200_set {
 	int contact_calc = 0;
 	long long launches = 0;
 	float time_step = 0.002f;
-	bool in_step = false;
+	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
+	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
 	// device-side rand() stream + bases (rng_chunk_kernel / basis_kernel)
-	bool fast_inner = true;   // specialised inner-node kernel (gcm_inner.cuh); false = generic kernel for every node
 	bool basis_on_device = true;
 	bool rng_ready = false;
 	long long rng_draws_per_step = 0;
@@ -118,12 +127,15 @@ struct gcm_b200_set {
 	DevBuf<int> d_chunk_first_slot;
 	DevBuf<unsigned short> d_teta_idx;
 	DevBuf<float> d_cos, d_sin;
-	// per-kernel CUDA-event profile (gcm_b200_set_profile): 0 inner stage, 1 border stage, 2 plastic, 3 halo
+	float* h_basis[2] = {nullptr, nullptr};     // host-mode bases: pinned staging, double buffered
+	cudaEvent_t basis_ev[2] = {nullptr, nullptr};
+	int basis_flip = 0;
+	// per-kernel CUDA-event profile (gcm_b200_set_profile)
 	bool profile = false;
 	struct ProfRec { int which; long long units; cudaEvent_t a, b; };
 	std::vector<ProfRec> prof;
-	double prof_ms[6] = {0, 0, 0, 0, 0, 0};
-	long long prof_launches[6] = {0, 0, 0, 0, 0, 0}, prof_units[6] = {0, 0, 0, 0, 0, 0};
+	double prof_ms[PROF_N] = {0, 0, 0, 0, 0, 0};
+	long long prof_launches[PROF_N] = {0, 0, 0, 0, 0, 0}, prof_units[PROF_N] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -134,144 +146,16 @@ Zone* get_zone(gcm_b200_set* s, int zone)
 	return s->zones[zone].get();
 }
 
-void build_halo_plan(gcm_b200_set* s)
-{
-	if(s->plan_built) return;
-	s->halo_groups.clear();
-	s->peers.clear();
-	std::map<std::pair<int,int>, HaloGroup*> groups;
-	for(int zi : s->local_zones) {
-		HostMesh& hm = s->zones[zi]->hm;
-		for(int i = 0; i < hm.N; i++) {
-			if(hm.flags[i] & gcm::NF_LOCAL) continue;
-			int oz = hm.remote_zone[i], on = hm.remote_num[i];
-			if(oz < 0 || oz >= s->n_zones) throw HostError{gcmh::INPUT_EXCEPTION, "remote node refers to an unknown zone"};
-			int owner_rank = s->zone_rank[oz];
-			if(owner_rank == s->my_rank) {
-				auto key = std::make_pair(zi, oz);
-				HaloGroup*& g = groups[key];
-				if(!g) { s->halo_groups.emplace_back(new HaloGroup()); g = s->halo_groups.back().get(); g->dst_zone = zi; g->src_zone = oz; }
-				g->h_dst.push_back(i); g->h_src.push_back(on);
-			} else {
-				PeerPlan& p = s->peers[owner_rank];
-				p.recv_zone.push_back(zi); p.recv_node.push_back(i);
-				p.req_pairs.push_back(oz); p.req_pairs.push_back(on);
-			}
-		}
-	}
-	s->plan_built = true;
-}
-
-// DataBus::sync_nodes, same-process branch, on the host mirrors (start-up: coords + 13 values).
-void host_sync_nodes(gcm_b200_set* s)
-{
-	for(auto& gp : s->halo_groups) {
-		HostMesh& d = s->zones[gp->dst_zone]->hm;
-		HostMesh& o = s->zones[gp->src_zone]->hm;
-		for(size_t k = 0; k < gp->h_dst.size(); k++) {
-			int di = gp->h_dst[k], si = gp->h_src[k];
-			if(si < 0 || si >= o.N) throw HostError{gcmh::INPUT_EXCEPTION, "remote node index out of range"};
-			memcpy(&d.coords[3*(size_t)di], &o.coords[3*(size_t)si], 3 * sizeof(float));
-			memcpy(&d.values[9*(size_t)di], &o.values[9*(size_t)si], 9 * sizeof(float));
-			memcpy(&d.mat[4*(size_t)di], &o.mat[4*(size_t)si], 4 * sizeof(float));
-		}
-	}
-}
-
-// Host node-major values -> both device layers (start-up; includes halo slots).
-void upload_values(gcm_b200_set* s, Zone& z)
-{
-	const HostMesh& hm = z.hm;
-	const int n = hm.N;
-	if(!n) return;
-	if(!z.aos.p) z.aos.alloc(9 * (size_t)n);
-	CK(cudaMemcpyAsync(z.aos.p, hm.values.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z.u0.p, z.u1.p, z.aos.p, z.flags.p, n, 0);
-	s->launches++;
-	CK(cudaStreamSynchronize(s->stream));
-	z.cur = 0;
-}
-
-void upload_zone(gcm_b200_set* s, Zone& z)
-{
-	HostMesh& hm = z.hm;
-	const size_t N = hm.N;
-	z.stride = (N + 31) / 32 * 32;
-	z.xyz.upload(hm.coords, s->stream);   // node-major staging; lives on in the records
-	std::vector<float> soa(4 * z.stride, 0.f);
-	for(size_t i = 0; i < N; i++)
-		for(int k = 0; k < 4; k++) soa[k * z.stride + i] = hm.mat[4*i + k];
-	z.mat.upload(soa, s->stream);
-	CK(cudaStreamSynchronize(s->stream));
-	z.u0.alloc(GCM_REC * (N + 1)); z.u1.alloc(GCM_REC * (N + 1));
-	CK(cudaMemsetAsync(z.u0.p, 0, GCM_REC * (N + 1) * sizeof(float), s->stream));
-	CK(cudaMemsetAsync(z.u1.p, 0, GCM_REC * (N + 1) * sizeof(float), s->stream));
-	if(N) {
-		gcm::coords_to_records_kernel<<<(int)((N + 255) / 256), 256, 0, s->stream>>>(z.u0.p, z.u1.p, z.xyz.p, (int)N);
-		s->launches++;
-	}
-	z.flags.upload(hm.flags, s->stream);
-	z.n2t_off.upload(hm.n2t_off, s->stream);
-	z.n2t.upload(hm.n2t, s->stream);
-	z.tets.upload(hm.tets, s->stream);
-	z.tet_hv.upload(hm.tet_hv, s->stream);
-	z.border_slot.upload(hm.border_slot, s->stream);
-	z.border_nodes.upload(hm.border_nodes, s->stream);
-	z.inner_nodes.upload(hm.inner_nodes, s->stream);
-	z.inner_fast.upload(hm.inner_fast, s->stream);
-	z.inner_generic.upload(hm.inner_generic, s->stream);
-	z.w0.upload(hm.w0, s->stream);
-	z.mat_tab.upload(hm.mat_table, s->stream);
-	z.mat_id.upload(hm.mat_id, s->stream);
-	z.n2x.upload(hm.n2x, s->stream);
-	z.cond_id.upload(hm.cond_id, s->stream);
-	z.basis.alloc(hm.basis.size());
-	CK(cudaStreamSynchronize(s->stream));
-	for(int k = 0; k < 2; k++) {
-		if(hm.basis.size()) CK(cudaMallocHost(&z.h_basis[k], hm.basis.size() * sizeof(float)));
-		CK(cudaEventCreateWithFlags(&z.basis_ev[k], cudaEventDisableTiming));
-	}
-	upload_values(s, z);
-	z.on_device = true;
-}
-
-gcm::MeshView make_view(gcm_b200_set* s, Zone& z)
-{
-	gcm::MeshView m;
-	memset(&m, 0, sizeof(m));
-	m.n_nodes = z.hm.N; m.n_tets = z.hm.T; m.stride = z.stride;
-	m.u = z.ucur(); m.mat = z.mat.p; m.flags = z.flags.p;
-	m.n2t_off = z.n2t_off.p; m.n2t = z.n2t.p; m.tets = z.tets.p; m.tet_hv = z.tet_hv.p;
-	m.border_slot = z.border_slot.p; m.basis = z.basis.p; m.cond_id = z.cond_id.p; m.contact = nullptr;
-	m.tau = s->time_step; m.time = z.hm.current_time; m.min_h = z.hm.min_h;
-	m.n_conds = (int)s->conds.size();
-	for(int c = 0; c < m.n_conds; c++) {
-		const CondSpec& cs = s->conds[c];
-		m.conds[c] = cs.bc;
-		// check_stresses (TetrMesh_1stOrder.cpp:2024-2025) + BorderCondition::do_calc's scale
-		const float t = z.hm.current_time;
-		bool active = (cs.duration < 0) ? true : !(t > cs.start + cs.duration);    // PulseForm::isActive
-		float scale;                                                            // StepPulseForm::calcMagnitudeNorm
-		if(t < cs.start) scale = 0.0f;
-		else if(cs.duration < 0) scale = 1.0f;
-		else if(t <= cs.start + cs.duration) scale = 1.0f;
-		else scale = 0.0f;
-		m.conds[c].active = active ? 1 : 0;
-		m.conds[c].scale = scale;
-	}
-	return m;
-}
-
 struct ProfScope {
-	gcm_b200_set* s; int which; long long units; cudaEvent_t a = nullptr, b = nullptr;
-	ProfScope(gcm_b200_set* s_, int w, long long u) : s(s_), which(w), units(u) {
+	gcm_b200_set* s; int which; long long units; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+	ProfScope(gcm_b200_set* s_, int w, long long u, cudaStream_t st_ = nullptr) : s(s_), which(w), units(u), st(st_ ? st_ : s_->stream) {
 		if(!s->profile) return;
 		CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-		CK(cudaEventRecord(a, s->stream));
+		CK(cudaEventRecord(a, st));
 	}
 	~ProfScope() {
 		if(!a) return;
-		cudaEventRecord(b, s->stream);
+		cudaEventRecord(b, st);
 		s->prof.push_back({which, units, a, b});
 	}
 };
@@ -288,23 +172,219 @@ void prof_drain(gcm_b200_set* s)
 	s->prof.clear();
 }
 
+void assign_offsets(gcm_b200_set* s)
+{
+	size_t n = 0, t = 0, e = 0, b = 0;
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		z.node_off = n; z.tet_off = t; z.entry_off = e; z.slot_off = b;
+		n += z.hm.N; t += z.hm.T; e += z.hm.n2t.size(); b += z.hm.border_nodes.size();
+	}
+}
+
+// Halo plan from the placement flags: every Remote node is refreshed from its owner before each
+// stage (the reference builds its index lists before preprocessing too, main.cpp:124-130).
+void build_halo_plan(gcm_b200_set* s)
+{
+	if(s->plan_built) return;
+	s->halo_dst.clear(); s->halo_src.clear();
+	s->peers.clear();
+	size_t n = 0;
+	for(int zi : s->local_zones) { s->zones[zi]->node_off = n; n += s->zones[zi]->hm.N; }
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		HostMesh& hm = z.hm;
+		for(int i = 0; i < hm.N; i++) {
+			if(hm.flags[i] & gcm::NF_LOCAL) continue;
+			int oz = hm.remote_zone[i], on = hm.remote_num[i];
+			if(oz < 0 || oz >= s->n_zones) throw HostError{gcmh::INPUT_EXCEPTION, "remote node refers to an unknown zone"};
+			int owner_rank = s->zone_rank[oz];
+			if(owner_rank == s->my_rank) {
+				Zone* o = s->zones[oz].get();
+				if(!o || !o->loaded || on < 0 || on >= o->hm.N) throw HostError{gcmh::INPUT_EXCEPTION, "remote node index out of range"};
+				s->halo_dst.push_back((int)(z.node_off + i));
+				s->halo_src.push_back((int)(o->node_off + on));
+			} else {
+				PeerPlan& p = s->peers[owner_rank];
+				p.recv_zone.push_back(zi); p.recv_node.push_back(i);
+				p.req_pairs.push_back(oz); p.req_pairs.push_back(on);
+			}
+		}
+	}
+	s->plan_built = true;
+}
+
+// merged index -> (host mesh, local index)
+HostMesh& locate(gcm_b200_set* s, int merged, int* local)
+{
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		if((size_t)merged >= z.node_off && (size_t)merged < z.node_off + z.hm.N) { *local = merged - (int)z.node_off; return z.hm; }
+	}
+	throw HostError{gcmh::INPUT_EXCEPTION, "bad merged node index"};
+}
+
+// DataBus::sync_nodes, same-process branch, on the host mirrors (start-up: coords + 13 values).
+void host_sync_nodes(gcm_b200_set* s)
+{
+	for(size_t k = 0; k < s->halo_dst.size(); k++) {
+		int di, si;
+		HostMesh& d = locate(s, s->halo_dst[k], &di);
+		HostMesh& o = locate(s, s->halo_src[k], &si);
+		memcpy(&d.coords[3*(size_t)di], &o.coords[3*(size_t)si], 3 * sizeof(float));
+		memcpy(&d.values[9*(size_t)di], &o.values[9*(size_t)si], 9 * sizeof(float));
+		memcpy(&d.mat[4*(size_t)di], &o.mat[4*(size_t)si], 4 * sizeof(float));
+	}
+}
+
+// Host node-major values of one zone -> both device layers (start-up; includes halo slots).
+void upload_values(gcm_b200_set* s, Zone& z)
+{
+	DeviceMesh& dm = s->dm;
+	const int n = z.hm.N;
+	if(!n) return;
+	float* stage = dm.aos.p + 9 * z.node_off;
+	CK(cudaMemcpyAsync(stage, z.hm.values.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.u0.p + GCM_REC * z.node_off, dm.u1.p + GCM_REC * z.node_off,
+		stage, dm.flags.p + z.node_off, n, 0);
+	s->launches++;
+	CK(cudaStreamSynchronize(s->stream));
+}
+
+template<class T> std::vector<T> shifted(const std::vector<T>& v, long long off)
+{
+	std::vector<T> r(v.size());
+	for(size_t i = 0; i < v.size(); i++) r[i] = (T)(v[i] + off);
+	return r;
+}
+
+void upload_mesh(gcm_b200_set* s)
+{
+	DeviceMesh& dm = s->dm;
+	cudaStream_t st = s->stream;
+	assign_offsets(s);
+	size_t N = 0, T = 0, E = 0, NB = 0, nf = 0, ng = 0, ni = 0;
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		z.fast_off = nf; z.generic_off = ng; z.inner_off = ni;
+		N += z.hm.N; T += z.hm.T; E += z.hm.n2t.size(); NB += z.hm.border_nodes.size();
+		nf += z.hm.inner_fast.size(); ng += z.hm.inner_generic.size(); ni += z.hm.inner_nodes.size();
+	}
+	if(T >= (1u << 30) || E >= 0x7fffffffull || N >= 0x7fffffffull / GCM_REC * 4) throw HostError{gcmh::CONFIG_EXCEPTION, "mesh too large for 32-bit device indices"};
+	dm.N = N; dm.T = T; dm.E = E; dm.NB = NB; dm.n_fast = nf; dm.n_generic = ng; dm.n_inner = ni;
+	dm.stride = (N + 31) / 32 * 32;
+	dm.u0.alloc(GCM_REC * (N + 1)); dm.u1.alloc(GCM_REC * (N + 1));
+	CK(cudaMemsetAsync(dm.u0.p, 0, GCM_REC * (N + 1) * sizeof(float), st));
+	CK(cudaMemsetAsync(dm.u1.p, 0, GCM_REC * (N + 1) * sizeof(float), st));
+	dm.mat.alloc(4 * dm.stride); dm.tet_hv.alloc(2 * T); dm.basis.alloc(9 * NB); dm.normals.alloc(3 * NB);
+	dm.w0.alloc(N); dm.aos.alloc(9 * N); dm.flags.alloc(N); dm.n2t_off.alloc(N + 1); dm.n2t.alloc(E); dm.tets.alloc(4 * T);
+	dm.border_slot.alloc(N); dm.cond_id.alloc(NB); dm.n2x.alloc(4 * E); dm.mat_id.alloc(N);
+	dm.border_list.alloc(NB); dm.fast_list.alloc(nf); dm.generic_list.alloc(ng); dm.inner_list.alloc(ni);
+	if(dm.basis.p) CK(cudaMemsetAsync(dm.basis.p, 0, 9 * NB * sizeof(float), st));
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		HostMesh& hm = z.hm;
+		const size_t n = hm.N;
+		// node records: coordinates (static) + values
+		{
+			DevBuf<float> xyz; xyz.upload(hm.coords, st);
+			if(n) {
+				gcm::coords_to_records_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(dm.u0.p + GCM_REC * z.node_off, dm.u1.p + GCM_REC * z.node_off, xyz.p, (int)n);
+				s->launches++;
+			}
+			CK(cudaStreamSynchronize(st));
+		}
+		for(int k = 0; k < 4; k++) {
+			std::vector<float> pl(n);
+			for(size_t i = 0; i < n; i++) pl[i] = hm.mat[4*i + k];
+			dm.mat.put(pl, k * dm.stride + z.node_off, st);
+		}
+		dm.flags.put(hm.flags, z.node_off, st);
+		{
+			std::vector<int> off(hm.n2t_off.begin(), hm.n2t_off.end() - 1);
+			dm.n2t_off.put(shifted(off, (long long)z.entry_off), z.node_off, st);
+		}
+		dm.n2t.put(shifted(hm.n2t, (long long)z.tet_off), z.entry_off, st);
+		dm.tets.put(shifted(hm.tets, (long long)z.node_off), 4 * z.tet_off, st);
+		dm.tet_hv.put(hm.tet_hv, 2 * z.tet_off, st);
+		{
+			std::vector<int> bs(hm.border_slot);
+			for(auto& v : bs) if(v >= 0) v += (int)z.slot_off;
+			dm.border_slot.put(bs, z.node_off, st);
+		}
+		dm.cond_id.put(hm.cond_id, z.slot_off, st);
+		{
+			std::vector<int> x(hm.n2x);
+			for(size_t e = 0; e < x.size() / 4; e++) {
+				x[4*e] += (int)z.node_off; x[4*e+1] += (int)z.node_off; x[4*e+2] += (int)z.node_off;
+				unsigned w = (unsigned)x[4*e+3];
+				x[4*e+3] = (int)((((w & 0x3fffffffu) + (unsigned)z.tet_off) & 0x3fffffffu) | (w & 0xc0000000u));
+			}
+			dm.n2x.put(x, 4 * z.entry_off, st);
+		}
+		dm.w0.put(hm.w0, z.node_off, st);
+		dm.mat_id.put(hm.mat_id, z.node_off, st);
+		dm.normals.put(hm.normals, 3 * z.slot_off, st);
+		dm.border_list.put(shifted(hm.border_nodes, (long long)z.node_off), z.slot_off, st);
+		dm.fast_list.put(shifted(hm.inner_fast, (long long)z.node_off), z.fast_off, st);
+		dm.generic_list.put(shifted(hm.inner_generic, (long long)z.node_off), z.generic_off, st);
+		dm.inner_list.put(shifted(hm.inner_nodes, (long long)z.node_off), z.inner_off, st);
+	}
+	{
+		std::vector<int> last(1, (int)E);
+		dm.n2t_off.put(last, N, st);
+	}
+	dm.n_mat = (int)(s->materials.materials.size() / 3);
+	dm.mat_tab.upload(s->materials.table, st);
+	dm.halo_dst.upload(s->halo_dst, st); dm.halo_src.upload(s->halo_src, st);
+	dm.n_halo = s->halo_dst.size();
+	CK(cudaStreamSynchronize(st));
+	dm.cur = 0;
+	dm.ready = true;
+	for(int zi : s->local_zones) upload_values(s, *s->zones[zi]);
+}
+
+gcm::MeshView make_view(gcm_b200_set* s, float tau)
+{
+	DeviceMesh& dm = s->dm;
+	gcm::MeshView m;
+	memset(&m, 0, sizeof(m));
+	m.n_nodes = (int)dm.N; m.n_tets = (int)dm.T; m.stride = dm.stride;
+	m.u = dm.ucur(); m.mat = dm.mat.p; m.flags = dm.flags.p;
+	m.n2t_off = dm.n2t_off.p; m.n2t = dm.n2t.p; m.tets = dm.tets.p; m.tet_hv = dm.tet_hv.p;
+	m.border_slot = dm.border_slot.p; m.basis = dm.basis.p; m.cond_id = dm.cond_id.p; m.contact = nullptr;
+	const float t = s->zones[s->local_zones[0]]->hm.current_time;   // TetrMeshSet::get_current_time()
+	m.tau = tau; m.time = t; m.min_h = 0;
+	m.n_conds = (int)s->conds.size();
+	for(int c = 0; c < m.n_conds; c++) {
+		const CondSpec& cs = s->conds[c];
+		m.conds[c] = cs.bc;
+		// check_stresses (TetrMesh_1stOrder.cpp:2024-2025) + BorderCondition::do_calc's scale
+		bool active = (cs.duration < 0) ? true : !(t > cs.start + cs.duration);    // PulseForm::isActive
+		float scale;                                                            // StepPulseForm::calcMagnitudeNorm
+		if(t < cs.start) scale = 0.0f;
+		else if(cs.duration < 0) scale = 1.0f;
+		else if(t <= cs.start + cs.duration) scale = 1.0f;
+		else scale = 0.0f;
+		m.conds[c].active = active ? 1 : 0;
+		m.conds[c].scale = scale;
+	}
+	return m;
+}
+
 // Lay the step's rand() stream out for the device: draw positions of the border nodes, chunk
 // start windows from the current host generator state, the one-step jump matrix.
 void rng_device_init(gcm_b200_set* s)
 {
 	std::vector<uint32_t> slot_pos;
 	unsigned long long pos = 0;
-	int slot_total = 0;
 	for(int zi : s->local_zones) {
-		Zone& z = *s->zones[zi];
-		const HostMesh& hm = z.hm;
-		z.slot_offset = slot_total;
+		const HostMesh& hm = s->zones[zi]->hm;
 		for(int i = 0; i < hm.N; i++) {
 			if(!hm.is_local(i)) continue;
 			if(hm.is_border(i)) { slot_pos.push_back((uint32_t)pos); pos += 1; }
 			else pos += 3;
 		}
-		slot_total += (int)hm.border_nodes.size();
 	}
 	if(pos >= 0xffffffffull) throw HostError{gcmh::CONFIG_EXCEPTION, "too many rand() draws per step for the device generator"};
 	s->rng_draws_per_step = (long long)pos;
@@ -336,10 +416,6 @@ void rng_device_init(gcm_b200_set* s)
 	s->d_teta_idx.alloc(slot_pos.size() + 1);
 	s->d_cos.upload(std::vector<float>(ct, ct + 360), s->stream);
 	s->d_sin.upload(std::vector<float>(sn, sn + 360), s->stream);
-	for(int zi : s->local_zones) {
-		Zone& z = *s->zones[zi];
-		if(!z.normals.p) z.normals.upload(z.hm.normals, s->stream);
-	}
 	CK(cudaStreamSynchronize(s->stream));
 	s->rng_ready = true;
 }
@@ -348,109 +424,123 @@ void begin_step(gcm_b200_set* s)
 {
 	// get_max_possible_tau(): only its side effect survives: new local bases,
 	// meshes in local_meshes order, nodes in index order, one libc rand() stream.
+	DeviceMesh& dm = s->dm;
+	for(int zi : s->local_zones) s->zones[zi]->stage_done = false;
 	if(s->basis_on_device) {
 		if(!s->rng_ready) rng_device_init(s);
-		if(s->rng_chunks) {
-			ProfScope ps(s, 4, s->rng_draws_per_step);
+		if(s->rng_chunks && dm.NB) {
+			ProfScope ps(s, PROF_RNG, s->rng_draws_per_step);
 			gcm::rng_chunk_kernel<<<(s->rng_chunks + 127) / 128, 128, 0, s->stream>>>(s->d_chunk_state.p, s->rng_chunks,
 				s->d_jump.p, s->d_slot_pos.p, s->d_chunk_first_slot.p, s->d_teta_idx.p);
-			s->launches++;
-			for(int zi : s->local_zones) {
-				Zone& z = *s->zones[zi];
-				int nb = (int)z.hm.border_nodes.size();
-				if(!nb) continue;
-				gcm::basis_kernel<<<(nb + 127) / 128, 128, 0, s->stream>>>(z.basis.p, z.normals.p, s->d_teta_idx.p, z.slot_offset, nb, s->d_cos.p, s->d_sin.p);
-				s->launches++;
-			}
+			gcm::basis_kernel<<<(int)((dm.NB + 127) / 128), 128, 0, s->stream>>>(dm.basis.p, dm.normals.p, s->d_teta_idx.p, 0, (int)dm.NB, s->d_cos.p, s->d_sin.p);
+			s->launches += 2;
 		}
 		// keep the host generator in step with the device one
 		uint32_t w[31];
 		s->rng.get_window(w);
 		gcmh::rng_apply_jump(s->rng_jump, w);
 		s->rng.set_window(w);
-		s->in_step = true;
 		return;
 	}
+	if(!dm.NB) { for(int zi : s->local_zones) s->zones[zi]->hm.create_random_axes(s->rng); return; }
+	if(!s->h_basis[0])
+		for(int k = 0; k < 2; k++) {
+			CK(cudaMallocHost(&s->h_basis[k], 9 * dm.NB * sizeof(float)));
+			CK(cudaEventCreateWithFlags(&s->basis_ev[k], cudaEventDisableTiming));
+		}
+	const int b = s->basis_flip; s->basis_flip ^= 1;
+	CK(cudaEventSynchronize(s->basis_ev[b]));
 	for(int zi : s->local_zones) {
 		Zone& z = *s->zones[zi];
 		z.hm.create_random_axes(s->rng);
-		const size_t nb = z.hm.basis.size();
-		if(nb) {
-			int b = z.basis_flip; z.basis_flip ^= 1;
-			CK(cudaEventSynchronize(z.basis_ev[b]));
-			memcpy(z.h_basis[b], z.hm.basis.data(), nb * sizeof(float));
-			CK(cudaMemcpyAsync(z.basis.p, z.h_basis[b], nb * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-			CK(cudaEventRecord(z.basis_ev[b], s->stream));
-		}
+		if(!z.hm.basis.empty()) memcpy(s->h_basis[b] + 9 * z.slot_off, z.hm.basis.data(), z.hm.basis.size() * sizeof(float));
 	}
-	s->in_step = true;
+	CK(cudaMemcpyAsync(dm.basis.p, s->h_basis[b], 9 * dm.NB * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaEventRecord(s->basis_ev[b], s->stream));
 }
 
 void sync_nodes_device(gcm_b200_set* s)
 {
-	for(auto& gp : s->halo_groups) {
-		Zone& d = *s->zones[gp->dst_zone];
-		Zone& o = *s->zones[gp->src_zone];
-		int n = (int)gp->h_dst.size();
-		if(!n) continue;
-		if(!gp->dst.p) { gp->dst.upload(gp->h_dst, s->stream); gp->src.upload(gp->h_src, s->stream); }
-		{
-			ProfScope ps(s, 3, n);
-			gcm::halo_copy_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(d.ucur(), gp->dst.p, o.ucur(), gp->src.p, n);
-		}
-		s->launches++;
-	}
+	DeviceMesh& dm = s->dm;
+	const int n = (int)dm.n_halo;
+	if(!n) return;
+	ProfScope ps(s, PROF_HALO, n);
+	gcm::halo_copy_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.halo_dst.p, dm.ucur(), dm.halo_src.p, n);
+	s->launches++;
 }
 
-void zone_stage(gcm_b200_set* s, int zi, float tau, int stage)
+// One stage for the nodes of one zone (zone >= 0) or of every local zone (zone < 0).
+void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 {
-	Zone& z = *s->zones[zi];
+	DeviceMesh& dm = s->dm;
+	Zone* z = zone >= 0 ? s->zones[zone].get() : nullptr;
 	if(stage == 3) {
-		int n = z.hm.N;
+		const size_t off = z ? z->node_off : 0;
+		const int n = (int)(z ? (size_t)z->hm.N : dm.N);
 		if(n) {
-			ProfScope ps(s, 2, (long long)(z.hm.border_nodes.size() + z.hm.inner_nodes.size()));
-			gcm::plastic_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z.ucur(), z.mat.p, z.flags.p, n, z.stride, s->d_err, zi);
+			ProfScope ps(s, PROF_PLASTIC, n);
+			gcm::plastic_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.mat.p, dm.flags.p, (int)off, n, dm.stride, s->d_err, zone);
 			s->launches++;
 		}
 		return;
 	}
-	gcm::MeshView m = make_view(s, z);
-	m.tau = tau;
-	gcm::StageTap* tap = s->tap_on ? z.tap.p : nullptr;
-	int nb = (int)z.hm.border_nodes.size(), ni = (int)z.hm.inner_nodes.size();
+	gcm::MeshView m = make_view(s, tau);
+	if(s->tap_on && !dm.tap.p) { dm.tap.alloc(3 * dm.N); CK(cudaMemsetAsync(dm.tap.p, 0xff, 3 * dm.N * sizeof(gcm::StageTap), s->stream)); }
+	gcm::StageTap* tap = s->tap_on ? dm.tap.p : nullptr;
+	const int nb = (int)(z ? z->hm.border_nodes.size() : dm.NB);
+	const int* bl = dm.border_list.p + (z ? z->slot_off : 0);
+	cudaStream_t bst = s->stream;
 	if(nb) {
-		ProfScope ps(s, 1, nb);
-		gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, s->stream>>>(m, z.border_nodes.p, nb, stage, z.unext(), s->d_err, zi, tap);
+		if(s->concurrent) {
+			bst = s->aux;
+			CK(cudaEventRecord(s->ev_fork, s->stream));
+			CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
+		}
+		ProfScope ps(s, PROF_BORDER, nb, bst);
+		gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 		s->launches++;
 	}
 	if(!s->fast_inner) {
+		const int ni = (int)(z ? z->hm.inner_nodes.size() : dm.n_inner);
 		if(ni) {
-			ProfScope ps(s, 0, ni);
-			gcm::stage_generic_kernel<<<(ni + 127) / 128, 128, 0, s->stream>>>(m, z.inner_nodes.p, ni, stage, z.unext(), s->d_err, zi, tap);
+			ProfScope ps(s, PROF_INNER, ni);
+			gcm::stage_generic_kernel<<<(ni + 127) / 128, 128, 0, s->stream>>>(m, dm.inner_list.p + (z ? z->inner_off : 0), ni, stage, dm.unext(), s->d_err, zone, tap);
 			s->launches++;
 		}
 	} else {
-		const int ng = (int)z.hm.inner_generic.size(), nf = (int)z.hm.inner_fast.size();
+		const int ng = (int)(z ? z->hm.inner_generic.size() : dm.n_generic);
+		const int nf = (int)(z ? z->hm.inner_fast.size() : dm.n_fast);
 		if(ng) {
-			ProfScope ps(s, 5, ng);
-			gcm::stage_generic_kernel<<<(ng + 127) / 128, 128, 0, s->stream>>>(m, z.inner_generic.p, ng, stage, z.unext(), s->d_err, zi, tap);
+			ProfScope ps(s, PROF_INNER_GENERIC, ng);
+			gcm::stage_generic_kernel<<<(ng + 127) / 128, 128, 0, s->stream>>>(m, dm.generic_list.p + (z ? z->generic_off : 0), ng, stage, dm.unext(), s->d_err, zone, tap);
 			s->launches++;
 		}
 		if(nf) {
-			ProfScope ps(s, 0, nf);
-			const int n_mat = (int)(z.hm.materials.size() / 3);
-			const unsigned char* mid = n_mat > 1 ? z.mat_id.p : nullptr;
-			const gcm::MatTab* tab = reinterpret_cast<const gcm::MatTab*>(z.mat_tab.p);
+			ProfScope ps(s, PROF_INNER, nf);
+			const unsigned char* mid = dm.n_mat > 1 ? dm.mat_id.p : nullptr;
+			const gcm::MatTab* tab = reinterpret_cast<const gcm::MatTab*>(dm.mat_tab.p);
+			const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
+			const int* fl = dm.fast_list.p + (z ? z->fast_off : 0);
 			const dim3 grid((nf + 127) / 128), block(128);
-			if(stage == 0) gcm::stage_inner_kernel<0><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p, reinterpret_cast<const int4*>(z.n2x.p));
-			else if(stage == 1) gcm::stage_inner_kernel<1><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p, reinterpret_cast<const int4*>(z.n2x.p));
-			else gcm::stage_inner_kernel<2><<<grid, block, 0, s->stream>>>(m, z.inner_fast.p, nf, z.unext(), s->d_err, zi, tap, tab, n_mat, mid, z.w0.p, reinterpret_cast<const int4*>(z.n2x.p));
+			if(stage == 0) gcm::stage_inner_kernel<0><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x);
+			else if(stage == 1) gcm::stage_inner_kernel<1><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x);
+			else gcm::stage_inner_kernel<2><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x);
 			s->launches++;
 		}
 	}
-	// copy-back loop of TetrMesh_1stOrder.cpp:1925-1932 == buffer swap: the halo slots of the new
-	// current layer are refreshed by the sync_nodes that precedes every stage
-	z.cur ^= 1;
+	if(nb && s->concurrent) {
+		CK(cudaEventRecord(s->ev_join, s->aux));
+		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+	}
+	CK(cudaGetLastError());
+}
+
+// copy-back loop of TetrMesh_1stOrder.cpp:1925-1932 == buffer swap, once every local zone has
+// run the stage; the halo slots of the new current layer are refreshed by the next sync_nodes
+void finish_axis_stage(gcm_b200_set* s)
+{
+	s->dm.cur ^= 1;
+	for(int zi : s->local_zones) s->zones[zi]->stage_done = false;
 }
 
 const char* step_error_text(int code)
@@ -482,6 +572,17 @@ int step_error_exc(int code)
 	}
 }
 
+void peer_dev_prepare(gcm_b200_set* s, PeerPlan& p)
+{
+	if(p.dev_ready) return;
+	std::vector<int> r(p.recv_node.size()), q(p.send_node.size());
+	for(size_t k = 0; k < r.size(); k++) r[k] = (int)(s->zones[p.recv_zone[k]]->node_off + p.recv_node[k]);
+	for(size_t k = 0; k < q.size(); k++) q[k] = (int)(s->zones[p.send_zone[k]]->node_off + p.send_node[k]);
+	p.d_recv.upload(r, s->stream);
+	p.d_send.upload(q, s->stream);
+	p.dev_ready = true;
+}
+
 } // namespace
 
 #define GUARD_BEGIN try {
@@ -489,9 +590,14 @@ int step_error_exc(int code)
 	catch(CudaError& e) { return fail(gcmh::CONFIG_EXCEPTION, "CUDA: " + e.msg); } \
 	catch(std::exception& e) { return fail(gcmh::CONFIG_EXCEPTION, e.what()); }
 
+#define NEED_SET(s) do { if(!(s)) return fail(gcmh::CONFIG_EXCEPTION, "null set"); } while(0)
+#define NEED_DEVICE(s) do { if(!(s) || !(s)->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed"); \
+	if((s)->device < 0) return fail(gcmh::CONFIG_EXCEPTION, "host-only set (device -1): there is no CPU execution path for the step"); \
+	CK(cudaSetDevice((s)->device)); } while(0)
+
 extern "C" {
 
-const char* gcm_b200_version(void) { return "gcm_b200 0.1 (sm_100a)"; }
+const char* gcm_b200_version(void) { return "gcm_b200 0.2 (sm_100a)"; }
 const char* gcm_b200_last_error(void) { return g_last_error.c_str(); }
 
 int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* zone_rank, int my_rank)
@@ -511,9 +617,16 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(zone_rank) s->zone_rank.assign(zone_rank, zone_rank + n_zones);
 	s->zones.resize(n_zones);
 	for(int z = 0; z < n_zones; z++)
-		if(s->zone_rank[z] == my_rank) { s->zones[z].reset(new Zone()); s->local_zones.push_back(z); }
+		if(s->zone_rank[z] == my_rank) {
+			s->zones[z].reset(new Zone());
+			s->zones[z]->hm.registry = &s->materials;
+			s->local_zones.push_back(z);
+		}
 	if(device >= 0) {
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 		CK(cudaMalloc(&s->d_err, 4 * sizeof(int)));
 		CK(cudaMemset(s->d_err, 0, 4 * sizeof(int)));
 		CK(cudaMallocHost(&s->h_err, 4 * sizeof(int)));
@@ -527,21 +640,27 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 int gcm_b200_set_destroy(gcm_b200_set* s)
 {
 	if(!s) return 0;
-	if(s->device >= 0) cudaSetDevice(s->device);
-	if(s->stream) { cudaStreamSynchronize(s->stream); }
-	s->zones.clear();
-	s->halo_groups.clear();
-	s->peers.clear();
-	if(s->d_err) cudaFree(s->d_err);
-	if(s->h_err) cudaFreeHost(s->h_err);
-	if(s->stream) cudaStreamDestroy(s->stream);
-	delete s;
+	if(s->device >= 0) {
+		cudaSetDevice(s->device);
+		if(s->stream) cudaStreamSynchronize(s->stream);
+		if(s->aux) cudaStreamSynchronize(s->aux);
+		prof_drain(s);
+		for(int k = 0; k < 2; k++) { if(s->h_basis[k]) cudaFreeHost(s->h_basis[k]); if(s->basis_ev[k]) cudaEventDestroy(s->basis_ev[k]); }
+		if(s->ev_fork) cudaEventDestroy(s->ev_fork);
+		if(s->ev_join) cudaEventDestroy(s->ev_join);
+		if(s->d_err) cudaFree(s->d_err);
+		if(s->h_err) cudaFreeHost(s->h_err);
+	}
+	cudaStream_t a = s->stream, b = s->aux;
+	delete s;   // frees the device buffers
+	if(a) cudaStreamDestroy(a);
+	if(b) cudaStreamDestroy(b);
 	return 0;
 }
 
 int gcm_b200_set_seed(gcm_b200_set* s, unsigned seed)
 {
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	s->rng.seed(seed);
 	s->rng_ready = false;
 	return 0;
@@ -549,14 +668,21 @@ int gcm_b200_set_seed(gcm_b200_set* s, unsigned seed)
 
 int gcm_b200_set_kernel_mode(gcm_b200_set* s, int fast_inner)
 {
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	s->fast_inner = fast_inner != 0;
+	return 0;
+}
+
+int gcm_b200_set_concurrency(gcm_b200_set* s, int on)
+{
+	NEED_SET(s);
+	s->concurrent = on != 0;
 	return 0;
 }
 
 int gcm_b200_set_basis_mode(gcm_b200_set* s, int on_device)
 {
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	s->basis_on_device = on_device != 0;
 	s->rng_ready = false;
 	return 0;
@@ -564,7 +690,7 @@ int gcm_b200_set_basis_mode(gcm_b200_set* s, int on_device)
 
 int gcm_b200_set_collision_detector(gcm_b200_set* s, int type, int is_static, float threshold)
 {
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	if(type != 0) return fail(gcmh::UNIMPLEMENTED_EXCEPTION, "only VoidCollisionDetector is built so far");
 	s->detector_type = type; s->detector_static = is_static; s->detector_threshold = threshold;
 	return 0;
@@ -572,7 +698,7 @@ int gcm_b200_set_collision_detector(gcm_b200_set* s, int type, int is_static, fl
 
 int gcm_b200_set_contact_calculator(gcm_b200_set* s, int type)
 {
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	s->contact_calc = type;
 	return 0;
 }
@@ -584,6 +710,7 @@ int gcm_b200_zone_load(gcm_b200_set* s, int zone, int n_nodes, int n_tets, const
 	GUARD_BEGIN
 	Zone* z = get_zone(s, zone);
 	if(!z) return fail(gcmh::CONFIG_EXCEPTION, "zone is not local to this process");
+	if(s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "zones cannot be reloaded after preprocess");
 	if(n_nodes < 0 || n_tets < 0 || !coords || !tets) return fail(gcmh::INPUT_EXCEPTION, "bad mesh arrays");
 	HostMesh& hm = z->hm;
 	hm.zone = zone; hm.N = n_nodes; hm.T = n_tets;
@@ -600,9 +727,8 @@ int gcm_b200_zone_load(gcm_b200_set* s, int zone, int n_nodes, int n_tets, const
 			for(int k = 0; k < 3; k++) hm.coords[3*(size_t)i + k] = 0;   // arrive via sync_nodes
 		}
 	}
-	hm.mat.resize(4*(size_t)n_nodes);
+	hm.mat.assign(4*(size_t)n_nodes, 0.f);
 	if(material) memcpy(hm.mat.data(), material, 4*(size_t)n_nodes * sizeof(float));
-	else for(int i = 0; i < n_nodes; i++) { hm.mat[4*(size_t)i] = 0; hm.mat[4*(size_t)i+1] = 0; hm.mat[4*(size_t)i+2] = 0; hm.mat[4*(size_t)i+3] = 0; }
 	hm.values.assign(9*(size_t)n_nodes, 0.f);
 	hm.current_time = 0;
 	z->loaded = true;
@@ -630,7 +756,7 @@ int gcm_b200_zone_set_values(gcm_b200_set* s, int zone, const float* values)
 	for(int i = 0; i < hm.N; i++)
 		if(hm.flags[i] & gcm::NF_LOCAL)
 			memcpy(&hm.values[9*(size_t)i], &values[9*(size_t)i], 9 * sizeof(float));
-	if(z->on_device) { CK(cudaSetDevice(s->device)); upload_values(s, *z); }
+	if(s->dm.ready) { CK(cudaSetDevice(s->device)); upload_values(s, *z); }
 	return 0;
 	GUARD_END
 }
@@ -641,16 +767,15 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values)
 	Zone* z = get_zone(s, zone);
 	if(!z || !z->loaded || !values) return fail(gcmh::CONFIG_EXCEPTION, "zone not loaded");
 	HostMesh& hm = z->hm;
-	if(z->on_device) {
+	if(s->dm.ready && hm.N) {
 		CK(cudaSetDevice(s->device));
+		DeviceMesh& dm = s->dm;
 		const int n = hm.N;
-		if(n) {
-			if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
-			gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), n);
-			s->launches++;
-			CK(cudaMemcpyAsync(hm.values.data(), z->aos.p, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-			CK(cudaStreamSynchronize(s->stream));
-		}
+		float* stage = dm.aos.p + 9 * z->node_off;
+		gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + GCM_REC * z->node_off, n);
+		s->launches++;
+		CK(cudaMemcpyAsync(hm.values.data(), stage, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
 	}
 	memcpy(values, hm.values.data(), 9*(size_t)hm.N * sizeof(float));
 	return 0;
@@ -661,13 +786,14 @@ int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* ho
 {
 	GUARD_BEGIN
 	Zone* z = get_zone(s, zone);
-	if(!z || !z->on_device || !host_values) return fail(gcmh::CONFIG_EXCEPTION, "zone is not on the device");
+	if(!z || !s->dm.ready || !host_values) return fail(gcmh::CONFIG_EXCEPTION, "zone is not on the device");
 	CK(cudaSetDevice(s->device));
+	DeviceMesh& dm = s->dm;
 	const int n = z->hm.N;
 	if(!n) return 0;
-	if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
-	CK(cudaMemcpyAsync(z->aos.p, host_values, 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->ucur(), nullptr, z->aos.p, z->flags.p, n, 1);
+	float* stage = dm.aos.p + 9 * z->node_off;
+	CK(cudaMemcpyAsync(stage, host_values, 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur() + GCM_REC * z->node_off, nullptr, stage, dm.flags.p + z->node_off, n, 1);
 	s->launches++;
 	CK(cudaGetLastError());
 	return 0;
@@ -678,14 +804,15 @@ int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_v
 {
 	GUARD_BEGIN
 	Zone* z = get_zone(s, zone);
-	if(!z || !z->on_device || !host_values) return fail(gcmh::CONFIG_EXCEPTION, "zone is not on the device");
+	if(!z || !s->dm.ready || !host_values) return fail(gcmh::CONFIG_EXCEPTION, "zone is not on the device");
 	CK(cudaSetDevice(s->device));
+	DeviceMesh& dm = s->dm;
 	const int n = z->hm.N;
 	if(!n) return 0;
-	if(!z->aos.p) z->aos.alloc(9 * (size_t)n);
-	gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(z->aos.p, z->ucur(), n);
+	float* stage = dm.aos.p + 9 * z->node_off;
+	gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + GCM_REC * z->node_off, n);
 	s->launches++;
-	CK(cudaMemcpyAsync(host_values, z->aos.p, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaMemcpyAsync(host_values, stage, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 	return 0;
 	GUARD_END
 }
@@ -730,10 +857,7 @@ int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const floa
 			if(c[0] < box[1] && c[0] > box[0] && c[1] < box[3] && c[1] > box[2] && c[2] < box[5] && c[2] > box[4])
 				hm.cond_id[b] = id;
 		}
-		if(z.on_device) {
-			z.cond_id.upload(hm.cond_id, s->stream);
-			CK(cudaStreamSynchronize(s->stream));
-		}
+		if(s->dm.ready) s->dm.cond_id.put(hm.cond_id, z.slot_off, s->stream);
 	}
 	return 0;
 	GUARD_END
@@ -742,15 +866,17 @@ int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const floa
 int gcm_b200_set_preprocess(gcm_b200_set* s)
 {
 	GUARD_BEGIN
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
+	if(s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is already preprocessed");
 	for(int zi : s->local_zones)
 		if(!s->zones[zi]->loaded) return fail(gcmh::CONFIG_EXCEPTION, "a local zone was not loaded");
 	build_halo_plan(s);
 	host_sync_nodes(s);
 	for(int zi : s->local_zones) s->zones[zi]->hm.pre_process_mesh();
+	assign_offsets(s);
 	if(s->device >= 0) {
 		CK(cudaSetDevice(s->device));
-		for(int zi : s->local_zones) upload_zone(s, *s->zones[zi]);
+		upload_mesh(s);
 	}
 	s->preprocessed = true;
 	return 0;
@@ -760,11 +886,10 @@ int gcm_b200_set_preprocess(gcm_b200_set* s)
 int gcm_b200_set_begin_step(gcm_b200_set* s)
 {
 	GUARD_BEGIN
-	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
-	if(s->device < 0) return fail(gcmh::CONFIG_EXCEPTION, "host-only set (device -1): there is no CPU execution path for the step");
-	CK(cudaSetDevice(s->device));
+	NEED_DEVICE(s);
 	s->time_step = 0.002f;   // TetrMeshSet.cpp:105-106
 	begin_step(s);
+	CK(cudaGetLastError());
 	return 0;
 	GUARD_END
 }
@@ -772,8 +897,7 @@ int gcm_b200_set_begin_step(gcm_b200_set* s)
 int gcm_b200_set_sync_nodes(gcm_b200_set* s)
 {
 	GUARD_BEGIN
-	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
-	CK(cudaSetDevice(s->device));
+	NEED_DEVICE(s);
 	sync_nodes_device(s);
 	return 0;
 	GUARD_END
@@ -782,13 +906,29 @@ int gcm_b200_set_sync_nodes(gcm_b200_set* s)
 int gcm_b200_zone_do_next_part_step(gcm_b200_set* s, int zone, float tau, int stage)
 {
 	GUARD_BEGIN
+	NEED_DEVICE(s);
 	Zone* z = get_zone(s, zone);
-	if(!z || !z->on_device) return fail(gcmh::CONFIG_EXCEPTION, "zone is not on the device");
+	if(!z) return fail(gcmh::CONFIG_EXCEPTION, "zone is not local to this process");
 	if(stage < 0 || stage > 3) return fail(gcmh::METHOD_EXCEPTION, "Bad stage number");
-	CK(cudaSetDevice(s->device));
-	if(s->tap_on && !z->tap.p) { z->tap.alloc(3 * (size_t)z->hm.N); CK(cudaMemsetAsync(z->tap.p, 0xff, 3 * (size_t)z->hm.N * sizeof(gcm::StageTap), s->stream)); }
-	zone_stage(s, zone, tau, stage);
-	CK(cudaGetLastError());
+	if(z->stage_done) return fail(gcmh::CONFIG_EXCEPTION, "zone already ran this stage; every local zone must run a stage before the next one");
+	run_stage(s, zone, tau, stage);
+	if(stage < 3) {
+		z->stage_done = true;
+		bool all = true;
+		for(int zi : s->local_zones) all = all && s->zones[zi]->stage_done;
+		if(all) finish_axis_stage(s);
+	}
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_set_do_next_part_step(gcm_b200_set* s, float tau, int stage)
+{
+	GUARD_BEGIN
+	NEED_DEVICE(s);
+	if(stage < 0 || stage > 3) return fail(gcmh::METHOD_EXCEPTION, "Bad stage number");
+	run_stage(s, -1, tau, stage);
+	if(stage < 3) finish_axis_stage(s);
 	return 0;
 	GUARD_END
 }
@@ -799,7 +939,6 @@ int gcm_b200_set_end_step(gcm_b200_set* s)
 	// proceed_rheology: VoidRheologyCalculator (no-op); calc_destruction_criterias: evaluated on
 	// download; update_current_time (TetrMesh_1stOrder.cpp:2403-2406)
 	for(int zi : s->local_zones) s->zones[zi]->hm.current_time += s->time_step;
-	s->in_step = false;
 	return 0;
 }
 
@@ -811,8 +950,7 @@ int gcm_b200_set_do_next_step(gcm_b200_set* s)
 	if(rc) return rc;
 	for(int stage = 0; stage < 4; stage++) {
 		if((rc = gcm_b200_set_sync_nodes(s))) return rc;
-		for(int zi : s->local_zones)
-			if((rc = gcm_b200_zone_do_next_part_step(s, zi, s->time_step, stage))) return rc;
+		if((rc = gcm_b200_set_do_next_part_step(s, s->time_step, stage))) return rc;
 	}
 	return gcm_b200_set_end_step(s);
 }
@@ -826,13 +964,17 @@ int gcm_b200_set_do_steps(gcm_b200_set* s, int n_steps)
 int gcm_b200_set_synchronize(gcm_b200_set* s)
 {
 	GUARD_BEGIN
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
-	CK(cudaSetDevice(s->device));
+	NEED_DEVICE(s);
 	CK(cudaMemcpyAsync(s->h_err, s->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
 	if(s->h_err[0]) {
 		char buf[256];
-		snprintf(buf, sizeof buf, "%s (zone %d, node %d, stage %d)", step_error_text(s->h_err[0]), s->h_err[1], s->h_err[2], s->h_err[3]);
+		int zone = -1, node = s->h_err[2];   // kernels report merged node indices
+		for(int zi : s->local_zones) {
+			Zone& z = *s->zones[zi];
+			if((size_t)node >= z.node_off && (size_t)node < z.node_off + z.hm.N) { zone = zi; node -= (int)z.node_off; break; }
+		}
+		snprintf(buf, sizeof buf, "%s (zone %d, node %d, stage %d)", step_error_text(s->h_err[0]), zone, node, s->h_err[3]);
 		int exc = step_error_exc(s->h_err[0]);
 		CK(cudaMemsetAsync(s->d_err, 0, 4 * sizeof(int), s->stream));
 		return fail(exc, buf);
@@ -853,7 +995,7 @@ void* gcm_b200_set_stream(gcm_b200_set* s) { return s ? (void*)s->stream : nullp
 int gcm_b200_halo_counts(gcm_b200_set* s, int peer_rank, int* n_recv, int* n_send)
 {
 	GUARD_BEGIN
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	build_halo_plan(s);
 	auto it = s->peers.find(peer_rank);
 	if(n_recv) *n_recv = it == s->peers.end() ? 0 : (int)it->second.recv_node.size();
@@ -894,7 +1036,7 @@ int gcm_b200_halo_set_sends(gcm_b200_set* s, int peer_rank, int n_send, const in
 int gcm_b200_halo_pack_host(gcm_b200_set* s, int peer_rank, float* buf16)
 {
 	GUARD_BEGIN
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	auto it = s->peers.find(peer_rank);
 	if(it == s->peers.end()) return 0;
 	PeerPlan& p = it->second;
@@ -913,7 +1055,7 @@ int gcm_b200_halo_pack_host(gcm_b200_set* s, int peer_rank, float* buf16)
 int gcm_b200_halo_unpack_host(gcm_b200_set* s, int peer_rank, const float* buf16)
 {
 	GUARD_BEGIN
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
+	NEED_SET(s);
 	auto it = s->peers.find(peer_rank);
 	if(it == s->peers.end()) return 0;
 	PeerPlan& p = it->second;
@@ -929,42 +1071,18 @@ int gcm_b200_halo_unpack_host(gcm_b200_set* s, int peer_rank, const float* buf16
 	GUARD_END
 }
 
-static void peer_dev_prepare(gcm_b200_set* s, PeerPlan& p)
-{
-	if(p.dev_ready) return;
-	auto build = [&](const std::vector<int>& zs, const std::vector<int>& ns, std::vector<std::unique_ptr<PeerPlan::Seg>>& segs) {
-		segs.clear();
-		size_t k = 0;
-		while(k < zs.size()) {
-			size_t e = k;
-			while(e < zs.size() && zs[e] == zs[k]) e++;
-			std::unique_ptr<PeerPlan::Seg> sg(new PeerPlan::Seg());
-			sg->zone = zs[k]; sg->offset = (int)k; sg->n = (int)(e - k);
-			std::vector<int> idx(ns.begin() + k, ns.begin() + e);
-			sg->idx.upload(idx, s->stream);
-			CK(cudaStreamSynchronize(s->stream));
-			segs.push_back(std::move(sg));
-			k = e;
-		}
-	};
-	build(p.recv_zone, p.recv_node, p.recv_segs);
-	build(p.send_zone, p.send_node, p.send_segs);
-	p.dev_ready = true;
-}
-
 int gcm_b200_halo_pack(gcm_b200_set* s, int peer_rank, float* dev_buf)
 {
 	GUARD_BEGIN
-	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
+	NEED_DEVICE(s);
 	auto it = s->peers.find(peer_rank);
 	if(it == s->peers.end()) return 0;
-	CK(cudaSetDevice(s->device));
 	PeerPlan& p = it->second;
 	peer_dev_prepare(s, p);
-	int total = (int)p.send_node.size();
-	for(auto& sg : p.send_segs) {
-		Zone& z = *s->zones[sg->zone];
-		gcm::halo_pack_kernel<<<(sg->n + 255) / 256, 256, 0, s->stream>>>(dev_buf, z.ucur(), sg->idx.p, sg->n, total, sg->offset);
+	const int n = (int)p.send_node.size();
+	if(n) {
+		ProfScope ps(s, PROF_HALO, n);
+		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dev_buf, s->dm.ucur(), p.d_send.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
@@ -975,16 +1093,15 @@ int gcm_b200_halo_pack(gcm_b200_set* s, int peer_rank, float* dev_buf)
 int gcm_b200_halo_unpack(gcm_b200_set* s, int peer_rank, const float* dev_buf)
 {
 	GUARD_BEGIN
-	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
+	NEED_DEVICE(s);
 	auto it = s->peers.find(peer_rank);
 	if(it == s->peers.end()) return 0;
-	CK(cudaSetDevice(s->device));
 	PeerPlan& p = it->second;
 	peer_dev_prepare(s, p);
-	int total = (int)p.recv_node.size();
-	for(auto& sg : p.recv_segs) {
-		Zone& z = *s->zones[sg->zone];
-		gcm::halo_unpack_kernel<<<(sg->n + 255) / 256, 256, 0, s->stream>>>(z.ucur(), dev_buf, sg->idx.p, sg->n, total, sg->offset);
+	const int n = (int)p.recv_node.size();
+	if(n) {
+		ProfScope ps(s, PROF_HALO, n);
+		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->dm.ucur(), dev_buf, p.d_recv.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
@@ -1028,9 +1145,9 @@ int gcm_b200_zone_get_bases(gcm_b200_set* s, int zone, float* bases)
 	Zone* z = get_zone(s, zone);
 	if(!z || !z->hm.preprocessed || !bases) return fail(gcmh::CONFIG_EXCEPTION, "zone not preprocessed");
 	HostMesh& hm = z->hm;
-	if(z->on_device && s->basis_on_device && !hm.basis.empty()) {
+	if(s->dm.ready && s->basis_on_device && !hm.basis.empty()) {
 		cudaSetDevice(s->device);
-		if(cudaMemcpyAsync(hm.basis.data(), z->basis.p, hm.basis.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess
+		if(cudaMemcpyAsync(hm.basis.data(), s->dm.basis.p + 9 * z->slot_off, hm.basis.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess
 		   || cudaStreamSynchronize(s->stream) != cudaSuccess)
 			return fail(gcmh::CONFIG_EXCEPTION, "CUDA: reading the bases failed");
 	}
@@ -1053,22 +1170,25 @@ int gcm_b200_zone_get_min_max_h(gcm_b200_set* s, int zone, float* min_h, float* 
 	return 0;
 }
 
-int gcm_b200_set_enable_tap(gcm_b200_set* s, int on) { if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set"); s->tap_on = on != 0; return 0; }
+int gcm_b200_set_enable_tap(gcm_b200_set* s, int on) { NEED_SET(s); s->tap_on = on != 0; return 0; }
 
 int gcm_b200_zone_get_tap(gcm_b200_set* s, int zone, int* owners, int* outer, int* tries)
 {
 	GUARD_BEGIN
 	Zone* z = get_zone(s, zone);
-	if(!z || !z->tap.p) return fail(gcmh::CONFIG_EXCEPTION, "tap was not enabled");
+	if(!z || !s->dm.tap.p) return fail(gcmh::CONFIG_EXCEPTION, "tap was not enabled");
 	CK(cudaSetDevice(s->device));
-	size_t n = 3 * (size_t)z->hm.N;
+	const size_t n = z->hm.N;
 	std::vector<gcm::StageTap> h(n);
-	CK(cudaMemcpyAsync(h.data(), z->tap.p, n * sizeof(gcm::StageTap), cudaMemcpyDeviceToHost, s->stream));
-	CK(cudaStreamSynchronize(s->stream));
-	for(size_t i = 0; i < n; i++) {
-		if(owners) for(int k = 0; k < 5; k++) owners[5*i + k] = h[i].owner[k];
-		if(outer) outer[i] = h[i].outer_count;
-		if(tries) tries[i] = h[i].tries;
+	for(int st = 0; st < 3; st++) {
+		CK(cudaMemcpyAsync(h.data(), s->dm.tap.p + (size_t)st * s->dm.N + z->node_off, n * sizeof(gcm::StageTap), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		for(size_t i = 0; i < n; i++) {
+			const size_t o = (size_t)st * n + i;
+			if(owners) for(int k = 0; k < 5; k++) owners[5*o + k] = h[i].owner[k] >= 0 ? h[i].owner[k] - (int)z->tet_off : h[i].owner[k];
+			if(outer) outer[o] = h[i].outer_count;
+			if(tries) tries[o] = h[i].tries;
+		}
 	}
 	return 0;
 	GUARD_END
@@ -1078,24 +1198,25 @@ long long gcm_b200_set_launch_count(gcm_b200_set* s) { return s ? s->launches : 
 
 int gcm_b200_set_profile(gcm_b200_set* s, int on)
 {
-	if(!s) return fail(gcmh::CONFIG_EXCEPTION, "null set");
-	cudaSetDevice(s->device);
+	NEED_SET(s);
+	if(s->device >= 0) cudaSetDevice(s->device);
 	prof_drain(s);
 	s->profile = on != 0;
-	if(on) for(int k = 0; k < 6; k++) { s->prof_ms[k] = 0; s->prof_launches[k] = 0; s->prof_units[k] = 0; }
+	if(on) for(int k = 0; k < PROF_N; k++) { s->prof_ms[k] = 0; s->prof_launches[k] = 0; s->prof_units[k] = 0; }
 	return 0;
 }
 
 int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long long* launches, long long* units)
 {
-	if(!s || which < 0 || which > 5) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
-	cudaSetDevice(s->device);
+	if(!s || which < 0 || which >= PROF_N) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
+	if(s->device >= 0) cudaSetDevice(s->device);
 	prof_drain(s);
 	if(total_ms) *total_ms = s->prof_ms[which];
 	if(launches) *launches = s->prof_launches[which];
 	if(units) *units = s->prof_units[which];
 	return 0;
 }
+
 int gcm_b200_set_virt_count(gcm_b200_set* s) { (void)s; return 0; }
 
 } // extern "C"

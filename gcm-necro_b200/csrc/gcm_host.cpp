@@ -397,9 +397,9 @@ void HostMesh::pre_process_mesh()
 void HostMesh::build_fast_path_tables()
 {
 	// ---- distinct materials of local nodes and their identity-basis eigensystems -----------
-	materials.clear(); mat_table.clear();
+	MaterialRegistry& reg = registry ? *registry : own_registry;
+	std::vector<float>& materials = reg.materials; std::vector<float>& mat_table = reg.table; std::vector<char>& mat_ok = reg.ok;
 	mat_id.assign(N, 255);
-	std::vector<char> mat_ok;
 	for(int i = 0; i < N; i++) {
 		if(!is_local(i)) continue;
 		const float* mt = &mat[4*(size_t)i];

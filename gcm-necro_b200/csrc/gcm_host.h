@@ -44,6 +44,10 @@ void rng_apply_jump(const uint32_t m[961], uint32_t w[31]);
 // cosf/sinf of the 360 angles create_random_axis can draw, from the host libm.
 void rng_teta_tables(float cos_t[360], float sin_t[360]);
 
+// Distinct (la, mu, rho) triples of the local nodes of a mesh set and their identity-basis
+// eigensystems: [n_mat][3 stages][9 + 81 + 81] = L, U, U1 for q = e_stage (gcm_inner.cuh: MatTab).
+struct MaterialRegistry { std::vector<float> materials, table; std::vector<char> ok; };
+
 struct HostMesh {
 	int zone = -1;
 	int N = 0, T = 0;
@@ -70,8 +74,8 @@ struct HostMesh {
 	std::vector<int> inner_fast, inner_generic;   // partition of inner_nodes
 	std::vector<float> w0;                        // [N] own-vertex factor of the zero-speed foot
 	std::vector<unsigned char> mat_id;            // [N] index into materials (255 = not tabulated)
-	std::vector<float> materials;                 // [n_mat][3] distinct (la, mu, rho)
-	std::vector<float> mat_table;                 // [n_mat][3 stages][9 + 81 + 81] L, U, U1 for q = e_stage
+	MaterialRegistry* registry = nullptr;         // shared by the zones of one set (else own_registry)
+	MaterialRegistry own_registry;
 	std::vector<int> n2x;                         // [len(n2t)][4] CSR entry -> (other vertices a, b, c in tet order, tet | k << 30)
 	void build_fast_path_tables();
 	float min_h = -1, max_h = -1;

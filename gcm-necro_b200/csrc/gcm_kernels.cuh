@@ -39,10 +39,11 @@ stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 // in place on the current layer for every local node.
 __global__ void __launch_bounds__(256)
 plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* __restrict__ flags,
-               int n_nodes, size_t stride, int* err, int zone)   // u: node records, mat: planes
+               int first, int n_nodes, size_t stride, int* err, int zone)   // u: node records, mat: planes
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n_nodes) return;
+	i += first;
 	if((flags[i] & (NF_LOCAL | NF_USED)) != (NF_LOCAL | NF_USED)) return;
 	float v[9];
 	bool bad = false;

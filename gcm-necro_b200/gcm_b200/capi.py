@@ -70,6 +70,8 @@ SIGNATURES = {
     "gcm_b200_set_begin_step": (_i, [_p]),
     "gcm_b200_set_sync_nodes": (_i, [_p]),
     "gcm_b200_zone_do_next_part_step": (_i, [_p, _i, _f, _i]),
+    "gcm_b200_set_do_next_part_step": (_i, [_p, _f, _i]),
+    "gcm_b200_set_concurrency": (_i, [_p, _i]),
     "gcm_b200_set_end_step": (_i, [_p]),
     "gcm_b200_set_synchronize": (_i, [_p]),
     "gcm_b200_set_current_time": (_f, [_p]),
@@ -279,6 +281,13 @@ class TetrMeshSet:
 
     def sync_nodes(self):
         self._ck(self.lib.gcm_b200_set_sync_nodes(self.h))
+
+    def do_next_part_step(self, tau, stage):
+        """One stage for every local zone (the per-mesh loop of TetrMeshSet.cpp:158-167)."""
+        self._ck(self.lib.gcm_b200_set_do_next_part_step(self.h, tau, stage))
+
+    def set_concurrency(self, on=True):
+        self._ck(self.lib.gcm_b200_set_concurrency(self.h, int(on)))
 
     def end_step(self):
         self._ck(self.lib.gcm_b200_set_end_step(self.h))

@@ -97,6 +97,5 @@ class DataBus:
         ms.begin_step()
         for stage in range(4):
             self.sync_nodes()
-            for z in sorted(ms.meshes):
-                ms.meshes[z].do_next_part_step(tau, stage)
+            ms.do_next_part_step(tau, stage)
         ms.end_step()

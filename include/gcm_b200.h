@@ -94,7 +94,15 @@ int gcm_b200_set_begin_step(gcm_b200_set* s);            /* :105-145 */
 int gcm_b200_set_sync_nodes(gcm_b200_set* s);            /* DataBus::sync_nodes, same-process part */
 /* TetrMesh_1stOrder::do_next_part_step(tau, stage), TetrMesh_1stOrder.cpp:1902-1934 */
 int gcm_b200_zone_do_next_part_step(gcm_b200_set* s, int zone, float tau, int stage);
+/* The per-mesh loop of one stage for every local zone at once, TetrMeshSet.cpp:158-167: the zones
+ * of a process live in one merged device mesh, so this is one launch per kernel class.  The
+ * per-zone call above may be used instead, but then every local zone must run a stage before
+ * the next gcm_b200_set_sync_nodes (the layer swap happens when the last one has). */
+int gcm_b200_set_do_next_part_step(gcm_b200_set* s, float tau, int stage);
 int gcm_b200_set_end_step(gcm_b200_set* s);              /* :173-181 */
+/* 1 (default): the border-node kernel runs on a second CUDA stream next to the inner-node kernel
+ * of the same stage (they write disjoint nodes); 0: everything on the one stream. */
+int gcm_b200_set_concurrency(gcm_b200_set* s, int on);
 /* Wait for the stream and surface device-side errors (NaN guard, outer-count, ...). */
 int gcm_b200_set_synchronize(gcm_b200_set* s);
 float gcm_b200_set_current_time(gcm_b200_set* s);

@@ -1,0 +1,40 @@
+"""N > 1: one process per rank.  The host half (halo index exchange, start-up sync, per-rank
+preprocessing) runs here on CPU over gloo with world_size 2; the full step with the NCCL halo
+exchange runs on the GPU box when it has >= 2 GPUs.
+
+Note on rand(): the reference seeds every MPI rank's libc separately, so a multi-rank run draws
+the border bases of each rank from its own stream.  The golden fixtures were produced by the
+reference on ONE rank; they match a 2-rank run for flags/faces always, and for values only on
+inner zones' nodes away from the border -- so the GPU test compares the multi-rank run with a
+single-process run of the product (bit-exact halo path) and the host test with the fixtures."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import util_parity as up
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(nproc, args, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py")] + args
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.parametrize("name", ["zones2", "zones3_jitter"])
+def test_two_ranks_host_half_gloo(built, name):
+    r = _torchrun(2, ["host", name], 29531)
+    assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+@pytest.mark.gpu
+def test_two_ranks_nccl_halo_exchange(built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _torchrun(2, ["gpu", "mp16"], 29532)
+    assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])

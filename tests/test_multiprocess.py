@@ -28,7 +28,7 @@ def _torchrun(nproc, args, port):
 @pytest.mark.parametrize("name", ["zones2", "zones3_jitter"])
 def test_two_ranks_host_half_gloo(built, name):
     r = _torchrun(2, ["host", name], 29531)
-    assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-1500:], r.stderr[-6000:])
 
 
 @pytest.mark.gpu
@@ -37,4 +37,4 @@ def test_two_ranks_nccl_halo_exchange(built):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     r = _torchrun(2, ["gpu", "mp16"], 29532)
-    assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-1500:], r.stderr[-6000:])

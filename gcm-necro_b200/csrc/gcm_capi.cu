@@ -325,7 +325,7 @@ void upload_mesh(gcm_b200_set* s)
 		dm.w0.put(hm.w0, z.node_off, st);
 		dm.mat_id.put(hm.mat_id, z.node_off, st);
 		dm.normals.put(hm.normals, 3 * z.slot_off, st);
-		dm.border_list.put(shifted(hm.border_nodes, (long long)z.node_off), z.slot_off, st);
+		dm.border_list.put(shifted(hm.border_launch, (long long)z.node_off), z.slot_off, st);
 		dm.fast_list.put(shifted(hm.inner_fast, (long long)z.node_off), z.fast_off, st);
 		dm.generic_list.put(shifted(hm.inner_generic, (long long)z.node_off), z.generic_off, st);
 		dm.inner_list.put(shifted(hm.inner_nodes, (long long)z.node_off), z.inner_off, st);

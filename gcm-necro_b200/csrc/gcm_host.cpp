@@ -387,6 +387,25 @@ void HostMesh::pre_process_mesh()
 	if(!err.empty()) throw HostError{MESH_EXCEPTION, err};
 	basis.assign(9*(size_t)NB, 0.f);
 	cond_id.assign(NB, -1);
+	// launch order (scheduling only): a node whose incident border faces are not coplanar sits on
+	// an edge or corner and typically burns all 11 alpha tries on the tangential axes
+	{
+		std::vector<char> sharp(NB, 0);
+		#pragma omp parallel for schedule(static)
+		for(int s = 0; s < NB; s++) {
+			const int i = border_nodes[s];
+			const float* nn = &normals[3*(size_t)s];
+			for(int e = n2f_off[i]; e < n2f_off[i+1]; e++) {
+				const int* fv = &faces[3*(size_t)n2f[e]];
+				float fnr[3];
+				elem_normal(P(coords, fv[0]), P(coords, fv[1]), P(coords, fv[2]), fnr);
+				if(!(fnr[0]*nn[0] + fnr[1]*nn[1] + fnr[2]*nn[2] > 0.999f)) sharp[s] = 1;
+			}
+		}
+		border_launch.clear();
+		for(int s = 0; s < NB; s++) if(sharp[s]) border_launch.push_back(border_nodes[s]);
+		for(int s = 0; s < NB; s++) if(!sharp[s]) border_launch.push_back(border_nodes[s]);
+	}
 	build_fast_path_tables();
 	preprocessed = true;
 }

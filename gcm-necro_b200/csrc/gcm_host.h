@@ -65,6 +65,8 @@ struct HostMesh {
 	std::vector<float> tet_hv;        // [T][2] tetr_h, signed volume
 	std::vector<int> border_nodes;    // local border nodes, ascending
 	std::vector<int> border_slot;     // [N] index into border_nodes or -1
+	std::vector<int> border_launch;   // border_nodes permuted for the kernel launch: nodes on sharp
+	                                  // edges (many alpha retries) first, so warps stay homogeneous
 	std::vector<int> inner_nodes;     // local inner nodes, ascending
 	std::vector<float> normals;       // [n_border][3] find_border_node_normal(min_h)
 	std::vector<float> basis;         // [n_border][9] local basis of the current step

@@ -84,6 +84,39 @@ GCM_HD void load_tet(const MeshView& m, int t, TetGeom& g)
 	for(int k = 0; k < 4; k++) g.p[k] = load_xyz(m, g.v[k]);
 }
 
+// Conservative pre-filter of point_in_tetr for a candidate tet that has the base node X as a
+// vertex (every first-ring candidate has).  The predicate tests P = X + d * 0.99 h / |d| (the
+// rescale of TetrMesh_1stOrder.cpp:1304-1307) with  sum|sub-volumes| < 1.001 Vol,  i.e. the sum
+// of the negative barycentric coordinates of P must stay above -5e-4.  The coordinates follow
+// from Cramer's rule on the edges X->A, X->B, X->C in plain float (error ~1e-5 for tets with
+// 6|Vol| > 0.02 * longest edge^3, flagged by a positive stored |Vol|):
+//   -1  some coordinate < -1e-3        -> the predicate certainly fails
+//   +1  all four coordinates > -1e-4   -> it certainly passes
+//    0  anything else (or tet / displacement outside the filter's assumptions) -> evaluate it
+GCM_HD int owner_prefilter(const TetGeom& g, int base, const Vec3& X, float dx, float dy, float dz, float delta)
+{
+	if(!(g.vol > 0) || !(delta > 0) || !((double)delta < (double)g.h * 0.99)) return 0;
+	const int k = (g.v[0] == base) ? 0 : (g.v[1] == base) ? 1 : (g.v[2] == base) ? 2 : (g.v[3] == base) ? 3 : -1;
+	if(k < 0) return 0;
+	const Vec3 A = g.p[k == 0 ? 1 : 0], B = g.p[k <= 1 ? 2 : 1], C = g.p[k == 3 ? 2 : 3];
+	const float eax = A.x - X.x, eay = A.y - X.y, eaz = A.z - X.z;
+	const float ebx = B.x - X.x, eby = B.y - X.y, ebz = B.z - X.z;
+	const float ecx = C.x - X.x, ecy = C.y - X.y, ecz = C.z - X.z;
+	const float bcx = eby * ecz - ebz * ecy, bcy = ebz * ecx - ebx * ecz, bcz = ebx * ecy - eby * ecx;
+	const float cax = ecy * eaz - ecz * eay, cay = ecz * eax - ecx * eaz, caz = ecx * eay - ecy * eax;
+	const float abx = eay * ebz - eaz * eby, aby = eaz * ebx - eax * ebz, abz = eax * eby - eay * ebx;
+	const float D = eax * bcx + eay * bcy + eaz * bcz;
+	const float sD = 0.99f * g.h / delta * D;
+	// lambda_j = n_j / D  ->  compare n_j * D with multiples of D^2
+	const float la = sD * (dx * bcx + dy * bcy + dz * bcz);
+	const float lb = sD * (dx * cax + dy * cay + dz * caz);
+	const float lc = sD * (dx * abx + dy * aby + dz * abz);
+	const float D2 = D * D;
+	const float lx = D2 - (la + lb + lc);
+	const float mn = fminf(fminf(la, lb), fminf(lc, lx));
+	return mn < -1e-3f * D2 ? -1 : (mn > -1e-4f * D2 ? 1 : 0);
+}
+
 // First ring of gcm/meshtypes/TetrMesh_1stOrder.cpp:1468-1602: the candidates are the base
 // node's incident tets in stored order, the first one passing point_in_tetr wins.
 //   base      = index whose `elements` list and stored coordinates are used (nodes[base_node])
@@ -101,7 +134,10 @@ GCM_HD int find_owner_first_ring(const MeshView& m, int base, const Vec3& node_p
 	for(int e = e0; e < e1; e++) {
 		int t = m.n2t[e];
 		load_tet(m, t, g);
-		if(point_in_tetr(X, dx, dy, dz, delta, g.p[0], g.p[1], g.p[2], g.p[3], g.h, g.vol))
+		int verdict = owner_prefilter(g, base, X, dx, dy, dz, delta);
+		if(verdict == 0)
+			verdict = point_in_tetr(X, dx, dy, dz, delta, g.p[0], g.p[1], g.p[2], g.p[3], g.h, g.vol) ? 1 : -1;
+		if(verdict > 0)
 			return t;
 		if(!inside_R) {
 			for(int j = 0; j < 4; j++) {
@@ -422,16 +458,20 @@ GCM_HD int node_stage_nocontact(const MeshView& m, int node, int stage, float ou
 		slot = m.border_slot[node];
 		basis = m.basis + 9*(size_t)slot;
 	}
-	float L[9], U[81], U1[81];
+	float L[9], U[81];
 	FeetOut feet;
 	int tries = 0;
-	int outer_count = prepare_node(m, cur, stage, basis, L, U, U1, feet, false, &tries);
+	int outer_count = prepare_node(m, cur, stage, basis, L, U, nullptr, feet, false, &tries);
 	if(tap) {
 		for(int k = 0; k < 5; k++) tap->owner[k] = (outer_count >= 0 && k < feet.n_points) ? feet.owner[k] : -2;
 		tap->outer_count = outer_count; tap->tries = tries;
 	}
 	if(outer_count < 0) return -outer_count;
 	if(outer_count == 0) {
+		// Omega^-1 is only needed on this branch: build it now (same routine, same inputs)
+		float U1[81];
+		const float* q = basis + 3*stage;
+		elastic_matrix(cur.la, cur.mu, cur.rho, q[0], q[1], q[2], L, nullptr, U1);
 		volume_calc(U, U1, feet, out);
 		return ERR_NONE;
 	}

@@ -117,6 +117,7 @@ struct gcm_b200_set {
 	float time_step = 0.002f;
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
+	int inner_min_blocks = 5;   // register budget variant of stage_inner_kernel (4, 5 or 6 blocks/SM)
 	// device-side rand() stream + bases (rng_chunk_kernel / basis_kernel)
 	bool basis_on_device = true;
 	bool rng_ready = false;
@@ -522,9 +523,11 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 			const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
 			const int* fl = dm.fast_list.p + (z ? z->fast_off : 0);
 			const dim3 grid((nf + 127) / 128), block(128);
-			if(stage == 0) gcm::stage_inner_kernel<0><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x);
-			else if(stage == 1) gcm::stage_inner_kernel<1><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x);
-			else gcm::stage_inner_kernel<2><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x);
+#define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x)
+#define GCM_LAUNCH_INNER_MB(MB_) do { if(stage == 0) GCM_LAUNCH_INNER(0, MB_); else if(stage == 1) GCM_LAUNCH_INNER(1, MB_); else GCM_LAUNCH_INNER(2, MB_); } while(0)
+			if(s->inner_min_blocks == 4) GCM_LAUNCH_INNER_MB(4);
+			else if(s->inner_min_blocks == 6) GCM_LAUNCH_INNER_MB(6);
+			else GCM_LAUNCH_INNER_MB(5);
 			s->launches++;
 		}
 	}
@@ -632,6 +635,9 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 		CK(cudaMallocHost(&s->h_err, 4 * sizeof(int)));
 	}
 	s->rng.seed(1);   // libc default when srand() was never called
+	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
+	if(const char* e = getenv("GCM_B200_FAST_INNER")) s->fast_inner = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_INNER_MB")) s->inner_min_blocks = atoi(e);
 	*out = s.release();
 	return 0;
 	GUARD_END

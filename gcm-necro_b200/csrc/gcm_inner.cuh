@@ -93,9 +93,16 @@ __device__ __forceinline__ void tet_order(const Cand& c, const F3& X, F3& p0, F3
 
 // The reference's predicate (TetrMesh_1stOrder.cpp:1295-1402) for a displacement dks along axis
 // S; only coordinate S of the tested point moves.  Division-free unless within 1e-5 of 1.001.
+// Arguments by value (registers): a by-reference Cand would pin the candidate to the stack of the
+// hot loop for the sake of this rarely taken call.
 template<int S>
-__device__ __noinline__ bool exact_in_tetr(const Cand& c, const F3& X, float dks, float delta)
+__device__ __noinline__ bool exact_in_tetr(int k, float h, float vol, float ax, float ay, float az, float bx, float by, float bz,
+                                           float cx, float cy, float cz, float Xx, float Xy, float Xz, float dks, float delta)
 {
+	Cand c;
+	c.k = k; c.h = h; c.vol = vol;
+	c.qa = make_float4(0.f, ax, ay, az); c.qb = make_float4(0.f, bx, by, bz); c.qc = make_float4(0.f, cx, cy, cz);
+	F3 X; X.x = Xx; X.y = Xy; X.z = Xz;
 	const bool rescale = (delta > 0) && ((double)delta < (double)c.h * 0.99);
 	float d_s = dks;
 	if(rescale) d_s = (float)( (double)(dks * c.h) * 0.99 / (double)delta );
@@ -160,30 +167,22 @@ __device__ __forceinline__ void load_cand(Cand& c, const int4 x, const float4* _
 	c.h = hv.x; c.vol = hv.y;
 }
 
-// First passing candidate for ONE foot (cold path: used when the two feet of a direction
-// disagree, and to classify a failed search).  *expand as in find_owner_first_ring.
-template<int S>
-__device__ __noinline__ int search_one(const int4* __restrict__ n2x, int e0, int e1, const float4* __restrict__ rec,
-                                       const float2* __restrict__ hv2, const F3& X, float dks, Cand& c, bool* expand)
+// Cold path: a node the specialised scan cannot settle (the two feet of a direction disagree on a
+// candidate, or no owner in the first ring) goes through the literal per-node routine, which also
+// classifies the failure exactly as the reference does.
+__device__ __noinline__ void inner_node_generic(const MeshView& m, int node, int stage, float* __restrict__ un,
+                                                int* err, int zone, StageTap* tap)
 {
-	const float R2 = dks * dks;
-	const float delta = sqrtf(R2);
-	bool inside_R = false;
-	for(int e = e0; e < e1; e++) {
-		load_cand<S>(c, __ldg(n2x + e), rec, hv2);
-		if(exact_in_tetr<S>(c, X, dks, delta)) return c.t;
-		if(!inside_R) {
-			// vertices in tet order up to (not including) the node itself, :1541-1555
-			const float ax = X.x - c.qa.y, ay = X.y - c.qa.z, az = X.z - c.qa.w;
-			const float bx = X.x - c.qb.y, by = X.y - c.qb.z, bz = X.z - c.qb.w;
-			const float cx = X.x - c.qc.y, cy = X.y - c.qc.z, cz = X.z - c.qc.w;
-			if(c.k >= 1 && ax * ax + ay * ay + az * az < R2) inside_R = true;
-			if(c.k >= 2 && bx * bx + by * by + bz * bz < R2) inside_R = true;
-			if(c.k >= 3 && cx * cx + cy * cy + cz * cz < R2) inside_R = true;
-		}
-	}
-	*expand = inside_R;
-	return -1;
+	float out[9];
+	StageTap t;
+	const int e = node_stage_nocontact(m, node, stage, out, tap ? &t : nullptr);
+	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
+	if(e) { report_error(err, e, zone, node, stage); return; }
+	const float* r = m.u + (size_t)node * GCM_REC;
+	float4* __restrict__ o = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
+	o[0] = make_float4(out[0], out[1], out[2], out[3]);
+	o[1] = make_float4(out[4], out[5], out[6], out[7]);
+	o[2] = make_float4(out[8], r[9], r[10], r[11]);
 }
 
 // Interpolated state at the foot X + dks e_S inside candidate c (TetrMesh_1stOrder.cpp:1764-1880).
@@ -225,8 +224,9 @@ __device__ __forceinline__ void load_values(const Cand& c, const float4* __restr
 }
 
 // One thread per listed inner node, axis stage S.  mat_id == nullptr: single material (id 0).
-template<int S>
-__global__ void __launch_bounds__(128)
+// MB = minimum resident blocks per SM the register allocation is tuned for (occupancy vs spills).
+template<int S, int MB>
+__global__ void __launch_bounds__(128, MB)
 stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
                    float* __restrict__ un, int* err, int zone, StageTap* tap,
                    const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
@@ -270,41 +270,34 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		const float dk2 = - sL[mid][2 + dir] * m.tau;
 		const float sgn = dir == 0 ? -1.0f : 1.0f;
 		const float de1 = sqrtf(dk1 * dk1), de2 = sqrtf(dk2 * dk2);   // delta; off-axis components are +-0
-		Cand c, c2;
-		int own1 = -1, own2 = -1;
-		bool split = false;
+		Cand c;
+		int owner = -1;
+		bool cold = false;
 		int4 xn = __ldg(n2x + e0);
 		for(int e = e0; e < e1; e++) {
 			const int4 x = xn;
 			if(e + 1 < e1) xn = __ldg(n2x + e + 1);
 			load_cand<S>(c, x, rec, hv2);
 			const double h99 = (double)c.h * 0.99;
-			int v1, v2;
-			if(c.vol > 0 && de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99) {
+			int v1 = 0;
+			if(c.vol > 0 && de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99)
 				v1 = prefilter<S>(c, X, sgn);
-				if(v1 == 0) {
-					v1 = exact_in_tetr<S>(c, X, dk1, de1) ? 1 : -1;
-					v2 = exact_in_tetr<S>(c, X, dk2, de2) ? 1 : -1;
-				} else v2 = v1;
-			} else {
-				v1 = exact_in_tetr<S>(c, X, dk1, de1) ? 1 : -1;
-				v2 = exact_in_tetr<S>(c, X, dk2, de2) ? 1 : -1;
+			if(v1 == 0) {
+				const bool in1 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
+				                                  c.qc.y, c.qc.z, c.qc.w, X.x, X.y, X.z, dk1, de1);
+				const bool in2 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
+				                                  c.qc.y, c.qc.z, c.qc.w, X.x, X.y, X.z, dk2, de2);
+				if(in1 != in2) { cold = true; break; }
+				v1 = in1 ? 1 : -1;
 			}
-			if(v1 != v2) { split = true; break; }
-			if(v1 > 0) { own1 = own2 = c.t; break; }
+			if(v1 > 0) { owner = c.t; break; }
 		}
-		if(split || own1 < 0) {
-			// cold path: each foot on its own, literally
-			bool ex1 = false, ex2 = false;
-			own1 = search_one<S>(n2x, e0, e1, rec, hv2, X, dk1, c, &ex1);
-			own2 = search_one<S>(n2x, e0, e1, rec, hv2, X, dk2, c2, &ex2);
-			if(own1 < 0 || own2 < 0) {
-				report_error(err, (own1 < 0 ? ex1 : ex2) ? ERR_RING_OVERFLOW : ERR_INNER_NO_OWNER, zone, node, S);
-				return;
-			}
-		} else c2 = c;
-		tp.owner[dir] = own1;
-		tp.owner[2 + dir] = own2;
+		if(cold || owner < 0) {
+			inner_node_generic(m, node, S, un, err, zone, tap);
+			return;
+		}
+		tp.owner[dir] = owner;
+		tp.owner[2 + dir] = owner;
 
 		float va[9], vb[9], vc[9], v[9];
 		load_values(c, rec, va, vb, vc);
@@ -317,8 +310,7 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 				if((u_pattern(S, dir) >> j) & 1) om += U[dir * 9 + j] * v[j];
 			omega[dir] = om;
 		}
-		if(own2 != own1) load_values(c2, rec, va, vb, vc);
-		if(!interp_axis<S>(c2, X, dk2, own, va, vb, vc, v)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
+		if(!interp_axis<S>(c, X, dk2, own, va, vb, vc, v)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
 		{
 			float om = 0, om4 = 0;
 			#pragma unroll

@@ -68,6 +68,7 @@ struct Zone {
 	bool loaded = false;
 	size_t node_off = 0, tet_off = 0, entry_off = 0, slot_off = 0;
 	size_t fast_off = 0, generic_off = 0, inner_off = 0;   // ranges of this zone in the merged node lists
+	size_t st0_off = 0, st0_n = 0, c0_off = 0, c0_n = 0, c1_off = 0, c1_n = 0;   // contact launch lists
 	bool stage_done = false;
 };
 
@@ -118,6 +119,15 @@ struct gcm_b200_set {
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
 	int inner_min_blocks = 5;   // register budget variant of stage_inner_kernel (4, 5 or 6 blocks/SM)
+	// contact: virtual nodes of the last collision pass and the launch lists derived from them
+	std::vector<gcmh::VirtNodeHost> virt;
+	std::vector<std::vector<int> > axis_plus0;   // per local zone (local_meshes order), per border slot
+	DevBuf<gcm::VirtNode> d_virt;
+	DevBuf<int> d_axis_plus0, d_border_stage0, d_contact_nodes, d_border_by_slot;
+	DevBuf<float> d_gather;
+	size_t st0_total = 0, c0_total = 0;
+	bool contact_active = false;
+	long long step_count = 0;
 	// device-side rand() stream + bases (rng_chunk_kernel / basis_kernel)
 	bool basis_on_device = true;
 	bool rng_ready = false;
@@ -421,7 +431,9 @@ void rng_device_init(gcm_b200_set* s)
 	s->rng_ready = true;
 }
 
-void begin_step(gcm_b200_set* s)
+void run_collision_detection(gcm_b200_set* s);
+
+void begin_step_bases(gcm_b200_set* s)
 {
 	// get_max_possible_tau(): only its side effect survives: new local bases,
 	// meshes in local_meshes order, nodes in index order, one libc rand() stream.
@@ -460,6 +472,14 @@ void begin_step(gcm_b200_set* s)
 	CK(cudaEventRecord(s->basis_ev[b], s->stream));
 }
 
+void begin_step(gcm_b200_set* s)
+{
+	begin_step_bases(s);
+	// TetrMeshSet.cpp:111-120: a static detector runs at t == 0 only
+	if(s->detector_type != 0 && (!s->detector_static || s->zones[s->local_zones[0]]->hm.current_time == 0.0f))
+		run_collision_detection(s);
+}
+
 void sync_nodes_device(gcm_b200_set* s)
 {
 	DeviceMesh& dm = s->dm;
@@ -488,8 +508,13 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 	gcm::MeshView m = make_view(s, tau);
 	if(s->tap_on && !dm.tap.p) { dm.tap.alloc(3 * dm.N); CK(cudaMemsetAsync(dm.tap.p, 0xff, 3 * dm.N * sizeof(gcm::StageTap), s->stream)); }
 	gcm::StageTap* tap = s->tap_on ? dm.tap.p : nullptr;
-	const int nb = (int)(z ? z->hm.border_nodes.size() : dm.NB);
+	int nb = (int)(z ? z->hm.border_nodes.size() : dm.NB);
 	const int* bl = dm.border_list.p + (z ? z->slot_off : 0);
+	const bool contact = stage == 0 && s->contact_active;
+	if(contact) {   // border nodes in contact on axis 0 take the contact kernel instead
+		nb = (int)(z ? z->st0_n : s->st0_total);
+		bl = s->d_border_stage0.p + (z ? z->st0_off : 0);
+	}
 	cudaStream_t bst = s->stream;
 	if(nb) {
 		if(s->concurrent) {
@@ -535,7 +560,107 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 		CK(cudaEventRecord(s->ev_join, s->aux));
 		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
 	}
+	if(contact) {
+		// phase 0: partner body comes later in local_meshes -> its current layer is what the reference
+		// reads; phase 1: partner already advanced -> read the next layer, zone after zone
+		// (TetrMeshSet.cpp:158-167 advances the meshes one after the other)
+		const int first = s->step_count == 0 ? 1 : 0;
+		auto launch = [&](size_t off, size_t n, int partner_next, int zn) {
+			if(!n) return;
+			ProfScope ps(s, PROF_BORDER, (long long)n);
+			gcm::stage_contact_kernel<<<(int)((n + 63) / 64), 64, 0, s->stream>>>(m, s->d_contact_nodes.p + off, (int)n, stage, dm.unext(),
+				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap);
+			s->launches++;
+		};
+		if(z) { launch(z->c0_off, z->c0_n, 0, zone); launch(z->c1_off, z->c1_n, 1, zone); }
+		else {
+			launch(0, s->c0_total, 0, -1);
+			for(int zi : s->local_zones) launch(s->zones[zi]->c1_off, s->zones[zi]->c1_n, 1, zi);
+		}
+	}
 	CK(cudaGetLastError());
+}
+
+// CollisionDetector::find_collisions + the bookkeeping around it in TetrMeshSet::do_next_step
+// (TetrMeshSet.cpp:111-120): runs on the host (gcmh::find_collisions) on the border nodes' current
+// values and bases, then lays the result out for stage_contact_kernel.
+void run_collision_detection(gcm_b200_set* s)
+{
+	DeviceMesh& dm = s->dm;
+	std::vector<HostMesh*> meshes;
+	for(int zi : s->local_zones) meshes.push_back(&s->zones[zi]->hm);
+	if(dm.NB) {
+		// current values of the border nodes and (device mode) this step's bases -> host mirrors
+		if(!s->d_border_by_slot.p) {
+			std::vector<int> bys;
+			for(int zi : s->local_zones) {
+				Zone& z = *s->zones[zi];
+				for(int b : z.hm.border_nodes) bys.push_back((int)(z.node_off + b));
+			}
+			s->d_border_by_slot.upload(bys, s->stream);
+			s->d_gather.alloc(9 * dm.NB);
+		}
+		gcm::gather_records_kernel<<<(int)((dm.NB + 255) / 256), 256, 0, s->stream>>>(s->d_gather.p, dm.ucur(), s->d_border_by_slot.p, (int)dm.NB);
+		s->launches++;
+		std::vector<float> g(9 * dm.NB), bs(9 * dm.NB);
+		CK(cudaMemcpyAsync(g.data(), s->d_gather.p, g.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+		if(s->basis_on_device) CK(cudaMemcpyAsync(bs.data(), dm.basis.p, bs.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		for(int zi : s->local_zones) {
+			Zone& z = *s->zones[zi];
+			HostMesh& hm = z.hm;
+			for(size_t b = 0; b < hm.border_nodes.size(); b++)
+				memcpy(&hm.values[9*(size_t)hm.border_nodes[b]], &g[9 * (z.slot_off + b)], 9 * sizeof(float));
+			if(s->basis_on_device && !hm.basis.empty()) memcpy(hm.basis.data(), &bs[9 * z.slot_off], hm.basis.size() * sizeof(float));
+		}
+	}
+	gcmh::find_collisions(meshes, s->detector_threshold, s->virt, s->axis_plus0);
+
+	std::map<int, int> order;   // zone number -> position in local_meshes
+	for(size_t a = 0; a < s->local_zones.size(); a++) order[s->local_zones[a]] = (int)a;
+	std::vector<gcm::VirtNode> dv(s->virt.size());
+	for(size_t k = 0; k < s->virt.size(); k++) {
+		const gcmh::VirtNodeHost& h = s->virt[k];
+		gcm::VirtNode& v = dv[k];
+		for(int q = 0; q < 3; q++) v.pos[q] = h.coords[q];
+		for(int q = 0; q < 9; q++) v.val[q] = h.values[q];
+		v.la = h.values[9]; v.mu = h.values[10]; v.rho = h.values[11];
+		v.base = (int)(s->zones[h.remote_zone]->node_off + h.base_node);
+		v.real = (int)(s->zones[h.real_zone]->node_off + h.real_node);
+		v.phase = order[h.remote_zone] < order[h.real_zone] ? 1 : 0;
+	}
+	std::vector<int> axis(dm.NB, -1), st0, c0, c1;
+	for(size_t a = 0; a < s->local_zones.size(); a++) {
+		Zone& z = *s->zones[s->local_zones[a]];
+		for(size_t b = 0; b < z.hm.border_nodes.size(); b++) axis[z.slot_off + b] = s->axis_plus0[a][b];
+	}
+	// lists: stage-0 border nodes not in contact (launch order), contact nodes by phase, per zone
+	for(size_t a = 0; a < s->local_zones.size(); a++) {
+		Zone& z = *s->zones[s->local_zones[a]];
+		z.st0_off = st0.size(); z.c0_off = c0.size();
+		for(int node : z.hm.border_launch) {
+			const int v = s->axis_plus0[a][z.hm.border_slot[node]];
+			if(v < 0) st0.push_back((int)(z.node_off + node));
+			else if(dv[v].phase == 0) c0.push_back((int)(z.node_off + node));
+		}
+		z.st0_n = st0.size() - z.st0_off; z.c0_n = c0.size() - z.c0_off;
+	}
+	for(size_t a = 0; a < s->local_zones.size(); a++) {
+		Zone& z = *s->zones[s->local_zones[a]];
+		z.c1_off = c0.size() + c1.size();
+		for(int node : z.hm.border_launch) {
+			const int v = s->axis_plus0[a][z.hm.border_slot[node]];
+			if(v >= 0 && dv[v].phase == 1) c1.push_back((int)(z.node_off + node));
+		}
+		z.c1_n = c0.size() + c1.size() - z.c1_off;
+	}
+	s->st0_total = st0.size(); s->c0_total = c0.size();
+	std::vector<int> cn(c0); cn.insert(cn.end(), c1.begin(), c1.end());
+	s->d_virt.upload(dv, s->stream);
+	s->d_axis_plus0.upload(axis, s->stream);
+	s->d_border_stage0.upload(st0, s->stream);
+	s->d_contact_nodes.upload(cn, s->stream);
+	s->contact_active = !s->virt.empty();
 }
 
 // copy-back loop of TetrMesh_1stOrder.cpp:1925-1932 == buffer swap, once every local zone has
@@ -555,7 +680,7 @@ const char* step_error_text(int code)
 	case gcm::ERR_BOTH_CONTACT: return "Both direction of contact are marked as contact";
 	case gcm::ERR_INTERP_SUM: return "Sum of factors is greater than 1.0";
 	case gcm::ERR_INNER_NO_OWNER: return "Inner node without owner tetrahedron (find_border_cross path is not built)";
-	case gcm::ERR_RING_OVERFLOW: return "Owner search needs a second ring of tetrahedrons (not built on device)";
+	case gcm::ERR_RING_OVERFLOW: return "Owner search needs more than the first and second ring of tetrahedrons (not built on device)";
 	case gcm::ERR_BAD_RHEOLOGY: return "Bad rheology";
 	case gcm::ERR_VIRT_OUTER_COUNT: return "Illegal number of outer characteristics";
 	case gcm::ERR_BAD_Q: return "Bad vector q";
@@ -697,7 +822,9 @@ int gcm_b200_set_basis_mode(gcm_b200_set* s, int on_device)
 int gcm_b200_set_collision_detector(gcm_b200_set* s, int type, int is_static, float threshold)
 {
 	NEED_SET(s);
-	if(type != 0) return fail(gcmh::UNIMPLEMENTED_EXCEPTION, "only VoidCollisionDetector is built so far");
+	if(type != 0 && type != 1) return fail(gcmh::UNIMPLEMENTED_EXCEPTION, "unknown collision detector (0 = Void, 1 = Bruteforce)");
+	if(type != 0 && s->local_zones.size() != (size_t)s->n_zones)
+		return fail(gcmh::UNIMPLEMENTED_EXCEPTION, "contact between bodies of different processes (sync_faces_in_intersection / sync_tetrs) is not built");
 	s->detector_type = type; s->detector_static = is_static; s->detector_threshold = threshold;
 	return 0;
 }
@@ -945,6 +1072,7 @@ int gcm_b200_set_end_step(gcm_b200_set* s)
 	// proceed_rheology: VoidRheologyCalculator (no-op); calc_destruction_criterias: evaluated on
 	// download; update_current_time (TetrMesh_1stOrder.cpp:2403-2406)
 	for(int zi : s->local_zones) s->zones[zi]->hm.current_time += s->time_step;
+	s->step_count++;
 	return 0;
 }
 
@@ -1223,6 +1351,16 @@ int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long
 	return 0;
 }
 
-int gcm_b200_set_virt_count(gcm_b200_set* s) { (void)s; return 0; }
+int gcm_b200_set_virt_count(gcm_b200_set* s) { return s ? (int)s->virt.size() : 0; }
+
+int gcm_b200_set_get_virt(gcm_b200_set* s, float* out16)
+{
+	if(!s || !out16) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
+	for(size_t k = 0; k < s->virt.size(); k++) {
+		memcpy(out16 + 16 * k, s->virt[k].coords, 3 * sizeof(float));
+		memcpy(out16 + 16 * k + 3, s->virt[k].values, 13 * sizeof(float));
+	}
+	return 0;
+}
 
 } // extern "C"

@@ -570,4 +570,147 @@ void rng_teta_tables(float cos_t[360], float sin_t[360])
 	}
 }
 
+// ---- collision discovery (host; the per-step contact kernel consumes its output) ------------
+// TetrMesh_1stOrder::vector_intersects_triangle, gcm/meshtypes/TetrMesh_1stOrder.cpp:2194-2290.
+// As written there, the distance / direction test (t < 0 || t > l) and the three same_orientation
+// tests are overwritten before use: the answer is the area test alone (plus vn != 0).
+static bool vector_intersects_triangle(const float* p1, const float* p2, const float* p3, const float* p0,
+                                       const float* v, float /*l*/, float* p)
+{
+	const float* chk[5] = {p1, p2, p3, p0, v};
+	static const char* what[5] = {"NAN or INF in p1", "NAN or INF in p2", "NAN or INF in p3", "NAN or INF in p0", "NAN or INF in v"};
+	for(int a = 0; a < 5; a++)
+		for(int i = 0; i < 3; i++)
+			if(std::isnan(chk[a][i]) || std::isinf(chk[a][i])) throw HostError{MESH_EXCEPTION, what[a]};
+	float n[3];
+	Vec3 q1 = {p1[0], p1[1], p1[2]}, q2 = {p2[0], p2[1], p2[2]}, q3 = {p3[0], p3[1], p3[2]};
+	elem_normal(q1, q2, q3, n);
+	for(int i = 0; i < 3; i++)
+		if(std::isnan(n[i]) || std::isinf(n[i])) throw HostError{MESH_EXCEPTION, "NAN or INF in n"};
+	float vn = n[0]*v[0] + n[1]*v[1] + n[2]*v[2];
+	if(vn == 0) return false;
+	float d = - (n[0]*p1[0] + n[1]*p1[1] + n[2]*p1[2]);
+	float t = - ((n[0]*p0[0] + n[1]*p0[1] + n[2]*p0[2]) + d) / vn;
+	for(int i = 0; i < 3; i++) p[i] = p0[i] + t * v[i];
+	float area = fabsf( gcm::tri_area(p3[0] - p1[0], p3[1] - p1[1], p3[2] - p1[2], p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]) );
+	float areas[3];
+	areas[0] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
+	areas[1] = fabsf( gcm::tri_area(p1[0] - p[0], p1[1] - p[1], p1[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
+	areas[2] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p1[0] - p[0], p1[1] - p[1], p1[2] - p[2]) );
+	if( (double)fabsf(areas[0] + areas[1] + areas[2] - area) > (double)area * 0.0001 )
+		return false;
+	return true;
+}
+
+// TetrMesh_1stOrder::interpolate_triangle, :2292-2311
+static void interpolate_triangle(const float* p1, const float* p2, const float* p3, const float* p,
+                                 const float* v1, const float* v2, const float* v3, float* v, int n)
+{
+	for(int i = 0; i < 3; i++)
+		if(std::isnan(p[i]) || std::isinf(p[i])) throw HostError{MESH_EXCEPTION, "NAN or INF in virt node coords"};
+	float areas[3];
+	areas[0] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
+	areas[1] = fabsf( gcm::tri_area(p1[0] - p[0], p1[1] - p[1], p1[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
+	areas[2] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p1[0] - p[0], p1[1] - p[1], p1[2] - p[2]) );
+	float l = areas[0] + areas[1] + areas[2];
+	float _l1 = areas[0] / l;
+	float _l2 = areas[2] / l;
+	float _l3 = areas[1] / l;
+	for(int i = 0; i < n; i++)
+		v[i] = _l1*v1[i] + _l2*v2[i] + _l3*v3[i];
+}
+
+void find_collisions(std::vector<HostMesh*>& meshes, float threshold, std::vector<VirtNodeHost>& virt,
+                     std::vector<std::vector<int> >& axis_plus0)
+{
+	const int M = (int)meshes.size();
+	virt.clear();
+	axis_plus0.assign(M, std::vector<int>());
+	for(int a = 0; a < M; a++) {
+		HostMesh& hm = *meshes[a];
+		axis_plus0[a].assign(hm.border_nodes.size(), -1);
+		for(int i = 0; i < hm.N; i++) hm.flags[i] &= ~1;   // clear_contact_state: setContactType(Free)
+	}
+	for(int a = 0; a < M; a++)
+		for(int b = 0; b < M; b++) {
+			if(a == b) continue;
+			HostMesh& m1 = *meshes[a];
+			HostMesh& m2 = *meshes[b];
+			// CollisionDetector::find_intersection, gcm/system/CollisionDetector.cpp:34-47
+			float lo[3], hi[3];
+			bool hit = true;
+			for(int j = 0; j < 3; j++) {
+				lo[j] = fmaxf(m1.outline_min[j] - threshold, m2.outline_min[j] - threshold);
+				hi[j] = fminf(m1.outline_max[j] + threshold, m2.outline_max[j] + threshold);
+				if(lo[j] > hi[j]) { hit = false; break; }
+			}
+			if(!hit) continue;
+			// find_nodes_in_intersection (:49-66): local border nodes inside the box, index order
+			std::vector<int> nodes;
+			for(size_t s = 0; s < m1.border_nodes.size(); s++) {
+				const float* c = &m1.coords[3*(size_t)m1.border_nodes[s]];
+				if(c[0] < lo[0] || c[0] > hi[0] || c[1] < lo[1] || c[1] > hi[1] || c[2] < lo[2] || c[2] > hi[2]) continue;
+				nodes.push_back((int)s);
+			}
+			// find_faces_in_intersection (:87-103): faces with at least one vertex inside the box
+			std::vector<int> fcs;
+			const int F = (int)(m2.faces.size() / 3);
+			for(int f = 0; f < F; f++) {
+				int out = 0;
+				for(int j = 0; j < 3; j++) {
+					const float* c = &m2.coords[3*(size_t)m2.faces[3*(size_t)f + j]];
+					if(c[0] < lo[0] || c[0] > hi[0] || c[1] < lo[1] || c[1] > hi[1] || c[2] < lo[2] || c[2] > hi[2]) out++;
+				}
+				if(out != 3) fcs.push_back(f);
+			}
+			// each node against the faces in order, first hit wins (:44-84); the node loop is parallel,
+			// the virt_nodes numbering is then assigned in node order as the serial loop would
+			const int nn = (int)nodes.size();
+			std::vector<int> hit_face(nn, -1);
+			std::vector<float> hit_p(3*(size_t)nn, 0.f);
+			std::string err;
+			#pragma omp parallel for schedule(dynamic, 64)
+			for(int k = 0; k < nn; k++) {
+				const int s = nodes[k];
+				const float* p0 = &m1.coords[3*(size_t)m1.border_nodes[s]];
+				const float* dir = &m1.basis[9*(size_t)s];     // local_basis->ksi[0]
+				try {
+					for(size_t l = 0; l < fcs.size(); l++) {
+						const int* fv = &m2.faces[3*(size_t)fcs[l]];
+						float p[3];
+						if(vector_intersects_triangle(&m2.coords[3*(size_t)fv[0]], &m2.coords[3*(size_t)fv[1]], &m2.coords[3*(size_t)fv[2]],
+						                              p0, dir, threshold, p)) {
+							hit_face[k] = fcs[l];
+							hit_p[3*(size_t)k] = p[0]; hit_p[3*(size_t)k+1] = p[1]; hit_p[3*(size_t)k+2] = p[2];
+							break;
+						}
+					}
+				} catch(HostError& e) {
+					#pragma omp critical
+					err = e.msg;
+				}
+			}
+			if(!err.empty()) throw HostError{MESH_EXCEPTION, err};
+			for(int k = 0; k < nn; k++) {
+				if(hit_face[k] < 0) continue;
+				const int s = nodes[k];
+				const int* fv = &m2.faces[3*(size_t)hit_face[k]];
+				VirtNodeHost vn;
+				memcpy(vn.coords, &hit_p[3*(size_t)k], 3 * sizeof(float));
+				float vals[3][13];
+				for(int j = 0; j < 3; j++) {
+					memcpy(vals[j], &m2.values[9*(size_t)fv[j]], 9 * sizeof(float));
+					memcpy(vals[j] + 9, &m2.mat[4*(size_t)fv[j]], 4 * sizeof(float));
+				}
+				interpolate_triangle(&m2.coords[3*(size_t)fv[0]], &m2.coords[3*(size_t)fv[1]], &m2.coords[3*(size_t)fv[2]],
+				                     vn.coords, vals[0], vals[1], vals[2], vn.values, 13);
+				vn.remote_zone = m2.zone; vn.remote_face = hit_face[k]; vn.base_node = fv[0];
+				vn.real_zone = m1.zone; vn.real_node = m1.border_nodes[s];
+				m1.flags[vn.real_node] |= 1;                 // setContactType(InContact)
+				axis_plus0[a][s] = (int)virt.size();         // contact_data->axis_plus[0]
+				virt.push_back(vn);
+			}
+		}
+}
+
 } // namespace gcmh

@@ -102,4 +102,24 @@ struct HostMesh {
 	void translate(float dx, float dy, float dz);
 };
 
+// A virtual (contact) node: the point where the ray from a border node along its first basis axis
+// meets a border face of another body, with the state interpolated on that face
+// (gcm/system/BruteforceCollisionDetector.cpp:44-84).
+struct VirtNodeHost {
+	float coords[3];
+	float values[13];          // 9 state values + la, mu, rho, yield_limit
+	int remote_zone;           // zone of the face it lies on (remote_zone_num)
+	int remote_face;           // that face's index (remote_num)
+	int base_node;             // vert[0] of the face: the node whose `elements` the virt node borrows (absolute_num)
+	int real_zone, real_node;  // the border node it was created for
+};
+
+// BruteforceCollisionDetector::find_collisions, local/local part (:7-92), over the meshes of one
+// process in local_meshes order.  Needs the current bases (hm.basis) and the current values of
+// the border nodes (hm.values).  Clears and refills `virt`; axis_plus0[m][slot] = virt index or -1
+// for every border slot of mesh m (clear_contact_state + the detector's marks); sets / clears the
+// InContact flag.  Throws HostError (the NaN checks of vector_intersects_triangle).
+void find_collisions(std::vector<HostMesh*>& meshes, float threshold, std::vector<VirtNodeHost>& virt,
+                     std::vector<std::vector<int> >& axis_plus0);
+
 } // namespace gcmh

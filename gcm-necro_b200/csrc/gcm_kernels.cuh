@@ -35,6 +35,48 @@ stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 		un[(size_t)node * GCM_REC + k] = out[k];
 }
 
+// Border nodes in contact on axis `stage` (only axis 0 can be: BruteforceCollisionDetector.cpp:58-60):
+// the contact branch of do_next_part_step (TetrMethod_Plastic_1stOrder.cpp:299-421), one thread per
+// node.  list[i] = real node, its virtual node = axis_plus0[border_slot].  partner_next = 1 when
+// the partner body was already advanced in this stage (the reference advances its meshes one
+// after the other): the virtual node's feet then read the NEXT layer `un`.
+__global__ void __launch_bounds__(64)
+stage_contact_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
+                     float* __restrict__ un, VirtNode* __restrict__ virt, const int* __restrict__ axis_plus0,
+                     const float* __restrict__ normals, int calc_type, int partner_next, int first_step,
+                     int* err, int zone, StageTap* tap)
+{
+	int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	const int slot = m.border_slot[node];
+	const int vidx = axis_plus0[slot];
+	MeshView mv = m;
+	if(partner_next) mv.u = un;
+	VirtNode vn = virt[vidx];
+	float out[9], vout[9];
+	bool vw = false;
+	StageTap t;
+	const float nrm[3] = {normals[3 * (size_t)slot], normals[3 * (size_t)slot + 1], normals[3 * (size_t)slot + 2]};
+	int e = node_stage_contact(m, mv, node, vn, vidx, stage, nrm, calc_type, out, tap ? &t : nullptr, vout, &vw, first_step != 0);
+	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
+	if(e) { report_error(err, e, zone, node, stage); return; }
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		un[(size_t)node * GCM_REC + k] = out[k];
+	if(vw) for(int k = 0; k < 9; k++) virt[vidx].val[k] = vout[k];
+}
+
+// Gather the records of listed nodes (collision discovery reads border-node values on the host).
+__global__ void gather_records_kernel(float* __restrict__ out9, const float* __restrict__ u, const int* __restrict__ list, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	const int node = list[i];
+	#pragma unroll
+	for(int k = 0; k < 9; k++) out9[9 * (size_t)i + k] = u[(size_t)node * GCM_REC + k];
+}
+
 // Stage 3: the plastic corrector drop_deviator (TetrMethod_Plastic_1stOrder.cpp:51-71,192-199),
 // in place on the current layer for every local node.
 __global__ void __launch_bounds__(256)

@@ -154,6 +154,57 @@ GCM_HD int find_owner_first_ring(const MeshView& m, int base, const Vec3& node_p
 	return -1;
 }
 
+GCM_HD bool tet_has_vertex(const MeshView& m, int t, int v)
+{
+	const int* tv = m.tets + 4*(size_t)t;
+	return tv[0] == v || tv[1] == v || tv[2] == v || tv[3] == v;
+}
+
+// Second ring of find_owner_tetr (:1564-1597): all tets incident to any vertex of the first
+// ring, ascending, de-duplicated, minus the first ring; the first one passing wins.  Evaluated
+// without materialising the list: the winner is the smallest passing tet id, so every unchecked
+// candidate with an id below the best so far is tested (a tet reachable through several vertices
+// is simply tested again).  Each distinct ring-1 vertex is expanded once.  *expand = some vertex
+// of the second ring lies within |dx| of the node (the reference would build a third ring).
+// Needed for virtual contact nodes, whose borrowed base node can be a full face edge away.
+GCM_HD int find_owner_second_ring(const MeshView& m, int base, const Vec3& node_pos,
+                                  float dx, float dy, float dz, TetGeom& g, bool* expand)
+{
+	const Vec3 X = load_xyz(m, base);
+	const float R2 = dx * dx + dy * dy + dz * dz;
+	const float delta = sqrtf(R2);
+	const int e0 = m.n2t_off[base], e1 = m.n2t_off[base + 1];
+	int best = 0x7fffffff;
+	bool inside_R = false;
+	for(int a = e0; a < e1; a++) {
+		const int* tv1 = m.tets + 4*(size_t)m.n2t[a];
+		for(int j = 0; j < 4; j++) {
+			const int v = tv1[j];
+			if(v == base) continue;
+			bool seen = false;
+			for(int b = e0; b < a && !seen; b++) seen = tet_has_vertex(m, m.n2t[b], v);
+			if(seen) continue;
+			for(int c = m.n2t_off[v]; c < m.n2t_off[v + 1]; c++) {
+				const int t2 = m.n2t[c];
+				if(t2 >= best || tet_has_vertex(m, t2, base)) continue;
+				TetGeom q;
+				load_tet(m, t2, q);
+				if(point_in_tetr(X, dx, dy, dz, delta, q.p[0], q.p[1], q.p[2], q.p[3], q.h, q.vol)) { best = t2; continue; }
+				for(int k = 0; k < 4; k++) {
+					const float lx = q.p[k].x, ly = q.p[k].y, lz = q.p[k].z;
+					if( ( (node_pos.x - lx) * (node_pos.x - lx)
+						+ (node_pos.y - ly) * (node_pos.y - ly)
+						+ (node_pos.z - lz) * (node_pos.z - lz) ) < R2 )
+						inside_R = true;
+				}
+			}
+		}
+	}
+	if(best != 0x7fffffff) { load_tet(m, best, g); *expand = false; return best; }
+	*expand = inside_R;
+	return -1;
+}
+
 // Interpolated state at a foot (gcm/meshtypes/TetrMesh_1stOrder.cpp:1764-1880).
 // out[0..8] = values, out[9..11] = la, mu, rho (only virtual nodes read those).
 GCM_HD int interpolate_foot(const MeshView& m, const TetGeom& g, float x, float y, float z,
@@ -272,11 +323,22 @@ GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& c
 				}
 		}
 
+		// A foot on the contact side is classified `outer` whatever the search returns (:594-603), so
+		// the search (which the reference still runs, ring after ring into the gap) is skipped;
+		// its tap entry is -3 ("not searched").
+		const bool forced_outer = cur.has_contact_data
+			&& ( ((cur.axis_plus[stage] != -1) && (dksi[i] > 0)) || ((cur.axis_minus[stage] != -1) && (dksi[i] < 0)) );
 		TetGeom g;
 		bool expand = false;
-		int owner = find_owner_first_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
-		if(owner < 0 && expand)
-			return -ERR_RING_OVERFLOW;
+		int owner = -3;
+		if(!forced_outer) {
+			owner = find_owner_first_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
+			if(owner < 0 && expand) {
+				owner = find_owner_second_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
+				if(owner < 0 && expand)
+					return -ERR_RING_OVERFLOW;   // a third ring would be needed
+			}
+		}
 		out.owner[count] = owner;
 
 		if( cur.has_contact_data && (cur.axis_plus[stage] != -1) && (dksi[i] > 0) ) {
@@ -484,6 +546,175 @@ GCM_HD int node_stage_nocontact(const MeshView& m, int node, int stage, float ou
 	int cid = m.cond_id ? m.cond_id[slot] : -1;
 	if(cid >= 0 && m.conds[cid].active) bc = &m.conds[cid];
 	border_calc(*bc, U, feet, basis + 3*stage, out);
+	return ERR_NONE;
+}
+
+// ---- two-body contact ------------------------------------------------------------------------
+// A virtual node as the device sees it (built from gcmh::VirtNodeHost): position on the partner
+// body's border face, the 13 values interpolated there at discovery time, and the partner-mesh
+// node whose `elements` / local_num it borrows (TetrMeshSet.cpp:236-271).
+struct VirtNode {
+	float pos[3];
+	float val[9];
+	float la, mu, rho;
+	int base;      // merged index of the borrowed node (vert[0] of the face)
+	int real;      // merged index of the border node it belongs to
+	int phase;     // 0: partner zone comes later in local_meshes (reads the current layer);
+	               // 1: partner zone was already advanced this stage (reads the next layer)
+};
+
+// AdhesionContactCalculator::do_calc, gcm/methods/contact/AdhesionContactCalculator.cpp:19-142:
+// 18 unknowns (real 9 + virtual 9); rows 0-5 real inner Omega rows, 6-11 virtual inner Omega rows,
+// 12-14 equal velocities, 15-17 equal traction (sigma . n).  x[0..8] = real node, x[9..17] = virtual.
+GCM_HD void adhesion_calc(const float* U, const FeetOut& feet, const float* Uv, const FeetOut& vfeet,
+                          const float outer_normal[3], double x[18])
+{
+	double A[324];
+	for(int i = 0; i < 324; i++) A[i] = 0;
+	for(int i = 0; i < 18; i++) x[i] = 0;
+	int pos = 0;
+	for(int i = 0; i < 9; i++)
+		if(feet.inner[i] && pos < 6) {
+			x[pos] = (double)omega_row(U, i, feet.val[feet.ppoint[i]]);
+			for(int j = 0; j < 9; j++) A[pos*18 + j] = (double)U[i*9 + j];
+			pos++;
+		}
+	pos = 0;
+	for(int i = 0; i < 9; i++)
+		if(vfeet.inner[i] && pos < 6) {
+			x[6 + pos] = (double)omega_row(Uv, i, vfeet.val[vfeet.ppoint[i]]);
+			for(int j = 0; j < 9; j++) A[(6 + pos)*18 + 9 + j] = (double)Uv[i*9 + j];
+			pos++;
+		}
+	A[12*18 + 0] = 1; A[12*18 + 9] = -1;
+	A[13*18 + 1] = 1; A[13*18 + 10] = -1;
+	A[14*18 + 2] = 1; A[14*18 + 11] = -1;
+	const int c[3][3] = {{3, 4, 5}, {4, 6, 7}, {5, 7, 8}};
+	for(int r = 0; r < 3; r++)
+		for(int k = 0; k < 3; k++) {
+			A[(15 + r)*18 + c[r][k]] = (double)outer_normal[k];
+			A[(15 + r)*18 + 9 + c[r][k]] = (double)(-outer_normal[k]);
+		}
+	lu_solve<18>(A, x);
+}
+
+// One border node in contact on axis `stage` (axis_plus[stage] = its virtual node), i.e. the
+// contact branch of do_next_part_step, gcm/methods/TetrMethod_Plastic_1stOrder.cpp:299-421.
+//   m   view whose `u` is the layer the REAL node reads (its own mesh, current layer)
+//   mv  view whose `u` is the layer the VIRTUAL node's feet read in the partner mesh: the current
+//       layer, or the next one when the partner was already advanced in this stage (the
+//       reference runs its meshes one after the other, TetrMeshSet.cpp:158-167)
+//   normal = find_border_node_normal of the real node (prepare_node :83-84)
+// first_step: this is the first step after loading (only matters to Friction, see below).
+// out[9] = new values of the real node.  virt_out (optional) receives the virtual node's values
+// when the calculator rewrites them (Friction's swapped Adhesion call); *virt_written says so.
+GCM_HD int node_stage_contact(const MeshView& m, const MeshView& mv, int node, const VirtNode& vn, int vidx,
+                              int stage, const float normal[3], int calc_type, float out[9], StageTap* tap,
+                              float virt_out[9], bool* virt_written, bool first_step)
+{
+	if(virt_written) *virt_written = false;
+	CurNode cur;
+	cur.base = node;
+	cur.pos = load_xyz(m, node);
+	for(int k = 0; k < 9; k++) {
+		float v = m.u[(size_t)node * GCM_REC + k];
+		if(isnan(v) || isinf(v)) return ERR_NAN;
+		cur.val[k] = v;
+	}
+	cur.la = m.mat[node]; cur.mu = m.mat[m.stride + node]; cur.rho = m.mat[2*m.stride + node];
+	cur.is_border = true;
+	cur.has_contact_data = true;
+	for(int k = 0; k < 3; k++) { cur.axis_plus[k] = -1; cur.axis_minus[k] = -1; }
+	cur.axis_plus[stage] = vidx;
+	const int slot = m.border_slot[node];
+	const float* basis = m.basis + 9*(size_t)slot;
+
+	float L[9], U[81];
+	FeetOut feet;
+	int tries = 0;
+	int outer_count = prepare_node(m, cur, stage, basis, L, U, nullptr, feet, false, &tries);
+	if(tap) {
+		for(int k = 0; k < 5; k++) tap->owner[k] = (outer_count >= 0 && k < feet.n_points) ? feet.owner[k] : -2;
+		tap->outer_count = outer_count; tap->tries = tries;
+	}
+	if(outer_count < 0) return -outer_count;
+	if(outer_count == 0) {
+		float U1[81];
+		const float* q = basis + 3*stage;
+		elastic_matrix(cur.la, cur.mu, cur.rho, q[0], q[1], q[2], L, nullptr, U1);
+		volume_calc(U, U1, feet, out);
+		return ERR_NONE;
+	}
+	if(outer_count != 3) return ERR_OUTER_COUNT;
+
+	// the virtual node, marked as in contact from the other side (:310-315)
+	CurNode vc;
+	vc.base = vn.base;
+	vc.pos.x = vn.pos[0]; vc.pos.y = vn.pos[1]; vc.pos.z = vn.pos[2];
+	for(int k = 0; k < 9; k++) vc.val[k] = vn.val[k];
+	vc.la = vn.la; vc.mu = vn.mu; vc.rho = vn.rho;
+	vc.is_border = true;
+	vc.has_contact_data = true;
+	for(int k = 0; k < 3; k++) { vc.axis_plus[k] = -1; vc.axis_minus[k] = -1; }
+	vc.axis_minus[stage] = vidx;
+	float Lv[9], Uv[81];
+	FeetOut vfeet;
+	int vtries = 0;
+	int virt_outer = prepare_node(mv, vc, stage, basis, Lv, Uv, nullptr, vfeet, false, &vtries);   // basis_num = the real node's
+	if(virt_outer < 0) return -virt_outer;
+	if(virt_outer != 3) return ERR_VIRT_OUTER_COUNT;
+
+	double x[18];
+	if(calc_type == CC_ADHESION) {
+		adhesion_calc(U, feet, Uv, vfeet, normal, x);
+		for(int j = 0; j < 9; j++) out[j] = (float)x[j];
+		return ERR_NONE;
+	}
+
+	// FrictionContactCalculator::do_calc, gcm/methods/contact/FrictionContactCalculator.cpp:23-132
+	// (k = 0.1; the free-border shortcut is disabled there by `if (false)`)
+	const float* on = normal;
+	float vel_rel[3] = {cur.val[0] - vn.val[0], cur.val[1] - vn.val[1], cur.val[2] - vn.val[2]};
+	float dsxx = -vn.val[3] + cur.val[3], dsxy = -vn.val[4] + cur.val[4], dsxz = -vn.val[5] + cur.val[5],
+	      dsyy = -vn.val[6] + cur.val[6], dsyz = -vn.val[7] + cur.val[7], dszz = -vn.val[8] + cur.val[8];
+	float rho = cur.rho, c1 = sqrtf( (cur.la + 2 * cur.mu) / rho );
+	float vel_norm_abs = vel_rel[0]*on[0] + vel_rel[1]*on[1] + vel_rel[2]*on[2];
+	float vel_tang[3] = {vel_rel[0] - vel_norm_abs*on[0], vel_rel[1] - vel_norm_abs*on[1], vel_rel[2] - vel_norm_abs*on[2]};
+	float vel_tang_abs = sqrtf(vel_tang[0]*vel_tang[0] + vel_tang[1]*vel_tang[1] + vel_tang[2]*vel_tang[2]);
+	const float kf = (float)0.1;
+	adhesion_calc(U, feet, Uv, vfeet, normal, x);
+	float nd[9];
+	for(int j = 0; j < 9; j++) nd[j] = (float)x[j];
+	float frc_nd[3] = { nd[3]*on[0] + nd[4]*on[1] + nd[5]*on[2],
+	                    nd[4]*on[0] + nd[6]*on[1] + nd[7]*on[2],
+	                    nd[5]*on[0] + nd[7]*on[1] + nd[8]*on[2] };
+	float frc_tan = (vel_tang[0]*frc_nd[0] + vel_tang[1]*frc_nd[1] + vel_tang[2]*frc_nd[2]) / vel_tang_abs;
+	float frc_nrm = on[0]*frc_nd[0] + on[1]*frc_nd[1] + on[2]*frc_nd[2];
+	if(kf * frc_nrm > frc_tan) {
+		// sliding: ExternalForceCalculator with sigma_n, k sigma_n along the tangential velocity
+		float tp[3] = { dsxx*on[0] + dsxy*on[1] + dsxz*on[2],
+		                dsxy*on[0] + dsyy*on[1] + dsyz*on[2],
+		                dsxz*on[0] + dsyz*on[1] + dszz*on[2] };
+		// - 0.5*rho*c1*vel_norm_abs - 0.5*scalar_product(tp, n): the 0.5 literals promote to double
+		float sn = (float)( ((-0.5 * (double)rho) * (double)c1) * (double)vel_norm_abs
+		                    - 0.5 * (double)(tp[0]*on[0] + tp[1]*on[1] + tp[2]*on[2]) );
+		if((double)sn > 0.0) sn = -sn;
+		BorderCond bc;
+		bc.type = BC_EXT_FORCE; bc.scale = 1; bc.active = 1;
+		// set_parameters(sn, k*sn, vel_tang / |vel_tang|): the direction is normalised once more there
+		bc.p_normal = sn; bc.p_tangential = kf * sn;
+		float d0 = vel_tang[0] / vel_tang_abs, d1 = vel_tang[1] / vel_tang_abs, d2 = vel_tang[2] / vel_tang_abs;
+		float dtmp = sqrtf(d0*d0 + d1*d1 + d2*d2);
+		bc.dir[0] = d0 / dtmp; bc.dir[1] = d1 / dtmp; bc.dir[2] = d2 / dtmp;
+		border_calc(bc, U, feet, normal, out);
+		return ERR_NONE;
+	}
+	// "adhesion" branch with new_node / virt_node swapped (:123): the solution lands in the VIRTUAL
+	// node's values and the real node keeps what new_node held (the previous step's result)
+	// new_nodes == nodes at the start of every step but the first, where new_nodes still holds the
+	// values the node was added with (add_node runs before any initial state is written: zeros)
+	for(int j = 0; j < 9; j++) out[j] = first_step ? 0.0f : cur.val[j];
+	if(virt_out) { for(int j = 0; j < 9; j++) virt_out[j] = nd[j]; if(virt_written) *virt_written = true; }
 	return ERR_NONE;
 }
 

@@ -92,6 +92,7 @@ SIGNATURES = {
     "gcm_b200_zone_get_tap": (_i, [_p, _i, _ip, _ip, _ip]),
     "gcm_b200_set_launch_count": (C.c_longlong, [_p]),
     "gcm_b200_set_virt_count": (_i, [_p]),
+    "gcm_b200_set_get_virt": (_i, [_p, _fp]),
     "gcm_b200_set_profile": (_i, [_p, _i]),
     "gcm_b200_set_profile_read": (_i, [_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
 }
@@ -303,6 +304,14 @@ class TetrMeshSet:
 
     def enable_tap(self, on=True):
         self._ck(self.lib.gcm_b200_set_enable_tap(self.h, int(on)))
+
+    def get_virt_nodes(self):
+        """Virtual (contact) nodes of the last collision pass: [n, 16] = coords(3) + values(13)."""
+        n = self.lib.gcm_b200_set_virt_count(self.h)
+        v = np.empty((n, 16), np.float32)
+        if n:
+            self._ck(self.lib.gcm_b200_set_get_virt(self.h, _fptr(v)))
+        return v
 
     def launch_count(self):
         return self.lib.gcm_b200_set_launch_count(self.h)

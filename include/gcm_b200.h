@@ -145,6 +145,7 @@ int gcm_b200_set_profile(gcm_b200_set* s, int on);
 int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long long* launches, long long* units);
 /* Virtual (contact) nodes of the last collision pass: n and [16] floats each (coords, values). */
 int gcm_b200_set_virt_count(gcm_b200_set* s);
+int gcm_b200_set_get_virt(gcm_b200_set* s, float* out16);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,9 @@ int main(int argc, char** argv)
 	vector<Cond> conds;
 	float la = 7e9f, mu = 1e9f, rho = 7.8e6f, yield = 1e16f;
 	int steps = 1, seed = 12345, tap_step = -1;
-	string out;
+	string out, detector = "void", contact_calc = "adhesion";
+	bool detector_static = false;
+	vector<vector<float> > translates;
 	for(int a = 1; a < argc; a++) {
 		string s = argv[a];
 		if(s == "--mesh") { while(a + 1 < argc && argv[a+1][0] != '-') mesh_files.push_back(argv[++a]); }
@@ -55,6 +57,10 @@ int main(int argc, char** argv)
 		else if(s == "--seed") seed = atoi(argv[++a]);
 		else if(s == "--out") out = argv[++a];
 		else if(s == "--tap-step") tap_step = atoi(argv[++a]);
+		else if(s == "--detector") detector = argv[++a];
+		else if(s == "--static") detector_static = true;
+		else if(s == "--contact-calc") contact_calc = argv[++a];
+		else if(s == "--translate") { vector<float> t; for(int k = 0; k < 4; k++) t.push_back(atof(argv[++a])); translates.push_back(t); }
 		else if(s == "--border") {
 			Cond c; memset(&c, 0, sizeof c);
 			string t = argv[++a];
@@ -104,6 +110,7 @@ int main(int argc, char** argv)
 			}
 		}
 	};
+	for(auto& t : translates) zs[(int)t[0]]->hm.translate(t[1], t[2], t[3]);
 	try {
 		host_sync(true);
 		for(auto& zp : zs) zp->hm.pre_process_mesh();
@@ -138,8 +145,32 @@ int main(int argc, char** argv)
 	vector<int> tap;   // records: zone node stage owner[5] outer tries
 	int rc = 0;
 	const float tau = 0.002f;
+	vector<gcmh::VirtNodeHost> virt;
+	vector<vector<int> > axis_plus0(NZ);
+	for(int z = 0; z < NZ; z++) axis_plus0[z].assign(zs[z]->hm.border_nodes.size(), -1);
+	auto make_view = [&](Z& z) {
+		HostMesh& hm = z.hm;
+		gcm::MeshView m; memset(&m, 0, sizeof m);
+		m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
+		m.u = z.u[z.cur].data(); m.mat = z.mat.data(); m.flags = hm.flags.data();
+		m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
+		m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
+		m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
+		return m;
+	};
 	for(int step = 0; step < steps && !rc; step++) {
 		for(auto& zp : zs) zp->hm.create_random_axes(rng);
+		// TetrMeshSet.cpp:111-120: collisions unless the detector is static and t != 0
+		if(detector == "brute" && (!detector_static || step == 0)) {
+			vector<HostMesh*> ms;
+			for(auto& zp : zs) {
+				Z& z = *zp;
+				for(int i = 0; i < z.hm.N; i++) for(int k = 0; k < 9; k++) z.hm.values[9*(size_t)i+k] = z.u[z.cur][GCM_REC*(size_t)i+k];
+				ms.push_back(&z.hm);
+			}
+			try { gcmh::find_collisions(ms, 1.0f, virt, axis_plus0); }
+			catch(gcmh::HostError& e) { die("collisions: " + e.msg); }
+		}
 		for(int stage = 0; stage < 4 && !rc; stage++) {
 			// sync_nodes on the SoA layers
 			for(auto& zp : zs) {
@@ -179,7 +210,23 @@ int main(int argc, char** argv)
 				for(int i = 0; i < hm.N; i++) {
 					if(!hm.is_local(i)) continue;
 					float o[9]; gcm::StageTap t;
-					int e = gcm::node_stage_nocontact(m, i, stage, o, &t);
+					int e;
+					const int slot = hm.border_slot[i];
+					const int vidx = (stage == 0 && slot >= 0) ? axis_plus0[zi][slot] : -1;
+					if(vidx >= 0) {
+						// contact branch; the partner mesh is read as it is NOW (zones advance one after the other)
+						gcmh::VirtNodeHost& vh = virt[vidx];
+						gcm::MeshView mv = make_view(*zs[vh.remote_zone]);
+						gcm::VirtNode vn;
+						for(int k = 0; k < 3; k++) vn.pos[k] = vh.coords[k];
+						for(int k = 0; k < 9; k++) vn.val[k] = vh.values[k];
+						vn.la = vh.values[9]; vn.mu = vh.values[10]; vn.rho = vh.values[11];
+						vn.base = vh.base_node; vn.real = i; vn.phase = 0;
+						float vo[9]; bool vw = false;
+						e = gcm::node_stage_contact(m, mv, i, vn, vidx, stage, &hm.normals[3*(size_t)slot], contact_calc == "friction" ? 1 : 0, o, &t, vo, &vw, step == 0);
+						if(vw) for(int k = 0; k < 9; k++) vh.values[k] = vo[k];
+					} else
+						e = gcm::node_stage_nocontact(m, i, stage, o, &t);
 					if(e) {
 						#pragma omp critical
 						{ if(!err) { err = e; fprintf(stderr, "gcm_emul: error %d zone %d node %d stage %d\n", e, zi, i, stage); } }

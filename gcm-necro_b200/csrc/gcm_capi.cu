@@ -69,6 +69,8 @@ struct Zone {
 	size_t node_off = 0, tet_off = 0, entry_off = 0, slot_off = 0;
 	size_t fast_off = 0, generic_off = 0, inner_off = 0;   // ranges of this zone in the merged node lists
 	size_t st0_off = 0, st0_n = 0, c0_off = 0, c0_n = 0, c1_off = 0, c1_n = 0;   // contact launch lists
+	size_t sharp_off = 0, flat_off = 0;          // ranges in the merged sharp / flat border lists
+	size_t st0s_off = 0, st0s_n = 0;             // stage-0 sharp border nodes not in contact
 	bool stage_done = false;
 };
 
@@ -78,7 +80,8 @@ struct DeviceMesh {
 	size_t n_fast = 0, n_generic = 0, n_inner = 0;
 	DevBuf<float> u0, u1, mat, tet_hv, basis, normals, w0, aos, mat_tab;
 	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x;
-	DevBuf<int> border_list, fast_list, generic_list, inner_list;
+	DevBuf<int> sharp_list, flat_list, fast_list, generic_list, inner_list;
+	size_t n_sharp = 0, n_flat = 0;
 	DevBuf<unsigned char> mat_id;
 	DevBuf<gcm::StageTap> tap;
 	DevBuf<int> halo_dst, halo_src;
@@ -123,7 +126,8 @@ struct gcm_b200_set {
 	std::vector<gcmh::VirtNodeHost> virt;
 	std::vector<std::vector<int> > axis_plus0;   // per local zone (local_meshes order), per border slot
 	DevBuf<gcm::VirtNode> d_virt;
-	DevBuf<int> d_axis_plus0, d_border_stage0, d_contact_nodes, d_border_by_slot;
+	DevBuf<int> d_axis_plus0, d_border_stage0, d_sharp_stage0, d_contact_nodes, d_border_by_slot;
+	size_t st0s_total = 0;
 	DevBuf<float> d_gather;
 	size_t st0_total = 0, c0_total = 0;
 	bool contact_active = false;
@@ -274,15 +278,16 @@ void upload_mesh(gcm_b200_set* s)
 	DeviceMesh& dm = s->dm;
 	cudaStream_t st = s->stream;
 	assign_offsets(s);
-	size_t N = 0, T = 0, E = 0, NB = 0, nf = 0, ng = 0, ni = 0;
+	size_t N = 0, T = 0, E = 0, NB = 0, nf = 0, ng = 0, ni = 0, nsh = 0, nfl = 0;
 	for(int zi : s->local_zones) {
 		Zone& z = *s->zones[zi];
-		z.fast_off = nf; z.generic_off = ng; z.inner_off = ni;
+		z.fast_off = nf; z.generic_off = ng; z.inner_off = ni; z.sharp_off = nsh; z.flat_off = nfl;
+		nsh += z.hm.n_sharp; nfl += z.hm.border_launch.size() - z.hm.n_sharp;
 		N += z.hm.N; T += z.hm.T; E += z.hm.n2t.size(); NB += z.hm.border_nodes.size();
 		nf += z.hm.inner_fast.size(); ng += z.hm.inner_generic.size(); ni += z.hm.inner_nodes.size();
 	}
 	if(T >= (1u << 30) || E >= 0x7fffffffull || N >= 0x7fffffffull / GCM_REC * 4) throw HostError{gcmh::CONFIG_EXCEPTION, "mesh too large for 32-bit device indices"};
-	dm.N = N; dm.T = T; dm.E = E; dm.NB = NB; dm.n_fast = nf; dm.n_generic = ng; dm.n_inner = ni;
+	dm.N = N; dm.T = T; dm.E = E; dm.NB = NB; dm.n_fast = nf; dm.n_generic = ng; dm.n_inner = ni; dm.n_sharp = nsh; dm.n_flat = nfl;
 	dm.stride = (N + 31) / 32 * 32;
 	dm.u0.alloc(GCM_REC * (N + 1)); dm.u1.alloc(GCM_REC * (N + 1));
 	CK(cudaMemsetAsync(dm.u0.p, 0, GCM_REC * (N + 1) * sizeof(float), st));
@@ -290,7 +295,7 @@ void upload_mesh(gcm_b200_set* s)
 	dm.mat.alloc(4 * dm.stride); dm.tet_hv.alloc(2 * T); dm.basis.alloc(9 * NB); dm.normals.alloc(3 * NB);
 	dm.w0.alloc(N); dm.aos.alloc(9 * N); dm.flags.alloc(N); dm.n2t_off.alloc(N + 1); dm.n2t.alloc(E); dm.tets.alloc(4 * T);
 	dm.border_slot.alloc(N); dm.cond_id.alloc(NB); dm.n2x.alloc(4 * E); dm.mat_id.alloc(N);
-	dm.border_list.alloc(NB); dm.fast_list.alloc(nf); dm.generic_list.alloc(ng); dm.inner_list.alloc(ni);
+	dm.sharp_list.alloc(nsh); dm.flat_list.alloc(nfl); dm.fast_list.alloc(nf); dm.generic_list.alloc(ng); dm.inner_list.alloc(ni);
 	if(dm.basis.p) CK(cudaMemsetAsync(dm.basis.p, 0, 9 * NB * sizeof(float), st));
 	for(int zi : s->local_zones) {
 		Zone& z = *s->zones[zi];
@@ -336,7 +341,12 @@ void upload_mesh(gcm_b200_set* s)
 		dm.w0.put(hm.w0, z.node_off, st);
 		dm.mat_id.put(hm.mat_id, z.node_off, st);
 		dm.normals.put(hm.normals, 3 * z.slot_off, st);
-		dm.border_list.put(shifted(hm.border_launch, (long long)z.node_off), z.slot_off, st);
+		{
+			std::vector<int> sh(hm.border_launch.begin(), hm.border_launch.begin() + hm.n_sharp);
+			std::vector<int> fl(hm.border_launch.begin() + hm.n_sharp, hm.border_launch.end());
+			dm.sharp_list.put(shifted(sh, (long long)z.node_off), z.sharp_off, st);
+			dm.flat_list.put(shifted(fl, (long long)z.node_off), z.flat_off, st);
+		}
 		dm.fast_list.put(shifted(hm.inner_fast, (long long)z.node_off), z.fast_off, st);
 		dm.generic_list.put(shifted(hm.inner_generic, (long long)z.node_off), z.generic_off, st);
 		dm.inner_list.put(shifted(hm.inner_nodes, (long long)z.node_off), z.inner_off, st);
@@ -508,23 +518,34 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 	gcm::MeshView m = make_view(s, tau);
 	if(s->tap_on && !dm.tap.p) { dm.tap.alloc(3 * dm.N); CK(cudaMemsetAsync(dm.tap.p, 0xff, 3 * dm.N * sizeof(gcm::StageTap), s->stream)); }
 	gcm::StageTap* tap = s->tap_on ? dm.tap.p : nullptr;
-	int nb = (int)(z ? z->hm.border_nodes.size() : dm.NB);
-	const int* bl = dm.border_list.p + (z ? z->slot_off : 0);
+	// border nodes: flat ones one thread per node, sharp ones 16 lanes per node (speculative alpha tries)
+	int nb = (int)(z ? z->hm.border_launch.size() - z->hm.n_sharp : dm.n_flat);
+	const int* bl = dm.flat_list.p + (z ? z->flat_off : 0);
+	int nsh = (int)(z ? (size_t)z->hm.n_sharp : dm.n_sharp);
+	const int* shl = dm.sharp_list.p + (z ? z->sharp_off : 0);
 	const bool contact = stage == 0 && s->contact_active;
 	if(contact) {   // border nodes in contact on axis 0 take the contact kernel instead
 		nb = (int)(z ? z->st0_n : s->st0_total);
 		bl = s->d_border_stage0.p + (z ? z->st0_off : 0);
+		nsh = (int)(z ? z->st0s_n : s->st0s_total);
+		shl = s->d_sharp_stage0.p + (z ? z->st0s_off : 0);
 	}
 	cudaStream_t bst = s->stream;
-	if(nb) {
+	if(nb || nsh) {
 		if(s->concurrent) {
 			bst = s->aux;
 			CK(cudaEventRecord(s->ev_fork, s->stream));
 			CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
 		}
-		ProfScope ps(s, PROF_BORDER, nb, bst);
-		gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-		s->launches++;
+		ProfScope ps(s, PROF_BORDER, nb + nsh, bst);
+		if(nsh) {
+			gcm::stage_sharp_kernel<<<(nsh * 16 + 63) / 64, 64, 0, bst>>>(m, shl, nsh, stage, dm.unext(), s->d_err, zone, tap);
+			s->launches++;
+		}
+		if(nb) {
+			gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
+			s->launches++;
+		}
 	}
 	if(!s->fast_inner) {
 		const int ni = (int)(z ? z->hm.inner_nodes.size() : dm.n_inner);
@@ -556,7 +577,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 			s->launches++;
 		}
 	}
-	if(nb && s->concurrent) {
+	if((nb || nsh) && s->concurrent) {
 		CK(cudaEventRecord(s->ev_join, s->aux));
 		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
 	}
@@ -629,21 +650,22 @@ void run_collision_detection(gcm_b200_set* s)
 		v.real = (int)(s->zones[h.real_zone]->node_off + h.real_node);
 		v.phase = order[h.remote_zone] < order[h.real_zone] ? 1 : 0;
 	}
-	std::vector<int> axis(dm.NB, -1), st0, c0, c1;
+	std::vector<int> axis(dm.NB, -1), st0, st0s, c0, c1;
 	for(size_t a = 0; a < s->local_zones.size(); a++) {
 		Zone& z = *s->zones[s->local_zones[a]];
 		for(size_t b = 0; b < z.hm.border_nodes.size(); b++) axis[z.slot_off + b] = s->axis_plus0[a][b];
 	}
-	// lists: stage-0 border nodes not in contact (launch order), contact nodes by phase, per zone
+	// lists: stage-0 border nodes not in contact (sharp / flat, launch order), contact nodes by phase
 	for(size_t a = 0; a < s->local_zones.size(); a++) {
 		Zone& z = *s->zones[s->local_zones[a]];
-		z.st0_off = st0.size(); z.c0_off = c0.size();
-		for(int node : z.hm.border_launch) {
+		z.st0_off = st0.size(); z.st0s_off = st0s.size(); z.c0_off = c0.size();
+		for(size_t q = 0; q < z.hm.border_launch.size(); q++) {
+			const int node = z.hm.border_launch[q];
 			const int v = s->axis_plus0[a][z.hm.border_slot[node]];
-			if(v < 0) st0.push_back((int)(z.node_off + node));
+			if(v < 0) ((int)q < z.hm.n_sharp ? st0s : st0).push_back((int)(z.node_off + node));
 			else if(dv[v].phase == 0) c0.push_back((int)(z.node_off + node));
 		}
-		z.st0_n = st0.size() - z.st0_off; z.c0_n = c0.size() - z.c0_off;
+		z.st0_n = st0.size() - z.st0_off; z.st0s_n = st0s.size() - z.st0s_off; z.c0_n = c0.size() - z.c0_off;
 	}
 	for(size_t a = 0; a < s->local_zones.size(); a++) {
 		Zone& z = *s->zones[s->local_zones[a]];
@@ -654,11 +676,12 @@ void run_collision_detection(gcm_b200_set* s)
 		}
 		z.c1_n = c0.size() + c1.size() - z.c1_off;
 	}
-	s->st0_total = st0.size(); s->c0_total = c0.size();
+	s->st0_total = st0.size(); s->st0s_total = st0s.size(); s->c0_total = c0.size();
 	std::vector<int> cn(c0); cn.insert(cn.end(), c1.begin(), c1.end());
 	s->d_virt.upload(dv, s->stream);
 	s->d_axis_plus0.upload(axis, s->stream);
 	s->d_border_stage0.upload(st0, s->stream);
+	s->d_sharp_stage0.upload(st0s, s->stream);
 	s->d_contact_nodes.upload(cn, s->stream);
 	s->contact_active = !s->virt.empty();
 }

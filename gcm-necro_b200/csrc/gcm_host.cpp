@@ -404,6 +404,7 @@ void HostMesh::pre_process_mesh()
 		}
 		border_launch.clear();
 		for(int s = 0; s < NB; s++) if(sharp[s]) border_launch.push_back(border_nodes[s]);
+		n_sharp = (int)border_launch.size();
 		for(int s = 0; s < NB; s++) if(!sharp[s]) border_launch.push_back(border_nodes[s]);
 	}
 	build_fast_path_tables();

@@ -65,6 +65,7 @@ struct HostMesh {
 	std::vector<float> tet_hv;        // [T][2] tetr_h, signed volume
 	std::vector<int> border_nodes;    // local border nodes, ascending
 	std::vector<int> border_slot;     // [N] index into border_nodes or -1
+	int n_sharp = 0;                  // the first n_sharp entries of border_launch are the sharp ones
 	std::vector<int> border_launch;   // border_nodes permuted for the kernel launch: nodes on sharp
 	                                  // edges (many alpha retries) first, so warps stay homogeneous
 	std::vector<int> inner_nodes;     // local inner nodes, ascending

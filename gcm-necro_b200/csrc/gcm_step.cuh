@@ -498,14 +498,31 @@ struct StageTap { int owner[5]; int outer_count; int tries; };
 
 // One mesh node, one axis stage (stage 0..2), without contact:
 // gcm/methods/TetrMethod_Plastic_1stOrder.cpp:190-297.  Writes out[9]; returns a StepError.
+// `Decide` (only_try >= 0): callable bool(outer_count, try, ctx) that returns true on the one lane
+// whose try decides the node; every lane of the group must call it (it votes).  The default
+// (only_try = -1) runs the sequential retry loop.  Returns -1000 on the lanes that lost the vote.
+struct NoDecide { GCM_HD bool operator()(int, int, void*) const { return true; } };
+
+template<class Decide>
+GCM_HD int node_stage_nocontact_t(const MeshView& m, int node, int stage, float out[9], StageTap* tap,
+                                  int only_try, Decide decide, void* decide_ctx);
+
 GCM_HD int node_stage_nocontact(const MeshView& m, int node, int stage, float out[9], StageTap* tap)
+{
+	return node_stage_nocontact_t(m, node, stage, out, tap, -1, NoDecide(), nullptr);
+}
+
+template<class Decide>
+GCM_HD int node_stage_nocontact_t(const MeshView& m, int node, int stage, float out[9], StageTap* tap,
+                                  int only_try, Decide decide, void* decide_ctx)
 {
 	CurNode cur;
 	cur.base = node;
 	cur.pos = load_xyz(m, node);
+	bool bad_value = false;
 	for(int k = 0; k < 9; k++) {
 		float v = m.u[(size_t)node * GCM_REC + k];
-		if(isnan(v) || isinf(v)) return ERR_NAN;
+		if(isnan(v) || isinf(v)) { if(only_try < 0) return ERR_NAN; bad_value = true; }
 		cur.val[k] = v;
 	}
 	cur.la = m.mat[node]; cur.mu = m.mat[m.stride + node]; cur.rho = m.mat[2*m.stride + node];
@@ -523,7 +540,29 @@ GCM_HD int node_stage_nocontact(const MeshView& m, int node, int stage, float ou
 	float L[9], U[81];
 	FeetOut feet;
 	int tries = 0;
-	int outer_count = prepare_node(m, cur, stage, basis, L, U, nullptr, feet, false, &tries);
+	int outer_count;
+	if(only_try < 0) {
+		outer_count = prepare_node(m, cur, stage, basis, L, U, nullptr, feet, false, &tries);
+	} else {
+		// one alpha try of the retry loop (speculative evaluation of all 11 tries by 11 lanes,
+		// stage_sharp_kernel): same eigensystem, same dksi, alpha = value the loop would have then
+		const float* ksi = basis + 3*stage;
+		int e = (bad_value || only_try > 10) ? 0 : elastic_matrix(cur.la, cur.mu, cur.rho, ksi[0], ksi[1], ksi[2], L, U, nullptr);
+		if(only_try > 10) outer_count = 1;          // padding lane of the group: votes "no"
+		else if(bad_value) outer_count = -ERR_NAN;
+		else if(e) outer_count = -e;
+		else {
+			float dksi[9];
+			for(int i = 0; i < 9; i++) dksi[i] = - L[i] * m.tau;
+			float alpha = 0;
+			for(int t = 0; t < only_try; t++) alpha = (float)((double)alpha + 0.1);
+			outer_count = find_nodes_on_previous_time_layer(m, cur, stage, alpha, dksi, ksi, feet, false);
+		}
+		tries = only_try + 1;
+		// the lanes of a node now agree on which try decides: the first with a legal outer count or an
+		// error, else the last one (prepare_node's loop, :105-108)
+		if(!decide(outer_count, only_try, decide_ctx)) return -1000;
+	}
 	if(tap) {
 		for(int k = 0; k < 5; k++) tap->owner[k] = (outer_count >= 0 && k < feet.n_points) ? feet.owner[k] : -2;
 		tap->outer_count = outer_count; tap->tries = tries;

@@ -122,6 +122,7 @@ struct gcm_b200_set {
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
 	int inner_min_blocks = 5;   // register budget variant of stage_inner_kernel (4, 5 or 6 blocks/SM)
+	bool use_n2x_generic = false; // generic (border) search through the expanded CSR too (measured: no gain)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
 	std::vector<std::vector<int> > axis_plus0;   // per local zone (local_meshes order), per border slot
@@ -373,6 +374,7 @@ gcm::MeshView make_view(gcm_b200_set* s, float tau)
 	m.n_nodes = (int)dm.N; m.n_tets = (int)dm.T; m.stride = dm.stride;
 	m.u = dm.ucur(); m.mat = dm.mat.p; m.flags = dm.flags.p;
 	m.n2t_off = dm.n2t_off.p; m.n2t = dm.n2t.p; m.tets = dm.tets.p; m.tet_hv = dm.tet_hv.p;
+	m.n2x = s->use_n2x_generic ? dm.n2x.p : nullptr;
 	m.border_slot = dm.border_slot.p; m.basis = dm.basis.p; m.cond_id = dm.cond_id.p; m.contact = nullptr;
 	const float t = s->zones[s->local_zones[0]]->hm.current_time;   // TetrMeshSet::get_current_time()
 	m.tau = tau; m.time = t; m.min_h = 0;
@@ -786,6 +788,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
 	if(const char* e = getenv("GCM_B200_FAST_INNER")) s->fast_inner = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_MB")) s->inner_min_blocks = atoi(e);
+	if(const char* e = getenv("GCM_B200_N2X_GENERIC")) s->use_n2x_generic = atoi(e) != 0;
 	*out = s.release();
 	return 0;
 	GUARD_END

@@ -44,6 +44,7 @@ struct MeshView {
 	const int* flags;        // [n_nodes]
 	const int* n2t_off;      // [n_nodes+1]  node -> incident tets (ascending ids), CSR
 	const int* n2t;
+	const int* n2x;          // [len(n2t)][4] or NULL: CSR entry -> other three vertices (tet order), tet | k << 30
 	const int* tets;         // [n_tets][4]
 	const float* tet_hv;     // [n_tets][2]  (tetr_h, signed volume) -- static geometry
 	const int* border_slot;  // [n_nodes]    index into the border arrays or -1
@@ -63,8 +64,14 @@ struct MeshView {
 
 GCM_HD Vec3 load_xyz(const MeshView& m, int i)
 {
+	Vec3 v;
+#if defined(__CUDA_ARCH__)
+	const float4 q = reinterpret_cast<const float4*>(m.u)[3 * (size_t)i + 2];   // (szz, x, y, z)
+	v.x = q.y; v.y = q.z; v.z = q.w;
+#else
 	const float* r = m.u + (size_t)i * GCM_REC;
-	Vec3 v; v.x = r[9]; v.y = r[10]; v.z = r[11];
+	v.x = r[9]; v.y = r[10]; v.z = r[11];
+#endif
 	return v;
 }
 
@@ -132,8 +139,29 @@ GCM_HD int find_owner_first_ring(const MeshView& m, int base, const Vec3& node_p
 	bool inside_R = false;
 	int e0 = m.n2t_off[base], e1 = m.n2t_off[base + 1];
 	for(int e = e0; e < e1; e++) {
-		int t = m.n2t[e];
-		load_tet(m, t, g);
+		int t;
+		if(m.n2x) {
+			// expanded CSR entry: the other three vertices (tet order) and the position k of `base`;
+			// saves the tets[t] hop and the load of the base node's own coordinates
+			const int* x = m.n2x + 4*(size_t)e;
+#if defined(__CUDA_ARCH__)
+			const int4 q = *reinterpret_cast<const int4*>(x);
+			const int xa = q.x, xb = q.y, xc = q.z, w = q.w;
+#else
+			const int xa = x[0], xb = x[1], xc = x[2], w = x[3];
+#endif
+			const int k = (int)((unsigned)w >> 30);
+			t = w & 0x3fffffff;
+			const Vec3 A = load_xyz(m, xa), B = load_xyz(m, xb), C = load_xyz(m, xc);
+			g.v[0] = k == 0 ? base : xa;  g.p[0] = k == 0 ? X : A;
+			g.v[1] = k == 0 ? xa : (k == 1 ? base : xb);  g.p[1] = k == 0 ? A : (k == 1 ? X : B);
+			g.v[2] = k <= 1 ? xb : (k == 2 ? base : xc);  g.p[2] = k <= 1 ? B : (k == 2 ? X : C);
+			g.v[3] = k == 3 ? base : xc;  g.p[3] = k == 3 ? X : C;
+			g.h = m.tet_hv[2*(size_t)t]; g.vol = m.tet_hv[2*(size_t)t + 1];
+		} else {
+			t = m.n2t[e];
+			load_tet(m, t, g);
+		}
 		int verdict = owner_prefilter(g, base, X, dx, dy, dz, delta);
 		if(verdict == 0)
 			verdict = point_in_tetr(X, dx, dy, dz, delta, g.p[0], g.p[1], g.p[2], g.p[3], g.h, g.vol) ? 1 : -1;

@@ -13,6 +13,7 @@ __device__ __forceinline__ void report_error(int* err, int code, int zone, int n
 
 } // namespace gcm
 #include "gcm_inner.cuh"
+#include "gcm_border_coop.cuh"
 namespace gcm {
 
 // One thread per listed node, one axis stage: TetrMesh_1stOrder::do_next_part_step's two

@@ -289,6 +289,96 @@ GCM_HD int elastic_matrix(float la, float mu, float ro, float qjx, float qjy, fl
 	return ERR_NONE;
 }
 
+// Row-wise access to the same eigensystem, for kernels that spread the rows of one node over the
+// lanes of a warp (stage_border_coop_kernel).  elastic_dirs() = everything elastic_matrix() derives
+// from (la, mu, ro, q) before filling the matrices; elastic_U_row / elastic_U1_row evaluate one row
+// with the very expressions elastic_matrix() uses (tests/test_host_logic.py compares them bitwise).
+struct ElasticDirs {
+	float n[3][3];
+	float l, c1, c2, c3;
+	float N00[6], N01[6], N02[6], N11[6], N12[6], N22[6];
+};
+
+GCM_HD int elastic_dirs(float la, float mu, float ro, float qjx, float qjy, float qjz, ElasticDirs& d)
+{
+	if((la <= 0) || (mu <= 0) || (ro <= 0))
+		return ERR_BAD_RHEOLOGY;
+	if( qjx*qjx + qjy*qjy + qjz*qjz <= 0 )
+		return ERR_BAD_Q;
+	elastic_axes(qjx, qjy, qjz, d.n, &d.l);
+	d.c1 = sqrtf((la+2*mu)/ro);
+	d.c2 = sqrtf(mu/ro);
+	d.c3 = sqrtf(la*la/(ro*(la+2*mu)));
+	create_matrix_N(d.n, 0, 0, d.N00);
+	create_matrix_N(d.n, 0, 1, d.N01);
+	create_matrix_N(d.n, 0, 2, d.N02);
+	create_matrix_N(d.n, 1, 1, d.N11);
+	create_matrix_N(d.n, 1, 2, d.N12);
+	create_matrix_N(d.n, 2, 2, d.N22);
+	return ERR_NONE;
+}
+
+// Lambda(i,i)
+GCM_HD float elastic_L(const ElasticDirs& d, int i)
+{
+	switch(i) {
+	case 0: return d.c1 * d.l;
+	case 1: return -d.c1 * d.l;
+	case 2: case 4: return d.c2 * d.l;
+	case 3: case 5: return -d.c2 * d.l;
+	default: return 0;
+	}
+}
+
+// Row i of Omega (U)
+GCM_HD void elastic_U_row(const ElasticDirs& d, float la, float mu, float ro, int i, float row[9])
+{
+	const float w[6] = {1, 2, 2, 1, 2, 1};
+	const float c1 = d.c1, c2 = d.c2;
+	const int a = i < 2 ? 0 : (i < 4 ? 1 : (i < 6 ? 2 : -1));
+	for(int k = 0; k < 3; k++) row[k] = a >= 0 ? d.n[a][k] : 0;
+	for(int q = 0; q < 6; q++) {
+		float v;
+		switch(i) {
+		case 0: v = -w[q]*d.N00[q]/(c1*ro); break;
+		case 1: v = w[q]*d.N00[q]/(c1*ro); break;
+		case 2: v = -w[q]*d.N01[q]/(c2*ro); break;
+		case 3: v = w[q]*d.N01[q]/(c2*ro); break;
+		case 4: v = -w[q]*d.N02[q]/(c2*ro); break;
+		case 5: v = w[q]*d.N02[q]/(c2*ro); break;
+		case 6: v = w[q]*d.N12[q]; break;
+		case 7: v = w[q]*(d.N11[q]-d.N22[q]); break;
+		default: v = w[q]*(d.N11[q]+d.N22[q]-2*la*d.N00[q]/(la+2*mu)); break;
+		}
+		row[3+q] = v;
+	}
+}
+
+// Row r of Omega^-1 (U1)
+GCM_HD void elastic_U1_row(const ElasticDirs& d, float ro, int r, float row[9])
+{
+	const float c1 = d.c1, c2 = d.c2, c3 = d.c3;
+	if(r < 3) {
+		row[0] = d.n[0][r]; row[1] = d.n[0][r];
+		row[2] = d.n[1][r]; row[3] = d.n[1][r];
+		row[4] = d.n[2][r]; row[5] = d.n[2][r];
+		row[6] = 0; row[7] = 0; row[8] = 0;
+	} else {
+		const int i = r - 3;
+		const float I[6] = {1, 0, 0, 1, 0, 1};
+		row[0] = -ro*((c1-c3)*d.N00[i] + c3*I[i]);
+		row[1] = ro*((c1-c3)*d.N00[i] + c3*I[i]);
+		row[2] = -2*ro*c2*d.N01[i];
+		row[3] = 2*ro*c2*d.N01[i];
+		row[4] = -2*ro*c2*d.N02[i];
+		row[5] = 2*ro*c2*d.N02[i];
+		row[6] = 4*d.N12[i];
+		row[7] = d.N11[i] - d.N22[i];
+		row[8] = I[i] - d.N00[i];
+	}
+	for(int c = 0; c < 9; c++) row[c] /= 2;
+}
+
 // gcm/methods/TetrMethod_Plastic_1stOrder.cpp:51-71 (drop_deviator).  In place: s = values[3..8]
 // (sxx,sxy,sxz,syy,syz,szz); writes only when yielding, exactly as the reference.
 GCM_HD bool drop_deviator(float v[9], float yield_limit)

@@ -276,6 +276,85 @@ struct FeetOut {
 	int n_points;
 };
 
+// One distinct characteristic foot of find_nodes_on_previous_time_layer (:491-671): displacement
+// (bent by alpha / replaced by the "last chance" centre of elements[0]), owner search, interpolation
+// and the inner / outer classification.  val[12] must hold the node's own values on entry
+// (previous_nodes[count] = *cur_node).  alpha is already clamped to <= 1.  Returns a StepError.
+GCM_HD int foot_point(const MeshView& m, const CurNode& cur, int stage, float alpha, float dks, const float ksi[3],
+                      const float Xc[3], const float curc[3], const float tetr_center[3], bool with_material,
+                      bool* inner, int* owner_out, float val[12])
+{
+	float dx[3], dx_ksi[3];
+	float safe_direction[3];
+	for(int j = 0; j < 3; j++)
+		safe_direction[j] = - ( curc[j] - Xc[j] );
+	const bool contact_axis = cur.has_contact_data
+		&& ( (cur.axis_plus[stage] != -1) || (cur.axis_minus[stage] != -1) );
+	for(int j = 0; j < 3; j++)
+		dx_ksi[j] = dks * ksi[j];
+	float safe_direction_projection_modul = 1;
+	float fc[3];
+	for(int j = 0; j < 3; j++) {
+		bool bend;
+		if(contact_axis) {
+			if(cur.axis_plus[stage] != -1) bend = !(dks >= 0);
+			else bend = !(dks <= 0);
+		} else {
+			bend = !(dks >= 0);
+		}
+		if(!bend) {
+			dx[j] = dx_ksi[j];
+		} else {
+			float sdp = safe_direction_projection_modul * safe_direction[j];
+			dx[j] = dx_ksi[j] * (1 - alpha) + sdp * alpha;
+		}
+		dx[j] += ( curc[j] - Xc[j] );
+		fc[j] = Xc[j] + dx[j];
+	}
+	if((double)alpha > 0.95) {
+		if( ! ( cur.is_border && (stage == 0) && (dks > 0) ) )
+			for(int z = 0; z < 3; z++) {
+				dx[z] = tetr_center[z] - Xc[z];
+				fc[z] = Xc[z] + dx[z];
+			}
+	}
+
+	// A foot on the contact side is classified `outer` whatever the search returns (:594-603), so
+	// the search (which the reference still runs, ring after ring into the gap) is skipped;
+	// its tap entry is -3 ("not searched").
+	const bool forced_outer = cur.has_contact_data
+		&& ( ((cur.axis_plus[stage] != -1) && (dks > 0)) || ((cur.axis_minus[stage] != -1) && (dks < 0)) );
+	TetGeom g;
+	bool expand = false;
+	int owner = -3;
+	if(!forced_outer) {
+		owner = find_owner_first_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
+		if(owner < 0 && expand) {
+			owner = find_owner_second_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
+			if(owner < 0 && expand)
+				return ERR_RING_OVERFLOW;   // a third ring would be needed
+		}
+	}
+	*owner_out = owner;
+
+	if( cur.has_contact_data && (cur.axis_plus[stage] != -1) && (dks > 0) ) {
+		*inner = false;
+	} else if( cur.has_contact_data && (cur.axis_minus[stage] != -1) && (dks < 0) ) {
+		*inner = false;
+	} else if(owner >= 0) {
+		int e = interpolate_foot(m, g, fc[0], fc[1], fc[2], val, with_material);
+		if(e) return e;
+		*inner = true;
+	} else if(dks == 0) {
+		*inner = true;   // previous_nodes[count] = *cur_node (already copied)
+	} else if(!cur.is_border) {
+		return ERR_INNER_NO_OWNER;
+	} else {
+		*inner = false;
+	}
+	return ERR_NONE;
+}
+
 // gcm/methods/TetrMethod_Plastic_1stOrder.cpp:430-681.  ksi = random_axis[basis_num].ksi[stage].
 // Returns the outer count, or -(StepError) on a condition the reference throws on.
 GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& cur, int stage,
@@ -301,9 +380,6 @@ GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& c
 		alpha = 1.0;
 
 	int count = 0;
-	float dx[3], dx_ksi[3];
-	const bool contact_axis = cur.has_contact_data
-		&& ( (cur.axis_plus[stage] != -1) || (cur.axis_minus[stage] != -1) );
 
 	for(int i = 0; i < 9; i++)
 	{
@@ -322,68 +398,12 @@ GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& c
 		for(int k = 0; k < 9; k++) out.val[count][k] = cur.val[k];
 		out.val[count][9] = cur.la; out.val[count][10] = cur.mu; out.val[count][11] = cur.rho;
 
-		for(int j = 0; j < 3; j++)
-			dx_ksi[j] = dksi[i] * ksi[j];
-		float safe_direction_projection_modul = 1;
-		float fc[3];
-		for(int j = 0; j < 3; j++) {
-			bool bend;
-			if(contact_axis) {
-				if(cur.axis_plus[stage] != -1) bend = !(dksi[i] >= 0);
-				else bend = !(dksi[i] <= 0);
-			} else {
-				bend = !(dksi[i] >= 0);
-			}
-			if(!bend) {
-				dx[j] = dx_ksi[j];
-			} else {
-				float sdp = safe_direction_projection_modul * safe_direction[j];
-				dx[j] = dx_ksi[j] * (1 - alpha) + sdp * alpha;
-			}
-			dx[j] += ( curc[j] - Xc[j] );
-			fc[j] = Xc[j] + dx[j];
-		}
-		if((double)alpha > 0.95) {
-			if( ! ( cur.is_border && (stage == 0) && (dksi[i] > 0) ) )
-				for(int z = 0; z < 3; z++) {
-					dx[z] = tetr_center[z] - Xc[z];
-					fc[z] = Xc[z] + dx[z];
-				}
-		}
-
-		// A foot on the contact side is classified `outer` whatever the search returns (:594-603), so
-		// the search (which the reference still runs, ring after ring into the gap) is skipped;
-		// its tap entry is -3 ("not searched").
-		const bool forced_outer = cur.has_contact_data
-			&& ( ((cur.axis_plus[stage] != -1) && (dksi[i] > 0)) || ((cur.axis_minus[stage] != -1) && (dksi[i] < 0)) );
-		TetGeom g;
-		bool expand = false;
-		int owner = -3;
-		if(!forced_outer) {
-			owner = find_owner_first_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
-			if(owner < 0 && expand) {
-				owner = find_owner_second_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
-				if(owner < 0 && expand)
-					return -ERR_RING_OVERFLOW;   // a third ring would be needed
-			}
-		}
-		out.owner[count] = owner;
-
-		if( cur.has_contact_data && (cur.axis_plus[stage] != -1) && (dksi[i] > 0) ) {
-			out.inner[i] = false;
-		} else if( cur.has_contact_data && (cur.axis_minus[stage] != -1) && (dksi[i] < 0) ) {
-			out.inner[i] = false;
-		} else if(owner >= 0) {
-			int e = interpolate_foot(m, g, fc[0], fc[1], fc[2], out.val[count], with_material);
-			if(e) return -e;
-			out.inner[i] = true;
-		} else if(dksi[i] == 0) {
-			out.inner[i] = true;   // previous_nodes[count] = *cur_node (already copied)
-		} else if(!cur.is_border) {
-			return -ERR_INNER_NO_OWNER;
-		} else {
-			out.inner[i] = false;
-		}
+		bool inn = false;
+		int own = -1;
+		int fe = foot_point(m, cur, stage, alpha, dksi[i], ksi, Xc, curc, tetr_center, with_material, &inn, &own, out.val[count]);
+		if(fe) return -fe;
+		out.inner[i] = inn;
+		out.owner[count] = own;
 		count++;
 	}
 	out.n_points = count;
@@ -441,6 +461,64 @@ GCM_HD void volume_calc(const float* U, const float* U1, const FeetOut& feet, fl
 	}
 }
 
+// Condition row k (0, 1, 2 = first, second, third outer characteristic) of the five border
+// calculators: the non-zero entries of the row (the caller zeroed it) and its right-hand side.
+// local_n = (n, t1, t2) from create_local_basis(outer_normal), needed by ExternalForce / Velocity.
+GCM_HD void border_cond_row(const BorderCond& bc, int k, const float outer_normal[3], const float local_n[3][3],
+                            double* row, double* rhs)
+{
+	const float scale = bc.scale;
+	switch(bc.type) {
+	case BC_FREE: {
+		// FreeBorderCalculator.cpp:59-74
+		const int c[3][3] = {{3,4,5},{4,6,7},{5,7,8}};
+		row[c[k][0]] = (double)outer_normal[0];
+		row[c[k][1]] = (double)outer_normal[1];
+		row[c[k][2]] = (double)outer_normal[2];
+	} break;
+	case BC_FIXED:
+		// FixedBorderCalculator.cpp:52-58
+		row[k] = 1;
+		break;
+	case BC_EXT_FORCE: {
+		// ExternalForceCalculator.cpp:76-110
+		const float* n0 = local_n[0];
+		if(k == 0) {
+			row[3] = (double)(n0[0] * n0[0]);
+			row[4] = (double)(2 * n0[1] * n0[0]);
+			row[5] = (double)(2 * n0[2] * n0[0]);
+			row[6] = (double)(n0[1] * n0[1]);
+			row[7] = (double)(2 * n0[2] * n0[1]);
+			row[8] = (double)(n0[2] * n0[2]);
+			*rhs = (double)(scale * bc.p_normal);
+		} else {
+			const float* t = local_n[k];
+			row[3] = (double)(n0[0] * t[0]);
+			row[4] = (double)(n0[1] * t[0] + n0[0] * t[1]);
+			row[5] = (double)(n0[2] * t[0] + n0[0] * t[2]);
+			row[6] = (double)(n0[1] * t[1]);
+			row[7] = (double)(n0[2] * t[1] + n0[1] * t[2]);
+			row[8] = (double)(n0[2] * t[2]);
+			*rhs = (double)(scale * bc.p_tangential * (t[0]*bc.dir[0] + t[1]*bc.dir[1] + t[2]*bc.dir[2]));
+		}
+	} break;
+	case BC_EXT_VELOCITY: {
+		// ExternalVelocityCalculator.cpp:70-98
+		const float* t = local_n[k];
+		row[0] = (double)t[0];
+		row[1] = (double)t[1];
+		row[2] = (double)t[2];
+		if(k == 0) *rhs = (double)(scale * bc.p_normal);
+		else *rhs = (double)(scale * bc.p_tangential * (t[0]*bc.dir[0] + t[1]*bc.dir[1] + t[2]*bc.dir[2]));
+	} break;
+	case BC_EXT_VALUES:
+		// ExternalValuesCalculator.cpp:63-78
+		row[bc.vars_index[k]] = 1;
+		*rhs = (double)bc.vars_values[k];
+		break;
+	}
+}
+
 // The five border calculators of gcm/methods/border/*.cpp behind one switch:
 // inner rows = Omega rows, the three outer rows (in index order) = condition rows.
 // outer_normal = basis.ksi[stage] (TetrMethod_Plastic_1stOrder.cpp:289-297).
@@ -466,55 +544,7 @@ GCM_HD void border_calc(const BorderCond& bc, const float* U, const FeetOut& fee
 		const int k = 3 - outer_count;   // 0, 1, 2: which condition row
 		if(outer_count <= 0) continue;
 		outer_count--;
-		switch(bc.type) {
-		case BC_FREE: {
-			// FreeBorderCalculator.cpp:59-74
-			const int c[3][3] = {{3,4,5},{4,6,7},{5,7,8}};
-			A[i*9+c[k][0]] = (double)outer_normal[0];
-			A[i*9+c[k][1]] = (double)outer_normal[1];
-			A[i*9+c[k][2]] = (double)outer_normal[2];
-		} break;
-		case BC_FIXED:
-			// FixedBorderCalculator.cpp:52-58
-			A[i*9+k] = 1;
-			break;
-		case BC_EXT_FORCE: {
-			// ExternalForceCalculator.cpp:76-110
-			const float* n0 = local_n[0];
-			if(k == 0) {
-				A[i*9+3] = (double)(n0[0] * n0[0]);
-				A[i*9+4] = (double)(2 * n0[1] * n0[0]);
-				A[i*9+5] = (double)(2 * n0[2] * n0[0]);
-				A[i*9+6] = (double)(n0[1] * n0[1]);
-				A[i*9+7] = (double)(2 * n0[2] * n0[1]);
-				A[i*9+8] = (double)(n0[2] * n0[2]);
-				b[i] = (double)(scale * bc.p_normal);
-			} else {
-				const float* t = local_n[k];
-				A[i*9+3] = (double)(n0[0] * t[0]);
-				A[i*9+4] = (double)(n0[1] * t[0] + n0[0] * t[1]);
-				A[i*9+5] = (double)(n0[2] * t[0] + n0[0] * t[2]);
-				A[i*9+6] = (double)(n0[1] * t[1]);
-				A[i*9+7] = (double)(n0[2] * t[1] + n0[1] * t[2]);
-				A[i*9+8] = (double)(n0[2] * t[2]);
-				b[i] = (double)(scale * bc.p_tangential * (t[0]*bc.dir[0] + t[1]*bc.dir[1] + t[2]*bc.dir[2]));
-			}
-		} break;
-		case BC_EXT_VELOCITY: {
-			// ExternalVelocityCalculator.cpp:70-98
-			const float* t = local_n[k];
-			A[i*9+0] = (double)t[0];
-			A[i*9+1] = (double)t[1];
-			A[i*9+2] = (double)t[2];
-			if(k == 0) b[i] = (double)(scale * bc.p_normal);
-			else b[i] = (double)(scale * bc.p_tangential * (t[0]*bc.dir[0] + t[1]*bc.dir[1] + t[2]*bc.dir[2]));
-		} break;
-		case BC_EXT_VALUES:
-			// ExternalValuesCalculator.cpp:63-78
-			A[i*9+bc.vars_index[k]] = 1;
-			b[i] = (double)bc.vars_values[k];
-			break;
-		}
+		border_cond_row(bc, k, outer_normal, local_n, A + i*9, &b[i]);
 	}
 	lu_solve<9>(A, b);
 	for(int j = 0; j < 9; j++)

@@ -82,3 +82,45 @@ def test_create_cube_counts():
     h = np.nonzero(zs[0].placement == 0)[0]
     assert np.array_equal(zs[0].coords[h], zs[1].coords[zs[0].remote_num[h]])
     assert np.all(zs[1].placement[zs[0].remote_num[h]] == 1)
+
+
+ROWS_SRC = r'''
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+#include "gcm_math.cuh"
+int main() {
+    srand(7);
+    for(int it = 0; it < 2000; it++) {
+        float la = 1e3f + (rand() % 100000) * 7e4f, mu = 1e3f + (rand() % 100000) * 1e4f, ro = 1.f + (rand() % 10000) * 780.f;
+        float q[3] = {(rand() % 2001 - 1000) / 1000.f, (rand() % 2001 - 1000) / 1000.f, (rand() % 2001 - 1000) / 1000.f};
+        if(it < 3) { q[0] = it == 0; q[1] = it == 1; q[2] = it == 2; }
+        if(q[0] == 0 && q[1] == 0 && q[2] == 0) continue;
+        float L[9], U[81], U1[81], row[9];
+        if(gcm::elastic_matrix(la, mu, ro, q[0], q[1], q[2], L, U, U1)) continue;
+        gcm::ElasticDirs d;
+        if(gcm::elastic_dirs(la, mu, ro, q[0], q[1], q[2], d)) { printf("dirs failed\n"); return 1; }
+        for(int i = 0; i < 9; i++) {
+            float li = gcm::elastic_L(d, i);
+            if(memcmp(&li, &L[i], 4) && !(li == 0 && L[i] == 0)) { printf("L mismatch %d\n", i); return 1; }
+            gcm::elastic_U_row(d, la, mu, ro, i, row);
+            for(int j = 0; j < 9; j++) if(row[j] != U[i*9+j]) { printf("U mismatch %d %d\n", i, j); return 1; }
+            gcm::elastic_U1_row(d, ro, i, row);
+            for(int j = 0; j < 9; j++) if(row[j] != U1[i*9+j]) { printf("U1 mismatch %d %d\n", i, j); return 1; }
+        }
+    }
+    printf("OK\n"); return 0;
+}
+'''
+
+
+def test_elastic_row_functions_match_full_matrix(built):
+    """elastic_U_row / elastic_U1_row / elastic_L (used by the half-warp border kernel) == elastic_matrix."""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "r.cpp")
+        open(src, "w").write(ROWS_SRC)
+        exe = os.path.join(d, "r")
+        csrc = os.path.join(ROOT, "gcm-necro_b200", "csrc")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", csrc, src, "-o", exe], check=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout

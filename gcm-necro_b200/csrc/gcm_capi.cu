@@ -124,6 +124,7 @@ struct gcm_b200_set {
 	int inner_min_blocks = 5;   // register budget variant of stage_inner_kernel (4, 5 or 6 blocks/SM)
 	bool coop_border = false;    // flat border nodes: 16 lanes per node (gcm_border_coop.cuh) instead of 1 thread;
 	                             // bit-identical but measured slower (redundant per-lane work), kept as an option
+	bool lean_border = true;     // flat border nodes through node_stage_border_lean (row-wise eigensystem)
 	int border_min_blocks = 3;   // register budget variant of the per-thread border kernel (3..8 blocks of 128 / SM)
 	bool use_n2x_generic = false; // generic (border) search through the expanded CSR too (measured: no gain)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
@@ -549,6 +550,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 		}
 		if(nb) {
 			if(s->coop_border) gcm::stage_border_coop_kernel<<<(int)(((size_t)nb * 16 + 127) / 128), 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
+			else if(s->lean_border) gcm::stage_border_lean_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 			else if(s->border_min_blocks == 4) gcm::stage_generic_kernel_mb<4><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 			else if(s->border_min_blocks == 5) gcm::stage_generic_kernel_mb<5><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 			else if(s->border_min_blocks == 6) gcm::stage_generic_kernel_mb<6><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
@@ -798,6 +800,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_INNER_MB")) s->inner_min_blocks = atoi(e);
 	if(const char* e = getenv("GCM_B200_COOP_BORDER")) s->coop_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_MB")) s->border_min_blocks = atoi(e);
+	if(const char* e = getenv("GCM_B200_LEAN_BORDER")) s->lean_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_N2X_GENERIC")) s->use_n2x_generic = atoi(e) != 0;
 	*out = s.release();
 	return 0;

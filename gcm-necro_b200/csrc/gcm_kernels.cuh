@@ -55,6 +55,24 @@ stage_generic_kernel_mb(const __grid_constant__ MeshView m, const int* __restric
 		un[(size_t)node * GCM_REC + k] = out[k];
 }
 
+// Border nodes, one thread per node, small-footprint routine (node_stage_border_lean).
+__global__ void __launch_bounds__(128, 4)
+stage_border_lean_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
+                         int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
+{
+	int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	int node = list[idx];
+	float out[9];
+	StageTap t;
+	int e = node_stage_border_lean(m, node, stage, out, tap ? &t : nullptr);
+	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
+	if(e) { report_error(err, e, zone, node, stage); return; }
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		un[(size_t)node * GCM_REC + k] = out[k];
+}
+
 // Border nodes on sharp edges / corners usually burn all 11 alpha tries of prepare_node
 // (TetrMethod_Plastic_1stOrder.cpp:105-108) on their tangential axes -- one thread doing them in
 // sequence is the longest thread of the whole stage by an order of magnitude.  The tries are

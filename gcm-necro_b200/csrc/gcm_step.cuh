@@ -646,6 +646,144 @@ GCM_HD int node_stage_nocontact_t(const MeshView& m, int node, int stage, float 
 	return ERR_NONE;
 }
 
+// Out-of-line copy of the general routine for rarely taken fallbacks (keeps its 1.7 KB of arrays
+// off the caller's stack frame).
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+static inline
+#endif
+int node_stage_nocontact_cold(const MeshView& m, int node, int stage, float out[9], StageTap* tap)
+{
+	return node_stage_nocontact(m, node, stage, out, tap);
+}
+
+// Border node without contact, small-footprint variant of node_stage_nocontact: the same calls
+// (foot_point per distinct foot, the retry loop of prepare_node, the calculators) but Omega and
+// Omega^-1 are produced row by row (elastic_U_row / elastic_U1_row, bitwise equal to the entries of
+// elastic_matrix) instead of as two 81-float arrays, and the five-point pattern of the
+// characteristic speeds is assumed (checked; anything else goes to the general routine).  The
+// thread's stack shrinks from ~1.7 KB to ~0.4 KB on the two tangential stages (outer == 0), which
+// is what keeps the border launch out of L2-resident local memory.
+GCM_HD int node_stage_border_lean(const MeshView& m, int node, int stage, float out[9], StageTap* tap)
+{
+	CurNode cur;
+	cur.base = node;
+	cur.pos = load_xyz(m, node);
+	for(int k = 0; k < 9; k++) {
+		float v = m.u[(size_t)node * GCM_REC + k];
+		if(isnan(v) || isinf(v)) return ERR_NAN;
+		cur.val[k] = v;
+	}
+	cur.la = m.mat[node]; cur.mu = m.mat[m.stride + node]; cur.rho = m.mat[2*m.stride + node];
+	cur.is_border = true;
+	cur.has_contact_data = true;
+	for(int k = 0; k < 3; k++) { cur.axis_plus[k] = -1; cur.axis_minus[k] = -1; }
+	const int slot = m.border_slot[node];
+	const float* basis = m.basis + 9*(size_t)slot;
+	const float ksi[3] = {basis[3*stage], basis[3*stage + 1], basis[3*stage + 2]};
+
+	ElasticDirs d;
+	{
+		int e = elastic_dirs(cur.la, cur.mu, cur.rho, ksi[0], ksi[1], ksi[2], d);
+		if(e) return e;
+	}
+	// dksi[i] = - L(i,i) * tau of the five distinct points (characteristics 0, 1, 2, 3, 6)
+	float dk[5];
+	for(int p = 0; p < 5; p++) dk[p] = - elastic_L(d, p < 4 ? p : 6) * m.tau;
+	bool usual = true;
+	for(int p = 1; p < 5; p++)
+		for(int q = 0; q < p; q++)
+			if( (double)fabsf(dk[p] - dk[q]) <= 0.01 * (double)fabsf(dk[p] + dk[q]) ) usual = false;
+	if(!usual) return node_stage_nocontact_cold(m, node, stage, out, tap);
+
+	const float Xc[3] = {cur.pos.x, cur.pos.y, cur.pos.z};
+	float tetr_center[3];
+	{
+		int tetr_num = m.n2t[m.n2t_off[node]];
+		const int* tv = m.tets + 4*(size_t)tetr_num;
+		Vec3 a = load_xyz(m, tv[0]), b = load_xyz(m, tv[1]), c = load_xyz(m, tv[2]), e = load_xyz(m, tv[3]);
+		tetr_center[0] = ( a.x + b.x + c.x + e.x ) / 4;
+		tetr_center[1] = ( a.y + b.y + c.y + e.y ) / 4;
+		tetr_center[2] = ( a.z + b.z + c.z + e.z ) / 4;
+	}
+	float val[5][9];
+	bool inn[5];
+	int own[5];
+	int outer_count = 0, tries = 0;
+	float alpha = 0;
+	do {
+		const float a = ((double)alpha > 1.0) ? 1.0f : alpha;
+		int ferr = 0;
+		for(int p = 0; p < 5 && !ferr; p++) {
+			float v12[12];
+			for(int k = 0; k < 9; k++) v12[k] = cur.val[k];
+			v12[9] = cur.la; v12[10] = cur.mu; v12[11] = cur.rho;
+			inn[p] = true; own[p] = -2;
+			ferr = foot_point(m, cur, stage, a, dk[p], ksi, Xc, Xc, tetr_center, false, &inn[p], &own[p], v12);
+			for(int k = 0; k < 9; k++) val[p][k] = v12[k];
+		}
+		tries++;
+		if(ferr) {
+			if(tap) { for(int k = 0; k < 5; k++) tap->owner[k] = -2; tap->outer_count = -ferr; tap->tries = tries; }
+			return ferr;
+		}
+		outer_count = (inn[0] ? 0 : 1) + (inn[1] ? 0 : 1) + (inn[2] ? 0 : 2) + (inn[3] ? 0 : 2) + (inn[4] ? 0 : 3);
+		alpha = (float)((double)alpha + 0.1);
+	} while( (outer_count != 0) && (outer_count != 3) && ((double)alpha < 1.01) );
+	if(tap) {
+		for(int k = 0; k < 5; k++) tap->owner[k] = own[k];
+		tap->outer_count = outer_count; tap->tries = tries;
+	}
+	if(outer_count != 0 && outer_count != 3) return ERR_OUTER_COUNT;
+
+	const int pp[9] = {0, 1, 2, 3, 2, 3, 4, 4, 4};
+	float omega[9];
+	float row[9];
+	if(outer_count == 0) {
+		for(int i = 0; i < 9; i++) {
+			elastic_U_row(d, cur.la, cur.mu, cur.rho, i, row);
+			omega[i] = omega_row(row, 0, val[pp[i]]);
+		}
+		for(int r = 0; r < 9; r++) {
+			elastic_U1_row(d, cur.rho, r, row);
+			float v = 0;
+			for(int j = 0; j < 9; j++) v += row[j] * omega[j];
+			out[r] = v;
+		}
+		return ERR_NONE;
+	}
+	// outer_count == 3: border calculators
+	BorderCond def;
+	def.type = BC_FREE; def.scale = 1; def.active = 1;
+	const BorderCond* bc = &def;
+	int cid = m.cond_id ? m.cond_id[slot] : -1;
+	if(cid >= 0 && m.conds[cid].active) bc = &m.conds[cid];
+	float local_n[3][3];
+	local_n[0][0] = ksi[0]; local_n[0][1] = ksi[1]; local_n[0][2] = ksi[2];
+	if(bc->type == BC_EXT_FORCE || bc->type == BC_EXT_VELOCITY)
+		create_local_basis(local_n[0], local_n[1], local_n[2]);
+	double A[81];
+	double b[9];
+	int k = 0;
+	for(int i = 0; i < 9; i++) {
+		if(inn[pp[i]]) {
+			elastic_U_row(d, cur.la, cur.mu, cur.rho, i, row);
+			b[i] = (double)omega_row(row, 0, val[pp[i]]);
+			for(int j = 0; j < 9; j++) A[i*9+j] = (double)row[j];
+		} else {
+			b[i] = 0;
+			for(int j = 0; j < 9; j++) A[i*9+j] = 0;
+			if(k < 3) border_cond_row(*bc, k, ksi, local_n, A + i*9, &b[i]);
+			k++;
+		}
+	}
+	lu_solve<9>(A, b);
+	for(int j = 0; j < 9; j++)
+		out[j] = (float)b[j];
+	return ERR_NONE;
+}
+
 // ---- two-body contact ------------------------------------------------------------------------
 // A virtual node as the device sees it (built from gcmh::VirtNodeHost): position on the partner
 // body's border face, the 13 values interpolated there at discovery time, and the partner-mesh

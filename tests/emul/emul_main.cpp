@@ -77,6 +77,7 @@ int main(int argc, char** argv)
 		else die("unknown argument " + s);
 	}
 	const int NZ = (int)mesh_files.size();
+	const bool lean_border = !(getenv("GCM_EMUL_LEAN_BORDER") && atoi(getenv("GCM_EMUL_LEAN_BORDER")) == 0);
 	vector<std::unique_ptr<Z>> zs;
 	for(int z = 0; z < NZ; z++) {
 		FILE* f = fopen(mesh_files[z].c_str(), "rb"); if(!f) die("cannot open mesh");
@@ -225,7 +226,9 @@ int main(int argc, char** argv)
 						float vo[9]; bool vw = false;
 						e = gcm::node_stage_contact(m, mv, i, vn, vidx, stage, &hm.normals[3*(size_t)slot], contact_calc == "friction" ? 1 : 0, o, &t, vo, &vw, step == 0);
 						if(vw) for(int k = 0; k < 9; k++) vh.values[k] = vo[k];
-					} else
+					} else if(slot >= 0 && lean_border)
+						e = gcm::node_stage_border_lean(m, i, stage, o, &t);
+					else
 						e = gcm::node_stage_nocontact(m, i, stage, o, &t);
 					if(e) {
 						#pragma omp critical

@@ -79,7 +79,7 @@ struct DeviceMesh {
 	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0;
 	size_t n_fast = 0, n_generic = 0, n_inner = 0;
 	DevBuf<float> u0, u1, mat, tet_hv, basis, normals, w0, aos, mat_tab;
-	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x;
+	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, didx;
 	DevBuf<int> sharp_list, flat_list, fast_list, generic_list, inner_list;
 	size_t n_sharp = 0, n_flat = 0;
 	DevBuf<unsigned char> mat_id;
@@ -121,11 +121,12 @@ struct gcm_b200_set {
 	float time_step = 0.002f;
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
-	int inner_min_blocks = 5;   // register budget variant of stage_inner_kernel (4, 5 or 6 blocks/SM)
+	int inner_min_blocks = 6;   // register budget variant of stage_inner_kernel (4, 5 or 6 blocks/SM)
 	bool coop_border = false;    // flat border nodes: 16 lanes per node (gcm_border_coop.cuh) instead of 1 thread;
 	                             // bit-identical but measured slower (redundant per-lane work), kept as an option
-	bool lean_border = true;     // flat border nodes through node_stage_border_lean (row-wise eigensystem)
+	bool lean_border = false;    // flat border nodes through node_stage_border_lean (row-wise eigensystem; measured 14 % slower)
 	int border_min_blocks = 3;   // register budget variant of the per-thread border kernel (3..8 blocks of 128 / SM)
+	bool dir_index = true;       // inner kernel scans through the angular candidate index (gcm_inner.cuh)
 	bool use_n2x_generic = false; // generic (border) search through the expanded CSR too (measured: no gain)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
@@ -367,6 +368,20 @@ void upload_mesh(gcm_b200_set* s)
 	CK(cudaStreamSynchronize(st));
 	dm.cur = 0;
 	dm.ready = true;
+	if(s->dir_index && nf) {
+		// angular candidate index of the inner kernel: three planes of N uint4, built on the device
+		dm.didx.alloc(12 * N);
+		CK(cudaMemsetAsync(dm.didx.p, 0, 12 * N * sizeof(int), st));
+		const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
+		uint4* dx = reinterpret_cast<uint4*>(dm.didx.p);
+		const int g = (int)((nf + 127) / 128);
+		gcm::build_dir_index_kernel<0><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx);
+		gcm::build_dir_index_kernel<1><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + N);
+		gcm::build_dir_index_kernel<2><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + 2 * N);
+		s->launches += 3;
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(st));
+	}
 	for(int zi : s->local_zones) upload_values(s, *s->zones[zi]);
 }
 
@@ -581,11 +596,13 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 			const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
 			const int* fl = dm.fast_list.p + (z ? z->fast_off : 0);
 			const dim3 grid((nf + 127) / 128), block(128);
-#define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x)
-#define GCM_LAUNCH_INNER_MB(MB_) do { if(stage == 0) GCM_LAUNCH_INNER(0, MB_); else if(stage == 1) GCM_LAUNCH_INNER(1, MB_); else GCM_LAUNCH_INNER(2, MB_); } while(0)
-			if(s->inner_min_blocks == 4) GCM_LAUNCH_INNER_MB(4);
-			else if(s->inner_min_blocks == 6) GCM_LAUNCH_INNER_MB(6);
-			else GCM_LAUNCH_INNER_MB(5);
+			const uint4* dx = s->dir_index ? reinterpret_cast<const uint4*>(dm.didx.p) + (size_t)stage * dm.N : nullptr;
+#define GCM_LAUNCH_INNER(S_, MB_, IDX_) gcm::stage_inner_kernel<S_, MB_, IDX_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x, dx)
+#define GCM_LAUNCH_INNER_MB(MB_, IDX_) do { if(stage == 0) GCM_LAUNCH_INNER(0, MB_, IDX_); else if(stage == 1) GCM_LAUNCH_INNER(1, MB_, IDX_); else GCM_LAUNCH_INNER(2, MB_, IDX_); } while(0)
+			if(!dx) GCM_LAUNCH_INNER_MB(5, false);
+			else if(s->inner_min_blocks == 4) GCM_LAUNCH_INNER_MB(4, true);
+			else if(s->inner_min_blocks == 6) GCM_LAUNCH_INNER_MB(6, true);
+			else GCM_LAUNCH_INNER_MB(5, true);
 			s->launches++;
 		}
 	}
@@ -801,6 +818,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_COOP_BORDER")) s->coop_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_MB")) s->border_min_blocks = atoi(e);
 	if(const char* e = getenv("GCM_B200_LEAN_BORDER")) s->lean_border = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_DIR_INDEX")) s->dir_index = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_N2X_GENERIC")) s->use_n2x_generic = atoi(e) != 0;
 	*out = s.release();
 	return 0;

@@ -223,14 +223,56 @@ __device__ __forceinline__ void load_values(const Cand& c, const float4* __restr
 	vc[0] = c0.x; vc[1] = c0.y; vc[2] = c0.z; vc[3] = c0.w; vc[4] = c1.x; vc[5] = c1.y; vc[6] = c1.z; vc[7] = c1.w; vc[8] = c.qc.x;
 }
 
+// Angular candidate index, built once on the device after the mesh upload.  The pre-filter's
+// verdict for a candidate depends on static data only (the vertex coordinates, h(tet) and the
+// SIGN of the displacement along axis S -- the length is rescaled away, see above), so the
+// candidates it rejects ("certainly fails") are the same on every step: their positions in the
+// node's list are cleared from a 32-bit mask per (node, axis, sign) and the per-step scan visits
+// the surviving positions in list order with the unchanged pre-filter / exact predicate.  Same
+// function, same inputs, same compiler flags -> the skipped verdicts are exactly the -1 ones.
+//   didx[S * n_nodes + node] = (mask for dksi < 0, mask for dksi > 0, min h over the list, w0)
+// The step-time guard  0 < delta < 0.99 * min h  implies the pre-filter's own precondition
+// delta < 0.99 h(tet) for every candidate (rounding of h * 0.99 is monotone in h); a node that
+// fails it, or has more than 32 candidates (min h stored as -1), takes the literal per-node routine.
+template<int S>
+__global__ void __launch_bounds__(128)
+build_dir_index_kernel(const float* __restrict__ u, const int* __restrict__ n2t_off, const float* __restrict__ tet_hv,
+                       const int* __restrict__ list, int n_list, const float* __restrict__ w0,
+                       const int4* __restrict__ n2x, uint4* __restrict__ didx)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u);
+	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(tet_hv);
+	const float4 o2 = rec[3 * (size_t)node + 2];
+	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
+	const int e0 = n2t_off[node], e1 = n2t_off[node + 1];
+	unsigned mm = 0, mp = 0;
+	float hmin = -1.0f;
+	if(e1 - e0 <= 32) {
+		for(int e = e0; e < e1; e++) {
+			Cand c;
+			load_cand<S>(c, __ldg(n2x + e), rec, hv2);
+			hmin = (e == e0 || c.h < hmin) ? c.h : hmin;
+			const bool shaped = c.vol > 0;
+			if(!(shaped && prefilter<S>(c, X, -1.0f) < 0)) mm |= 1u << (e - e0);
+			if(!(shaped && prefilter<S>(c, X, 1.0f) < 0)) mp |= 1u << (e - e0);
+		}
+	}
+	didx[node] = make_uint4(mm, mp, __float_as_uint(hmin), __float_as_uint(w0[node]));
+}
+
 // One thread per listed inner node, axis stage S.  mat_id == nullptr: single material (id 0).
 // MB = minimum resident blocks per SM the register allocation is tuned for (occupancy vs spills).
-template<int S, int MB>
+// IDX: scan through the angular candidate index (didx = plane S of it); otherwise scan the whole
+// candidate list (didx unused, w0 from its own array).
+template<int S, int MB, bool IDX>
 __global__ void __launch_bounds__(128, MB)
 stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
                    float* __restrict__ un, int* err, int zone, StageTap* tap,
                    const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
-                   const float* __restrict__ w0, const int4* __restrict__ n2x)
+                   const float* __restrict__ w0, const int4* __restrict__ n2x, const uint4* __restrict__ didx)
 {
 	__shared__ float sU[GCM_MAX_MATERIALS][81];
 	__shared__ float sU1[GCM_MAX_MATERIALS][81];
@@ -257,11 +299,25 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	for(int k = 0; k < 9; k++) bad |= (isnan(own[k]) || isinf(own[k]));
 	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
 
-	const int e0 = m.n2t_off[node], e1 = m.n2t_off[node + 1];
+	const int e0 = m.n2t_off[node], e1 = IDX ? 0 : m.n2t_off[node + 1];
 	const float* U = sU[mid];
 	const float* U1 = sU1[mid];
 	float omega[9];
 	StageTap tp;
+	uint4 ix = make_uint4(0u, 0u, 0u, 0u);
+	if(IDX) {
+		ix = __ldg(didx + node);
+		// all four displacements must be rescaled by every candidate (then the index is valid)
+		const double h99 = (double)__uint_as_float(ix.z) * 0.99;
+		bool ok = true;
+		#pragma unroll
+		for(int q = 0; q < 4; q++) {
+			const float dk = - sL[mid][q] * m.tau;
+			const float de = sqrtf(dk * dk);
+			ok = ok && de > 0 && (double)de < h99;
+		}
+		if(!ok) { inner_node_generic(m, node, S, un, err, zone, tap); return; }
+	}
 
 	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
 	#pragma unroll
@@ -273,14 +329,22 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		Cand c;
 		int owner = -1;
 		bool cold = false;
-		int4 xn = __ldg(n2x + e0);
-		for(int e = e0; e < e1; e++) {
-			const int4 x = xn;
-			if(e + 1 < e1) xn = __ldg(n2x + e + 1);
+		unsigned mask = dir == 0 ? ix.x : ix.y;
+		int4 xn = make_int4(0, 0, 0, 0);
+		if(!IDX) xn = __ldg(n2x + e0);
+		for(int e = e0; IDX ? mask != 0 : e < e1; e++) {
+			int4 x = xn;
+			if(IDX) {
+				// surviving positions in list order; the first one is the owner almost always
+				x = __ldg(n2x + e0 + __ffs(mask) - 1);
+				mask &= mask - 1;
+			} else {
+				if(e + 1 < e1) xn = __ldg(n2x + e + 1);
+			}
 			load_cand<S>(c, x, rec, hv2);
 			const double h99 = (double)c.h * 0.99;
 			int v1 = 0;
-			if(c.vol > 0 && de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99)
+			if(c.vol > 0 && (IDX || (de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99)))
 				v1 = prefilter<S>(c, X, sgn);
 			if(v1 == 0) {
 				const bool in1 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
@@ -325,7 +389,7 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every
 	// factor but the node's own is exactly 0, the own one is the static weight w0
 	float vz[9];
-	const float wz = w0[node];
+	const float wz = IDX ? __uint_as_float(ix.w) : w0[node];
 	#pragma unroll
 	for(int k = 0; k < 9; k++) vz[k] = own[k] * wz;
 	if(tap) {

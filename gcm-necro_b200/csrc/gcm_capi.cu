@@ -121,12 +121,13 @@ struct gcm_b200_set {
 	float time_step = 0.002f;
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
-	int inner_min_blocks = 6;   // register budget variant of stage_inner_kernel (4, 5 or 6 blocks/SM)
 	bool coop_border = false;    // flat border nodes: 16 lanes per node (gcm_border_coop.cuh) instead of 1 thread;
 	                             // bit-identical but measured slower (redundant per-lane work), kept as an option
 	bool lean_border = false;    // flat border nodes through node_stage_border_lean (row-wise eigensystem; measured 14 % slower)
 	int border_min_blocks = 3;   // register budget variant of the per-thread border kernel (3..8 blocks of 128 / SM)
 	bool dir_index = true;       // inner kernel scans through the angular candidate index (gcm_inner.cuh)
+	int direct_min_blocks = 4;   // register budget variant of stage_inner_direct_kernel (3, 4, 5 or 6 blocks of 128 / SM)
+	int direct_prefetch = 0;     // 1: records of both directions' first survivors requested together, 0: one direction at a time
 	bool use_n2x_generic = false; // generic (border) search through the expanded CSR too (measured: no gain)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
@@ -369,15 +370,15 @@ void upload_mesh(gcm_b200_set* s)
 	dm.cur = 0;
 	dm.ready = true;
 	if(s->dir_index && nf) {
-		// angular candidate index of the inner kernel: three planes of N uint4, built on the device
-		dm.didx.alloc(12 * N);
-		CK(cudaMemsetAsync(dm.didx.p, 0, 12 * N * sizeof(int), st));
+		// angular candidate index of the inner kernel: three planes of N 64-byte entries, built on the device
+		dm.didx.alloc(3 * 4 * GCM_DIDX_QUADS * N);
+		CK(cudaMemsetAsync(dm.didx.p, 0, 3 * 4 * GCM_DIDX_QUADS * N * sizeof(int), st));
 		const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
 		uint4* dx = reinterpret_cast<uint4*>(dm.didx.p);
 		const int g = (int)((nf + 127) / 128);
 		gcm::build_dir_index_kernel<0><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx);
-		gcm::build_dir_index_kernel<1><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + N);
-		gcm::build_dir_index_kernel<2><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + 2 * N);
+		gcm::build_dir_index_kernel<1><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + GCM_DIDX_QUADS * N);
+		gcm::build_dir_index_kernel<2><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + 2 * GCM_DIDX_QUADS * N);
 		s->launches += 3;
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(st));
@@ -596,13 +597,22 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 			const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
 			const int* fl = dm.fast_list.p + (z ? z->fast_off : 0);
 			const dim3 grid((nf + 127) / 128), block(128);
-			const uint4* dx = s->dir_index ? reinterpret_cast<const uint4*>(dm.didx.p) + (size_t)stage * dm.N : nullptr;
-#define GCM_LAUNCH_INNER(S_, MB_, IDX_) gcm::stage_inner_kernel<S_, MB_, IDX_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x, dx)
-#define GCM_LAUNCH_INNER_MB(MB_, IDX_) do { if(stage == 0) GCM_LAUNCH_INNER(0, MB_, IDX_); else if(stage == 1) GCM_LAUNCH_INNER(1, MB_, IDX_); else GCM_LAUNCH_INNER(2, MB_, IDX_); } while(0)
-			if(!dx) GCM_LAUNCH_INNER_MB(5, false);
-			else if(s->inner_min_blocks == 4) GCM_LAUNCH_INNER_MB(4, true);
-			else if(s->inner_min_blocks == 6) GCM_LAUNCH_INNER_MB(6, true);
-			else GCM_LAUNCH_INNER_MB(5, true);
+			const uint4* dx = s->dir_index ? reinterpret_cast<const uint4*>(dm.didx.p) + (size_t)stage * GCM_DIDX_QUADS * dm.N : nullptr;
+#define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x)
+#define GCM_LAUNCH_DIRECT(S_, MB_, PF_) gcm::stage_inner_direct_kernel<S_, MB_, PF_><<<dgrid, block, 0, s->stream>>>(m, nbeg, nrange, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, n2x, dx)
+#define GCM_LAUNCH_DIRECT_S(MB_, PF_) do { if(stage == 0) GCM_LAUNCH_DIRECT(0, MB_, PF_); else if(stage == 1) GCM_LAUNCH_DIRECT(1, MB_, PF_); else GCM_LAUNCH_DIRECT(2, MB_, PF_); } while(0)
+#define GCM_LAUNCH_DIRECT_MB(MB_) do { if(s->direct_prefetch == 0) GCM_LAUNCH_DIRECT_S(MB_, 0); else GCM_LAUNCH_DIRECT_S(MB_, 1); } while(0)
+			const int nbeg = (int)(z ? z->node_off : 0), nrange = (int)(z ? (size_t)z->hm.N : dm.N);
+			const dim3 dgrid((unsigned)((nrange + 127) / 128));
+			if(dx) {
+				if(s->direct_min_blocks == 3) GCM_LAUNCH_DIRECT_MB(3);
+				else if(s->direct_min_blocks == 5) GCM_LAUNCH_DIRECT_MB(5);
+				else if(s->direct_min_blocks == 6) GCM_LAUNCH_DIRECT_MB(6);
+				else GCM_LAUNCH_DIRECT_MB(4);
+			}
+			else if(stage == 0) GCM_LAUNCH_INNER(0, 5);
+			else if(stage == 1) GCM_LAUNCH_INNER(1, 5);
+			else GCM_LAUNCH_INNER(2, 5);
 			s->launches++;
 		}
 	}
@@ -814,11 +824,12 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	s->rng.seed(1);   // libc default when srand() was never called
 	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
 	if(const char* e = getenv("GCM_B200_FAST_INNER")) s->fast_inner = atoi(e) != 0;
-	if(const char* e = getenv("GCM_B200_INNER_MB")) s->inner_min_blocks = atoi(e);
 	if(const char* e = getenv("GCM_B200_COOP_BORDER")) s->coop_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_MB")) s->border_min_blocks = atoi(e);
 	if(const char* e = getenv("GCM_B200_LEAN_BORDER")) s->lean_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_DIR_INDEX")) s->dir_index = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_DIRECT_MB")) s->direct_min_blocks = atoi(e);
+	if(const char* e = getenv("GCM_B200_DIRECT_PF")) s->direct_prefetch = atoi(e);
 	if(const char* e = getenv("GCM_B200_N2X_GENERIC")) s->use_n2x_generic = atoi(e) != 0;
 	*out = s.release();
 	return 0;

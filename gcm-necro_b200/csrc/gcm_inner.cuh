@@ -223,56 +223,16 @@ __device__ __forceinline__ void load_values(const Cand& c, const float4* __restr
 	vc[0] = c0.x; vc[1] = c0.y; vc[2] = c0.z; vc[3] = c0.w; vc[4] = c1.x; vc[5] = c1.y; vc[6] = c1.z; vc[7] = c1.w; vc[8] = c.qc.x;
 }
 
-// Angular candidate index, built once on the device after the mesh upload.  The pre-filter's
-// verdict for a candidate depends on static data only (the vertex coordinates, h(tet) and the
-// SIGN of the displacement along axis S -- the length is rescaled away, see above), so the
-// candidates it rejects ("certainly fails") are the same on every step: their positions in the
-// node's list are cleared from a 32-bit mask per (node, axis, sign) and the per-step scan visits
-// the surviving positions in list order with the unchanged pre-filter / exact predicate.  Same
-// function, same inputs, same compiler flags -> the skipped verdicts are exactly the -1 ones.
-//   didx[S * n_nodes + node] = (mask for dksi < 0, mask for dksi > 0, min h over the list, w0)
-// The step-time guard  0 < delta < 0.99 * min h  implies the pre-filter's own precondition
-// delta < 0.99 h(tet) for every candidate (rounding of h * 0.99 is monotone in h); a node that
-// fails it, or has more than 32 candidates (min h stored as -1), takes the literal per-node routine.
-template<int S>
-__global__ void __launch_bounds__(128)
-build_dir_index_kernel(const float* __restrict__ u, const int* __restrict__ n2t_off, const float* __restrict__ tet_hv,
-                       const int* __restrict__ list, int n_list, const float* __restrict__ w0,
-                       const int4* __restrict__ n2x, uint4* __restrict__ didx)
-{
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_list) return;
-	const int node = list[idx];
-	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u);
-	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(tet_hv);
-	const float4 o2 = rec[3 * (size_t)node + 2];
-	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
-	const int e0 = n2t_off[node], e1 = n2t_off[node + 1];
-	unsigned mm = 0, mp = 0;
-	float hmin = -1.0f;
-	if(e1 - e0 <= 32) {
-		for(int e = e0; e < e1; e++) {
-			Cand c;
-			load_cand<S>(c, __ldg(n2x + e), rec, hv2);
-			hmin = (e == e0 || c.h < hmin) ? c.h : hmin;
-			const bool shaped = c.vol > 0;
-			if(!(shaped && prefilter<S>(c, X, -1.0f) < 0)) mm |= 1u << (e - e0);
-			if(!(shaped && prefilter<S>(c, X, 1.0f) < 0)) mp |= 1u << (e - e0);
-		}
-	}
-	didx[node] = make_uint4(mm, mp, __float_as_uint(hmin), __float_as_uint(w0[node]));
-}
-
-// One thread per listed inner node, axis stage S.  mat_id == nullptr: single material (id 0).
+// One thread per listed inner node, axis stage S, scanning the node's whole candidate list.
+// This is the index-free form of the inner kernel (kept as the A/B reference of the indexed one
+// below: GCM_B200_DIR_INDEX=0).  mat_id == nullptr: single material (id 0).
 // MB = minimum resident blocks per SM the register allocation is tuned for (occupancy vs spills).
-// IDX: scan through the angular candidate index (didx = plane S of it); otherwise scan the whole
-// candidate list (didx unused, w0 from its own array).
-template<int S, int MB, bool IDX>
+template<int S, int MB>
 __global__ void __launch_bounds__(128, MB)
 stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
                    float* __restrict__ un, int* err, int zone, StageTap* tap,
                    const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
-                   const float* __restrict__ w0, const int4* __restrict__ n2x, const uint4* __restrict__ didx)
+                   const float* __restrict__ w0, const int4* __restrict__ n2x)
 {
 	__shared__ float sU[GCM_MAX_MATERIALS][81];
 	__shared__ float sU1[GCM_MAX_MATERIALS][81];
@@ -299,25 +259,11 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	for(int k = 0; k < 9; k++) bad |= (isnan(own[k]) || isinf(own[k]));
 	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
 
-	const int e0 = m.n2t_off[node], e1 = IDX ? 0 : m.n2t_off[node + 1];
+	const int e0 = m.n2t_off[node], e1 = m.n2t_off[node + 1];
 	const float* U = sU[mid];
 	const float* U1 = sU1[mid];
 	float omega[9];
 	StageTap tp;
-	uint4 ix = make_uint4(0u, 0u, 0u, 0u);
-	if(IDX) {
-		ix = __ldg(didx + node);
-		// all four displacements must be rescaled by every candidate (then the index is valid)
-		const double h99 = (double)__uint_as_float(ix.z) * 0.99;
-		bool ok = true;
-		#pragma unroll
-		for(int q = 0; q < 4; q++) {
-			const float dk = - sL[mid][q] * m.tau;
-			const float de = sqrtf(dk * dk);
-			ok = ok && de > 0 && (double)de < h99;
-		}
-		if(!ok) { inner_node_generic(m, node, S, un, err, zone, tap); return; }
-	}
 
 	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
 	#pragma unroll
@@ -329,22 +275,14 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		Cand c;
 		int owner = -1;
 		bool cold = false;
-		unsigned mask = dir == 0 ? ix.x : ix.y;
-		int4 xn = make_int4(0, 0, 0, 0);
-		if(!IDX) xn = __ldg(n2x + e0);
-		for(int e = e0; IDX ? mask != 0 : e < e1; e++) {
-			int4 x = xn;
-			if(IDX) {
-				// surviving positions in list order; the first one is the owner almost always
-				x = __ldg(n2x + e0 + __ffs(mask) - 1);
-				mask &= mask - 1;
-			} else {
-				if(e + 1 < e1) xn = __ldg(n2x + e + 1);
-			}
+		int4 xn = __ldg(n2x + e0);
+		for(int e = e0; e < e1; e++) {
+			const int4 x = xn;
+			if(e + 1 < e1) xn = __ldg(n2x + e + 1);
 			load_cand<S>(c, x, rec, hv2);
 			const double h99 = (double)c.h * 0.99;
 			int v1 = 0;
-			if(c.vol > 0 && (IDX || (de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99)))
+			if(c.vol > 0 && de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99)
 				v1 = prefilter<S>(c, X, sgn);
 			if(v1 == 0) {
 				const bool in1 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
@@ -389,11 +327,270 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every
 	// factor but the node's own is exactly 0, the own one is the static weight w0
 	float vz[9];
-	const float wz = IDX ? __uint_as_float(ix.w) : w0[node];
+	const float wz = w0[node];
 	#pragma unroll
 	for(int k = 0; k < 9; k++) vz[k] = own[k] * wz;
 	if(tap) {
 		tp.owner[4] = m.n2t[e0];
+		tp.outer_count = 0; tp.tries = 1;
+		tap[(size_t)S * m.n_nodes + node] = tp;
+	}
+	#pragma unroll
+	for(int i = 6; i < 9; i++) {
+		float om = 0;
+		#pragma unroll
+		for(int j = 0; j < 9; j++)
+			if((u_pattern(S, i) >> j) & 1) om += U[i * 9 + j] * vz[j];
+		omega[i] = om;
+	}
+	// u' = Omega^-1 * omega (SimpleVolumeCalculator.cpp:24-31), skipping the structural zeros
+	float res[9];
+	#pragma unroll
+	for(int i = 0; i < 9; i++) {
+		float o = 0;
+		#pragma unroll
+		for(int j = 0; j < 9; j++)
+			if((u1_pattern(S, i) >> j) & 1) o += U1[i * 9 + j] * omega[j];
+		res[i] = o;
+	}
+	float4* __restrict__ out = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
+	out[0] = make_float4(res[0], res[1], res[2], res[3]);
+	out[1] = make_float4(res[4], res[5], res[6], res[7]);
+	out[2] = make_float4(res[8], X.x, X.y, X.z);
+}
+
+// ---- angular candidate index ------------------------------------------------------------------
+// Built once on the device after the mesh upload.  The pre-filter's verdict for a candidate
+// depends on static data only (the vertex coordinates, h(tet) and the SIGN of the displacement
+// along axis S -- the length is rescaled away, see the file header), so the candidates it rejects
+// ("certainly fails") are the same on every step.  Per (node, axis, sign) the index keeps the
+// positions of the surviving candidates as a 32-bit mask over the node's list and, inline, the
+// expanded-CSR entry and (h, Vol) of the FIRST survivor -- with the rejects gone that one is the
+// owner almost always, and having it in the index saves the two scattered 64-byte DRAM accesses
+// (CSR entry, tet_hv) per direction that dominated the kernel's traffic.  The per-step search is
+// unchanged: survivors in list order through the same pre-filter / exact predicate, first pass
+// wins.  Same function, same inputs, same compiler flags at build and at step time -> the skipped
+// verdicts are exactly the -1 ones.  Entry of one (axis, node), 4 x uint4 = 64 bytes:
+//   q0 = (survivors after the first, dksi < 0 | same, dksi > 0 | min h over the list | w0)
+//   q1 = first survivor, dksi < 0: (ia, ib, ic, t | k << 30)     q2 = same for dksi > 0
+//   q3 = (h-, Vol-, h+, Vol+) of those two
+// min h == 0 marks "not a node of the fast inner path" (all-zero entry: border, halo, generic);
+// ia == -1 "no survivor".  The step-time guard  0 < delta < 0.99 * min h  implies the pre-filter's
+// own precondition delta < 0.99 h(tet) for every candidate (rounding of h * 0.99 is monotone in
+// h); a node that fails it, or has more than 32 candidates (min h stored as -1), takes the
+// literal per-node routine.
+#define GCM_DIDX_QUADS 4
+template<int S>
+__global__ void __launch_bounds__(128)
+build_dir_index_kernel(const float* __restrict__ u, const int* __restrict__ n2t_off, const float* __restrict__ tet_hv,
+                       const int* __restrict__ list, int n_list, const float* __restrict__ w0,
+                       const int4* __restrict__ n2x, uint4* __restrict__ didx)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u);
+	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(tet_hv);
+	const float4 o2 = rec[3 * (size_t)node + 2];
+	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
+	const int e0 = n2t_off[node], e1 = n2t_off[node + 1];
+	unsigned mm = 0, mp = 0;
+	float hmin = -1.0f;
+	if(e1 - e0 <= 32) {
+		for(int e = e0; e < e1; e++) {
+			Cand c;
+			load_cand<S>(c, __ldg(n2x + e), rec, hv2);
+			hmin = (e == e0 || c.h < hmin) ? c.h : hmin;
+			const bool shaped = c.vol > 0;
+			if(!(shaped && prefilter<S>(c, X, -1.0f) < 0)) mm |= 1u << (e - e0);
+			if(!(shaped && prefilter<S>(c, X, 1.0f) < 0)) mp |= 1u << (e - e0);
+		}
+	}
+	int4 xm = make_int4(-1, -1, -1, 0), xp = make_int4(-1, -1, -1, 0);
+	float2 hm = make_float2(0.f, 0.f), hp = make_float2(0.f, 0.f);
+	if(mm) { xm = __ldg(n2x + e0 + __ffs(mm) - 1); hm = __ldg(hv2 + (xm.w & 0x3fffffff)); mm &= mm - 1; }
+	if(mp) { xp = __ldg(n2x + e0 + __ffs(mp) - 1); hp = __ldg(hv2 + (xp.w & 0x3fffffff)); mp &= mp - 1; }
+	uint4* __restrict__ o = didx + GCM_DIDX_QUADS * (size_t)node;
+	o[0] = make_uint4(mm, mp, __float_as_uint(hmin), __float_as_uint(w0[node]));
+	o[1] = make_uint4((unsigned)xm.x, (unsigned)xm.y, (unsigned)xm.z, (unsigned)xm.w);
+	o[2] = make_uint4((unsigned)xp.x, (unsigned)xp.y, (unsigned)xp.z, (unsigned)xp.w);
+	o[3] = make_uint4(__float_as_uint(hm.x), __float_as_uint(hm.y), __float_as_uint(hp.x), __float_as_uint(hp.y));
+}
+
+// ---- inner kernel, indexed -------------------------------------------------------------------
+// One thread per NODE of a contiguous node range (no list indirection): the node's index entry
+// says whether it is a fast inner node at all.  Two rounds of dependent loads per node-stage:
+// (index entry, own record) -> (records of the two first survivors' vertices: coordinates for the
+// predicate and values for the interpolation in one go).  A direction whose first survivor is not
+// the owner continues down its mask through the expanded CSR.  Arithmetic identical to
+// stage_inner_kernel.
+struct CandFull {
+	Cand c;
+	float4 a0, a1, b0, b1, c0, c1;     // first two record quads of A, B, C (the third is c.qa/qb/qc)
+};
+
+__device__ __forceinline__ void load_records(CandFull& f, const float4* __restrict__ rec)
+{
+	f.c.qa = __ldg(rec + 3 * (size_t)f.c.ia + 2);
+	f.c.qb = __ldg(rec + 3 * (size_t)f.c.ib + 2);
+	f.c.qc = __ldg(rec + 3 * (size_t)f.c.ic + 2);
+	f.a0 = __ldg(rec + 3 * (size_t)f.c.ia); f.a1 = __ldg(rec + 3 * (size_t)f.c.ia + 1);
+	f.b0 = __ldg(rec + 3 * (size_t)f.c.ib); f.b1 = __ldg(rec + 3 * (size_t)f.c.ib + 1);
+	f.c0 = __ldg(rec + 3 * (size_t)f.c.ic); f.c1 = __ldg(rec + 3 * (size_t)f.c.ic + 1);
+}
+
+__device__ __forceinline__ void set_entry(CandFull& f, const uint4 x, float h, float vol)
+{
+	f.c.ia = (int)x.x; f.c.ib = (int)x.y; f.c.ic = (int)x.z;
+	f.c.t = (int)(x.w & 0x3fffffffu); f.c.k = (int)(x.w >> 30);
+	f.c.h = h; f.c.vol = vol;
+}
+
+// Owner search of one direction starting from the (already loaded) first survivor; `rest` = the
+// later survivors.  Returns false when the node must take the literal routine.
+template<int S>
+__device__ __forceinline__ bool settle_dir(CandFull& f, unsigned rest, int node, const int* __restrict__ n2t_off, const F3& X, float sgn,
+                                           float dk1, float de1, float dk2, float de2,
+                                           const int4* __restrict__ n2x, const float4* __restrict__ rec, const float2* __restrict__ hv2)
+{
+	for(;;) {
+		const Cand& c = f.c;
+		int v1 = 0;
+		if(c.vol > 0) v1 = prefilter<S>(c, X, sgn);
+		if(v1 == 0) {
+			const bool in1 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
+			                                  c.qc.y, c.qc.z, c.qc.w, X.x, X.y, X.z, dk1, de1);
+			const bool in2 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
+			                                  c.qc.y, c.qc.z, c.qc.w, X.x, X.y, X.z, dk2, de2);
+			if(in1 != in2) return false;
+			v1 = in1 ? 1 : -1;
+		}
+		if(v1 > 0) return true;
+		if(!rest) return false;
+		const int4 x = __ldg(n2x + n2t_off[node] + __ffs(rest) - 1);
+		rest &= rest - 1;
+		const float2 hv = __ldg(hv2 + (x.w & 0x3fffffff));
+		set_entry(f, make_uint4((unsigned)x.x, (unsigned)x.y, (unsigned)x.z, (unsigned)x.w), hv.x, hv.y);
+		load_records(f, rec);
+	}
+}
+
+// The two feet of one direction inside its owner and their three Riemann invariants
+// (rows dir, 2 + dir, 4 + dir of Omega).  Returns false when the reference throws.
+template<int S>
+__device__ __forceinline__ bool feet_of_dir(const CandFull& f, int dir, const F3& X, float dk1, float dk2,
+                                            const float own[9], const float* __restrict__ U, float omega[9])
+{
+	const float va[9] = {f.a0.x, f.a0.y, f.a0.z, f.a0.w, f.a1.x, f.a1.y, f.a1.z, f.a1.w, f.c.qa.x};
+	const float vb[9] = {f.b0.x, f.b0.y, f.b0.z, f.b0.w, f.b1.x, f.b1.y, f.b1.z, f.b1.w, f.c.qb.x};
+	const float vc[9] = {f.c0.x, f.c0.y, f.c0.z, f.c0.w, f.c1.x, f.c1.y, f.c1.z, f.c1.w, f.c.qc.x};
+	float v[9];
+	if(!interp_axis<S>(f.c, X, dk1, own, va, vb, vc, v)) return false;
+	// omega_i = Omega(i,:) . u(foot of i)  (SimpleVolumeCalculator.cpp:14-23); ppoint_num = (0,1,2,3,2,3,4,4,4)
+	{
+		float om = 0;
+		#pragma unroll
+		for(int j = 0; j < 9; j++)
+			if((u_pattern(S, 0) >> j) & 1) om += U[dir * 9 + j] * v[j];
+		omega[dir] = om;
+	}
+	if(!interp_axis<S>(f.c, X, dk2, own, va, vb, vc, v)) return false;
+	{
+		float om = 0, om4 = 0;
+		#pragma unroll
+		for(int j = 0; j < 9; j++) {
+			if((u_pattern(S, 2) >> j) & 1) om += U[(2 + dir) * 9 + j] * v[j];
+			if((u_pattern(S, 4) >> j) & 1) om4 += U[(4 + dir) * 9 + j] * v[j];
+		}
+		omega[2 + dir] = om;
+		omega[4 + dir] = om4;
+	}
+	return true;
+}
+
+// PF: 1 = the records of both directions' first survivors are requested together, 0 = the second
+// direction's after the first direction's search (fewer live registers).
+template<int S, int MB, int PF>
+__global__ void __launch_bounds__(128, MB)
+stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, int n_range,
+                          float* __restrict__ un, int* err, int zone, StageTap* tap,
+                          const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
+                          const int4* __restrict__ n2x, const uint4* __restrict__ didx)
+{
+	static_assert(u_pattern(S, 0) == u_pattern(S, 1) && u_pattern(S, 2) == u_pattern(S, 3) && u_pattern(S, 4) == u_pattern(S, 5),
+	              "rows 2q and 2q+1 of Omega must share their sparsity pattern");
+	__shared__ float sU[GCM_MAX_MATERIALS][81];
+	__shared__ float sU1[GCM_MAX_MATERIALS][81];
+	__shared__ float sL[GCM_MAX_MATERIALS][4];
+	for(int i = threadIdx.x; i < n_mat * 81; i += blockDim.x) {
+		const MatTab& mt = tab[(i / 81) * 3 + S];
+		sU[i / 81][i % 81] = mt.U[i % 81];
+		sU1[i / 81][i % 81] = mt.U1[i % 81];
+	}
+	for(int i = threadIdx.x; i < n_mat * 4; i += blockDim.x) sL[i / 4][i % 4] = tab[(i / 4) * 3 + S].L[i % 4];
+	__syncthreads();
+
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_range) return;
+	const int node = node_begin + idx;
+	const uint4* __restrict__ ent = didx + GCM_DIDX_QUADS * (size_t)node;
+	const uint4 ix = __ldg(ent);
+	if(ix.z == 0u) return;                        // not a node of the fast inner path
+	const uint4 xm = __ldg(ent + 1), xp = __ldg(ent + 2), hq = __ldg(ent + 3);
+	const float4* __restrict__ rec = reinterpret_cast<const float4*>(m.u);
+	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(m.tet_hv);
+	const float4 o0 = rec[3 * (size_t)node], o1 = rec[3 * (size_t)node + 1], o2 = rec[3 * (size_t)node + 2];
+	const bool have = (int)xm.x >= 0 && (int)xp.x >= 0;
+	CandFull f0, f1;
+	set_entry(f0, xm, __uint_as_float(hq.x), __uint_as_float(hq.y));
+	set_entry(f1, xp, __uint_as_float(hq.z), __uint_as_float(hq.w));
+	if(have) load_records(f0, rec);
+	if(PF >= 1 && have) load_records(f1, rec);
+
+	const int mid = mat_id ? mat_id[node] : 0;
+	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
+	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
+	bool bad = false;
+	#pragma unroll
+	for(int k = 0; k < 9; k++) bad |= (isnan(own[k]) || isinf(own[k]));
+	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
+	const float* U = sU[mid];
+	const float* U1 = sU1[mid];
+	float dk[4], de[4];
+	{
+		// all four displacements must be rescaled by every candidate (then the index is valid)
+		const double h99 = (double)__uint_as_float(ix.z) * 0.99;
+		bool ok = have;
+		#pragma unroll
+		for(int q = 0; q < 4; q++) {
+			dk[q] = - sL[mid][q] * m.tau;             // dksi[i] = - L(i,i) * time_step
+			de[q] = sqrtf(dk[q] * dk[q]);             // delta; off-axis components are +-0
+			ok = ok && de[q] > 0 && (double)de[q] < h99;
+		}
+		if(!ok) { inner_node_generic(m, node, S, un, err, zone, tap); return; }
+	}
+	float omega[9];
+	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
+	if(!settle_dir<S>(f0, ix.x, node, m.n2t_off, X, -1.0f, dk[0], de[0], dk[2], de[2], n2x, rec, hv2)) {
+		inner_node_generic(m, node, S, un, err, zone, tap); return;
+	}
+	if(PF == 0) load_records(f1, rec);
+	if(!feet_of_dir<S>(f0, 0, X, dk[0], dk[2], own, U, omega)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
+	if(!settle_dir<S>(f1, ix.y, node, m.n2t_off, X, 1.0f, dk[1], de[1], dk[3], de[3], n2x, rec, hv2)) {
+		inner_node_generic(m, node, S, un, err, zone, tap); return;
+	}
+	if(!feet_of_dir<S>(f1, 1, X, dk[1], dk[3], own, U, omega)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
+
+	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every
+	// factor but the node's own is exactly 0, the own one is the static weight w0
+	float vz[9];
+	const float wz = __uint_as_float(ix.w);
+	#pragma unroll
+	for(int k = 0; k < 9; k++) vz[k] = own[k] * wz;
+	if(tap) {
+		StageTap tp;
+		tp.owner[0] = f0.c.t; tp.owner[2] = f0.c.t; tp.owner[1] = f1.c.t; tp.owner[3] = f1.c.t;
+		tp.owner[4] = m.n2t[m.n2t_off[node]];
 		tp.outer_count = 0; tp.tries = 1;
 		tap[(size_t)S * m.n_nodes + node] = tp;
 	}

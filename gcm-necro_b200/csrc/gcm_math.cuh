@@ -38,6 +38,38 @@ enum StepError {
 	ERR_FOOT_PATTERN = 12     // characteristic dedupe did not give the 5-point pattern (0,1,2,3,2,3,4,4,4)
 };
 
+// x / y with the IEEE result, arranged so that a zero numerator never reaches the divider.
+// nvcc expands a division into an inline fast path plus a subroutine for "special" operands, and
+// a ZERO numerator is special: one lane with x == 0 (a foot on a tet face, a structural zero of
+// the border system -- both the common case here) drags its whole warp through the subroutine;
+// ncu showed a quarter of the border kernel's instructions there.  0 / y = +-0 for any non-zero,
+// non-NaN y, so those lanes divide 1 / y instead and select the signed zero afterwards.
+// (The device build spells the division as the __fdiv_rn / __ddiv_rn intrinsic -- the same
+// round-to-nearest IEEE operation -- because the optimiser folds  x == 0 ? +-0 : x / c  back into
+// the plain x / c for a constant c, which is exactly what this helper is here to avoid.)
+GCM_HD float div_z(float x, float y)
+{
+	const bool z = (x == 0.0f) && (fabsf(y) > 0.0f);
+#if defined(__CUDA_ARCH__)
+	const float q = __fdiv_rn(z ? 1.0f : x, y);
+#else
+	const float q = (z ? 1.0f : x) / y;
+#endif
+	const float zr = copysignf(0.0f, x);
+	return z ? (signbit(y) ? -zr : zr) : q;
+}
+GCM_HD double div_z(double x, double y)
+{
+	const bool z = (x == 0.0) && (fabs(y) > 0.0);
+#if defined(__CUDA_ARCH__)
+	const double q = __ddiv_rn(z ? 1.0 : x, y);
+#else
+	const double q = (z ? 1.0 : x) / y;
+#endif
+	const double zr = copysign(0.0, x);
+	return z ? (signbit(y) ? -zr : zr) : q;
+}
+
 // gcm/system/quick_math.cpp:26-29
 GCM_HD float determinant(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3)
 {
@@ -47,7 +79,7 @@ GCM_HD float determinant(float x1, float y1, float z1, float x2, float y2, float
 // gcm/system/quick_math.cpp:7-10
 GCM_HD float tetr_volume(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3)
 {
-	return determinant(x1, y1, z1, x2, y2, z2, x3, y3, z3) / 6;
+	return div_z(determinant(x1, y1, z1, x2, y2, z2, x3, y3, z3), 6.0f);
 }
 
 // gcm/system/quick_math.cpp:13-23
@@ -122,9 +154,9 @@ GCM_HD bool point_in_tetr(const Vec3& base, float _dx, float _dy, float _dz, flo
 {
 	float dx, dy, dz;
 	if( (delta > 0) && ((double)delta < (double)min_h * 0.99) ) {
-		dx = (float)( (double)(_dx * min_h) * 0.99 / (double)delta );
-		dy = (float)( (double)(_dy * min_h) * 0.99 / (double)delta );
-		dz = (float)( (double)(_dz * min_h) * 0.99 / (double)delta );
+		dx = (float)div_z( (double)(_dx * min_h) * 0.99, (double)delta );
+		dy = (float)div_z( (double)(_dy * min_h) * 0.99, (double)delta );
+		dz = (float)div_z( (double)(_dz * min_h) * 0.99, (double)delta );
 	} else {
 		dx = _dx; dy = _dy; dz = _dz;
 	}
@@ -144,10 +176,10 @@ GCM_HD bool interp_factors(const Vec3& v0, const Vec3& v1, const Vec3& v2, const
 {
 	float s[4];
 	sub_volumes(v0, v1, v2, v3, x, y, z, s);
-	f[0] = fabsf(s[0] / vol);
-	f[1] = fabsf(s[1] / vol);
-	f[2] = fabsf(s[2] / vol);
-	f[3] = fabsf(s[3] / vol);
+	f[0] = fabsf(div_z(s[0], vol));
+	f[1] = fabsf(div_z(s[1], vol));
+	f[2] = fabsf(div_z(s[2], vol));
+	f[3] = fabsf(div_z(s[3], vol));
 	float sum = f[0] + f[1] + f[2] + f[3];
 	if((double)sum > 1.0) {
 		if((double)sum < 1.25) {
@@ -274,12 +306,12 @@ GCM_HD int elastic_matrix(float la, float mu, float ro, float qjx, float qjy, fl
 		}
 		// the reference writes  -N/(c*ro)  for w==1 and  -2*N/(c*ro)  for w==2; 1*N == N exactly
 		for(int i = 0; i < 6; i++) {
-			GCM_U(0,3+i) = -w[i]*N00[i]/(c1*ro);
-			GCM_U(1,3+i) = w[i]*N00[i]/(c1*ro);
-			GCM_U(2,3+i) = -w[i]*N01[i]/(c2*ro);
-			GCM_U(3,3+i) = w[i]*N01[i]/(c2*ro);
-			GCM_U(4,3+i) = -w[i]*N02[i]/(c2*ro);
-			GCM_U(5,3+i) = w[i]*N02[i]/(c2*ro);
+			GCM_U(0,3+i) = div_z(-w[i]*N00[i], c1*ro);
+			GCM_U(1,3+i) = div_z(w[i]*N00[i], c1*ro);
+			GCM_U(2,3+i) = div_z(-w[i]*N01[i], c2*ro);
+			GCM_U(3,3+i) = div_z(w[i]*N01[i], c2*ro);
+			GCM_U(4,3+i) = div_z(-w[i]*N02[i], c2*ro);
+			GCM_U(5,3+i) = div_z(w[i]*N02[i], c2*ro);
 			GCM_U(6,3+i) = w[i]*N12[i];
 			GCM_U(7,3+i) = w[i]*(N11[i]-N22[i]);
 			GCM_U(8,3+i) = w[i]*(N11[i]+N22[i]-2*la*N00[i]/(la+2*mu));
@@ -340,12 +372,12 @@ GCM_HD void elastic_U_row(const ElasticDirs& d, float la, float mu, float ro, in
 	for(int q = 0; q < 6; q++) {
 		float v;
 		switch(i) {
-		case 0: v = -w[q]*d.N00[q]/(c1*ro); break;
-		case 1: v = w[q]*d.N00[q]/(c1*ro); break;
-		case 2: v = -w[q]*d.N01[q]/(c2*ro); break;
-		case 3: v = w[q]*d.N01[q]/(c2*ro); break;
-		case 4: v = -w[q]*d.N02[q]/(c2*ro); break;
-		case 5: v = w[q]*d.N02[q]/(c2*ro); break;
+		case 0: v = div_z(-w[q]*d.N00[q], c1*ro); break;
+		case 1: v = div_z(w[q]*d.N00[q], c1*ro); break;
+		case 2: v = div_z(-w[q]*d.N01[q], c2*ro); break;
+		case 3: v = div_z(w[q]*d.N01[q], c2*ro); break;
+		case 4: v = div_z(-w[q]*d.N02[q], c2*ro); break;
+		case 5: v = div_z(w[q]*d.N02[q], c2*ro); break;
 		case 6: v = w[q]*d.N12[q]; break;
 		case 7: v = w[q]*(d.N11[q]-d.N22[q]); break;
 		default: v = w[q]*(d.N11[q]+d.N22[q]-2*la*d.N00[q]/(la+2*mu)); break;
@@ -428,7 +460,7 @@ GCM_HD void lu_solve(double* A, double* b)
 		double ajj = A[j*N+j];
 		if(ajj != 0.0) {
 			for(int i = j + 1; i < N; i++) {
-				double aij = A[i*N+j] / ajj;
+				double aij = div_z(A[i*N+j], ajj);
 				A[i*N+j] = aij;
 				for(int k = j + 1; k < N; k++)
 					A[i*N+k] = A[i*N+k] - aij * A[j*N+k];
@@ -445,7 +477,7 @@ GCM_HD void lu_solve(double* A, double* b)
 	for(int i = N - 1; i >= 0; i--) {
 		double t = x[i];
 		for(int j = i + 1; j < N; j++) t -= A[i*N+j] * x[j];
-		x[i] = t / A[i*N+i];
+		x[i] = div_z(t, A[i*N+i]);
 	}
 	for(int i = 0; i < N; i++) b[i] = x[i];
 }

@@ -70,6 +70,29 @@ GCM_HD double div_z(double x, double y)
 	return z ? (signbit(y) ? -zr : zr) : q;
 }
 
+// x / 6 (the `/ 6` of quick_math.cpp:9), correctly rounded, without the divider: with
+// c = RN(1/6),  q0 = RN(x c),  r = x - 6 q0 (exact in an FMA),  q = RN(q0 + r c)  equals RN(x / 6)
+// for every float with biased exponent 2..254 -- checked exhaustively over all 2^32 bit patterns
+// by tests/emul/div6_check.c (the only misses are zeros/denormals/results that go denormal, and
+// infinities); those, never seen in practice, take the real division.  A third of the inner
+// kernel's instructions were inline division expansions before this.
+GCM_HD float div6(float x)
+{
+#if defined(__CUDA_ARCH__)
+	const float ax = fabsf(x);
+	if(ax >= 2.3509887e-38f && ax <= 3.4028235e38f) {     // 2^-125 <= |x| <= FLT_MAX
+		const float c = 0.16666667163372039794921875f;
+		const float q0 = __fmul_rn(x, c);
+		const float r = __fmaf_rn(-6.0f, q0, x);
+		return __fmaf_rn(r, c, q0);
+	}
+	if(x == 0.0f) return x;
+	return __fdiv_rn(x, 6.0f);
+#else
+	return x / 6;
+#endif
+}
+
 // gcm/system/quick_math.cpp:26-29
 GCM_HD float determinant(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3)
 {
@@ -79,7 +102,7 @@ GCM_HD float determinant(float x1, float y1, float z1, float x2, float y2, float
 // gcm/system/quick_math.cpp:7-10
 GCM_HD float tetr_volume(float x1, float y1, float z1, float x2, float y2, float z2, float x3, float y3, float z3)
 {
-	return div_z(determinant(x1, y1, z1, x2, y2, z2, x3, y3, z3), 6.0f);
+	return div6(determinant(x1, y1, z1, x2, y2, z2, x3, y3, z3));
 }
 
 // gcm/system/quick_math.cpp:13-23
@@ -176,10 +199,13 @@ GCM_HD bool interp_factors(const Vec3& v0, const Vec3& v1, const Vec3& v2, const
 {
 	float s[4];
 	sub_volumes(v0, v1, v2, v3, x, y, z, s);
-	f[0] = fabsf(div_z(s[0], vol));
-	f[1] = fabsf(div_z(s[1], vol));
-	f[2] = fabsf(div_z(s[2], vol));
-	f[3] = fabsf(div_z(s[3], vol));
+	// fabs(s / Vol); an exactly zero sub-volume (the foot lies in a face plane of the owner: half
+	// of them on axis-aligned meshes) needs no division: |+-0 / Vol| = +0 for any Vol != 0
+	#pragma unroll
+	for(int i = 0; i < 4; i++) {
+		if(s[i] == 0.0f && fabsf(vol) > 0.0f) f[i] = 0.0f;
+		else f[i] = fabsf(div_z(s[i], vol));
+	}
 	float sum = f[0] + f[1] + f[2] + f[3];
 	if((double)sum > 1.0) {
 		if((double)sum < 1.25) {

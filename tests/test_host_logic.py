@@ -124,3 +124,16 @@ def test_elastic_row_functions_match_full_matrix(built):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", csrc, src, "-o", exe], check=True)
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 0 and "OK" in r.stdout, r.stdout
+
+
+def test_div6_fma_form_matches_ieee_division(tmp_path):
+    """gcm_math.cuh div6: the FMA form equals x / 6.0f wherever the device code uses it (sampled here,
+    every 64th mantissa of every exponent; run tests/emul/div6_check with stride 1 for all 2^32)."""
+    import subprocess
+    src = os.path.join(os.path.dirname(__file__), "emul", "div6_check.c")
+    exe = str(tmp_path / "div6_check")
+    subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-mfma", src, "-o", exe, "-lm"])
+    out = subprocess.run([exe, "64"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "in exponents 2..254: 0" in out.stdout
+    assert "0x3e2aaaab" in out.stdout

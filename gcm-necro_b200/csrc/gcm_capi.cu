@@ -78,7 +78,7 @@ struct Zone {
 struct DeviceMesh {
 	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0;
 	size_t n_fast = 0, n_generic = 0, n_inner = 0;
-	DevBuf<float> u0, u1, mat, tet_hv, basis, normals, w0, aos, mat_tab;
+	DevBuf<float> u0, u1, mat, tet_hv, basis, basis_next, normals, w0, aos, mat_tab;
 	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, didx;
 	DevBuf<int> sharp_list, flat_list, fast_list, generic_list, inner_list;
 	size_t n_sharp = 0, n_flat = 0;
@@ -105,8 +105,10 @@ struct gcm_b200_set {
 	gcmh::GlibcRand rng;
 	gcmh::MaterialRegistry materials;
 	DeviceMesh dm;
-	cudaStream_t stream = nullptr, aux = nullptr;
-	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	cudaStream_t stream = nullptr, aux = nullptr, rng_stream = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_rng_done = nullptr, ev_step_mark = nullptr;
+	bool bases_ahead = true;     // device generator: the NEXT step's bases are produced on rng_stream during this step
+	bool ahead_valid = false;    // dm.basis_next holds the bases of the coming step
 	int* d_err = nullptr;
 	int* h_err = nullptr;
 	std::vector<CondSpec> conds;
@@ -472,13 +474,33 @@ void begin_step_bases(gcm_b200_set* s)
 	DeviceMesh& dm = s->dm;
 	for(int zi : s->local_zones) s->zones[zi]->stage_done = false;
 	if(s->basis_on_device) {
-		if(!s->rng_ready) rng_device_init(s);
+		if(!s->rng_ready) { CK(cudaStreamSynchronize(s->rng_stream)); rng_device_init(s); s->ahead_valid = false; }
 		if(s->rng_chunks && dm.NB) {
-			ProfScope ps(s, PROF_RNG, s->rng_draws_per_step);
-			gcm::rng_chunk_kernel<<<(s->rng_chunks + 127) / 128, 128, 0, s->stream>>>(s->d_chunk_state.p, s->rng_chunks,
-				s->d_jump.p, s->d_slot_pos.p, s->d_chunk_first_slot.p, s->d_teta_idx.p);
-			gcm::basis_kernel<<<(int)((dm.NB + 127) / 128), 128, 0, s->stream>>>(dm.basis.p, dm.normals.p, s->d_teta_idx.p, 0, (int)dm.NB, s->d_cos.p, s->d_sin.p);
-			s->launches += 2;
+			// one call = the rand() draws of one step (the chunk states advance in place) + the bases from them
+			auto produce = [&](float* dst, cudaStream_t st) {
+				ProfScope ps(s, PROF_RNG, s->rng_draws_per_step, st);
+				gcm::rng_chunk_kernel<<<(s->rng_chunks + 127) / 128, 128, 0, st>>>(s->d_chunk_state.p, s->rng_chunks,
+					s->d_jump.p, s->d_slot_pos.p, s->d_chunk_first_slot.p, s->d_teta_idx.p);
+				gcm::basis_kernel<<<(int)((dm.NB + 127) / 128), 128, 0, st>>>(dst, dm.normals.p, s->d_teta_idx.p, 0, (int)dm.NB, s->d_cos.p, s->d_sin.p);
+				s->launches += 2;
+			};
+			if(s->ahead_valid) {
+				// produced during the previous step (the stream depends on nothing but its own position)
+				CK(cudaStreamWaitEvent(s->stream, s->ev_rng_done, 0));
+				std::swap(dm.basis.p, dm.basis_next.p);
+				s->ahead_valid = false;
+			} else {
+				produce(dm.basis.p, s->stream);
+			}
+			if(s->bases_ahead) {
+				// the other buffer was read by the previous step's kernels: start after everything queued so far
+				if(!dm.basis_next.p) dm.basis_next.alloc(9 * dm.NB);
+				CK(cudaEventRecord(s->ev_step_mark, s->stream));
+				CK(cudaStreamWaitEvent(s->rng_stream, s->ev_step_mark, 0));
+				produce(dm.basis_next.p, s->rng_stream);
+				CK(cudaEventRecord(s->ev_rng_done, s->rng_stream));
+				s->ahead_valid = true;
+			}
 		}
 		// keep the host generator in step with the device one
 		uint32_t w[31];
@@ -817,6 +839,9 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 		CK(cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
 		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+		CK(cudaStreamCreateWithFlags(&s->rng_stream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&s->ev_rng_done, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&s->ev_step_mark, cudaEventDisableTiming));
 		CK(cudaMalloc(&s->d_err, 4 * sizeof(int)));
 		CK(cudaMemset(s->d_err, 0, 4 * sizeof(int)));
 		CK(cudaMallocHost(&s->h_err, 4 * sizeof(int)));
@@ -827,6 +852,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_COOP_BORDER")) s->coop_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_MB")) s->border_min_blocks = atoi(e);
 	if(const char* e = getenv("GCM_B200_LEAN_BORDER")) s->lean_border = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_BASES_AHEAD")) s->bases_ahead = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_DIR_INDEX")) s->dir_index = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_DIRECT_MB")) s->direct_min_blocks = atoi(e);
 	if(const char* e = getenv("GCM_B200_DIRECT_PF")) s->direct_prefetch = atoi(e);
@@ -843,10 +869,14 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		cudaSetDevice(s->device);
 		if(s->stream) cudaStreamSynchronize(s->stream);
 		if(s->aux) cudaStreamSynchronize(s->aux);
+		if(s->rng_stream) cudaStreamSynchronize(s->rng_stream);
 		prof_drain(s);
 		for(int k = 0; k < 2; k++) { if(s->h_basis[k]) cudaFreeHost(s->h_basis[k]); if(s->basis_ev[k]) cudaEventDestroy(s->basis_ev[k]); }
 		if(s->ev_fork) cudaEventDestroy(s->ev_fork);
 		if(s->ev_join) cudaEventDestroy(s->ev_join);
+		if(s->ev_rng_done) cudaEventDestroy(s->ev_rng_done);
+		if(s->ev_step_mark) cudaEventDestroy(s->ev_step_mark);
+		if(s->rng_stream) cudaStreamDestroy(s->rng_stream);
 		if(s->d_err) cudaFree(s->d_err);
 		if(s->h_err) cudaFreeHost(s->h_err);
 	}

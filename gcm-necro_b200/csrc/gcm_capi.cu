@@ -136,6 +136,7 @@ struct gcm_b200_set {
 	std::vector<std::vector<int> > axis_plus0;   // per local zone (local_meshes order), per border slot
 	DevBuf<gcm::VirtNode> d_virt;
 	DevBuf<int> d_axis_plus0, d_border_stage0, d_sharp_stage0, d_contact_nodes, d_border_by_slot;
+	DevBuf<int> d_deep, d_ring_ws;   // contact nodes deferred to the list-building owner search, and its workspaces
 	size_t st0s_total = 0;
 	DevBuf<float> d_gather;
 	size_t st0_total = 0, c0_total = 0;
@@ -650,9 +651,19 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 		auto launch = [&](size_t off, size_t n, int partner_next, int zn) {
 			if(!n) return;
 			ProfScope ps(s, PROF_BORDER, (long long)n);
+			// pass 1: two list-free rings; nodes that need more are collected in d_deep and advanced
+			// by pass 2, whose few threads own a find_owner_general workspace each
+			const int deep_blocks = 32;
+			if(s->d_deep.n < n + 1) s->d_deep.alloc(n + 1);
+			if(!s->d_ring_ws.p) s->d_ring_ws.alloc((size_t)deep_blocks * 64 * GCM_RING_WS);
+			CK(cudaMemsetAsync(s->d_deep.p, 0, sizeof(int), s->stream));
 			gcm::stage_contact_kernel<<<(int)((n + 63) / 64), 64, 0, s->stream>>>(m, s->d_contact_nodes.p + off, (int)n, stage, dm.unext(),
-				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap);
-			s->launches++;
+				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap, s->d_deep.p, 0);
+			gcm::MeshView md = m;
+			md.ring_ws = s->d_ring_ws.p;
+			gcm::stage_contact_kernel<<<deep_blocks, 64, 0, s->stream>>>(md, s->d_contact_nodes.p + off, (int)n, stage, dm.unext(),
+				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap, s->d_deep.p, 1);
+			s->launches += 2;
 		};
 		if(z) { launch(z->c0_off, z->c0_n, 0, zone); launch(z->c1_off, z->c1_n, 1, zone); }
 		else {
@@ -764,7 +775,7 @@ const char* step_error_text(int code)
 	case gcm::ERR_BOTH_CONTACT: return "Both direction of contact are marked as contact";
 	case gcm::ERR_INTERP_SUM: return "Sum of factors is greater than 1.0";
 	case gcm::ERR_INNER_NO_OWNER: return "Inner node without owner tetrahedron (find_border_cross path is not built)";
-	case gcm::ERR_RING_OVERFLOW: return "Owner search needs more than the first and second ring of tetrahedrons (not built on device)";
+	case gcm::ERR_RING_OVERFLOW: return "Owner search needs more than the first and second ring of tetrahedrons (only contact nodes search further on the device; a ring is capped at 2048 tetrahedrons)";
 	case gcm::ERR_BAD_RHEOLOGY: return "Bad rheology";
 	case gcm::ERR_VIRT_OUTER_COUNT: return "Illegal number of outer characteristics";
 	case gcm::ERR_BAD_Q: return "Bad vector q";

@@ -117,31 +117,42 @@ stage_sharp_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 // node.  list[i] = real node, its virtual node = axis_plus0[border_slot].  partner_next = 1 when
 // the partner body was already advanced in this stage (the reference advances its meshes one
 // after the other): the virtual node's feet then read the NEXT layer `un`.
+//
+// Two passes.  The first (m.ring_ws == NULL, one thread per listed node) searches the first two
+// rings without any list; a node whose search would need a third ring (virtual nodes on
+// non-matching surface meshes) is appended to `deep` (deep[0] = count, deep[1..] = nodes) instead
+// of being advanced.  The second pass (deep_pass != 0, a fixed small grid whose threads each own a
+// find_owner_general workspace in m.ring_ws) strides over that list.  No node reads another
+// contact node's result of the same launch, so the split does not change any value.
 __global__ void __launch_bounds__(64)
 stage_contact_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
                      float* __restrict__ un, VirtNode* __restrict__ virt, const int* __restrict__ axis_plus0,
                      const float* __restrict__ normals, int calc_type, int partner_next, int first_step,
-                     int* err, int zone, StageTap* tap)
+                     int* err, int zone, StageTap* tap, int* deep, int deep_pass)
 {
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_list) return;
-	const int node = list[idx];
-	const int slot = m.border_slot[node];
-	const int vidx = axis_plus0[slot];
-	MeshView mv = m;
-	if(partner_next) mv.u = un;
-	VirtNode vn = virt[vidx];
-	float out[9], vout[9];
-	bool vw = false;
-	StageTap t;
-	const float nrm[3] = {normals[3 * (size_t)slot], normals[3 * (size_t)slot + 1], normals[3 * (size_t)slot + 2]};
-	int e = node_stage_contact(m, mv, node, vn, vidx, stage, nrm, calc_type, out, tap ? &t : nullptr, vout, &vw, first_step != 0);
-	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
-	if(e) { report_error(err, e, zone, node, stage); return; }
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		un[(size_t)node * GCM_REC + k] = out[k];
-	if(vw) for(int k = 0; k < 9; k++) virt[vidx].val[k] = vout[k];
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	const int n_work = deep_pass ? deep[0] : n_list;
+	const int step = deep_pass ? gridDim.x * blockDim.x : n_work;
+	for(int idx = tid; idx < n_work; idx += step) {
+		const int node = deep_pass ? deep[1 + idx] : list[idx];
+		const int slot = m.border_slot[node];
+		const int vidx = axis_plus0[slot];
+		MeshView mv = m;
+		if(partner_next) mv.u = un;
+		VirtNode vn = virt[vidx];
+		float out[9], vout[9];
+		bool vw = false;
+		StageTap t;
+		const float nrm[3] = {normals[3 * (size_t)slot], normals[3 * (size_t)slot + 1], normals[3 * (size_t)slot + 2]};
+		int e = node_stage_contact(m, mv, node, vn, vidx, stage, nrm, calc_type, out, tap ? &t : nullptr, vout, &vw, first_step != 0);
+		if(e == ERR_RING_OVERFLOW && !deep_pass && deep) { deep[1 + atomicAdd(&deep[0], 1)] = node; continue; }
+		if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
+		if(e) { report_error(err, e, zone, node, stage); continue; }
+		#pragma unroll
+		for(int k = 0; k < 9; k++)
+			un[(size_t)node * GCM_REC + k] = out[k];
+		if(vw) for(int k = 0; k < 9; k++) virt[vidx].val[k] = vout[k];
+	}
 }
 
 // Gather the records of listed nodes (collision discovery reads border-node values on the host).

@@ -51,6 +51,7 @@ struct MeshView {
 	const float* basis;      // [n_border][9] local basis ksi[3][3] of this step (border nodes)
 	const int* cond_id;      // [n_border]   index into conds[] or -1 = default
 	const int* contact;      // [n_border][6] axis_plus[3], axis_minus[3] (virt node ids) or NULL
+	int* ring_ws;            // NULL, or GCM_RING_WS ints per thread of the launch: workspace of find_owner_general
 	float tau;
 	float time;
 	float min_h;
@@ -233,6 +234,99 @@ GCM_HD int find_owner_second_ring(const MeshView& m, int base, const Vec3& node_
 	return -1;
 }
 
+// ---- find_owner_tetr with any number of rings (:1468-1602), lists materialised -------------------
+// Used when the first two rings (above, list-free) do not settle the search: virtual contact
+// nodes on non-matching surface meshes, whose displacement from the borrowed base node is a face
+// edge long.  `ws` = this thread's workspace of GCM_RING_WS ints:
+//   checked  [0, 3C)   every tet of the rings tested so far, ascending
+//   checking [3C, 4C)  the ring being tested (ring 1: the base node's list in stored order; later
+//                      rings ascending, as the reference's sort + unique leaves them)
+//   next     [4C, 5C)  the ring under construction, ascending, no duplicates
+// Returns the owner tet, -1 = NULL, -2 = workspace exhausted.
+#define GCM_RING_CAP 2048
+#define GCM_RING_WS (5 * GCM_RING_CAP)
+
+GCM_HD int ring_lower_bound(const int* a, int n, int v)
+{
+	int lo = 0, hi = n;
+	while(lo < hi) { const int mid = (lo + hi) >> 1; if(a[mid] < v) lo = mid + 1; else hi = mid; }
+	return lo;
+}
+
+// insert v into the ascending array a[0..n) unless present; returns the new length or -1 (full)
+GCM_HD int ring_insert(int* a, int n, int cap, int v)
+{
+	const int p = ring_lower_bound(a, n, v);
+	if(p < n && a[p] == v) return n;
+	if(n >= cap) return -1;
+	for(int i = n; i > p; i--) a[i] = a[i - 1];
+	a[p] = v;
+	return n + 1;
+}
+
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__     // cold: keep it out of the hot kernels' register allocation
+#else
+static inline
+#endif
+int find_owner_general(const MeshView& m, int base, const Vec3& node_pos,
+                       float dx, float dy, float dz, TetGeom& g, int* ws)
+{
+	const int C = GCM_RING_CAP;
+	int* checked = ws; int* checking = ws + 3 * C; int* next = ws + 4 * C;
+	int n_checked = 0, n_checking = 0;
+	const Vec3 X = load_xyz(m, base);
+	const float R2 = dx * dx + dy * dy + dz * dz;
+	const float delta = sqrtf(R2);
+	for(int e = m.n2t_off[base]; e < m.n2t_off[base + 1]; e++) {
+		if(n_checking >= C) return -2;
+		checking[n_checking++] = m.n2t[e];
+	}
+	bool inside_R = true;
+	while(inside_R) {
+		inside_R = false;
+		for(int i = 0; i < n_checking; i++) {
+			const int t = checking[i];
+			load_tet(m, t, g);
+			if(point_in_tetr(X, dx, dy, dz, delta, g.p[0], g.p[1], g.p[2], g.p[3], g.h, g.vol))
+				return t;
+			if(!inside_R) {
+				for(int j = 0; j < 4; j++) {
+					if(g.v[j] == base) break;   // `break`, not `continue` (:1544-1545)
+					const float lx = g.p[j].x, ly = g.p[j].y, lz = g.p[j].z;
+					if( ( (node_pos.x - lx) * (node_pos.x - lx)
+						+ (node_pos.y - ly) * (node_pos.y - ly)
+						+ (node_pos.z - lz) * (node_pos.z - lz) ) < R2 )
+						inside_R = true;
+				}
+			}
+		}
+		if(!inside_R) return -1;
+		// checked += checking; next = (all tets incident to a vertex of `checking`) minus checked
+		for(int i = 0; i < n_checking; i++) {
+			n_checked = ring_insert(checked, n_checked, 3 * C, checking[i]);
+			if(n_checked < 0) return -2;
+		}
+		int n_next = 0;
+		for(int i = 0; i < n_checking; i++) {
+			const int* tv = m.tets + 4*(size_t)checking[i];
+			for(int j = 0; j < 4; j++) {
+				const int v = tv[j];
+				for(int c = m.n2t_off[v]; c < m.n2t_off[v + 1]; c++) {
+					const int t2 = m.n2t[c];
+					const int p = ring_lower_bound(checked, n_checked, t2);
+					if(p < n_checked && checked[p] == t2) continue;
+					n_next = ring_insert(next, n_next, C, t2);
+					if(n_next < 0) return -2;
+				}
+			}
+		}
+		for(int i = 0; i < n_next; i++) checking[i] = next[i];
+		n_checking = n_next;
+	}
+	return -1;
+}
+
 // Interpolated state at a foot (gcm/meshtypes/TetrMesh_1stOrder.cpp:1764-1880).
 // out[0..8] = values, out[9..11] = la, mu, rho (only virtual nodes read those).
 GCM_HD int interpolate_foot(const MeshView& m, const TetGeom& g, float x, float y, float z,
@@ -331,8 +425,17 @@ GCM_HD int foot_point(const MeshView& m, const CurNode& cur, int stage, float al
 		owner = find_owner_first_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
 		if(owner < 0 && expand) {
 			owner = find_owner_second_ring(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, &expand);
-			if(owner < 0 && expand)
-				return ERR_RING_OVERFLOW;   // a third ring would be needed
+			if(owner < 0 && expand) {
+				// a third ring is needed: the list-building search, where the launch provides a workspace
+				// (the deep pass of the contact kernel); elsewhere the node is reported / deferred
+				int* ws = m.ring_ws;
+#if defined(__CUDA_ARCH__)
+				if(ws) ws += (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * GCM_RING_WS;
+#endif
+				if(!ws) return ERR_RING_OVERFLOW;
+				owner = find_owner_general(m, cur.base, cur.pos, dx[0], dx[1], dx[2], g, ws);
+				if(owner == -2) return ERR_RING_OVERFLOW;
+			}
 		}
 	}
 	*owner_out = owner;

@@ -224,7 +224,11 @@ int main(int argc, char** argv)
 						vn.la = vh.values[9]; vn.mu = vh.values[10]; vn.rho = vh.values[11];
 						vn.base = vh.base_node; vn.real = i; vn.phase = 0;
 						float vo[9]; bool vw = false;
-						e = gcm::node_stage_contact(m, mv, i, vn, vidx, stage, &hm.normals[3*(size_t)slot], contact_calc == "friction" ? 1 : 0, o, &t, vo, &vw, step == 0);
+						// workspace of the list-building owner search (the product's deep contact pass)
+						static thread_local std::vector<int> ring_ws(GCM_RING_WS);
+						gcm::MeshView mc = m;
+						mc.ring_ws = ring_ws.data(); mv.ring_ws = ring_ws.data();
+						e = gcm::node_stage_contact(mc, mv, i, vn, vidx, stage, &hm.normals[3*(size_t)slot], contact_calc == "friction" ? 1 : 0, o, &t, vo, &vw, step == 0);
 						if(vw) for(int k = 0; k < 9; k++) vh.values[k] = vo[k];
 					} else if(slot >= 0 && lean_border)
 						e = gcm::node_stage_border_lean(m, i, stage, o, &t);

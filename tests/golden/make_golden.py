@@ -2,6 +2,7 @@
 oracle/build_ref.sh from /root/reference) on the small parity cases of tests/util_parity.py.
 
     python tests/golden/make_golden.py            # regenerate every fixture
+    python tests/golden/make_golden.py NAME ...   # only the named cases
 
 Each fixture holds, per zone: final values[9] per node, node flags, border faces, the local
 bases of the last step, and for step `tap_step` the owner tetrahedron of every characteristic
@@ -18,7 +19,7 @@ import util_parity as up  # noqa: E402
 
 
 def main():
-    for name in up.CASE_NAMES:
+    for name in (sys.argv[1:] or up.CASE_NAMES):
         case = up.make_case(name)
         res = up.run_oracle(case, tap=True)
         d = dict(n_zones=len(res))

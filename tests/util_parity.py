@@ -91,13 +91,34 @@ def make_case(name):
         c["detector"] = "brute"
         c["static"] = name.endswith("_static")
         c["contact_calc"] = "friction" if name.startswith("friction") else "adhesion"
+    elif name == "readme_contact":
+        # BASELINE configs[0]: tasks/friction-test.xml + basic-contact-task-1cpu-zones.xml.  gmsh is not
+        # available, so the two bodies are structured boxes of the same extents and point spacing
+        # (cover-small.geo: [-8,8]^2 x [3,6]; cube.geo: [0,2]^3 translated z+0.99; meshPointDist 0.45):
+        # the surface meshes do not match (0.444 vs 0.5), the gap is 0.01, Bruteforce detector every step,
+        # default Free border + Adhesion contact.  State: the <stress> block's intended initial velocity
+        # of the cube (as shipped the reference applies nothing: SURVEY fact 6).
+        za = meshgen.make_box_zones(37, 37, 8, 1, spacing=(16.0 / 36, 16.0 / 36, 3.0 / 7), origin=(-8.0, -8.0, 3.0))[0]
+        zb = meshgen.make_box_zones(5, 5, 5, 1, spacing=(0.5, 0.5, 0.5))[0]
+        zb.zone = 1
+        c["zones"] = [za, zb]
+        c["translates"] = [(1, 0.0, 0.0, 0.99)]
+        sa = np.zeros((za.coords.shape[0], 9), np.float32)
+        sb = np.zeros((zb.coords.shape[0], 9), np.float32)
+        sb[:, 0] = 0.05; sb[:, 1] = 0.05; sb[:, 2] = 0.25
+        c["states"] = [sa, sb]
+        c["detector"] = "brute"
+        c["static"] = False
+        c["contact_calc"] = "adhesion"
+        c["steps"] = 3
     else:
         raise KeyError(name)
     return c
 
 
 CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zones3_jitter", "plastic8",
-              "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static"]
+              "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static",
+              "contact_offset", "readme_contact"]
 
 
 def _write_inputs(case, d):

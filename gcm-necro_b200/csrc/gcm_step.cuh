@@ -335,10 +335,28 @@ GCM_HD int interpolate_foot(const MeshView& m, const TetGeom& g, float x, float 
 	float f[4];
 	if(!interp_factors(g.p[0], g.p[1], g.p[2], g.p[3], x, y, z, g.vol, f))
 		return ERR_INTERP_SUM;
+#if defined(__CUDA_ARCH__)
+	// three 16-byte loads per vertex record instead of nine 4-byte ones
+	float r0[12], r1[12], r2[12], r3[12];
+	{
+		const float4* q = reinterpret_cast<const float4*>(m.u);
+		#pragma unroll
+		for(int w = 0; w < 3; w++) {
+			const float4 a = q[3 * (size_t)g.v[0] + w], b = q[3 * (size_t)g.v[1] + w];
+			const float4 c = q[3 * (size_t)g.v[2] + w], d = q[3 * (size_t)g.v[3] + w];
+			r0[4*w] = a.x; r0[4*w+1] = a.y; r0[4*w+2] = a.z; r0[4*w+3] = a.w;
+			r1[4*w] = b.x; r1[4*w+1] = b.y; r1[4*w+2] = b.z; r1[4*w+3] = b.w;
+			r2[4*w] = c.x; r2[4*w+1] = c.y; r2[4*w+2] = c.z; r2[4*w+3] = c.w;
+			r3[4*w] = d.x; r3[4*w+1] = d.y; r3[4*w+2] = d.z; r3[4*w+3] = d.w;
+		}
+	}
+#else
 	const float* r0 = m.u + (size_t)g.v[0] * GCM_REC;
 	const float* r1 = m.u + (size_t)g.v[1] * GCM_REC;
 	const float* r2 = m.u + (size_t)g.v[2] * GCM_REC;
 	const float* r3 = m.u + (size_t)g.v[3] * GCM_REC;
+#endif
+	#pragma unroll
 	for(int k = 0; k < 9; k++)
 		out[k] = interp4(r0[k], r1[k], r2[k], r3[k], f);
 	if(with_material) {
@@ -553,8 +571,11 @@ GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& c
 	for(int j = 0; j < 3; j++)
 		safe_direction[j] = - ( curc[j] - Xc[j] );
 
-	float tetr_center[3];
-	{
+	if(alpha > 1.0)
+		alpha = 1.0;
+	// centre of elements[0]: the "last chance" foot, read by foot_point only when alpha > 0.95
+	float tetr_center[3] = {0.f, 0.f, 0.f};
+	if((double)alpha > 0.95) {
 		int tetr_num = m.n2t[m.n2t_off[cur.base]];
 		const int* tv = m.tets + 4*(size_t)tetr_num;
 		Vec3 a = load_xyz(m, tv[0]), b = load_xyz(m, tv[1]), c = load_xyz(m, tv[2]), d = load_xyz(m, tv[3]);
@@ -562,8 +583,6 @@ GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& c
 		tetr_center[1] = ( a.y + b.y + c.y + d.y ) / 4;
 		tetr_center[2] = ( a.z + b.z + c.z + d.z ) / 4;
 	}
-	if(alpha > 1.0)
-		alpha = 1.0;
 
 	// first try of a real node: one shared walk over the first ring serves all moving feet
 	RingScan rs;
@@ -768,12 +787,22 @@ GCM_HD int node_stage_nocontact_t(const MeshView& m, int node, int stage, float 
 {
 	CurNode cur;
 	cur.base = node;
-	cur.pos = load_xyz(m, node);
 	bool bad_value = false;
+#if defined(__CUDA_ARCH__)
+	{
+		const float4* q = reinterpret_cast<const float4*>(m.u) + 3 * (size_t)node;
+		const float4 a = q[0], b = q[1], c = q[2];
+		cur.val[0] = a.x; cur.val[1] = a.y; cur.val[2] = a.z; cur.val[3] = a.w;
+		cur.val[4] = b.x; cur.val[5] = b.y; cur.val[6] = b.z; cur.val[7] = b.w; cur.val[8] = c.x;
+		cur.pos.x = c.y; cur.pos.y = c.z; cur.pos.z = c.w;
+	}
+#else
+	cur.pos = load_xyz(m, node);
+	for(int k = 0; k < 9; k++) cur.val[k] = m.u[(size_t)node * GCM_REC + k];
+#endif
 	for(int k = 0; k < 9; k++) {
-		float v = m.u[(size_t)node * GCM_REC + k];
+		const float v = cur.val[k];
 		if(isnan(v) || isinf(v)) { if(only_try < 0) return ERR_NAN; bad_value = true; }
-		cur.val[k] = v;
 	}
 	cur.la = m.mat[node]; cur.mu = m.mat[m.stride + node]; cur.rho = m.mat[2*m.stride + node];
 	cur.is_border = (m.flags[node] & NF_BORDER) != 0;

@@ -11,6 +11,7 @@
 #include "gcm_host.h"
 #include "gcm_kernels.cuh"
 
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -60,7 +61,23 @@ struct PeerPlan {   // exchange with one other process
 	std::vector<int> req_pairs;                  // (owner zone, owner node) per slot
 	std::vector<int> send_zone, send_node;       // my nodes the peer asked for
 	DevBuf<int> d_recv, d_send;                  // merged-mesh indices
+	DevBuf<float> send_buf, recv_buf;            // [9][n] staging of the library-driven (NCCL) exchange
 	bool dev_ready = false;
+};
+
+// NCCL entry points, resolved at run time (the library has no link-time dependency on NCCL and
+// loads without it; a process that already carries NCCL -- torch does -- shares that copy).
+struct NcclId { char internal[128]; };           // ncclUniqueId
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetUniqueId)(NcclId*) = nullptr;
+	int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
 };
 
 struct Zone {
@@ -114,6 +131,8 @@ struct gcm_b200_set {
 	std::vector<CondSpec> conds;
 	std::vector<int> halo_dst, halo_src;        // same-process halo, merged indices
 	std::map<int, PeerPlan> peers;
+	void* nccl_comm = nullptr;   // library-driven halo exchange (gcm_b200_set_comm_init); NULL = the host moves the halos
+	int comm_rank = -1, comm_size = 0;
 	bool plan_built = false;
 	bool preprocessed = false;
 	bool tap_on = false;
@@ -806,6 +825,73 @@ void peer_dev_prepare(gcm_b200_set* s, PeerPlan& p)
 	p.dev_ready = true;
 }
 
+NcclApi& nccl_api()
+{
+	static NcclApi api;
+	if(api.lib) return api;
+	// the copy already in the process (torch's) if there is one, else the system library
+	void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+	if(!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if(!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if(!h) throw HostError{gcmh::CONFIG_EXCEPTION, std::string("NCCL is not loadable: ") + (dlerror() ? dlerror() : "?")};
+#define GCM_NCCL_SYM(field, name) do { *(void**)(&api.field) = dlsym(h, name); \
+	if(!api.field) throw HostError{gcmh::CONFIG_EXCEPTION, std::string("NCCL symbol missing: ") + name}; } while(0)
+	GCM_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+	GCM_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+	GCM_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+	GCM_NCCL_SYM(Send, "ncclSend");
+	GCM_NCCL_SYM(Recv, "ncclRecv");
+	GCM_NCCL_SYM(GroupStart, "ncclGroupStart");
+	GCM_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+	GCM_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef GCM_NCCL_SYM
+	api.lib = h;
+	return api;
+}
+
+void nccl_check(int rc, const char* what)
+{
+	if(rc != 0) throw HostError{gcmh::CONFIG_EXCEPTION, std::string("NCCL ") + what + ": " + nccl_api().GetErrorString(rc)};
+}
+
+// DataBus::sync_nodes across processes (gcm/system/DataBus.cpp:81-115), all on the set's stream:
+// gather the nodes every neighbour asked for, one grouped ncclSend/ncclRecv per neighbour over
+// NVLink, scatter what arrived into the halo slots.
+void comm_exchange(gcm_b200_set* s)
+{
+	if(s->peers.empty()) return;
+	NcclApi& nc = nccl_api();
+	for(auto& kv : s->peers) {
+		PeerPlan& p = kv.second;
+		peer_dev_prepare(s, p);
+		if(!p.recv_node.empty() && !p.recv_buf.p) p.recv_buf.alloc(9 * p.recv_node.size());
+		const int n = (int)p.send_node.size();
+		if(!n) continue;
+		if(!p.send_buf.p) p.send_buf.alloc(9 * (size_t)n);
+		ProfScope ps(s, PROF_HALO, n);
+		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(p.send_buf.p, s->dm.ucur(), p.d_send.p, n, n, 0);
+		s->launches++;
+	}
+	CK(cudaGetLastError());
+	nccl_check(nc.GroupStart(), "group start");
+	for(auto& kv : s->peers) {
+		PeerPlan& p = kv.second;
+		const size_t ns = p.send_node.size(), nr = p.recv_node.size();
+		if(ns) nccl_check(nc.Send(p.send_buf.p, 9 * ns, 7 /* ncclFloat32 */, kv.first, s->nccl_comm, s->stream), "send");
+		if(nr) nccl_check(nc.Recv(p.recv_buf.p, 9 * nr, 7, kv.first, s->nccl_comm, s->stream), "recv");
+	}
+	nccl_check(nc.GroupEnd(), "group end");
+	for(auto& kv : s->peers) {
+		PeerPlan& p = kv.second;
+		const int n = (int)p.recv_node.size();
+		if(!n) continue;
+		ProfScope ps(s, PROF_HALO, n);
+		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->dm.ucur(), p.recv_buf.p, p.d_recv.p, n, n, 0);
+		s->launches++;
+	}
+	CK(cudaGetLastError());
+}
+
 } // namespace
 
 #define GUARD_BEGIN try {
@@ -881,6 +967,7 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		if(s->stream) cudaStreamSynchronize(s->stream);
 		if(s->aux) cudaStreamSynchronize(s->aux);
 		if(s->rng_stream) cudaStreamSynchronize(s->rng_stream);
+		if(s->nccl_comm) { nccl_api().CommDestroy(s->nccl_comm); s->nccl_comm = nullptr; }
 		prof_drain(s);
 		for(int k = 0; k < 2; k++) { if(s->h_basis[k]) cudaFreeHost(s->h_basis[k]); if(s->basis_ev[k]) cudaEventDestroy(s->basis_ev[k]); }
 		if(s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1185,14 +1272,51 @@ int gcm_b200_set_end_step(gcm_b200_set* s)
 	return 0;
 }
 
+int gcm_b200_comm_get_unique_id(void* id128)
+{
+	GUARD_BEGIN
+	if(!id128) return fail(gcmh::CONFIG_EXCEPTION, "null id buffer");
+	NcclId id;
+	nccl_check(nccl_api().GetUniqueId(&id), "get unique id");
+	memcpy(id128, &id, sizeof id);
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_set_comm_init(gcm_b200_set* s, const void* id128, int rank, int n_ranks)
+{
+	GUARD_BEGIN
+	NEED_DEVICE(s);
+	if(!id128 || rank < 0 || rank >= n_ranks) return fail(gcmh::CONFIG_EXCEPTION, "bad communicator arguments");
+	if(s->nccl_comm) return fail(gcmh::CONFIG_EXCEPTION, "communicator already initialised");
+	NcclId id;
+	memcpy(&id, id128, sizeof id);
+	nccl_check(nccl_api().CommInitRank(&s->nccl_comm, n_ranks, id, rank), "comm init");
+	s->comm_rank = rank; s->comm_size = n_ranks;
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_set_comm_sync_nodes(gcm_b200_set* s)
+{
+	GUARD_BEGIN
+	NEED_DEVICE(s);
+	if(!s->nccl_comm) return fail(gcmh::CONFIG_EXCEPTION, "no communicator: call gcm_b200_set_comm_init first");
+	comm_exchange(s);
+	return 0;
+	GUARD_END
+}
+
 int gcm_b200_set_do_next_step(gcm_b200_set* s)
 {
 	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
-	if(!s->peers.empty()) return fail(gcmh::CONFIG_EXCEPTION, "multi-process set: drive the stages with gcm_b200_halo_* between them");
+	if(!s->peers.empty() && !s->nccl_comm)
+		return fail(gcmh::CONFIG_EXCEPTION, "multi-process set: call gcm_b200_set_comm_init, or drive the stages with gcm_b200_halo_* between them");
 	int rc = gcm_b200_set_begin_step(s);
 	if(rc) return rc;
 	for(int stage = 0; stage < 4; stage++) {
 		if((rc = gcm_b200_set_sync_nodes(s))) return rc;
+		if(s->nccl_comm && (rc = gcm_b200_set_comm_sync_nodes(s))) return rc;
 		if((rc = gcm_b200_set_do_next_part_step(s, s->time_step, stage))) return rc;
 	}
 	return gcm_b200_set_end_step(s);

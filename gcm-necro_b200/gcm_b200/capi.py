@@ -83,6 +83,9 @@ SIGNATURES = {
     "gcm_b200_halo_unpack_host": (_i, [_p, _i, _fp]),
     "gcm_b200_halo_pack": (_i, [_p, _i, _p]),
     "gcm_b200_halo_unpack": (_i, [_p, _i, _p]),
+    "gcm_b200_comm_get_unique_id": (_i, [_p]),
+    "gcm_b200_set_comm_init": (_i, [_p, _p, _i, _i]),
+    "gcm_b200_set_comm_sync_nodes": (_i, [_p]),
     "gcm_b200_zone_counts": (_i, [_p, _i, _ip, _ip, _ip, _ip, _ip]),
     "gcm_b200_zone_get_flags": (_i, [_p, _i, _ip]),
     "gcm_b200_zone_get_faces": (_i, [_p, _i, _ip]),
@@ -355,3 +358,17 @@ class TetrMeshSet:
 
     def halo_unpack(self, peer, dev_ptr):
         self._ck(self.lib.gcm_b200_halo_unpack(self.h, peer, C.c_void_p(dev_ptr)))
+
+    def comm_get_unique_id(self) -> bytes:
+        """ncclUniqueId (128 bytes) for gcm_b200_set_comm_init; rank 0 makes it, the host broadcasts it."""
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.gcm_b200_comm_get_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, n_ranks: int):
+        """Collective: the set gets its own NCCL communicator and moves the halos itself from now on."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.gcm_b200_set_comm_init(self.h, buf, rank, n_ranks))
+
+    def comm_sync_nodes(self):
+        self._ck(self.lib.gcm_b200_set_comm_sync_nodes(self.h))

@@ -4,7 +4,10 @@
 ``sync_nodes_startup`` is the first ``DataBus::sync_nodes`` on host memory (coords + 13 values,
 main.cpp:127), ``do_next_step`` is ``TetrMeshSet::do_next_step`` (TetrMeshSet.cpp:101-184) with the
 cross-rank part of ``sync_nodes`` done as one grouped NCCL send/recv per neighbour before each
-stage, stream-ordered on the set's CUDA stream (no host synchronisation inside a step).
+stage, stream-ordered on the set's CUDA stream (no host synchronisation inside a step).  By default
+the set owns the communicator (``init_native_comm``: the id travels over torch.distributed once)
+and a step is one library call; ``GCM_B200_TORCH_HALO=1`` keeps the per-stage exchange in Python
+through ``torch.distributed`` P2P ops on caller-owned buffers (``gcm_b200_halo_pack/unpack``).
 With the gloo backend (CPU tests) only the planning / start-up exchange is available.
 """
 from __future__ import annotations
@@ -26,6 +29,7 @@ class DataBus:
         self.send_buf = {}
         self.recv_buf = {}
         self._stream = None
+        self._native = None      # True once the set moves the halos itself (init_native_comm)
 
     # ---- DataBus::create_custom_types ------------------------------------------------------
     def create_custom_types(self):
@@ -92,8 +96,25 @@ class DataBus:
                 if p in self.recv_buf:
                     self.ms.halo_unpack(p, self.recv_buf[p].data_ptr())
 
+    # ---- library-driven exchange: the set owns an NCCL communicator --------------------------
+    def init_native_comm(self):
+        """Collective, after pre_process_meshes: hand the set its own NCCL communicator so that a whole
+        step (halo exchange included) is ONE library call -- no per-stage Python on the critical path."""
+        ids = [self.ms.comm_get_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, group=self.group)
+        self.ms.comm_init(ids[0], self.rank, self.world)
+        self._native = True
+
     def do_next_step(self, tau=0.002):
         ms = self.ms
+        if self._native is None:
+            import os
+            self._native = False
+            if dist.get_backend(self.group) == "nccl" and os.environ.get("GCM_B200_TORCH_HALO", "0") != "1":
+                self.init_native_comm()
+        if self._native and tau == 0.002:
+            ms.do_next_step()
+            return
         ms.begin_step()
         for stage in range(4):
             self.sync_nodes()

@@ -123,6 +123,16 @@ int gcm_b200_halo_unpack_host(gcm_b200_set* s, int peer_rank, const float* buf16
  * device pointer owned by the caller (e.g. an NCCL send/recv buffer). Runs on the set's stream. */
 int gcm_b200_halo_pack(gcm_b200_set* s, int peer_rank, float* dev_buf);
 int gcm_b200_halo_unpack(gcm_b200_set* s, int peer_rank, const float* dev_buf);
+/* Library-driven exchange: the set owns an NCCL communicator (NCCL is resolved with dlopen, the
+ * process's own copy if it has one) and moves the halos itself, so that a whole step is one call.
+ * Replaces MPI::COMM_WORLD / MPI_Isend / MPI_Irecv of gcm/system/DataBus.cpp:81-115.
+ *   rank 0: gcm_b200_comm_get_unique_id(id) (128 bytes, ncclUniqueId); the host broadcasts it;
+ *   every rank, after gcm_b200_halo_set_sends: gcm_b200_set_comm_init(s, id, rank, n_ranks) (collective).
+ * gcm_b200_set_comm_sync_nodes = pack + grouped ncclSend/ncclRecv with every neighbour + unpack on the
+ * set's stream; gcm_b200_set_do_next_step calls it before each stage once a communicator exists. */
+int gcm_b200_comm_get_unique_id(void* id128);
+int gcm_b200_set_comm_init(gcm_b200_set* s, const void* id128, int rank, int n_ranks);
+int gcm_b200_set_comm_sync_nodes(gcm_b200_set* s);
 
 /* ---- inspection (what VTKSnapshotWriter / a debugger would read) -------------------------- */
 int gcm_b200_zone_counts(gcm_b200_set* s, int zone, int* n_nodes, int* n_tets, int* n_faces,

@@ -270,7 +270,11 @@ def main():
     achieved = (B_STAGE * in_units) / (in_ms * 1e-3) / 1e9 if in_ms > 0 else 0.0
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the inner kernel on this workload,
+        # from the committed ncu --set full capture (profiles/README.md says which)
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+        if args.size == t.get("size") and args.zones == t.get("zones") and world == 1:
+            traffic = t["bytes_per_launch"]
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "inner-node axis stage", "achieved": achieved, "peak": peak, "unit": "GB/s",

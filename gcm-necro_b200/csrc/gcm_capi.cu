@@ -96,7 +96,7 @@ struct DeviceMesh {
 	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0;
 	size_t n_fast = 0, n_generic = 0, n_inner = 0;
 	DevBuf<float> u0, u1, mat, tet_hv, basis, basis_next, normals, w0, aos, mat_tab;
-	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, didx;
+	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, didx, cold;
 	DevBuf<int> sharp_list, flat_list, fast_list, generic_list, inner_list;
 	size_t n_sharp = 0, n_flat = 0;
 	DevBuf<unsigned char> mat_id;
@@ -394,6 +394,7 @@ void upload_mesh(gcm_b200_set* s)
 	if(s->dir_index && nf) {
 		// angular candidate index of the inner kernel: three planes of N 64-byte entries, built on the device
 		dm.didx.alloc(3 * 4 * GCM_DIDX_QUADS * N);
+		dm.cold.alloc(N + 1);   // nodes deferred by the inner kernel: count, then node ids
 		CK(cudaMemsetAsync(dm.didx.p, 0, 3 * 4 * GCM_DIDX_QUADS * N * sizeof(int), st));
 		const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
 		uint4* dx = reinterpret_cast<uint4*>(dm.didx.p);
@@ -641,16 +642,20 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 			const dim3 grid((nf + 127) / 128), block(128);
 			const uint4* dx = s->dir_index ? reinterpret_cast<const uint4*>(dm.didx.p) + (size_t)stage * GCM_DIDX_QUADS * dm.N : nullptr;
 #define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x)
-#define GCM_LAUNCH_DIRECT(S_, MB_, PF_) gcm::stage_inner_direct_kernel<S_, MB_, PF_><<<dgrid, block, 0, s->stream>>>(m, nbeg, nrange, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, n2x, dx)
+#define GCM_LAUNCH_DIRECT(S_, MB_, PF_) gcm::stage_inner_direct_kernel<S_, MB_, PF_><<<dgrid, block, 0, s->stream>>>(m, nbeg, nrange, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, n2x, dx, dm.cold.p)
 #define GCM_LAUNCH_DIRECT_S(MB_, PF_) do { if(stage == 0) GCM_LAUNCH_DIRECT(0, MB_, PF_); else if(stage == 1) GCM_LAUNCH_DIRECT(1, MB_, PF_); else GCM_LAUNCH_DIRECT(2, MB_, PF_); } while(0)
 #define GCM_LAUNCH_DIRECT_MB(MB_) do { if(s->direct_prefetch == 0) GCM_LAUNCH_DIRECT_S(MB_, 0); else GCM_LAUNCH_DIRECT_S(MB_, 1); } while(0)
 			const int nbeg = (int)(z ? z->node_off : 0), nrange = (int)(z ? (size_t)z->hm.N : dm.N);
 			const dim3 dgrid((unsigned)((nrange + 127) / 128));
 			if(dx) {
+				CK(cudaMemsetAsync(dm.cold.p, 0, sizeof(int), s->stream));
 				if(s->direct_min_blocks == 3) GCM_LAUNCH_DIRECT_MB(3);
 				else if(s->direct_min_blocks == 5) GCM_LAUNCH_DIRECT_MB(5);
 				else if(s->direct_min_blocks == 6) GCM_LAUNCH_DIRECT_MB(6);
 				else GCM_LAUNCH_DIRECT_MB(4);
+				// whatever the index could not settle: the literal routine, right behind
+				gcm::stage_deferred_kernel<<<296, 128, 0, s->stream>>>(m, dm.cold.p, stage, dm.unext(), s->d_err, zone, tap);
+				s->launches++;
 			}
 			else if(stage == 0) GCM_LAUNCH_INNER(0, 5);
 			else if(stage == 1) GCM_LAUNCH_INNER(1, 5);

@@ -510,12 +510,15 @@ __device__ __forceinline__ bool feet_of_dir(const CandFull& f, int dir, const F3
 
 // PF: 1 = the records of both directions' first survivors are requested together, 0 = the second
 // direction's after the first direction's search (fewer live registers).
+// A node the index cannot settle (guard, disagreeing feet, no owner in the first ring) is appended to
+// `cold` (cold[0] = count) and advanced by stage_deferred_kernel right after this launch: keeping the
+// literal routine out of this kernel leaves its hot path spill-free at 128 registers (-7 % time).
 template<int S, int MB, int PF>
 __global__ void __launch_bounds__(128, MB)
 stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, int n_range,
                           float* __restrict__ un, int* err, int zone, StageTap* tap,
                           const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
-                          const int4* __restrict__ n2x, const uint4* __restrict__ didx)
+                          const int4* __restrict__ n2x, const uint4* __restrict__ didx, int* __restrict__ cold)
 {
 	static_assert(u_pattern(S, 0) == u_pattern(S, 1) && u_pattern(S, 2) == u_pattern(S, 3) && u_pattern(S, 4) == u_pattern(S, 5),
 	              "rows 2q and 2q+1 of Omega must share their sparsity pattern");
@@ -567,17 +570,17 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 			de[q] = sqrtf(dk[q] * dk[q]);             // delta; off-axis components are +-0
 			ok = ok && de[q] > 0 && (double)de[q] < h99;
 		}
-		if(!ok) { inner_node_generic(m, node, S, un, err, zone, tap); return; }
+		if(!ok) { cold[1 + atomicAdd(&cold[0], 1)] = node; return; }
 	}
 	float omega[9];
 	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
 	if(!settle_dir<S>(f0, ix.x, node, m.n2t_off, X, -1.0f, dk[0], de[0], dk[2], de[2], n2x, rec, hv2)) {
-		inner_node_generic(m, node, S, un, err, zone, tap); return;
+		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
 	}
 	if(PF == 0) load_records(f1, rec);
 	if(!feet_of_dir<S>(f0, 0, X, dk[0], dk[2], own, U, omega)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
 	if(!settle_dir<S>(f1, ix.y, node, m.n2t_off, X, 1.0f, dk[1], de[1], dk[3], de[3], n2x, rec, hv2)) {
-		inner_node_generic(m, node, S, un, err, zone, tap); return;
+		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
 	}
 	if(!feet_of_dir<S>(f1, 1, X, dk[1], dk[3], own, U, omega)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
 

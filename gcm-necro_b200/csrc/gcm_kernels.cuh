@@ -36,6 +36,27 @@ stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 		un[(size_t)node * GCM_REC + k] = out[k];
 }
 
+// The nodes the indexed inner kernel could not settle (cold[0] = how many, cold[1..] = which), through
+// the literal per-node routine; a small fixed grid strides over the list (it is empty on regular
+// meshes, a handful of nodes on jittered ones, every inner node if tau were too large for the index).
+__global__ void __launch_bounds__(128)
+stage_deferred_kernel(const __grid_constant__ MeshView m, const int* __restrict__ cold, int stage,
+                      float* __restrict__ un, int* err, int zone, StageTap* tap)
+{
+	const int n = cold[0];
+	for(int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+		const int node = cold[1 + idx];
+		float out[9];
+		StageTap t;
+		const int e = node_stage_nocontact_cold(m, node, stage, out, tap ? &t : nullptr);
+		if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
+		if(e) { report_error(err, e, zone, node, stage); continue; }
+		#pragma unroll
+		for(int k = 0; k < 9; k++)
+			un[(size_t)node * GCM_REC + k] = out[k];
+	}
+}
+
 // Same kernel with a register budget for MB resident blocks per SM (occupancy vs spills).
 template<int MB>
 __global__ void __launch_bounds__(128, MB)

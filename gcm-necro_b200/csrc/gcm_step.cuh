@@ -417,6 +417,7 @@ GCM_HD void scan_ring_both_senses(const MeshView& m, int base, const Vec3& X, co
 	rs.dmin2 = 3.4e38f;
 	bool open0 = true, open1 = true;
 	const float qn = sqrtf(q[0]*q[0] + q[1]*q[1] + q[2]*q[2]);
+	const float inv_qn = qn > 0 ? 1.0f / qn : 0.0f;    // the filter is conservative: its rounding is free
 	const int e0 = m.n2t_off[base], e1 = m.n2t_off[base + 1];
 	for(int e = e0; e < e1 && (open0 || open1); e++) {
 		const int t = m.n2t[e];
@@ -435,7 +436,7 @@ GCM_HD void scan_ring_both_senses(const MeshView& m, int base, const Vec3& X, co
 			const float cax = ecy * eaz - ecz * eay, cay = ecz * eax - ecx * eaz, caz = ecx * eay - ecy * eax;
 			const float abx = eay * ebz - eaz * eby, aby = eaz * ebx - eax * ebz, abz = eax * eby - eay * ebx;
 			const float D = eax * bcx + eay * bcy + eaz * bcz;
-			const float sD = 0.99f * g.h / qn * D;
+			const float sD = 0.99f * g.h * inv_qn * D;
 			// barycentric coordinates (times D^2) of X + 0.99 h q/|q|; those of the opposite sense are the negatives
 			const float la = sD * (q[0] * bcx + q[1] * bcy + q[2] * bcz);
 			const float lb = sD * (q[0] * cax + q[1] * cay + q[2] * caz);
@@ -816,17 +817,20 @@ GCM_HD int node_stage_nocontact_t(const MeshView& m, int node, int stage, float 
 		slot = m.border_slot[node];
 		basis = m.basis + 9*(size_t)slot;
 	}
+	// The feet need the wave speeds only; Omega (and Omega^-1 when every characteristic is inner) is
+	// built after the search, in ONE pass of the same routine on the same inputs -- the shared part of
+	// the eigensystem is then computed once per stage instead of twice and is not live across the search.
 	float L[9], U[81];
 	FeetOut feet;
 	int tries = 0;
 	int outer_count;
 	if(only_try < 0) {
-		outer_count = prepare_node(m, cur, stage, basis, L, U, nullptr, feet, false, &tries);
+		outer_count = prepare_node(m, cur, stage, basis, L, nullptr, nullptr, feet, false, &tries);
 	} else {
 		// one alpha try of the retry loop (speculative evaluation of all 11 tries by 11 lanes,
 		// stage_sharp_kernel): same eigensystem, same dksi, alpha = value the loop would have then
 		const float* ksi = basis + 3*stage;
-		int e = (bad_value || only_try > 10) ? 0 : elastic_matrix(cur.la, cur.mu, cur.rho, ksi[0], ksi[1], ksi[2], L, U, nullptr);
+		int e = (bad_value || only_try > 10) ? 0 : elastic_matrix(cur.la, cur.mu, cur.rho, ksi[0], ksi[1], ksi[2], L, nullptr, nullptr);
 		if(only_try > 10) outer_count = 1;          // padding lane of the group: votes "no"
 		else if(bad_value) outer_count = -ERR_NAN;
 		else if(e) outer_count = -e;
@@ -847,16 +851,16 @@ GCM_HD int node_stage_nocontact_t(const MeshView& m, int node, int stage, float 
 		tap->outer_count = outer_count; tap->tries = tries;
 	}
 	if(outer_count < 0) return -outer_count;
+	const float* q = basis + 3*stage;
 	if(outer_count == 0) {
-		// Omega^-1 is only needed on this branch: build it now (same routine, same inputs)
 		float U1[81];
-		const float* q = basis + 3*stage;
-		elastic_matrix(cur.la, cur.mu, cur.rho, q[0], q[1], q[2], L, nullptr, U1);
+		elastic_matrix(cur.la, cur.mu, cur.rho, q[0], q[1], q[2], L, U, U1);
 		volume_calc(U, U1, feet, out);
 		return ERR_NONE;
 	}
 	if(outer_count != 3) return ERR_OUTER_COUNT;
 	if(!cur.is_border) return ERR_NOT_BORDER;
+	elastic_matrix(cur.la, cur.mu, cur.rho, q[0], q[1], q[2], L, U, nullptr);
 	// default condition: FreeBorderCalculator with an always-on form (TetrMeshSet.cpp:11-21)
 	BorderCond def;
 	def.type = BC_FREE; def.scale = 1; def.active = 1;

@@ -132,6 +132,14 @@ struct gcm_b200_set {
 	std::vector<int> halo_dst, halo_src;        // same-process halo, merged indices
 	std::map<int, PeerPlan> peers;
 	void* nccl_comm = nullptr;   // library-driven halo exchange (gcm_b200_set_comm_init); NULL = the host moves the halos
+	// overlapped stage: nodes within two rings of a halo node owned by another process ("shell") wait for the
+	// exchange, everything else ("deep") runs beside it.  Lists in merged indices, deep part first.
+	bool overlap = false, ov_ready = false;   // measured slower (2 GPUs: 2.20 vs 1.97 ms/step): the second, latency-bound
+	                                           // border launch per stage costs more than the exchange it hides; GCM_B200_OVERLAP=1
+	DevBuf<int> ov_flat, ov_sharp, ov_generic, ov_fast_shell;
+	size_t ov_flat_deep = 0, ov_sharp_deep = 0, ov_generic_deep = 0;
+	cudaStream_t comm_stream = nullptr;
+	cudaEvent_t ev_comm_begin = nullptr, ev_comm_done = nullptr;
 	int comm_rank = -1, comm_size = 0;
 	bool plan_built = false;
 	bool preprocessed = false;
@@ -566,7 +574,8 @@ void sync_nodes_device(gcm_b200_set* s)
 }
 
 // One stage for the nodes of one zone (zone >= 0) or of every local zone (zone < 0).
-void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
+// part: 0 = every node; 1 = the deep nodes only, 2 = the shell nodes only (overlapped stage, zone < 0).
+void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 {
 	DeviceMesh& dm = s->dm;
 	Zone* z = zone >= 0 ? s->zones[zone].get() : nullptr;
@@ -588,6 +597,13 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 	const int* bl = dm.flat_list.p + (z ? z->flat_off : 0);
 	int nsh = (int)(z ? (size_t)z->hm.n_sharp : dm.n_sharp);
 	const int* shl = dm.sharp_list.p + (z ? z->sharp_off : 0);
+	if(part) {
+		const size_t fd = s->ov_flat_deep, sd = s->ov_sharp_deep;
+		nb = (int)(part == 1 ? fd : s->ov_flat.n - fd);
+		bl = s->ov_flat.p + (part == 1 ? 0 : fd);
+		nsh = (int)(part == 1 ? sd : s->ov_sharp.n - sd);
+		shl = s->ov_sharp.p + (part == 1 ? 0 : sd);
+	}
 	const bool contact = stage == 0 && s->contact_active;
 	if(contact) {   // border nodes in contact on axis 0 take the contact kernel instead
 		nb = (int)(z ? z->st0_n : s->st0_total);
@@ -626,11 +642,18 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 			s->launches++;
 		}
 	} else {
-		const int ng = (int)(z ? z->hm.inner_generic.size() : dm.n_generic);
-		const int nf = (int)(z ? z->hm.inner_fast.size() : dm.n_fast);
+		int ng = (int)(z ? z->hm.inner_generic.size() : dm.n_generic);
+		int nf = (int)(z ? z->hm.inner_fast.size() : dm.n_fast);
+		const int* gl = dm.generic_list.p + (z ? z->generic_off : 0);
+		if(part) {
+			const size_t gd = s->ov_generic_deep;
+			ng = (int)(part == 1 ? gd : s->ov_generic.n - gd);
+			gl = s->ov_generic.p + (part == 1 ? 0 : gd);
+			if(part == 2) nf = (int)s->ov_fast_shell.n;
+		}
 		if(ng) {
 			ProfScope ps(s, PROF_INNER_GENERIC, ng);
-			gcm::stage_generic_kernel<<<(ng + 127) / 128, 128, 0, s->stream>>>(m, dm.generic_list.p + (z ? z->generic_off : 0), ng, stage, dm.unext(), s->d_err, zone, tap);
+			gcm::stage_generic_kernel<<<(ng + 127) / 128, 128, 0, s->stream>>>(m, gl, ng, stage, dm.unext(), s->d_err, zone, tap);
 			s->launches++;
 		}
 		if(nf) {
@@ -642,10 +665,12 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage)
 			const dim3 grid((nf + 127) / 128), block(128);
 			const uint4* dx = s->dir_index ? reinterpret_cast<const uint4*>(dm.didx.p) + (size_t)stage * GCM_DIDX_QUADS * dm.N : nullptr;
 #define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x)
-#define GCM_LAUNCH_DIRECT(S_, MB_, PF_) gcm::stage_inner_direct_kernel<S_, MB_, PF_><<<dgrid, block, 0, s->stream>>>(m, nbeg, nrange, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, n2x, dx, dm.cold.p)
+#define GCM_LAUNCH_DIRECT(S_, MB_, PF_) gcm::stage_inner_direct_kernel<S_, MB_, PF_><<<dgrid, block, 0, s->stream>>>(m, nbeg, nrange, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, n2x, dx, dm.cold.p, dlist, part == 1 ? 1 : 0)
 #define GCM_LAUNCH_DIRECT_S(MB_, PF_) do { if(stage == 0) GCM_LAUNCH_DIRECT(0, MB_, PF_); else if(stage == 1) GCM_LAUNCH_DIRECT(1, MB_, PF_); else GCM_LAUNCH_DIRECT(2, MB_, PF_); } while(0)
 #define GCM_LAUNCH_DIRECT_MB(MB_) do { if(s->direct_prefetch == 0) GCM_LAUNCH_DIRECT_S(MB_, 0); else GCM_LAUNCH_DIRECT_S(MB_, 1); } while(0)
-			const int nbeg = (int)(z ? z->node_off : 0), nrange = (int)(z ? (size_t)z->hm.N : dm.N);
+			// deep pass: the whole range minus the nodes flagged shell; shell pass: the listed shell nodes
+			const int* dlist = part == 2 ? s->ov_fast_shell.p : nullptr;
+			const int nbeg = (int)(z ? z->node_off : 0), nrange = part == 2 ? nf : (int)(z ? (size_t)z->hm.N : dm.N);
 			const dim3 dgrid((unsigned)((nrange + 127) / 128));
 			if(dx) {
 				CK(cudaMemsetAsync(dm.cold.p, 0, sizeof(int), s->stream));
@@ -862,7 +887,7 @@ void nccl_check(int rc, const char* what)
 // DataBus::sync_nodes across processes (gcm/system/DataBus.cpp:81-115), all on the set's stream:
 // gather the nodes every neighbour asked for, one grouped ncclSend/ncclRecv per neighbour over
 // NVLink, scatter what arrived into the halo slots.
-void comm_exchange(gcm_b200_set* s)
+void comm_exchange(gcm_b200_set* s, cudaStream_t st)
 {
 	if(s->peers.empty()) return;
 	NcclApi& nc = nccl_api();
@@ -873,8 +898,8 @@ void comm_exchange(gcm_b200_set* s)
 		const int n = (int)p.send_node.size();
 		if(!n) continue;
 		if(!p.send_buf.p) p.send_buf.alloc(9 * (size_t)n);
-		ProfScope ps(s, PROF_HALO, n);
-		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(p.send_buf.p, s->dm.ucur(), p.d_send.p, n, n, 0);
+		ProfScope ps(s, PROF_HALO, n, st);
+		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.send_buf.p, s->dm.ucur(), p.d_send.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
@@ -882,19 +907,79 @@ void comm_exchange(gcm_b200_set* s)
 	for(auto& kv : s->peers) {
 		PeerPlan& p = kv.second;
 		const size_t ns = p.send_node.size(), nr = p.recv_node.size();
-		if(ns) nccl_check(nc.Send(p.send_buf.p, 9 * ns, 7 /* ncclFloat32 */, kv.first, s->nccl_comm, s->stream), "send");
-		if(nr) nccl_check(nc.Recv(p.recv_buf.p, 9 * nr, 7, kv.first, s->nccl_comm, s->stream), "recv");
+		if(ns) nccl_check(nc.Send(p.send_buf.p, 9 * ns, 7 /* ncclFloat32 */, kv.first, s->nccl_comm, st), "send");
+		if(nr) nccl_check(nc.Recv(p.recv_buf.p, 9 * nr, 7, kv.first, s->nccl_comm, st), "recv");
 	}
 	nccl_check(nc.GroupEnd(), "group end");
 	for(auto& kv : s->peers) {
 		PeerPlan& p = kv.second;
 		const int n = (int)p.recv_node.size();
 		if(!n) continue;
-		ProfScope ps(s, PROF_HALO, n);
-		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->dm.ucur(), p.recv_buf.p, p.d_recv.p, n, n, 0);
+		ProfScope ps(s, PROF_HALO, n, st);
+		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(s->dm.ucur(), p.recv_buf.p, p.d_recv.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
+}
+
+
+// Classifies the local nodes for the overlapped stage and lays the kernel lists out (deep part first).
+void build_overlap_plan(gcm_b200_set* s)
+{
+	DeviceMesh& dm = s->dm;
+	const size_t N = dm.N;
+	std::vector<char> mark(N, 0);
+	for(auto& kv : s->peers) {
+		const PeerPlan& p = kv.second;
+		for(size_t k = 0; k < p.recv_node.size(); k++) mark[s->zones[p.recv_zone[k]]->node_off + p.recv_node[k]] = 1;
+	}
+	// two rings: a node reads the vertices of its first-ring tets, and the literal routine may go one ring further
+	for(int pass = 0; pass < 2; pass++) {
+		std::vector<char> nxt(mark);
+		for(int zi : s->local_zones) {
+			const Zone& z = *s->zones[zi];
+			const HostMesh& hm = z.hm;
+			for(int t = 0; t < hm.T; t++) {
+				const int* tv = &hm.tets[4 * (size_t)t];
+				if(mark[z.node_off + tv[0]] || mark[z.node_off + tv[1]] || mark[z.node_off + tv[2]] || mark[z.node_off + tv[3]])
+					for(int j = 0; j < 4; j++) nxt[z.node_off + tv[j]] = 1;
+			}
+		}
+		mark.swap(nxt);
+	}
+	std::vector<int> flat[2], sharp[2], generic[2], fast_shell;
+	for(int zi : s->local_zones) {
+		const Zone& z = *s->zones[zi];
+		const HostMesh& hm = z.hm;
+		for(size_t k = 0; k < hm.border_launch.size(); k++) {
+			const int g = (int)(z.node_off + hm.border_launch[k]);
+			((int)k < hm.n_sharp ? sharp : flat)[mark[g] ? 1 : 0].push_back(g);
+		}
+		for(int i : hm.inner_generic) generic[mark[z.node_off + i] ? 1 : 0].push_back((int)(z.node_off + i));
+		for(int i : hm.inner_fast) if(mark[z.node_off + i]) fast_shell.push_back((int)(z.node_off + i));
+	}
+	auto put2 = [&](DevBuf<int>& d, std::vector<int>* v, size_t& n_deep) {
+		n_deep = v[0].size();
+		std::vector<int> all(v[0]);
+		all.insert(all.end(), v[1].begin(), v[1].end());
+		d.upload(all, s->stream);
+	};
+	put2(s->ov_flat, flat, s->ov_flat_deep);
+	put2(s->ov_sharp, sharp, s->ov_sharp_deep);
+	put2(s->ov_generic, generic, s->ov_generic_deep);
+	s->ov_fast_shell.upload(fast_shell, s->stream);
+	if(!fast_shell.empty() && dm.didx.p) {
+		gcm::mark_shell_kernel<<<(int)((fast_shell.size() + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<uint4*>(dm.didx.p), N, s->ov_fast_shell.p, (int)fast_shell.size());
+		s->launches++;
+		CK(cudaGetLastError());
+	}
+	CK(cudaStreamSynchronize(s->stream));
+	if(!s->comm_stream) {
+		CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&s->ev_comm_begin, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&s->ev_comm_done, cudaEventDisableTiming));
+	}
+	s->ov_ready = true;
 }
 
 } // namespace
@@ -954,6 +1039,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_COOP_BORDER")) s->coop_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_MB")) s->border_min_blocks = atoi(e);
 	if(const char* e = getenv("GCM_B200_LEAN_BORDER")) s->lean_border = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_OVERLAP")) s->overlap = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BASES_AHEAD")) s->bases_ahead = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_DIR_INDEX")) s->dir_index = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_DIRECT_MB")) s->direct_min_blocks = atoi(e);
@@ -972,6 +1058,7 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		if(s->stream) cudaStreamSynchronize(s->stream);
 		if(s->aux) cudaStreamSynchronize(s->aux);
 		if(s->rng_stream) cudaStreamSynchronize(s->rng_stream);
+		if(s->comm_stream) { cudaStreamSynchronize(s->comm_stream); cudaStreamDestroy(s->comm_stream); cudaEventDestroy(s->ev_comm_begin); cudaEventDestroy(s->ev_comm_done); }
 		if(s->nccl_comm) { nccl_api().CommDestroy(s->nccl_comm); s->nccl_comm = nullptr; }
 		prof_drain(s);
 		for(int k = 0; k < 2; k++) { if(s->h_basis[k]) cudaFreeHost(s->h_basis[k]); if(s->basis_ev[k]) cudaEventDestroy(s->basis_ev[k]); }
@@ -1298,6 +1385,7 @@ int gcm_b200_set_comm_init(gcm_b200_set* s, const void* id128, int rank, int n_r
 	memcpy(&id, id128, sizeof id);
 	nccl_check(nccl_api().CommInitRank(&s->nccl_comm, n_ranks, id, rank), "comm init");
 	s->comm_rank = rank; s->comm_size = n_ranks;
+	if(s->overlap && s->dir_index && s->fast_inner && !s->peers.empty()) build_overlap_plan(s);
 	return 0;
 	GUARD_END
 }
@@ -1307,7 +1395,25 @@ int gcm_b200_set_comm_sync_nodes(gcm_b200_set* s)
 	GUARD_BEGIN
 	NEED_DEVICE(s);
 	if(!s->nccl_comm) return fail(gcmh::CONFIG_EXCEPTION, "no communicator: call gcm_b200_set_comm_init first");
-	comm_exchange(s);
+	comm_exchange(s, s->stream);
+	return 0;
+	GUARD_END
+}
+
+// One axis stage with the cross-process exchange running beside the deep nodes: the halo slots the
+// exchange fills are read only by the shell nodes, which start when it has landed.
+static int overlapped_stage(gcm_b200_set* s, int stage)
+{
+	GUARD_BEGIN
+	NEED_DEVICE(s);
+	CK(cudaEventRecord(s->ev_comm_begin, s->stream));
+	CK(cudaStreamWaitEvent(s->comm_stream, s->ev_comm_begin, 0));
+	comm_exchange(s, s->comm_stream);
+	CK(cudaEventRecord(s->ev_comm_done, s->comm_stream));
+	run_stage(s, -1, s->time_step, stage, 1);
+	CK(cudaStreamWaitEvent(s->stream, s->ev_comm_done, 0));
+	run_stage(s, -1, s->time_step, stage, 2);
+	finish_axis_stage(s);
 	return 0;
 	GUARD_END
 }
@@ -1321,6 +1427,10 @@ int gcm_b200_set_do_next_step(gcm_b200_set* s)
 	if(rc) return rc;
 	for(int stage = 0; stage < 4; stage++) {
 		if((rc = gcm_b200_set_sync_nodes(s))) return rc;
+		if(s->nccl_comm && s->ov_ready && stage < 3 && !s->contact_active) {
+			if((rc = overlapped_stage(s, stage))) return rc;
+			continue;
+		}
 		if(s->nccl_comm && (rc = gcm_b200_set_comm_sync_nodes(s))) return rc;
 		if((rc = gcm_b200_set_do_next_part_step(s, s->time_step, stage))) return rc;
 	}

@@ -417,6 +417,18 @@ build_dir_index_kernel(const float* __restrict__ u, const int* __restrict__ n2t_
 	o[3] = make_uint4(__float_as_uint(hm.x), __float_as_uint(hm.y), __float_as_uint(hp.x), __float_as_uint(hp.y));
 }
 
+// Sets the "shell" bit (sign of w0) of the listed nodes in the three planes of the index.
+__global__ void mark_shell_kernel(uint4* __restrict__ didx, size_t n_nodes, const int* __restrict__ list, int n_list)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	for(int sgl = 0; sgl < 3; sgl++) {
+		uint4* e = didx + GCM_DIDX_QUADS * ((size_t)sgl * n_nodes + node);
+		if(e->z != 0u) e->w |= 0x80000000u;
+	}
+}
+
 // ---- inner kernel, indexed -------------------------------------------------------------------
 // One thread per NODE of a contiguous node range (no list indirection): the node's index entry
 // says whether it is a fast inner node at all.  Two rounds of dependent loads per node-stage:
@@ -510,6 +522,7 @@ __device__ __forceinline__ bool feet_of_dir(const CandFull& f, int dir, const F3
 
 // PF: 1 = the records of both directions' first survivors are requested together, 0 = the second
 // direction's after the first direction's search (fewer live registers).
+// list / skip_shell: see the body.
 // A node the index cannot settle (guard, disagreeing feet, no owner in the first ring) is appended to
 // `cold` (cold[0] = count) and advanced by stage_deferred_kernel right after this launch: keeping the
 // literal routine out of this kernel leaves its hot path spill-free at 128 registers (-7 % time).
@@ -518,7 +531,8 @@ __global__ void __launch_bounds__(128, MB)
 stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, int n_range,
                           float* __restrict__ un, int* err, int zone, StageTap* tap,
                           const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
-                          const int4* __restrict__ n2x, const uint4* __restrict__ didx, int* __restrict__ cold)
+                          const int4* __restrict__ n2x, const uint4* __restrict__ didx, int* __restrict__ cold,
+                          const int* __restrict__ list, int skip_shell)
 {
 	static_assert(u_pattern(S, 0) == u_pattern(S, 1) && u_pattern(S, 2) == u_pattern(S, 3) && u_pattern(S, 4) == u_pattern(S, 5),
 	              "rows 2q and 2q+1 of Omega must share their sparsity pattern");
@@ -535,10 +549,15 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if(idx >= n_range) return;
-	const int node = node_begin + idx;
+	// list == NULL: the contiguous range; else the listed nodes (the shell pass of the overlapped stage)
+	const int node = list ? list[idx] : node_begin + idx;
 	const uint4* __restrict__ ent = didx + GCM_DIDX_QUADS * (size_t)node;
-	const uint4 ix = __ldg(ent);
+	uint4 ix = __ldg(ent);
 	if(ix.z == 0u) return;                        // not a node of the fast inner path
+	// sign bit of w0 (a weight, >= 0) = "shell": within two rings of a halo node owned by another process;
+	// the deep pass leaves those to the pass that runs after the exchange
+	if(skip_shell && (ix.w & 0x80000000u)) return;
+	ix.w &= 0x7fffffffu;
 	const uint4 xm = __ldg(ent + 1), xp = __ldg(ent + 2), hq = __ldg(ent + 3);
 	const float4* __restrict__ rec = reinterpret_cast<const float4*>(m.u);
 	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(m.tet_hv);

@@ -155,7 +155,7 @@ struct gcm_b200_set {
 	bool lean_border = false;    // flat border nodes through node_stage_border_lean (row-wise eigensystem; measured 14 % slower)
 	int border_min_blocks = 4;   // register budget variant of the per-thread border kernel (3..8 blocks of 128 / SM)
 	bool dir_index = true;       // inner kernel scans through the angular candidate index (gcm_inner.cuh)
-	int direct_min_blocks = 4;   // register budget variant of stage_inner_direct_kernel (3, 4, 5 or 6 blocks of 128 / SM)
+	int direct_min_blocks = 5;   // register budget variant of stage_inner_direct_kernel (3, 4, 5 or 6 blocks of 128 / SM)
 	int direct_prefetch = 0;     // 1: records of both directions' first survivors requested together, 0: one direction at a time
 	bool use_n2x_generic = false; // generic (border) search through the expanded CSR too (measured: no gain)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them

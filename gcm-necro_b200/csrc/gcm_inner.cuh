@@ -469,14 +469,7 @@ __device__ __forceinline__ bool settle_dir(CandFull& f, unsigned rest, int node,
 		const Cand& c = f.c;
 		int v1 = 0;
 		if(c.vol > 0) v1 = prefilter<S>(c, X, sgn);
-		if(v1 == 0) {
-			const bool in1 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
-			                                  c.qc.y, c.qc.z, c.qc.w, X.x, X.y, X.z, dk1, de1);
-			const bool in2 = exact_in_tetr<S>(c.k, c.h, c.vol, c.qa.y, c.qa.z, c.qa.w, c.qb.y, c.qb.z, c.qb.w,
-			                                  c.qc.y, c.qc.z, c.qc.w, X.x, X.y, X.z, dk2, de2);
-			if(in1 != in2) return false;
-			v1 = in1 ? 1 : -1;
-		}
+		if(v1 == 0) return false;   // within 1e-3 of a face: the literal routine decides (deferred)
 		if(v1 > 0) return true;
 		if(!rest) return false;
 		const int4 x = __ldg(n2x + n2t_off[node] + __ffs(rest) - 1);

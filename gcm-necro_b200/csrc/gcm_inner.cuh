@@ -441,14 +441,21 @@ struct CandFull {
 	float4 a0, a1, b0, b1, c0, c1;     // first two record quads of A, B, C (the third is c.qa/qb/qc)
 };
 
-__device__ __forceinline__ void load_records(CandFull& f, const float4* __restrict__ rec)
+__device__ __forceinline__ void load_value_quads(CandFull& f, const float4* __restrict__ rec)
+{
+	f.a0 = __ldg(rec + 3 * (size_t)f.c.ia); f.a1 = __ldg(rec + 3 * (size_t)f.c.ia + 1);
+	f.b0 = __ldg(rec + 3 * (size_t)f.c.ib); f.b1 = __ldg(rec + 3 * (size_t)f.c.ib + 1);
+	f.c0 = __ldg(rec + 3 * (size_t)f.c.ic); f.c1 = __ldg(rec + 3 * (size_t)f.c.ic + 1);
+}
+
+// values = false: only the coordinate quads (what the search and the interpolation factors need);
+// the value quads then follow in feet_of_dir<S, true>, when the factors are known
+__device__ __forceinline__ void load_records(CandFull& f, const float4* __restrict__ rec, bool values = true)
 {
 	f.c.qa = __ldg(rec + 3 * (size_t)f.c.ia + 2);
 	f.c.qb = __ldg(rec + 3 * (size_t)f.c.ib + 2);
 	f.c.qc = __ldg(rec + 3 * (size_t)f.c.ic + 2);
-	f.a0 = __ldg(rec + 3 * (size_t)f.c.ia); f.a1 = __ldg(rec + 3 * (size_t)f.c.ia + 1);
-	f.b0 = __ldg(rec + 3 * (size_t)f.c.ib); f.b1 = __ldg(rec + 3 * (size_t)f.c.ib + 1);
-	f.c0 = __ldg(rec + 3 * (size_t)f.c.ic); f.c1 = __ldg(rec + 3 * (size_t)f.c.ic + 1);
+	if(values) load_value_quads(f, rec);
 }
 
 __device__ __forceinline__ void set_entry(CandFull& f, const uint4 x, float h, float vol)
@@ -460,7 +467,7 @@ __device__ __forceinline__ void set_entry(CandFull& f, const uint4 x, float h, f
 
 // Owner search of one direction starting from the (already loaded) first survivor; `rest` = the
 // later survivors.  Returns false when the node must take the literal routine.
-template<int S>
+template<int S, bool LATE>
 __device__ __forceinline__ bool settle_dir(CandFull& f, unsigned rest, int node, const int* __restrict__ n2t_off, const F3& X, float sgn,
                                            float dk1, float de1, float dk2, float de2,
                                            const int4* __restrict__ n2x, const float4* __restrict__ rec, const float2* __restrict__ hv2)
@@ -476,45 +483,74 @@ __device__ __forceinline__ bool settle_dir(CandFull& f, unsigned rest, int node,
 		rest &= rest - 1;
 		const float2 hv = __ldg(hv2 + (x.w & 0x3fffffff));
 		set_entry(f, make_uint4((unsigned)x.x, (unsigned)x.y, (unsigned)x.z, (unsigned)x.w), hv.x, hv.y);
-		load_records(f, rec);
+		load_records(f, rec, !LATE);
 	}
+}
+
+// Interpolation factors of the foot X + dks e_S inside candidate c, as (own, A, B, C)
+// (TetrMesh_1stOrder.cpp:1764-1857).  Returns false when the reference throws.
+template<int S>
+__device__ __forceinline__ bool axis_factors(const Cand& c, const F3& X, float dks, float w[4])
+{
+	F3 Fp = X;
+	if(S == 0) Fp.x = X.x + dks; else if(S == 1) Fp.y = X.y + dks; else Fp.z = X.z + dks;
+	F3 p0, p1, p2, p3;
+	tet_order(c, X, p0, p1, p2, p3);
+	float f[4];
+	if(!interp_factors(to_vec3(p0), to_vec3(p1), to_vec3(p2), to_vec3(p3), Fp.x, Fp.y, Fp.z, c.vol, f))
+		return false;
+	w[0] = c.k == 0 ? f[0] : (c.k == 1 ? f[1] : (c.k == 2 ? f[2] : f[3]));
+	w[1] = c.k == 0 ? f[1] : f[0];
+	w[2] = c.k <= 1 ? f[2] : f[1];
+	w[3] = c.k == 3 ? f[2] : f[3];
+	return true;
+}
+
+// ((v0 f0 + v1 f1) + v2 f2) + v3 f3 in tet order (:1858-1871); a + b == b + a, so k = 0 and k = 1 coincide
+__device__ __forceinline__ float axis_value(int k, const float w[4], float own, float a, float b, float c)
+{
+	const float tA = a * w[1], tB = b * w[2], tC = c * w[3], tX = own * w[0];
+	const float s1 = tA + (k <= 1 ? tX : tB);
+	const float s2 = s1 + (k <= 1 ? tB : (k == 2 ? tX : tC));
+	return s2 + (k == 3 ? tX : tC);
 }
 
 // The two feet of one direction inside its owner and their three Riemann invariants
 // (rows dir, 2 + dir, 4 + dir of Omega).  Returns false when the reference throws.
-template<int S>
-__device__ __forceinline__ bool feet_of_dir(const CandFull& f, int dir, const F3& X, float dk1, float dk2,
-                                            const float own[9], const float* __restrict__ U, float omega[9])
+// LATE: the value quads of the owner's vertices are requested here, after the factors of both feet
+// (they are 24 registers that need not be live during the search and the determinants).
+template<int S, bool LATE>
+__device__ __forceinline__ bool feet_of_dir(CandFull& f, int dir, const F3& X, float dk1, float dk2,
+                                            const float own[9], const float* __restrict__ U, float omega[9],
+                                            const float4* __restrict__ rec)
 {
+	float w1[4], w2[4];
+	if(!axis_factors<S>(f.c, X, dk1, w1)) return false;
+	if(!axis_factors<S>(f.c, X, dk2, w2)) return false;
+	if(LATE) load_value_quads(f, rec);
 	const float va[9] = {f.a0.x, f.a0.y, f.a0.z, f.a0.w, f.a1.x, f.a1.y, f.a1.z, f.a1.w, f.c.qa.x};
 	const float vb[9] = {f.b0.x, f.b0.y, f.b0.z, f.b0.w, f.b1.x, f.b1.y, f.b1.z, f.b1.w, f.c.qb.x};
 	const float vc[9] = {f.c0.x, f.c0.y, f.c0.z, f.c0.w, f.c1.x, f.c1.y, f.c1.z, f.c1.w, f.c.qc.x};
-	float v[9];
-	if(!interp_axis<S>(f.c, X, dk1, own, va, vb, vc, v)) return false;
 	// omega_i = Omega(i,:) . u(foot of i)  (SimpleVolumeCalculator.cpp:14-23); ppoint_num = (0,1,2,3,2,3,4,4,4)
-	{
-		float om = 0;
-		#pragma unroll
-		for(int j = 0; j < 9; j++)
-			if((u_pattern(S, 0) >> j) & 1) om += U[dir * 9 + j] * v[j];
-		omega[dir] = om;
-	}
-	if(!interp_axis<S>(f.c, X, dk2, own, va, vb, vc, v)) return false;
-	{
-		float om = 0, om4 = 0;
-		#pragma unroll
-		for(int j = 0; j < 9; j++) {
-			if((u_pattern(S, 2) >> j) & 1) om += U[(2 + dir) * 9 + j] * v[j];
-			if((u_pattern(S, 4) >> j) & 1) om4 += U[(4 + dir) * 9 + j] * v[j];
+	float om = 0, om2 = 0, om4 = 0;
+	#pragma unroll
+	for(int j = 0; j < 9; j++) {
+		if((u_pattern(S, 0) >> j) & 1) om += U[dir * 9 + j] * axis_value(f.c.k, w1, own[j], va[j], vb[j], vc[j]);
+		if(((u_pattern(S, 2) | u_pattern(S, 4)) >> j) & 1) {
+			const float v2 = axis_value(f.c.k, w2, own[j], va[j], vb[j], vc[j]);
+			if((u_pattern(S, 2) >> j) & 1) om2 += U[(2 + dir) * 9 + j] * v2;
+			if((u_pattern(S, 4) >> j) & 1) om4 += U[(4 + dir) * 9 + j] * v2;
 		}
-		omega[2 + dir] = om;
-		omega[4 + dir] = om4;
 	}
+	omega[dir] = om;
+	omega[2 + dir] = om2;
+	omega[4 + dir] = om4;
 	return true;
 }
 
 // PF: 1 = the records of both directions' first survivors are requested together, 0 = the second
-// direction's after the first direction's search (fewer live registers).
+// direction's after the first direction's search, 2 = after the first direction's interpolation
+// (fewest live registers).
 // list / skip_shell: see the body.
 // A node the index cannot settle (guard, disagreeing feet, no owner in the first ring) is appended to
 // `cold` (cold[0] = count) and advanced by stage_deferred_kernel right after this launch: keeping the
@@ -558,9 +594,9 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	const bool have = (int)xm.x >= 0 && (int)xp.x >= 0;
 	CandFull f0, f1;
 	set_entry(f0, xm, __uint_as_float(hq.x), __uint_as_float(hq.y));
-	set_entry(f1, xp, __uint_as_float(hq.z), __uint_as_float(hq.w));
-	if(have) load_records(f0, rec);
-	if(PF >= 1 && have) load_records(f1, rec);
+	if(PF != 2) set_entry(f1, xp, __uint_as_float(hq.z), __uint_as_float(hq.w));
+	if(have) load_records(f0, rec, PF != 2);
+	if(PF == 1 && have) load_records(f1, rec);
 
 	const int mid = mat_id ? mat_id[node] : 0;
 	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
@@ -586,15 +622,22 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	}
 	float omega[9];
 	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
-	if(!settle_dir<S>(f0, ix.x, node, m.n2t_off, X, -1.0f, dk[0], de[0], dk[2], de[2], n2x, rec, hv2)) {
+	if(!settle_dir<S, PF == 2>(f0, ix.x, node, m.n2t_off, X, -1.0f, dk[0], de[0], dk[2], de[2], n2x, rec, hv2)) {
 		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
 	}
 	if(PF == 0) load_records(f1, rec);
-	if(!feet_of_dir<S>(f0, 0, X, dk[0], dk[2], own, U, omega)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
-	if(!settle_dir<S>(f1, ix.y, node, m.n2t_off, X, 1.0f, dk[1], de[1], dk[3], de[3], n2x, rec, hv2)) {
+	if(!feet_of_dir<S, PF == 2>(f0, 0, X, dk[0], dk[2], own, U, omega, rec)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
+	if(PF == 2) {
+		// nothing of the second direction is live while the first one is interpolated: its entry is
+		// read again (the line is in L1) and its records are requested only now
+		const uint4 xp2 = __ldg(ent + 2), hq2 = __ldg(ent + 3);
+		set_entry(f1, xp2, __uint_as_float(hq2.z), __uint_as_float(hq2.w));
+		load_records(f1, rec, false);
+	}
+	if(!settle_dir<S, PF == 2>(f1, ix.y, node, m.n2t_off, X, 1.0f, dk[1], de[1], dk[3], de[3], n2x, rec, hv2)) {
 		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
 	}
-	if(!feet_of_dir<S>(f1, 1, X, dk[1], dk[3], own, U, omega)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
+	if(!feet_of_dir<S, PF == 2>(f1, 1, X, dk[1], dk[3], own, U, omega, rec)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
 
 	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every
 	// factor but the node's own is exactly 0, the own one is the static weight w0

@@ -153,6 +153,8 @@ struct gcm_b200_set {
 	bool coop_border = false;    // flat border nodes: 16 lanes per node (gcm_border_coop.cuh) instead of 1 thread;
 	                             // bit-identical but measured slower (redundant per-lane work), kept as an option
 	bool lean_border = false;    // flat border nodes through node_stage_border_lean (row-wise eigensystem; measured 14 % slower)
+	bool fused_border = true;    // sharp and flat border nodes in one launch (stage_border_fused_kernel)
+	int border_block = 128;      // threads per block of the flat border kernel (finer blocks = shorter tail)
 	int border_min_blocks = 4;   // register budget variant of the per-thread border kernel (3..8 blocks of 128 / SM)
 	bool dir_index = true;       // inner kernel scans through the angular candidate index (gcm_inner.cuh)
 	int direct_min_blocks = 8;   // register budget variant of stage_inner_direct_kernel (3..8 blocks of 128 / SM)
@@ -612,6 +614,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 		shl = s->d_sharp_stage0.p + (z ? z->st0s_off : 0);
 	}
 	cudaStream_t bst = s->stream;
+	bool fused_done = false;
 	if(nb || nsh) {
 		if(s->concurrent) {
 			bst = s->aux;
@@ -619,6 +622,13 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 			CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
 		}
 		ProfScope ps(s, PROF_BORDER, nb + nsh, bst);
+		if(nsh && nb && s->fused_border && !s->coop_border && !s->lean_border) {
+			const int blocks = (nsh * 16 + 127) / 128 + (nb + 127) / 128;
+			gcm::stage_border_fused_kernel<<<blocks, 128, 0, bst>>>(m, shl, nsh, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
+			s->launches++;
+			nsh = 0; nb = 0;
+			fused_done = true;
+		}
 		if(nsh) {
 			gcm::stage_sharp_kernel<<<(nsh * 16 + 63) / 64, 64, 0, bst>>>(m, shl, nsh, stage, dm.unext(), s->d_err, zone, tap);
 			s->launches++;
@@ -626,7 +636,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 		if(nb) {
 			if(s->coop_border) gcm::stage_border_coop_kernel<<<(int)(((size_t)nb * 16 + 127) / 128), 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 			else if(s->lean_border) gcm::stage_border_lean_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			else if(s->border_min_blocks == 4) gcm::stage_generic_kernel_mb<4><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
+			else if(s->border_min_blocks == 4) gcm::stage_generic_kernel_mb<4><<<(nb + s->border_block - 1) / s->border_block, s->border_block, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 			else if(s->border_min_blocks == 5) gcm::stage_generic_kernel_mb<5><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 			else if(s->border_min_blocks == 6) gcm::stage_generic_kernel_mb<6><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
 			else if(s->border_min_blocks == 8) gcm::stage_generic_kernel_mb<8><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
@@ -690,7 +700,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 			s->launches++;
 		}
 	}
-	if((nb || nsh) && s->concurrent) {
+	if((nb || nsh || fused_done) && s->concurrent) {
 		CK(cudaEventRecord(s->ev_join, s->aux));
 		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
 	}
@@ -1039,7 +1049,9 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
 	if(const char* e = getenv("GCM_B200_FAST_INNER")) s->fast_inner = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_COOP_BORDER")) s->coop_border = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_FUSED_BORDER")) s->fused_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_MB")) s->border_min_blocks = atoi(e);
+	if(const char* e = getenv("GCM_B200_BORDER_BLOCK")) { int b = atoi(e); if(b == 32 || b == 64 || b == 128) s->border_block = b; }
 	if(const char* e = getenv("GCM_B200_LEAN_BORDER")) s->lean_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_OVERLAP")) s->overlap = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BASES_AHEAD")) s->bases_ahead = atoi(e) != 0;

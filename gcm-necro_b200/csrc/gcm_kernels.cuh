@@ -133,6 +133,41 @@ stage_sharp_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		un[(size_t)node * GCM_REC + k] = out[k];
 }
 
+// Sharp and flat border nodes in ONE launch: the first blocks take the sharp nodes (16 lanes per
+// node, as stage_sharp_kernel), the rest the flat ones (one thread per node, as
+// stage_generic_kernel).  Both are long, latency-bound threads and the sharp launch is tiny, so
+// back to back on one stream the two cost the sum of their latencies; fused they cost the maximum.
+__global__ void __launch_bounds__(128, 4)
+stage_border_fused_kernel(const __grid_constant__ MeshView m, const int* __restrict__ sharp_list, int n_sharp,
+                          const int* __restrict__ flat_list, int n_flat,
+                          int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
+{
+	const int sharp_blocks = (n_sharp * 16 + 127) / 128;
+	float out[9];
+	StageTap tp;
+	int node, e;
+	if((int)blockIdx.x < sharp_blocks) {
+		const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+		const int idx = gid >> 4;
+		int t = threadIdx.x & 15;
+		const bool real = idx < n_sharp && t < 11;
+		node = sharp_list[real ? idx : 0];
+		if(!real) t = 11;                       // padding lane: goes through the same vote, never wins
+		e = node_stage_nocontact_t(m, node, stage, out, tap ? &tp : nullptr, t, SharpDecide(), nullptr);
+		if(e == -1000) return;                  // another lane's try decides this node
+	} else {
+		const int idx = (blockIdx.x - sharp_blocks) * blockDim.x + threadIdx.x;
+		if(idx >= n_flat) return;
+		node = flat_list[idx];
+		e = node_stage_nocontact(m, node, stage, out, tap ? &tp : nullptr);
+	}
+	if(tap) tap[(size_t)stage * m.n_nodes + node] = tp;
+	if(e) { report_error(err, e, zone, node, stage); return; }
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		un[(size_t)node * GCM_REC + k] = out[k];
+}
+
 // Border nodes in contact on axis `stage` (only axis 0 can be: BruteforceCollisionDetector.cpp:58-60):
 // the contact branch of do_next_part_step (TetrMethod_Plastic_1stOrder.cpp:299-421), one thread per
 // node.  list[i] = real node, its virtual node = axis_plus0[border_slot].  partner_next = 1 when

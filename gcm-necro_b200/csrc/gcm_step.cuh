@@ -923,29 +923,32 @@ GCM_HD int node_stage_border_lean(const MeshView& m, int node, int stage, float 
 	if(!usual) return node_stage_nocontact_cold(m, node, stage, out, tap);
 
 	const float Xc[3] = {cur.pos.x, cur.pos.y, cur.pos.z};
-	float tetr_center[3];
-	{
-		int tetr_num = m.n2t[m.n2t_off[node]];
-		const int* tv = m.tets + 4*(size_t)tetr_num;
-		Vec3 a = load_xyz(m, tv[0]), b = load_xyz(m, tv[1]), c = load_xyz(m, tv[2]), e = load_xyz(m, tv[3]);
-		tetr_center[0] = ( a.x + b.x + c.x + e.x ) / 4;
-		tetr_center[1] = ( a.y + b.y + c.y + e.y ) / 4;
-		tetr_center[2] = ( a.z + b.z + c.z + e.z ) / 4;
-	}
 	float val[5][9];
 	bool inn[5];
 	int own[5];
 	int outer_count = 0, tries = 0;
 	float alpha = 0;
+	RingScan rs;
+	scan_ring_both_senses(m, node, cur.pos, ksi, rs);   // serves the first try (alpha == 0)
 	do {
 		const float a = ((double)alpha > 1.0) ? 1.0f : alpha;
+		// centre of elements[0]: the "last chance" foot, read by foot_point only when alpha > 0.95
+		float tetr_center[3] = {0.f, 0.f, 0.f};
+		if((double)a > 0.95) {
+			int tetr_num = m.n2t[m.n2t_off[node]];
+			const int* tv = m.tets + 4*(size_t)tetr_num;
+			Vec3 ta = load_xyz(m, tv[0]), tb = load_xyz(m, tv[1]), tc = load_xyz(m, tv[2]), te = load_xyz(m, tv[3]);
+			tetr_center[0] = ( ta.x + tb.x + tc.x + te.x ) / 4;
+			tetr_center[1] = ( ta.y + tb.y + tc.y + te.y ) / 4;
+			tetr_center[2] = ( ta.z + tb.z + tc.z + te.z ) / 4;
+		}
 		int ferr = 0;
 		for(int p = 0; p < 5 && !ferr; p++) {
 			float v12[12];
 			for(int k = 0; k < 9; k++) v12[k] = cur.val[k];
 			v12[9] = cur.la; v12[10] = cur.mu; v12[11] = cur.rho;
 			inn[p] = true; own[p] = -2;
-			ferr = foot_point(m, cur, stage, a, dk[p], ksi, Xc, Xc, tetr_center, false, &inn[p], &own[p], v12);
+			ferr = foot_point(m, cur, stage, a, dk[p], ksi, Xc, Xc, tetr_center, false, &inn[p], &own[p], v12, &rs);
 			for(int k = 0; k < 9; k++) val[p][k] = v12[k];
 		}
 		tries++;

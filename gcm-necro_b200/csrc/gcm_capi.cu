@@ -428,6 +428,7 @@ gcm::MeshView make_view(gcm_b200_set* s, float tau)
 	m.u = dm.ucur(); m.mat = dm.mat.p; m.flags = dm.flags.p;
 	m.n2t_off = dm.n2t_off.p; m.n2t = dm.n2t.p; m.tets = dm.tets.p; m.tet_hv = dm.tet_hv.p;
 	m.n2x = s->use_n2x_generic ? dm.n2x.p : nullptr;
+	m.n2x_scan = dm.n2x.p;
 	m.border_slot = dm.border_slot.p; m.basis = dm.basis.p; m.cond_id = dm.cond_id.p; m.contact = nullptr;
 	const float t = s->zones[s->local_zones[0]]->hm.current_time;   // TetrMeshSet::get_current_time()
 	m.tau = tau; m.time = t; m.min_h = 0;

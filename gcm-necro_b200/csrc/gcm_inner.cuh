@@ -371,9 +371,10 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 // unchanged: survivors in list order through the same pre-filter / exact predicate, first pass
 // wins.  Same function, same inputs, same compiler flags at build and at step time -> the skipped
 // verdicts are exactly the -1 ones.  Entry of one (axis, node), 4 x uint4 = 64 bytes:
-//   q0 = (survivors after the first, dksi < 0 | same, dksi > 0 | min h over the list | w0)
-//   q1 = first survivor, dksi < 0: (ia, ib, ic, t | k << 30)     q2 = same for dksi > 0
-//   q3 = (h-, Vol-, h+, Vol+) of those two
+//   q0 = first survivor, dksi < 0: (ia, ib, ic, t | k << 30)
+//   q1 = (its h, its Vol, survivors after it, min h over the whole list)
+//   q2, q3 = the same for dksi > 0, with w0 in the last word (sign bit: "shell", see the kernel)
+// so that each direction reads its own 32 bytes when it needs them.
 // min h == 0 marks "not a node of the fast inner path" (all-zero entry: border, halo, generic);
 // ia == -1 "no survivor".  The step-time guard  0 < delta < 0.99 * min h  implies the pre-filter's
 // own precondition delta < 0.99 h(tet) for every candidate (rounding of h * 0.99 is monotone in
@@ -411,10 +412,10 @@ build_dir_index_kernel(const float* __restrict__ u, const int* __restrict__ n2t_
 	if(mm) { xm = __ldg(n2x + e0 + __ffs(mm) - 1); hm = __ldg(hv2 + (xm.w & 0x3fffffff)); mm &= mm - 1; }
 	if(mp) { xp = __ldg(n2x + e0 + __ffs(mp) - 1); hp = __ldg(hv2 + (xp.w & 0x3fffffff)); mp &= mp - 1; }
 	uint4* __restrict__ o = didx + GCM_DIDX_QUADS * (size_t)node;
-	o[0] = make_uint4(mm, mp, __float_as_uint(hmin), __float_as_uint(w0[node]));
-	o[1] = make_uint4((unsigned)xm.x, (unsigned)xm.y, (unsigned)xm.z, (unsigned)xm.w);
+	o[0] = make_uint4((unsigned)xm.x, (unsigned)xm.y, (unsigned)xm.z, (unsigned)xm.w);
+	o[1] = make_uint4(__float_as_uint(hm.x), __float_as_uint(hm.y), mm, __float_as_uint(hmin));
 	o[2] = make_uint4((unsigned)xp.x, (unsigned)xp.y, (unsigned)xp.z, (unsigned)xp.w);
-	o[3] = make_uint4(__float_as_uint(hm.x), __float_as_uint(hm.y), __float_as_uint(hp.x), __float_as_uint(hp.y));
+	o[3] = make_uint4(__float_as_uint(hp.x), __float_as_uint(hp.y), mp, __float_as_uint(w0[node]));
 }
 
 // Sets the "shell" bit (sign of w0) of the listed nodes in the three planes of the index.
@@ -425,7 +426,7 @@ __global__ void mark_shell_kernel(uint4* __restrict__ didx, size_t n_nodes, cons
 	const int node = list[idx];
 	for(int sgl = 0; sgl < 3; sgl++) {
 		uint4* e = didx + GCM_DIDX_QUADS * ((size_t)sgl * n_nodes + node);
-		if(e->z != 0u) e->w |= 0x80000000u;
+		if(e[1].w != 0u) e[3].w |= 0x80000000u;
 	}
 }
 
@@ -581,20 +582,20 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	// list == NULL: the contiguous range; else the listed nodes (the shell pass of the overlapped stage)
 	const int node = list ? list[idx] : node_begin + idx;
 	const uint4* __restrict__ ent = didx + GCM_DIDX_QUADS * (size_t)node;
-	uint4 ix = __ldg(ent);
-	if(ix.z == 0u) return;                        // not a node of the fast inner path
+	const uint4 e0q = __ldg(ent), e1q = __ldg(ent + 1);
+	if(e1q.w == 0u) return;                       // min h == 0: not a node of the fast inner path
+	uint4 e2q = make_uint4(0u, 0u, 0u, 0u), e3q = e2q;
+	if(PF != 2 || skip_shell) { e2q = __ldg(ent + 2); e3q = __ldg(ent + 3); }
 	// sign bit of w0 (a weight, >= 0) = "shell": within two rings of a halo node owned by another process;
 	// the deep pass leaves those to the pass that runs after the exchange
-	if(skip_shell && (ix.w & 0x80000000u)) return;
-	ix.w &= 0x7fffffffu;
-	const uint4 xm = __ldg(ent + 1), xp = __ldg(ent + 2), hq = __ldg(ent + 3);
+	if(skip_shell && (e3q.w & 0x80000000u)) return;
 	const float4* __restrict__ rec = reinterpret_cast<const float4*>(m.u);
 	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(m.tet_hv);
 	const float4 o0 = rec[3 * (size_t)node], o1 = rec[3 * (size_t)node + 1], o2 = rec[3 * (size_t)node + 2];
-	const bool have = (int)xm.x >= 0 && (int)xp.x >= 0;
+	const bool have = (int)e0q.x >= 0 && (PF == 2 || (int)e2q.x >= 0);
 	CandFull f0, f1;
-	set_entry(f0, xm, __uint_as_float(hq.x), __uint_as_float(hq.y));
-	if(PF != 2) set_entry(f1, xp, __uint_as_float(hq.z), __uint_as_float(hq.w));
+	set_entry(f0, e0q, __uint_as_float(e1q.x), __uint_as_float(e1q.y));
+	if(PF != 2) set_entry(f1, e2q, __uint_as_float(e3q.x), __uint_as_float(e3q.y));
 	if(have) load_records(f0, rec, PF != 2);
 	if(PF == 1 && have) load_records(f1, rec);
 
@@ -610,7 +611,7 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	float dk[4], de[4];
 	{
 		// all four displacements must be rescaled by every candidate (then the index is valid)
-		const double h99 = (double)__uint_as_float(ix.z) * 0.99;
+		const double h99 = (double)__uint_as_float(e1q.w) * 0.99;
 		bool ok = have;
 		#pragma unroll
 		for(int q = 0; q < 4; q++) {
@@ -622,7 +623,7 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	}
 	float omega[9];
 	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
-	if(!settle_dir<S, PF == 2>(f0, ix.x, node, m.n2t_off, X, -1.0f, dk[0], de[0], dk[2], de[2], n2x, rec, hv2)) {
+	if(!settle_dir<S, PF == 2>(f0, e1q.z, node, m.n2t_off, X, -1.0f, dk[0], de[0], dk[2], de[2], n2x, rec, hv2)) {
 		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
 	}
 	if(PF == 0) load_records(f1, rec);
@@ -630,11 +631,12 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	if(PF == 2) {
 		// nothing of the second direction is live while the first one is interpolated: its entry is
 		// read again (the line is in L1) and its records are requested only now
-		const uint4 xp2 = __ldg(ent + 2), hq2 = __ldg(ent + 3);
-		set_entry(f1, xp2, __uint_as_float(hq2.z), __uint_as_float(hq2.w));
+		e2q = __ldg(ent + 2); e3q = __ldg(ent + 3);
+		if((int)e2q.x < 0) { cold[1 + atomicAdd(&cold[0], 1)] = node; return; }   // no survivor on this side
+		set_entry(f1, e2q, __uint_as_float(e3q.x), __uint_as_float(e3q.y));
 		load_records(f1, rec, false);
 	}
-	if(!settle_dir<S, PF == 2>(f1, ix.y, node, m.n2t_off, X, 1.0f, dk[1], de[1], dk[3], de[3], n2x, rec, hv2)) {
+	if(!settle_dir<S, PF == 2>(f1, e3q.z, node, m.n2t_off, X, 1.0f, dk[1], de[1], dk[3], de[3], n2x, rec, hv2)) {
 		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
 	}
 	if(!feet_of_dir<S, PF == 2>(f1, 1, X, dk[1], dk[3], own, U, omega, rec)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
@@ -642,7 +644,7 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every
 	// factor but the node's own is exactly 0, the own one is the static weight w0
 	float vz[9];
-	const float wz = __uint_as_float(ix.w);
+	const float wz = __uint_as_float(e3q.w & 0x7fffffffu);
 	#pragma unroll
 	for(int k = 0; k < 9; k++) vz[k] = own[k] * wz;
 	if(tap) {

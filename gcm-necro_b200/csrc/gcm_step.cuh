@@ -45,6 +45,7 @@ struct MeshView {
 	const int* n2t_off;      // [n_nodes+1]  node -> incident tets (ascending ids), CSR
 	const int* n2t;
 	const int* n2x;          // [len(n2t)][4] or NULL: CSR entry -> other three vertices (tet order), tet | k << 30
+	const int* n2x_scan;     // the same table (or NULL) for scan_ring_both_senses, whatever n2x says
 	const int* tets;         // [n_tets][4]
 	const float* tet_hv;     // [n_tets][2]  (tetr_h, signed volume) -- static geometry
 	const int* border_slot;  // [n_nodes]    index into the border arrays or -1
@@ -420,15 +421,35 @@ GCM_HD void scan_ring_both_senses(const MeshView& m, int base, const Vec3& X, co
 	const float inv_qn = qn > 0 ? 1.0f / qn : 0.0f;    // the filter is conservative: its rounding is free
 	const int e0 = m.n2t_off[base], e1 = m.n2t_off[base + 1];
 	for(int e = e0; e < e1 && (open0 || open1); e++) {
-		const int t = m.n2t[e];
-		TetGeom g;
-		load_tet(m, t, g);
-		if(open0) rs.hmin[0] = fminf(rs.hmin[0], g.h);
-		if(open1) rs.hmin[1] = fminf(rs.hmin[1], g.h);
-		const int k = (g.v[0] == base) ? 0 : (g.v[1] == base) ? 1 : (g.v[2] == base) ? 2 : (g.v[3] == base) ? 3 : -1;
+		int t, k;
+		float gh, gvol;
+		Vec3 A, B, C;
+		if(m.n2x_scan) {
+			// expanded CSR entry: the other three vertices (tet order) and the position k of the node:
+			// no tets[t] hop, and the node's own coordinates are not loaded again
+			const int* x = m.n2x_scan + 4*(size_t)e;
+#if defined(__CUDA_ARCH__)
+			const int4 q4 = *reinterpret_cast<const int4*>(x);
+			const int xa = q4.x, xb = q4.y, xc = q4.z, w = q4.w;
+#else
+			const int xa = x[0], xb = x[1], xc = x[2], w = x[3];
+#endif
+			k = (int)((unsigned)w >> 30);
+			t = w & 0x3fffffff;
+			A = load_xyz(m, xa); B = load_xyz(m, xb); C = load_xyz(m, xc);
+			gh = m.tet_hv[2*(size_t)t]; gvol = m.tet_hv[2*(size_t)t + 1];
+		} else {
+			t = m.n2t[e];
+			TetGeom g;
+			load_tet(m, t, g);
+			k = (g.v[0] == base) ? 0 : (g.v[1] == base) ? 1 : (g.v[2] == base) ? 2 : (g.v[3] == base) ? 3 : -1;
+			A = g.p[k == 0 ? 1 : 0]; B = g.p[k <= 1 ? 2 : 1]; C = g.p[k == 3 ? 2 : 3];
+			gh = g.h; gvol = g.vol;
+		}
+		if(open0) rs.hmin[0] = fminf(rs.hmin[0], gh);
+		if(open1) rs.hmin[1] = fminf(rs.hmin[1], gh);
 		int v0 = 0, v1 = 0;    // verdicts for -q and +q
-		if(g.vol > 0 && k >= 0 && qn > 0) {
-			const Vec3 A = g.p[k == 0 ? 1 : 0], B = g.p[k <= 1 ? 2 : 1], C = g.p[k == 3 ? 2 : 3];
+		if(gvol > 0 && k >= 0 && qn > 0) {
 			const float eax = A.x - X.x, eay = A.y - X.y, eaz = A.z - X.z;
 			const float ebx = B.x - X.x, eby = B.y - X.y, ebz = B.z - X.z;
 			const float ecx = C.x - X.x, ecy = C.y - X.y, ecz = C.z - X.z;
@@ -436,7 +457,7 @@ GCM_HD void scan_ring_both_senses(const MeshView& m, int base, const Vec3& X, co
 			const float cax = ecy * eaz - ecz * eay, cay = ecz * eax - ecx * eaz, caz = ecx * eay - ecy * eax;
 			const float abx = eay * ebz - eaz * eby, aby = eaz * ebx - eax * ebz, abz = eax * eby - eay * ebx;
 			const float D = eax * bcx + eay * bcy + eaz * bcz;
-			const float sD = 0.99f * g.h * inv_qn * D;
+			const float sD = 0.99f * gh * inv_qn * D;
 			// barycentric coordinates (times D^2) of X + 0.99 h q/|q|; those of the opposite sense are the negatives
 			const float la = sD * (q[0] * bcx + q[1] * bcy + q[2] * bcz);
 			const float lb = sD * (q[0] * cax + q[1] * cay + q[2] * caz);
@@ -450,10 +471,11 @@ GCM_HD void scan_ring_both_senses(const MeshView& m, int base, const Vec3& X, co
 		}
 		if(open0) { if(v0 > 0) { rs.own[0] = t; open0 = false; } else if(v0 == 0) { rs.amb[0] = true; open0 = false; } }
 		if(open1) { if(v1 > 0) { rs.own[1] = t; open1 = false; } else if(v1 == 0) { rs.amb[1] = true; open1 = false; } }
-		for(int j = 0; j < 4; j++) {
-			if(g.v[j] == base) break;   // the reference `break`s (not `continue`s) here, :1544-1545
-			const float lx = g.p[j].x, ly = g.p[j].y, lz = g.p[j].z;
-			const float d2 = (X.x - lx) * (X.x - lx) + (X.y - ly) * (X.y - ly) + (X.z - lz) * (X.z - lz);
+		// the reference scans a tet's vertices in order and `break`s (not `continue`s) at the node itself
+		// (:1544-1545): only the vertices BEFORE position k are measured = the first k of (A, B, C)
+		for(int j = 0; j < 3 && j < (k < 0 ? 3 : k); j++) {
+			const Vec3& P = j == 0 ? A : (j == 1 ? B : C);
+			const float d2 = (X.x - P.x) * (X.x - P.x) + (X.y - P.y) * (X.y - P.y) + (X.z - P.z) * (X.z - P.z);
 			rs.dmin2 = fminf(rs.dmin2, d2);
 		}
 	}

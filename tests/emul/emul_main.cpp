@@ -154,7 +154,7 @@ int main(int argc, char** argv)
 		gcm::MeshView m; memset(&m, 0, sizeof m);
 		m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
 		m.u = z.u[z.cur].data(); m.mat = z.mat.data(); m.flags = hm.flags.data();
-		m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
+		m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 		m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 		m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
 		return m;
@@ -196,7 +196,7 @@ int main(int argc, char** argv)
 				gcm::MeshView m; memset(&m, 0, sizeof m);
 				m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
 				m.u = ucur; m.mat = z.mat.data(); m.flags = hm.flags.data();
-				m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
+				m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 				m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 				m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
 				m.n_conds = (int)conds.size();

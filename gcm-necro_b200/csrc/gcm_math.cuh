@@ -204,7 +204,13 @@ GCM_HD bool interp_factors(const Vec3& v0, const Vec3& v1, const Vec3& v2, const
 	#pragma unroll
 	for(int i = 0; i < 4; i++) {
 		if(s[i] == 0.0f && fabsf(vol) > 0.0f) f[i] = 0.0f;
-		else f[i] = fabsf(div_z(s[i], vol));
+		else {
+#if defined(__CUDA_ARCH__)
+			f[i] = fabsf(__fdiv_rn(s[i], vol));   // the numerator is not zero on this branch (or Vol is degenerate)
+#else
+			f[i] = fabsf(s[i] / vol);
+#endif
+		}
 	}
 	float sum = f[0] + f[1] + f[2] + f[3];
 	if((double)sum > 1.0) {

@@ -45,3 +45,18 @@ def test_no_cpu_fallback(built):
 def test_missing_library_fails_loudly(tmp_path):
     with pytest.raises(gcm_b200.GCMException):
         capi.load_library(str(tmp_path / "libgcm_b200.so"))
+
+
+def test_comm_entry_points_refuse_host_only_sets(built):
+    """The library-driven exchange is a device feature: a host-only set (device -1, what the gloo tests
+    use for planning) cannot get a communicator, cannot exchange, and a multi-process step without one
+    says what to do instead of running something else."""
+    ms = gcm_b200.TetrMeshSet(n_zones=1, device=-1)
+    z = __import__("gcm_b200.meshgen", fromlist=["make_cube"]).make_cube(4)
+    ms.get_mesh_by_zone_num(0).load(z, la=7e9, mu=1e9, rho=7.8e6)
+    ms.pre_process_meshes()
+    for call in (lambda: ms.comm_init(b"\0" * 128, 0, 1), ms.comm_sync_nodes, ms.do_next_step):
+        with pytest.raises(gcm_b200.GCMException) as e:
+            call()
+        assert e.value.code == gcm_b200.GCMException.CONFIG_EXCEPTION
+    ms.close()

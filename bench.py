@@ -259,10 +259,16 @@ def main():
     value = n_total * args.steps / (total_ms * 1e-3)
 
     # ---- per-kernel timing for the roofline (same steps, events around each launch) ----------
+    # The timed loop above runs the border kernels on a second stream beside the inner kernel; for the
+    # per-kernel durations the streams are serialised, so that each kernel is timed alone (the events sit
+    # on the stream the kernel is launched on) and not stretched by whatever shares the SMs with it.
+    concurrent = os.environ.get("GCM_B200_CONCURRENT", "1") != "0"
+    ms.set_concurrency(False)
     ms.profile(True)
     for _ in range(min(args.steps, 5)):
         step()
     ms.synchronize()
+    ms.set_concurrency(concurrent)
     prof = {k: ms.profile_read(i) for i, k in enumerate(["inner_stage", "border_stage", "plastic", "halo_copy", "rng_bases", "inner_generic"])}
     ms.profile(False)
     peak, peak_src = measured_peak_gbs()
@@ -282,6 +288,7 @@ def main():
                 "algorithmic_bytes_per_node_stage": B_STAGE, "avg_launch_ms": in_ms / max(in_launches, 1),
                 "nodes_per_launch": in_units / max(in_launches, 1),
                 "step_frac": value / world * B_STEP / 1e9 / peak,
+                "kernel_timing": "CUDA events around each launch, in a pass with the border stream serialised behind the inner kernel",
                 "kernel_ms_share": {k: v[0] for k, v in prof.items()}}
 
     # ---- end to end through the C ABI with HOST buffers ---------------------------------------

@@ -604,7 +604,7 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
 	bool bad = false;
 	#pragma unroll
-	for(int k = 0; k < 9; k++) bad |= (isnan(own[k]) || isinf(own[k]));
+	for(int k = 0; k < 9; k++) bad |= !(fabsf(own[k]) <= 3.4028235e38f);   // NaN or Inf (TetrMethod_Plastic_1stOrder.cpp:192-194): one compare
 	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
 	const float* U = sU[mid];
 	const float* U1 = sU1[mid];

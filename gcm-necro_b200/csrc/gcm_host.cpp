@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace gcmh {
@@ -621,6 +622,117 @@ static void interpolate_triangle(const float* p1, const float* p2, const float* 
 		v[i] = _l1*v1[i] + _l2*v2[i] + _l3*v3[i];
 }
 
+// 2-D bins over the faces that take part in one collision pass (see find_collisions).  Only a
+// conservative filter: whatever it returns is still put through vector_intersects_triangle in list
+// order, so the result is that of the full scan.
+struct FaceGrid {
+	bool ok = false;               // false: few faces / degenerate / non-finite input -> scan every face
+	int ax0 = 0, ax1 = 1;          // the two binned coordinate axes (longest sides of the faces' box)
+	double org[2] = {0, 0}, cell = 1, pad = 0;
+	int n[2] = {0, 0};
+	std::vector<int> start, items; // CSR: bin -> positions in fcs, ascending
+
+	void build(const HostMesh& m2, const std::vector<int>& fcs)
+	{
+		ok = false;
+		const size_t F = fcs.size();
+		if(F < 64) return;
+		if(const char* e = getenv("GCM_B200_FACE_GRID")) if(atoi(e) == 0) return;   // A/B switch for the tests
+		double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, mean = 0;
+		for(size_t l = 0; l < F; l++) {
+			double flo[3] = {1e300, 1e300, 1e300}, fhi[3] = {-1e300, -1e300, -1e300};
+			for(int j = 0; j < 3; j++) {
+				const float* c = &m2.coords[3*(size_t)m2.faces[3*(size_t)fcs[l] + j]];
+				for(int a = 0; a < 3; a++) {
+					if(!std::isfinite(c[a])) return;
+					flo[a] = std::min(flo[a], (double)c[a]); fhi[a] = std::max(fhi[a], (double)c[a]);
+				}
+			}
+			for(int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], flo[a]); hi[a] = std::max(hi[a], fhi[a]); }
+			mean += std::max(fhi[0] - flo[0], std::max(fhi[1] - flo[1], fhi[2] - flo[2]));
+		}
+		mean /= (double)F;
+		// drop the shortest side of the box
+		int drop = 0;
+		for(int a = 1; a < 3; a++) if(hi[a] - lo[a] < hi[drop] - lo[drop]) drop = a;
+		ax0 = drop == 0 ? 1 : 0; ax1 = drop == 2 ? 1 : 2;
+		const double e0 = hi[ax0] - lo[ax0], e1 = hi[ax1] - lo[ax1];
+		if(!(mean > 0) || !(e0 > 0) || !(e1 > 0)) return;
+		cell = std::max(mean, std::max(e0, e1) / 2048.0);
+		// a meeting point passes the area test up to ~1e-4 of the face size outside the triangle (plus
+		// float rounding of the point itself): bins overlap by 100x that
+		double big = 0;
+		for(int a = 0; a < 3; a++) big = std::max(big, std::max(std::fabs(lo[a]), std::fabs(hi[a])));
+		pad = 1e-2 * cell + 1e-5 * big;
+		org[0] = lo[ax0] - 2 * pad; org[1] = lo[ax1] - 2 * pad;
+		n[0] = (int)((e0 + 4 * pad) / cell) + 1; n[1] = (int)((e1 + 4 * pad) / cell) + 1;
+		std::vector<int> count((size_t)n[0] * n[1] + 1, 0);
+		auto range = [&](size_t l, int r[4]) {
+			double flo[2] = {1e300, 1e300}, fhi[2] = {-1e300, -1e300};
+			for(int j = 0; j < 3; j++) {
+				const float* c = &m2.coords[3*(size_t)m2.faces[3*(size_t)fcs[l] + j]];
+				flo[0] = std::min(flo[0], (double)c[ax0]); fhi[0] = std::max(fhi[0], (double)c[ax0]);
+				flo[1] = std::min(flo[1], (double)c[ax1]); fhi[1] = std::max(fhi[1], (double)c[ax1]);
+			}
+			for(int d = 0; d < 2; d++) {
+				r[2*d] = std::max(0, std::min(n[d] - 1, (int)std::floor((flo[d] - pad - org[d]) / cell)));
+				r[2*d+1] = std::max(0, std::min(n[d] - 1, (int)std::floor((fhi[d] + pad - org[d]) / cell)));
+			}
+		};
+		for(size_t l = 0; l < F; l++) {
+			int r[4]; range(l, r);
+			for(int i = r[0]; i <= r[1]; i++) for(int j = r[2]; j <= r[3]; j++) count[(size_t)i * n[1] + j + 1]++;
+		}
+		start.assign(count.size(), 0);
+		for(size_t b = 1; b < count.size(); b++) start[b] = start[b-1] + count[b];
+		items.assign((size_t)start.back(), 0);
+		std::vector<int> fill(start.begin(), start.end() - 1);
+		for(size_t l = 0; l < F; l++) {      // ascending l keeps every bin's list ascending
+			int r[4]; range(l, r);
+			for(int i = r[0]; i <= r[1]; i++) for(int j = r[2]; j <= r[3]; j++) items[(size_t)fill[(size_t)i * n[1] + j]++] = (int)l;
+		}
+		ok = true;
+	}
+
+	// Positions in fcs of every face whose bins the line p0 + t v (all t) crosses, ascending.
+	// Returns false when the caller has to scan every face (no grid, or non-finite node data: the
+	// full scan then raises the reference's own exception).
+	bool candidates(const float* p0, const float* v, std::vector<int>& out) const
+	{
+		if(!ok) return false;
+		for(int a = 0; a < 3; a++) if(!std::isfinite(p0[a]) || !std::isfinite(v[a])) return false;
+		const double p[2] = {p0[ax0], p0[ax1]}, d[2] = {v[ax0], v[ax1]};
+		out.clear();
+		auto add = [&](int i, int j0, int j1, bool swapped) {
+			for(int j = j0; j <= j1; j++) {
+				const size_t b = swapped ? (size_t)j * n[1] + i : (size_t)i * n[1] + j;
+				out.insert(out.end(), items.begin() + start[b], items.begin() + start[b+1]);
+			}
+		};
+		const int M = std::fabs(d[0]) >= std::fabs(d[1]) ? 0 : 1;   // major axis of the projected line
+		const int m = 1 - M;
+		auto clampi = [&](double x, int dim) { return std::max(0, std::min(n[dim] - 1, (int)std::floor((x - org[dim]) / cell))); };
+		if(d[M] == 0) {
+			// the line is normal to the binned plane: one point
+			const int i0 = clampi(p[M] - pad, M), i1 = clampi(p[M] + pad, M);
+			if(p[M] + pad < org[M] || p[M] - pad > org[M] + n[M] * cell || p[m] + pad < org[m] || p[m] - pad > org[m] + n[m] * cell) return true;
+			for(int i = i0; i <= i1; i++) add(M == 0 ? i : i, clampi(p[m] - pad, m), clampi(p[m] + pad, m), M == 1);
+		} else {
+			const double slope = d[m] / d[M];                        // |slope| <= 1
+			for(int i = 0; i < n[M]; i++) {
+				const double x0 = org[M] + i * cell - pad, x1 = org[M] + (i + 1) * cell + pad;
+				const double y0 = p[m] + slope * (x0 - p[M]), y1 = p[m] + slope * (x1 - p[M]);
+				const double ylo = std::min(y0, y1) - pad, yhi = std::max(y0, y1) + pad;
+				if(yhi < org[m] || ylo > org[m] + n[m] * cell) continue;
+				add(i, clampi(ylo, m), clampi(yhi, m), M == 1);
+			}
+		}
+		std::sort(out.begin(), out.end());
+		out.erase(std::unique(out.begin(), out.end()), out.end());
+		return true;
+	}
+};
+
 void find_collisions(std::vector<HostMesh*>& meshes, float threshold, std::vector<VirtNodeHost>& virt,
                      std::vector<std::vector<int> >& axis_plus0)
 {
@@ -670,13 +782,25 @@ void find_collisions(std::vector<HostMesh*>& meshes, float threshold, std::vecto
 			std::vector<int> hit_face(nn, -1);
 			std::vector<float> hit_p(3*(size_t)nn, 0.f);
 			std::string err;
+			// The test a face has to pass is "the LINE through the node along its first basis vector meets the
+			// face's plane inside the triangle" (no distance limit survives in the reference, see above), and
+			// the first face of the list that passes wins.  A face can only pass if the meeting point lies in
+			// its bounding box, so the faces are binned on a 2-D grid over the two longest sides of the
+			// intersection box and a node looks only at the bins its (projected) line crosses -- in list order,
+			// which gives the same face as the full scan, at O(bins crossed) instead of O(faces) per node.
+			FaceGrid grid;
+			grid.build(m2, fcs);
 			#pragma omp parallel for schedule(dynamic, 64)
 			for(int k = 0; k < nn; k++) {
 				const int s = nodes[k];
 				const float* p0 = &m1.coords[3*(size_t)m1.border_nodes[s]];
 				const float* dir = &m1.basis[9*(size_t)s];     // local_basis->ksi[0]
 				try {
-					for(size_t l = 0; l < fcs.size(); l++) {
+					std::vector<int> cand;       // positions in fcs, ascending
+					const bool all = !grid.candidates(p0, dir, cand);
+					const size_t nc = all ? fcs.size() : cand.size();
+					for(size_t c = 0; c < nc; c++) {
+						const size_t l = all ? c : (size_t)cand[c];
 						const int* fv = &m2.faces[3*(size_t)fcs[l]];
 						float p[3];
 						if(vector_intersects_triangle(&m2.coords[3*(size_t)fv[0]], &m2.coords[3*(size_t)fv[1]], &m2.coords[3*(size_t)fv[2]],

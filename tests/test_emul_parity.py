@@ -36,3 +36,36 @@ def test_bigger_cube_against_reference(built):
     case = dict(name="cube16", zones=[z], states=[meshgen.pwave_state(z.coords, up.LA, up.MU, up.RHO)],
                 material=(up.LA, up.MU, up.RHO, 1e16), steps=5, seed=777, borders=[], tap_step=4)
     assert up.compare(up.run_oracle(case), up.run_emul(case)) == []
+
+
+def test_face_grid_gives_the_full_scan_result(built):
+    """Collision discovery bins the partner's faces on a 2-D grid (gcm_host.cpp: FaceGrid); the hit face
+    and virtual node of every border node must be those of the reference's scan over all faces.
+    Two jittered, shifted bodies (non-matching surfaces, every kind of node normal), detector every step:
+    emulation with the grid == emulation without == the reference."""
+    import os
+    from gcm_b200 import meshgen
+    za = meshgen.make_box_zones(14, 14, 6, 1, jitter=0.15, jitter_border=True, seed=11)[0]
+    zb = meshgen.make_box_zones(10, 10, 5, 1, jitter=0.15, jitter_border=True, seed=12)[0]
+    zb.zone = 1
+    case = dict(name="grid_ab", zones=[za, zb],
+                states=[meshgen.generic_state(za.coords, up.LA, up.MU, up.RHO, seed=3),
+                        meshgen.generic_state(zb.coords, up.LA, up.MU, up.RHO, seed=4)],
+                material=(up.LA, up.MU, up.RHO, 1e16), steps=2, seed=5, borders=[], tap_step=1,
+                translates=[(1, 1.3, 2.1, 5.2)], detector="brute", static=False, contact_calc="adhesion")
+    ref = up.run_oracle(case)
+    old = os.environ.get("GCM_B200_FACE_GRID")
+    try:
+        os.environ["GCM_B200_FACE_GRID"] = "1"
+        with_grid = up.run_emul(case)
+        os.environ["GCM_B200_FACE_GRID"] = "0"
+        without = up.run_emul(case)
+    finally:
+        if old is None:
+            os.environ.pop("GCM_B200_FACE_GRID", None)
+        else:
+            os.environ["GCM_B200_FACE_GRID"] = old
+    assert up.compare(ref, with_grid) == []
+    assert up.compare(ref, without) == []
+    n_contact = sum(int((r["flags"] & 1).sum()) for r in with_grid)
+    assert n_contact > 50

@@ -157,8 +157,8 @@ struct gcm_b200_set {
 	int border_block = 128;      // threads per block of the flat border kernel (finer blocks = shorter tail)
 	int border_min_blocks = 4;   // register budget variant of the per-thread border kernel (3..8 blocks of 128 / SM)
 	bool dir_index = true;       // inner kernel scans through the angular candidate index (gcm_inner.cuh)
-	int direct_min_blocks = 8;   // register budget variant of stage_inner_direct_kernel (3..8 blocks of 128 / SM)
-	int direct_prefetch = 2;     // when the second direction's records are requested: 1 with the first's, 0 after its search, 2 after its interpolation
+	int direct_min_blocks = 8;   // register budget variant of stage_inner_direct_kernel (4, 6 or 8 blocks of 128 / SM)
+	int direct_prefetch = 2;     // when the second direction's records are requested: 0 after the first's search, 2 after its interpolation
 	bool use_n2x_generic = false; // generic (border) search through the expanded CSR too (measured: no gain)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
@@ -678,19 +678,17 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 #define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x)
 #define GCM_LAUNCH_DIRECT(S_, MB_, PF_) gcm::stage_inner_direct_kernel<S_, MB_, PF_><<<dgrid, block, 0, s->stream>>>(m, nbeg, nrange, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, n2x, dx, dm.cold.p, dlist, part == 1 ? 1 : 0)
 #define GCM_LAUNCH_DIRECT_S(MB_, PF_) do { if(stage == 0) GCM_LAUNCH_DIRECT(0, MB_, PF_); else if(stage == 1) GCM_LAUNCH_DIRECT(1, MB_, PF_); else GCM_LAUNCH_DIRECT(2, MB_, PF_); } while(0)
-#define GCM_LAUNCH_DIRECT_MB(MB_) do { if(s->direct_prefetch == 0) GCM_LAUNCH_DIRECT_S(MB_, 0); else if(s->direct_prefetch == 2) GCM_LAUNCH_DIRECT_S(MB_, 2); else GCM_LAUNCH_DIRECT_S(MB_, 1); } while(0)
+#define GCM_LAUNCH_DIRECT_MB(MB_) do { if(s->direct_prefetch == 0) GCM_LAUNCH_DIRECT_S(MB_, 0); else GCM_LAUNCH_DIRECT_S(MB_, 2); } while(0)
 			// deep pass: the whole range minus the nodes flagged shell; shell pass: the listed shell nodes
 			const int* dlist = part == 2 ? s->ov_fast_shell.p : nullptr;
 			const int nbeg = (int)(z ? z->node_off : 0), nrange = part == 2 ? nf : (int)(z ? (size_t)z->hm.N : dm.N);
 			const dim3 dgrid((unsigned)((nrange + 127) / 128));
 			if(dx) {
 				CK(cudaMemsetAsync(dm.cold.p, 0, sizeof(int), s->stream));
-				if(s->direct_min_blocks == 3) GCM_LAUNCH_DIRECT_MB(3);
-				else if(s->direct_min_blocks == 5) GCM_LAUNCH_DIRECT_MB(5);
+				// instantiated budgets: 4 (128 registers), 6 (80), 8 (64, the default); measured 3..8, see DESIGN.md
+				if(s->direct_min_blocks == 4) GCM_LAUNCH_DIRECT_MB(4);
 				else if(s->direct_min_blocks == 6) GCM_LAUNCH_DIRECT_MB(6);
-				else if(s->direct_min_blocks == 7) GCM_LAUNCH_DIRECT_MB(7);
-				else if(s->direct_min_blocks == 8) GCM_LAUNCH_DIRECT_MB(8);
-				else GCM_LAUNCH_DIRECT_MB(4);
+				else GCM_LAUNCH_DIRECT_MB(8);
 				// whatever the index could not settle: the literal routine, right behind
 				gcm::stage_deferred_kernel<<<296, 128, 0, s->stream>>>(m, dm.cold.p, stage, dm.unext(), s->d_err, zone, tap);
 				s->launches++;

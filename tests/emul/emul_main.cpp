@@ -41,7 +41,7 @@ int main(int argc, char** argv)
 	vector<string> mesh_files, state_files;
 	vector<Cond> conds;
 	float la = 7e9f, mu = 1e9f, rho = 7.8e6f, yield = 1e16f;
-	int steps = 1, seed = 12345, tap_step = -1;
+	int steps = 1, seed = 12345, tap_step = -1, ring_check = 0;
 	string out, detector = "void", contact_calc = "adhesion";
 	bool detector_static = false;
 	vector<vector<float> > translates;
@@ -57,6 +57,7 @@ int main(int argc, char** argv)
 		else if(s == "--seed") seed = atoi(argv[++a]);
 		else if(s == "--out") out = argv[++a];
 		else if(s == "--tap-step") tap_step = atoi(argv[++a]);
+		else if(s == "--ring-check") ring_check = atoi(argv[++a]);
 		else if(s == "--detector") detector = argv[++a];
 		else if(s == "--static") detector_static = true;
 		else if(s == "--contact-calc") contact_calc = argv[++a];
@@ -141,6 +142,45 @@ int main(int argc, char** argv)
 			for(int k = 0; k < 9; k++) z.u[0][GCM_REC*(size_t)i+k] = hm.values[9*(size_t)i+k];
 		}
 		z.u[1] = z.u[0];
+	}
+	if(ring_check > 0) {
+		// --ring-check N: the list-building device search (gcm::find_owner_general, what the deep contact
+		// pass runs) against the host's literal find_owner_tetr on N random (node, displacement) pairs per
+		// zone, displacements up to 2.5 mesh steps so that rings 1..4 and "not found" all occur.
+		// Prints "ring-check: <tested> <found> <mismatches>".
+		long tested = 0, found = 0, bad = 0;
+		std::vector<int> ws(GCM_RING_WS);
+		gcmh::GlibcRand rr; rr.seed(seed);
+		auto uni = [&]() { return (rr.next() % 2000001) / 1000000.0f - 1.0f; };
+		for(auto& zp : zs) {
+			Z& z = *zp; HostMesh& hm = z.hm;
+			gcm::MeshView m; memset(&m, 0, sizeof m);
+			m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
+			m.u = z.u[0].data(); m.mat = z.mat.data(); m.flags = hm.flags.data();
+			m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
+			for(int k = 0; k < ring_check; k++) {
+				const int node = (int)(rr.next() % (unsigned)hm.N);
+				if(!hm.is_local(node)) continue;
+				const float len = 2.5f * hm.min_h * 2.0f * fabsf(uni());
+				float d[3] = {uni(), uni(), uni()};
+				const float dn = sqrtf(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
+				if(!(dn > 0)) continue;
+				for(int j = 0; j < 3; j++) d[j] = d[j] / dn * len;
+				const float* X = &hm.coords[3*(size_t)node];
+				// half of the probes start from a position off the base node, as virtual nodes do
+				float pos[3] = {X[0], X[1], X[2]};
+				if(k & 1) for(int j = 0; j < 3; j++) pos[j] += 0.3f * hm.min_h * uni();
+				const int want = hm.find_owner_tetr(node, pos, d[0], d[1], d[2]);
+				gcm::Vec3 np; np.x = pos[0]; np.y = pos[1]; np.z = pos[2];
+				gcm::TetGeom g;
+				const int got = gcm::find_owner_general(m, node, np, d[0], d[1], d[2], g, ws.data());
+				tested++;
+				if(want >= 0) found++;
+				if(got != want) { if(bad < 5) fprintf(stderr, "ring-check mismatch: zone %d node %d want %d got %d\n", hm.zone, node, want, got); bad++; }
+			}
+		}
+		printf("ring-check: %ld %ld %ld\n", tested, found, bad);
+		return bad ? 3 : 0;
 	}
 	gcmh::GlibcRand rng; rng.seed(seed);
 	vector<int> tap;   // records: zone node stage owner[5] outer tries

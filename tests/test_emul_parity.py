@@ -69,3 +69,21 @@ def test_face_grid_gives_the_full_scan_result(built):
     assert up.compare(ref, without) == []
     n_contact = sum(int((r["flags"] & 1).sum()) for r in with_grid)
     assert n_contact > 50
+
+
+def test_any_ring_search_matches_host_restatement(built):
+    """gcm::find_owner_general (the list-building ring expansion the deep contact pass runs on the device)
+    against HostMesh::find_owner_tetr (the literal restatement of TetrMesh_1stOrder.cpp:1468-1602 used by
+    the preprocessing) on random nodes and displacements of up to 5 shortest altitudes -- first to fourth
+    ring, found and not found, probes started off the base node as virtual nodes are."""
+    import subprocess, tempfile
+    from gcm_b200 import meshgen
+    z = meshgen.make_box_zones(9, 8, 7, 1, jitter=0.2, jitter_border=True, seed=31)[0]
+    with tempfile.TemporaryDirectory() as d:
+        mp = os.path.join(d, "z.gcmb")
+        meshgen.write_gcmb(mp, z)
+        r = subprocess.run([up.EMUL, "--mesh", mp, "--seed", "77", "--ring-check", "4000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    tested, found, bad = [int(x) for x in r.stdout.split(":")[1].split()]
+    assert bad == 0
+    assert tested > 3000 and 0.2 * tested < found < 0.95 * tested

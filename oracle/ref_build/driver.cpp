@@ -210,6 +210,15 @@ int main(int argc, char** argv)
 			else if(s.type == "extvel") { ExternalVelocityCalculator* k = new ExternalVelocityCalculator(); k->set_parameters(s.p[0], s.p[1], s.p[2], s.p[3], s.p[4]); bc->calc = k; }
 			else if(s.type == "fixed") bc->calc = new FixedBorderCalculator();
 			else if(s.type == "free") bc->calc = new FreeBorderCalculator();
+			else if(s.type == "extvalues") {
+				// p0 = the three variable indices as decimal digits (i0 i1 i2), p1..p3 = their values
+				ExternalValuesCalculator* k = new ExternalValuesCalculator();
+				const int code = (int)s.p[0];
+				int vars[3] = {code / 100, (code / 10) % 10, code % 10};
+				float vals[3] = {s.p[1], s.p[2], s.p[3]};
+				k->set_parameters(vars, vals);
+				bc->calc = k;
+			}
 			else die("unknown border calculator");
 			bc->form = new StepPulseForm(s.start, s.dur);
 			bc->area = new BoxArea(s.box[0], s.box[1], s.box[2], s.box[3], s.box[4], s.box[5]);

@@ -68,11 +68,18 @@ int main(int argc, char** argv)
 			float p[5]; for(int k = 0; k < 5; k++) p[k] = atof(argv[++a]);
 			c.start = atof(argv[++a]); c.dur = atof(argv[++a]);
 			for(int k = 0; k < 6; k++) c.box[k] = atof(argv[++a]);
-			c.bc.type = t == "free" ? 0 : t == "fixed" ? 1 : t == "extforce" ? 2 : t == "extvel" ? 3 : -1;
+			c.bc.type = t == "free" ? 0 : t == "fixed" ? 1 : t == "extforce" ? 2 : t == "extvel" ? 3 : t == "extvalues" ? 4 : -1;
 			if(c.bc.type < 0) die("unknown border calculator");
-			c.bc.p_normal = p[0]; c.bc.p_tangential = p[1];
-			float d = sqrtf(p[2]*p[2] + p[3]*p[3] + p[4]*p[4]);
-			c.bc.dir[0] = p[2] / d; c.bc.dir[1] = p[3] / d; c.bc.dir[2] = p[4] / d;
+			if(c.bc.type == 4) {
+				// p0 = the three variable indices as decimal digits, p1..p3 = their values (as the oracle driver)
+				const int code = (int)p[0];
+				c.bc.vars_index[0] = code / 100; c.bc.vars_index[1] = (code / 10) % 10; c.bc.vars_index[2] = code % 10;
+				for(int k = 0; k < 3; k++) c.bc.vars_values[k] = p[1 + k];
+			} else {
+				c.bc.p_normal = p[0]; c.bc.p_tangential = p[1];
+				float d = sqrtf(p[2]*p[2] + p[3]*p[3] + p[4]*p[4]);
+				c.bc.dir[0] = p[2] / d; c.bc.dir[1] = p[3] / d; c.bc.dir[2] = p[4] / d;
+			}
 			conds.push_back(c);
 		}
 		else die("unknown argument " + s);

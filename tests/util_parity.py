@@ -27,7 +27,7 @@ LA, MU, RHO = 7e9, 1e9, 7.8e6   # tasks/friction-test.xml:15
 TAP_DT = np.dtype([("step", "i4"), ("zone", "i4"), ("node", "i4"), ("is_virt", "i4"), ("stage", "i4"),
                    ("ch", "i4"), ("count", "i4"), ("owner", "i4"), ("alpha", "f4"), ("dx", "f4", 3)])
 
-BORDER_TYPES = {"free": 0, "fixed": 1, "extforce": 2, "extvel": 3}
+BORDER_TYPES = {"free": 0, "fixed": 1, "extforce": 2, "extvel": 3, "extvalues": 4}
 
 
 def make_case(name):
@@ -75,6 +75,14 @@ def make_case(name):
         c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=9)]
         c["borders"] = [("fixed", (0, 0, 0, 0, 1), -1.0, -1.0, (-1, 8, -1, 8, -0.5, 0.5)),
                         ("extvel", (2.0, 1.0, 0.0, 1.0, 0.0), -1.0, -1.0, (-1, 8, -1, 8, 6.5, 7.5))]
+    elif name == "extvalues8":
+        # ExternalValuesCalculator: the three outer rows pin v = (0.5, -0.25, 1.0) on the z = 7 face,
+        # and sigma_xz, sigma_yz, sigma_zz on the z = 0 face (vars 5, 7, 8)
+        z = meshgen.make_cube(8)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=13)]
+        c["borders"] = [("extvalues", (12, 0.5, -0.25, 1.0, 0.0), -1.0, -1.0, (-1, 8, -1, 8, 6.5, 7.5)),
+                        ("extvalues", (578, 1e7, -2e7, 3e7, 0.0), -1.0, -1.0, (-1, 8, -1, 8, -0.5, 0.5))]
     elif name in ("contact6", "contact6_static", "friction6", "friction6_static", "contact_offset"):
         # two bodies, gap 0.01 along z (tasks/friction-test.xml geometry in miniature): body 1 sits on body 0
         if name == "contact_offset":
@@ -118,7 +126,7 @@ def make_case(name):
 
 CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zones3_jitter", "plastic8",
               "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static",
-              "contact_offset", "readme_contact"]
+              "contact_offset", "readme_contact", "extvalues8"]
 
 
 def _write_inputs(case, d):
@@ -232,7 +240,11 @@ def run_product(case, device=0, fast_inner=True):
         ms.set_contact_calculator(case.get("contact_calc", "adhesion"))
         ms.pre_process_meshes()
         for (t, p, start, dur, box) in case["borders"]:
-            ms.add_border_condition(BORDER_TYPES[t], box, params=p, start=start, duration=dur)
+            if t == "extvalues":   # p0 = the three variable indices as decimal digits, p1..p3 = their values
+                code = int(p[0])
+                ms.add_border_condition(4, box, start=start, duration=dur, vars=[code // 100, (code // 10) % 10, code % 10], vals=p[1:4])
+            else:
+                ms.add_border_condition(BORDER_TYPES[t], box, params=p, start=start, duration=dur)
         for k, st in enumerate(case["states"]):
             ms.get_mesh_by_zone_num(k).set_values(st)
         res = [dict() for _ in case["zones"]]

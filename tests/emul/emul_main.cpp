@@ -38,7 +38,7 @@ struct Cond { gcm::BorderCond bc; float start, dur, box[6]; };
 
 int main(int argc, char** argv)
 {
-	vector<string> mesh_files, state_files;
+	vector<string> mesh_files, state_files, mat_files;
 	vector<Cond> conds;
 	float la = 7e9f, mu = 1e9f, rho = 7.8e6f, yield = 1e16f;
 	int steps = 1, seed = 12345, tap_step = -1, ring_check = 0;
@@ -49,6 +49,7 @@ int main(int argc, char** argv)
 		string s = argv[a];
 		if(s == "--mesh") { while(a + 1 < argc && argv[a+1][0] != '-') mesh_files.push_back(argv[++a]); }
 		else if(s == "--state") { while(a + 1 < argc && argv[a+1][0] != '-') state_files.push_back(argv[++a]); }
+		else if(s == "--mat") { while(a + 1 < argc && argv[a+1][0] != '-') mat_files.push_back(argv[++a]); }
 		else if(s == "--la") la = atof(argv[++a]);
 		else if(s == "--mu") mu = atof(argv[++a]);
 		else if(s == "--rho") rho = atof(argv[++a]);
@@ -102,6 +103,10 @@ int main(int argc, char** argv)
 			hm.flags[i] = 16 | 4 | (placement[i] ? 2 : 0);
 			if(!placement[i]) for(int k = 0; k < 3; k++) hm.coords[3*(size_t)i+k] = 0;
 			hm.mat[4*(size_t)i] = la; hm.mat[4*(size_t)i+1] = mu; hm.mat[4*(size_t)i+2] = rho; hm.mat[4*(size_t)i+3] = yield;
+		}
+		if((int)mat_files.size() > z) {   // per-node (la, mu, rho, yield), as the oracle driver's --mat
+			FILE* g = fopen(mat_files[z].c_str(), "rb"); if(!g) die("cannot open material file");
+			read_vec(g, hm.mat, 4*(size_t)N); fclose(g);
 		}
 	}
 	auto host_sync = [&](bool with_coords) {

@@ -75,6 +75,16 @@ def make_case(name):
         c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=9)]
         c["borders"] = [("fixed", (0, 0, 0, 0, 1), -1.0, -1.0, (-1, 8, -1, 8, -0.5, 0.5)),
                         ("extvel", (2.0, 1.0, 0.0, 1.0, 0.0), -1.0, -1.0, (-1, 8, -1, 8, 6.5, 7.5))]
+    elif name == "twomat8":
+        # two materials in one body (TaskPreparator assigns rheology by area): the half x > 3.5 is lighter and
+        # stiffer in shear; feet near the interface interpolate across it, border nodes of both kinds
+        z = meshgen.make_box_zones(8, 8, 8, 1, jitter=0.1, seed=17)[0]
+        c["zones"] = [z]
+        m = np.empty((z.n_nodes, 4), np.float32)
+        m[:] = (LA, MU, RHO, 1e16)
+        m[z.coords[:, 0] > 3.5] = (3e9, 2e9, 2.7e6, 1e16)
+        c["materials"] = [m]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=19)]
     elif name == "extvalues8":
         # ExternalValuesCalculator: the three outer rows pin v = (0.5, -0.25, 1.0) on the z = 7 face,
         # and sigma_xz, sigma_yz, sigma_zz on the z = 0 face (vars 5, 7, 8)
@@ -124,6 +134,9 @@ def make_case(name):
     return c
 
 
+# cases checked against the reference through the CPU emulation only so far (no GPU run of them yet)
+CPU_ONLY_CASE_NAMES = ["twomat8"]
+
 CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zones3_jitter", "plastic8",
               "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static",
               "contact_offset", "readme_contact", "extvalues8"]
@@ -143,7 +156,13 @@ def _write_inputs(case, d):
 
 def _cli(case, meshes, states, out):
     la, mu, rho, yl = case["material"]
-    a = ["--mesh"] + meshes + ["--state"] + states + ["--la", repr(la), "--mu", repr(mu), "--rho", repr(rho),
+    mats = []
+    if case.get("materials") is not None:    # per-node (la, mu, rho, yield), one [N,4] array per zone
+        for k, m in enumerate(case["materials"]):
+            mp = os.path.join(os.path.dirname(meshes[0]), "z%d.mat" % k)
+            np.ascontiguousarray(m, np.float32).tofile(mp)
+            mats.append(mp)
+    a = ["--mesh"] + meshes + (["--mat"] + mats if mats else []) + ["--state"] + states + ["--la", repr(la), "--mu", repr(mu), "--rho", repr(rho),
                                                        "--yield", repr(yl), "--steps", str(case["steps"]),
                                                        "--seed", str(case["seed"]), "--out", out,
                                                        "--tap-step", str(case["tap_step"])]
@@ -232,7 +251,10 @@ def run_product(case, device=0, fast_inner=True):
         ms.srand(case["seed"])
         ms.set_kernel_mode(fast_inner)
         for k, z in enumerate(case["zones"]):
-            ms.get_mesh_by_zone_num(k).load(z, la=la, mu=mu, rho=rho, yield_limit=yl)
+            if case.get("materials") is not None:
+                ms.get_mesh_by_zone_num(k).load(z, material=case["materials"][k])
+            else:
+                ms.get_mesh_by_zone_num(k).load(z, la=la, mu=mu, rho=rho, yield_limit=yl)
         for (z, dx, dy, dz) in case.get("translates", []):
             ms.get_mesh_by_zone_num(z).translate(dx, dy, dz)
         if case.get("detector", "void") != "void":

@@ -169,3 +169,29 @@ def write_msh(path: str, z: ZoneMesh) -> None:
         for t in range(z.n_tets):
             f.write("%d 4 2 0 1 %d %d %d %d\n" % (t + 1, *(z.tets[t] + 1)))
         f.write("$EndElements\n")
+
+
+def make_delaunay_box(n_side: int, jitter: float = 0.3, seed: int = 0, min_quality: float = 0.02) -> ZoneMesh:
+    """Unstructured stand-in for a gmsh mesh (variant ii): the Delaunay
+    tetrahedralisation (scipy) of an n_side^3 lattice whose inner points are displaced by up to
+    +-jitter; border points stay on the box faces so that the surface is flat.  Node degrees, the
+    position of a node inside its tets and the tet orientations are all irregular.  Slivers
+    (6 |Vol| < min_quality * longest edge^3) on the flat faces are dropped, as a mesher would not
+    produce them.  Needs scipy (test-side utility; not used by the library)."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    k, j, i = np.meshgrid(np.arange(n_side), np.arange(n_side), np.arange(n_side), indexing="ij")
+    ijk = np.stack([i.ravel(), j.ravel(), k.ravel()], 1)
+    xyz = ijk.astype(np.float64)
+    d = rng.uniform(-jitter, jitter, size=xyz.shape)
+    on_face = (ijk == 0) | (ijk == n_side - 1)
+    d[on_face] = 0.0                       # a coordinate that lies on a face stays on it
+    xyz = (xyz + d).astype(np.float32)
+    tets = Delaunay(xyz.astype(np.float64)).simplices.astype(np.int32)
+    p = xyz[tets].astype(np.float64)
+    vol6 = np.abs(np.einsum("ij,ij->i", np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0]), p[:, 3] - p[:, 0]))
+    edges = np.stack([np.linalg.norm(p[:, a] - p[:, b], axis=1) for a in range(4) for b in range(a + 1, 4)], 1)
+    keep = vol6 > min_quality * edges.max(1) ** 3
+    tets = np.ascontiguousarray(tets[keep])
+    n = xyz.shape[0]
+    return ZoneMesh(0, xyz, np.ones(n, np.int32), np.full(n, -1, np.int32), np.full(n, -1, np.int32), tets)

@@ -75,6 +75,14 @@ def make_case(name):
         c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=9)]
         c["borders"] = [("fixed", (0, 0, 0, 0, 1), -1.0, -1.0, (-1, 8, -1, 8, -0.5, 0.5)),
                         ("extvel", (2.0, 1.0, 0.0, 1.0, 0.0), -1.0, -1.0, (-1, 8, -1, 8, 6.5, 7.5))]
+    elif name == "delaunay7":
+        # unstructured mesh (scipy Delaunay of a jittered lattice): node degrees 1..36 (some beyond the 32
+        # candidates the angular index holds), irregular vertex positions inside the tets, both orientations
+        z = meshgen.make_delaunay_box(7, jitter=0.3, seed=3)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=5)]
+        c["seed"] = 321
+        c["tap_step"] = 2
     elif name == "twomat8":
         # two materials in one body (TaskPreparator assigns rheology by area): the half x > 3.5 is lighter and
         # stiffer in shear; feet near the interface interpolate across it, border nodes of both kinds
@@ -135,7 +143,7 @@ def make_case(name):
 
 
 # cases checked against the reference through the CPU emulation only so far (no GPU run of them yet)
-CPU_ONLY_CASE_NAMES = ["twomat8"]
+CPU_ONLY_CASE_NAMES = ["twomat8", "delaunay7"]
 
 CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zones3_jitter", "plastic8",
               "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static",

@@ -75,6 +75,19 @@ def make_case(name):
         c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=9)]
         c["borders"] = [("fixed", (0, 0, 0, 0, 1), -1.0, -1.0, (-1, 8, -1, 8, -0.5, 0.5)),
                         ("extvel", (2.0, 1.0, 0.0, 1.0, 0.0), -1.0, -1.0, (-1, 8, -1, 8, 6.5, 7.5))]
+    elif name in ("delaunay_contact", "delaunay_friction"):
+        # two unstructured bodies, non-matching flat surfaces 0.01 apart, detector every step
+        za = meshgen.make_delaunay_box(7, jitter=0.3, seed=3)
+        zb = meshgen.make_delaunay_box(6, jitter=0.3, seed=4)
+        zb.zone = 1
+        c["zones"] = [za, zb]
+        c["states"] = [meshgen.generic_state(za.coords, LA, MU, RHO, seed=5), meshgen.generic_state(zb.coords, LA, MU, RHO, seed=6)]
+        c["translates"] = [(1, 0.4, 0.7, 6.01)]
+        c["detector"] = "brute"
+        c["static"] = False
+        c["contact_calc"] = "friction" if name.endswith("friction") else "adhesion"
+        c["seed"] = 99
+        c["tap_step"] = 2
     elif name == "delaunay7":
         # unstructured mesh (scipy Delaunay of a jittered lattice): node degrees 1..36 (some beyond the 32
         # candidates the angular index holds), irregular vertex positions inside the tets, both orientations
@@ -143,7 +156,7 @@ def make_case(name):
 
 
 # cases checked against the reference through the CPU emulation only so far (no GPU run of them yet)
-CPU_ONLY_CASE_NAMES = ["twomat8", "delaunay7"]
+CPU_ONLY_CASE_NAMES = ["twomat8", "delaunay7", "delaunay_contact", "delaunay_friction"]
 
 CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zones3_jitter", "plastic8",
               "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static",

@@ -71,7 +71,7 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values);
 int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* host_values);
 int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_values);
 /* A BorderCondition (calculator + StepPulseForm + BoxArea), TaskPreparator.cpp:388-441 and
- * gcm/methods/border/*.cpp.  calc_type: 0 Free, 1 Fixed, 2 ExternalForce, 3 ExternalVelocity,
+ * gcm/methods/border/ (every .cpp there).  calc_type: 0 Free, 1 Fixed, 2 ExternalForce, 3 ExternalVelocity,
  * 4 ExternalValues.  params[5] = set_parameters(normal, tangential, dir x,y,z) for 2/3;
  * for 4: vars[3] / vals[3].  start/duration = StepPulseForm; box[6] = BoxArea(minX,maxX,...).
  * Applies to every local zone; call after gcm_b200_set_preprocess. */

@@ -60,3 +60,17 @@ def test_comm_entry_points_refuse_host_only_sets(built):
             call()
         assert e.value.code == gcm_b200.GCMException.CONFIG_EXCEPTION
     ms.close()
+
+
+@pytest.mark.parametrize("compiler,flags", [("gcc", ["-std=c99", "-pedantic", "-x", "c"]), ("g++", ["-std=gnu++98", "-x", "c++"])])
+def test_header_is_plain_c_and_cxx98(tmp_path, compiler, flags):
+    """The boundary is a C ABI: include/gcm_b200.h must compile, warning-free, as C99 and as the C++98 the
+    reference is written in (gnu++98, the dialect oracle/build_ref.sh compiles its sources with; `long long`
+    in two inspection calls is the only thing beyond ISO C++98)."""
+    import subprocess
+    src = tmp_path / "hdr_check.c"
+    src.write_text('#include "gcm_b200.h"\nint main(void) { return gcm_b200_version() != 0 ? 0 : 1; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    r = subprocess.run([compiler] + flags + ["-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

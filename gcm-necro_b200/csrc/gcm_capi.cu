@@ -96,7 +96,15 @@ struct DeviceMesh {
 	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0;
 	size_t n_fast = 0, n_generic = 0, n_inner = 0;
 	DevBuf<float> u0, u1, mat, tet_hv, basis, basis_next, normals, w0, aos, mat_tab;
-	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, didx, cold;
+	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, cold;
+	// step-invariant cache of the inner kernel (gcm_inner.cuh): 3 planes of N entries, built lazily for a tau
+	DevBuf<gcm::InnerCacheEntry> icache;
+	DevBuf<int> icache_owner;        // [3][N][2] owner tets per direction, only kept when the parity tap is on
+	float icache_tau = -1.f;
+	bool icache_ready = false;
+	int n_cold = 0;                  // inner nodes that stay with the literal routine (cold[0] on the device)
+	float pf_fail = -1e-3f, pf_pass = -1e-4f;   // thresholds of the conservative owner pre-filter (prefilter_thresholds)
+	int exact_only = 0;
 	DevBuf<int> sharp_list, flat_list, fast_list, generic_list, inner_list;
 	size_t n_sharp = 0, n_flat = 0;
 	DevBuf<unsigned char> mat_id;
@@ -132,14 +140,6 @@ struct gcm_b200_set {
 	std::vector<int> halo_dst, halo_src;        // same-process halo, merged indices
 	std::map<int, PeerPlan> peers;
 	void* nccl_comm = nullptr;   // library-driven halo exchange (gcm_b200_set_comm_init); NULL = the host moves the halos
-	// overlapped stage: nodes within two rings of a halo node owned by another process ("shell") wait for the
-	// exchange, everything else ("deep") runs beside it.  Lists in merged indices, deep part first.
-	bool overlap = false, ov_ready = false;   // measured slower (2 GPUs: 2.20 vs 1.97 ms/step): the second, latency-bound
-	                                           // border launch per stage costs more than the exchange it hides; GCM_B200_OVERLAP=1
-	DevBuf<int> ov_flat, ov_sharp, ov_generic, ov_fast_shell;
-	size_t ov_flat_deep = 0, ov_sharp_deep = 0, ov_generic_deep = 0;
-	cudaStream_t comm_stream = nullptr;
-	cudaEvent_t ev_comm_begin = nullptr, ev_comm_done = nullptr;
 	int comm_rank = -1, comm_size = 0;
 	bool plan_built = false;
 	bool preprocessed = false;
@@ -150,16 +150,9 @@ struct gcm_b200_set {
 	float time_step = 0.002f;
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
-	bool coop_border = false;    // flat border nodes: 16 lanes per node (gcm_border_coop.cuh) instead of 1 thread;
-	                             // bit-identical but measured slower (redundant per-lane work), kept as an option
-	bool lean_border = false;    // flat border nodes through node_stage_border_lean (row-wise eigensystem; measured 14 % slower)
 	bool fused_border = true;    // sharp and flat border nodes in one launch (stage_border_fused_kernel)
-	int border_block = 128;      // threads per block of the flat border kernel (finer blocks = shorter tail)
-	int border_min_blocks = 4;   // register budget variant of the per-thread border kernel (3..8 blocks of 128 / SM)
-	bool dir_index = true;       // inner kernel scans through the angular candidate index (gcm_inner.cuh)
-	int direct_min_blocks = 8;   // register budget variant of stage_inner_direct_kernel (4, 6 or 8 blocks of 128 / SM)
-	int direct_prefetch = 2;     // when the second direction's records are requested: 0 after the first's search, 2 after its interpolation
-	bool use_n2x_generic = false; // generic (border) search through the expanded CSR too (measured: no gain)
+	bool inner_cache = true;     // inner nodes through the step-invariant owner/factor cache (gcm_inner.cuh); 0 = index-free scan kernel
+	bool fuse_plastic = true;    // whole-step calls: stage 3 as the epilogue of the stage-2 writers (and no exchange before it)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
 	std::vector<std::vector<int> > axis_plus0;   // per local zone (local_meshes order), per border slot
@@ -312,6 +305,35 @@ template<class T> std::vector<T> shifted(const std::vector<T>& v, long long off)
 	return r;
 }
 
+// Thresholds of the conservative owner pre-filter for this device mesh.  The reference evaluates
+// point_in_tetr at P = X + d rounded to float: each coordinate of P is off by up to ulp(|coordinate|)/2,
+// i.e. each barycentric coordinate by up to  n = sqrt(3) ulp(Cmax) / (2 min h).  The predicate passes iff
+// the negative barycentric coordinates sum to less than 5e-4 (sum|s| < 1.001 Vol); with at most three of
+// them negative, "all > -t_p" is certain to pass while 3 t_p + 3 n + 1e-5 < 5e-4, and "one < -t_f" certain
+// to fail once t_f > 5e-4 + 3 n + 1e-5.  2e-5 of each is left to the filter's own float rounding.  At
+// the benchmark scale (|coordinates| < 256, h = 0.577) this gives the 1e-4 / 1e-3 the filter was
+// validated with; a body far from the origin gets tighter values and, beyond |coordinate| / h ~ 3000,
+// no pre-filter at all (every candidate through the literal predicate).
+void prefilter_thresholds(gcm_b200_set* s)
+{
+	DeviceMesh& dm = s->dm;
+	float cmax = 0, hmin = -1;
+	for(int zi : s->local_zones) {
+		const HostMesh& hm = s->zones[zi]->hm;
+		for(size_t k = 0; k < hm.coords.size(); k++) cmax = fmaxf(cmax, fabsf(hm.coords[k]));
+		if(hm.min_h > 0 && (hmin < 0 || hm.min_h < hmin)) hmin = hm.min_h;
+	}
+	dm.pf_fail = -1e-3f; dm.pf_pass = -1e-4f; dm.exact_only = 0;
+	if(!(hmin > 0) || !std::isfinite(cmax)) { dm.exact_only = 1; return; }
+	cmax += 2 * hmin;                                         // the tested point is up to 0.99 h away from a node
+	const float ulp = nextafterf(cmax, INFINITY) - cmax;
+	const float n = 0.8660254f * ulp / hmin;
+	const float tp = fminf(1e-4f, (4.9e-4f - 3 * n) / 3 * 0.9f - 2e-5f);
+	const float tf = fmaxf(1e-3f, 1.1f * (5.1e-4f + 3 * n) + 2e-5f);
+	if(!(tp >= 2e-5f)) { dm.exact_only = 1; return; }
+	dm.pf_pass = -tp; dm.pf_fail = -tf;
+}
+
 void upload_mesh(gcm_b200_set* s)
 {
 	DeviceMesh& dm = s->dm;
@@ -401,21 +423,9 @@ void upload_mesh(gcm_b200_set* s)
 	CK(cudaStreamSynchronize(st));
 	dm.cur = 0;
 	dm.ready = true;
-	if(s->dir_index && nf) {
-		// angular candidate index of the inner kernel: three planes of N 64-byte entries, built on the device
-		dm.didx.alloc(3 * 4 * GCM_DIDX_QUADS * N);
-		dm.cold.alloc(N + 1);   // nodes deferred by the inner kernel: count, then node ids
-		CK(cudaMemsetAsync(dm.didx.p, 0, 3 * 4 * GCM_DIDX_QUADS * N * sizeof(int), st));
-		const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
-		uint4* dx = reinterpret_cast<uint4*>(dm.didx.p);
-		const int g = (int)((nf + 127) / 128);
-		gcm::build_dir_index_kernel<0><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx);
-		gcm::build_dir_index_kernel<1><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + GCM_DIDX_QUADS * N);
-		gcm::build_dir_index_kernel<2><<<g, 128, 0, st>>>(dm.u0.p, dm.n2t_off.p, dm.tet_hv.p, dm.fast_list.p, (int)nf, dm.w0.p, n2x, dx + 2 * GCM_DIDX_QUADS * N);
-		s->launches += 3;
-		CK(cudaGetLastError());
-		CK(cudaStreamSynchronize(st));
-	}
+	dm.cold.alloc(N + 1);   // inner nodes the cache could not take: count, then node ids
+	dm.icache_ready = false;
+	prefilter_thresholds(s);
 	for(int zi : s->local_zones) upload_values(s, *s->zones[zi]);
 }
 
@@ -427,7 +437,8 @@ gcm::MeshView make_view(gcm_b200_set* s, float tau)
 	m.n_nodes = (int)dm.N; m.n_tets = (int)dm.T; m.stride = dm.stride;
 	m.u = dm.ucur(); m.mat = dm.mat.p; m.flags = dm.flags.p;
 	m.n2t_off = dm.n2t_off.p; m.n2t = dm.n2t.p; m.tets = dm.tets.p; m.tet_hv = dm.tet_hv.p;
-	m.n2x = s->use_n2x_generic ? dm.n2x.p : nullptr;
+	m.n2x = nullptr;
+	m.pf_fail = dm.pf_fail; m.pf_pass = dm.pf_pass; m.exact_only = dm.exact_only;
 	m.n2x_scan = dm.n2x.p;
 	m.border_slot = dm.border_slot.p; m.basis = dm.basis.p; m.cond_id = dm.cond_id.p; m.contact = nullptr;
 	const float t = s->zones[s->local_zones[0]]->hm.current_time;   // TetrMeshSet::get_current_time()
@@ -576,9 +587,42 @@ void sync_nodes_device(gcm_b200_set* s)
 	s->launches++;
 }
 
+// Builds the step-invariant cache of the inner kernel for time step tau (once; again if tau changes
+// or the parity tap is switched on afterwards): the literal per-node routine over every inner node
+// of the fast list, three axes.
+void ensure_inner_cache(gcm_b200_set* s, float tau)
+{
+	DeviceMesh& dm = s->dm;
+	const bool want_tap = s->tap_on;
+	if(dm.icache_ready && dm.icache_tau == tau && (!want_tap || dm.icache_owner.p)) return;
+	const size_t N = dm.N;
+	const int nf = (int)dm.n_fast;
+	if(!dm.icache.p) dm.icache.alloc(3 * N);
+	if(want_tap && !dm.icache_owner.p) dm.icache_owner.alloc(3 * 2 * N);
+	CK(cudaMemsetAsync(dm.icache.p, 0, 3 * N * sizeof(gcm::InnerCacheEntry), s->stream));
+	CK(cudaMemsetAsync(dm.cold.p, 0, sizeof(int), s->stream));
+	dm.n_cold = 0;
+	if(nf) {
+		gcm::MeshView m = make_view(s, tau);
+		m.exact_only = 1;      // the reference's own predicate for every candidate: nothing to be conservative about
+		const int g = (nf + 127) / 128;
+		for(int st = 0; st < 3; st++)
+			gcm::build_inner_cache_kernel<<<g, 128, 0, s->stream>>>(m, dm.fast_list.p, nf, st, dm.icache.p + st * N, dm.cold.p,
+				dm.icache_owner.p ? dm.icache_owner.p + (size_t)st * 2 * N : nullptr);
+		gcm::merge_cold_kernel<<<(nf + 255) / 256, 256, 0, s->stream>>>(dm.icache.p, dm.icache.p + N, dm.icache.p + 2 * N, dm.fast_list.p, nf, dm.cold.p);
+		s->launches += 4;
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(s->h_err + 4, dm.cold.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		dm.n_cold = s->h_err[4];
+	}
+	dm.icache_tau = tau;
+	dm.icache_ready = true;
+}
+
 // One stage for the nodes of one zone (zone >= 0) or of every local zone (zone < 0).
-// part: 0 = every node; 1 = the deep nodes only, 2 = the shell nodes only (overlapped stage, zone < 0).
-void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
+// fuse: stage 2 only -- fold the plastic stage into the writers (whole-step calls).
+void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = false)
 {
 	DeviceMesh& dm = s->dm;
 	Zone* z = zone >= 0 ? s->zones[zone].get() : nullptr;
@@ -592,7 +636,10 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 		}
 		return;
 	}
+	const bool cached = s->fast_inner && s->inner_cache;
+	if(cached) ensure_inner_cache(s, tau);
 	gcm::MeshView m = make_view(s, tau);
+	const float* yp = (fuse && stage == 2) ? dm.mat.p + 3 * dm.stride : nullptr;
 	if(s->tap_on && !dm.tap.p) { dm.tap.alloc(3 * dm.N); CK(cudaMemsetAsync(dm.tap.p, 0xff, 3 * dm.N * sizeof(gcm::StageTap), s->stream)); }
 	gcm::StageTap* tap = s->tap_on ? dm.tap.p : nullptr;
 	// border nodes: flat ones one thread per node, sharp ones 16 lanes per node (speculative alpha tries)
@@ -600,13 +647,6 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 	const int* bl = dm.flat_list.p + (z ? z->flat_off : 0);
 	int nsh = (int)(z ? (size_t)z->hm.n_sharp : dm.n_sharp);
 	const int* shl = dm.sharp_list.p + (z ? z->sharp_off : 0);
-	if(part) {
-		const size_t fd = s->ov_flat_deep, sd = s->ov_sharp_deep;
-		nb = (int)(part == 1 ? fd : s->ov_flat.n - fd);
-		bl = s->ov_flat.p + (part == 1 ? 0 : fd);
-		nsh = (int)(part == 1 ? sd : s->ov_sharp.n - sd);
-		shl = s->ov_sharp.p + (part == 1 ? 0 : sd);
-	}
 	const bool contact = stage == 0 && s->contact_active;
 	if(contact) {   // border nodes in contact on axis 0 take the contact kernel instead
 		nb = (int)(z ? z->st0_n : s->st0_total);
@@ -615,91 +655,87 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, int part = 0)
 		shl = s->d_sharp_stage0.p + (z ? z->st0s_off : 0);
 	}
 	cudaStream_t bst = s->stream;
-	bool fused_done = false;
-	if(nb || nsh) {
+	const bool border_work = nb || nsh;
+	if(border_work) {
 		if(s->concurrent) {
 			bst = s->aux;
 			CK(cudaEventRecord(s->ev_fork, s->stream));
 			CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
 		}
 		ProfScope ps(s, PROF_BORDER, nb + nsh, bst);
-		if(nsh && nb && s->fused_border && !s->coop_border && !s->lean_border) {
+		if(nsh && nb && s->fused_border) {
 			const int blocks = (nsh * 16 + 127) / 128 + (nb + 127) / 128;
-			gcm::stage_border_fused_kernel<<<blocks, 128, 0, bst>>>(m, shl, nsh, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
+			gcm::stage_border_fused_kernel<<<blocks, 128, 0, bst>>>(m, shl, nsh, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp);
 			s->launches++;
-			nsh = 0; nb = 0;
-			fused_done = true;
-		}
-		if(nsh) {
-			gcm::stage_sharp_kernel<<<(nsh * 16 + 63) / 64, 64, 0, bst>>>(m, shl, nsh, stage, dm.unext(), s->d_err, zone, tap);
-			s->launches++;
-		}
-		if(nb) {
-			if(s->coop_border) gcm::stage_border_coop_kernel<<<(int)(((size_t)nb * 16 + 127) / 128), 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			else if(s->lean_border) gcm::stage_border_lean_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			else if(s->border_min_blocks == 4) gcm::stage_generic_kernel_mb<4><<<(nb + s->border_block - 1) / s->border_block, s->border_block, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			else if(s->border_min_blocks == 5) gcm::stage_generic_kernel_mb<5><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			else if(s->border_min_blocks == 6) gcm::stage_generic_kernel_mb<6><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			else if(s->border_min_blocks == 8) gcm::stage_generic_kernel_mb<8><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			else gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap);
-			s->launches++;
+		} else {
+			if(nsh) {
+				gcm::stage_sharp_kernel<<<(nsh * 16 + 63) / 64, 64, 0, bst>>>(m, shl, nsh, stage, dm.unext(), s->d_err, zone, tap, yp);
+				s->launches++;
+			}
+			if(nb) {
+				gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp);
+				s->launches++;
+			}
 		}
 	}
 	if(!s->fast_inner) {
 		const int ni = (int)(z ? z->hm.inner_nodes.size() : dm.n_inner);
 		if(ni) {
 			ProfScope ps(s, PROF_INNER, ni);
-			gcm::stage_generic_kernel<<<(ni + 127) / 128, 128, 0, s->stream>>>(m, dm.inner_list.p + (z ? z->inner_off : 0), ni, stage, dm.unext(), s->d_err, zone, tap);
+			gcm::stage_generic_kernel<<<(ni + 127) / 128, 128, 0, s->stream>>>(m, dm.inner_list.p + (z ? z->inner_off : 0), ni, stage, dm.unext(), s->d_err, zone, tap, yp);
 			s->launches++;
 		}
 	} else {
-		int ng = (int)(z ? z->hm.inner_generic.size() : dm.n_generic);
-		int nf = (int)(z ? z->hm.inner_fast.size() : dm.n_fast);
-		const int* gl = dm.generic_list.p + (z ? z->generic_off : 0);
-		if(part) {
-			const size_t gd = s->ov_generic_deep;
-			ng = (int)(part == 1 ? gd : s->ov_generic.n - gd);
-			gl = s->ov_generic.p + (part == 1 ? 0 : gd);
-			if(part == 2) nf = (int)s->ov_fast_shell.n;
-		}
+		const int ng = (int)(z ? z->hm.inner_generic.size() : dm.n_generic);
+		const int nf = (int)(z ? z->hm.inner_fast.size() : dm.n_fast);
 		if(ng) {
 			ProfScope ps(s, PROF_INNER_GENERIC, ng);
-			gcm::stage_generic_kernel<<<(ng + 127) / 128, 128, 0, s->stream>>>(m, gl, ng, stage, dm.unext(), s->d_err, zone, tap);
+			gcm::stage_generic_kernel<<<(ng + 127) / 128, 128, 0, s->stream>>>(m, dm.generic_list.p + (z ? z->generic_off : 0), ng, stage, dm.unext(), s->d_err, zone, tap, yp);
 			s->launches++;
 		}
 		if(nf) {
-			ProfScope ps(s, PROF_INNER, nf);
 			const unsigned char* mid = dm.n_mat > 1 ? dm.mat_id.p : nullptr;
 			const gcm::MatTab* tab = reinterpret_cast<const gcm::MatTab*>(dm.mat_tab.p);
-			const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
-			const int* fl = dm.fast_list.p + (z ? z->fast_off : 0);
-			const dim3 grid((nf + 127) / 128), block(128);
-			const uint4* dx = s->dir_index ? reinterpret_cast<const uint4*>(dm.didx.p) + (size_t)stage * GCM_DIDX_QUADS * dm.N : nullptr;
-#define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x)
-#define GCM_LAUNCH_DIRECT(S_, MB_, PF_) gcm::stage_inner_direct_kernel<S_, MB_, PF_><<<dgrid, block, 0, s->stream>>>(m, nbeg, nrange, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, n2x, dx, dm.cold.p, dlist, part == 1 ? 1 : 0)
-#define GCM_LAUNCH_DIRECT_S(MB_, PF_) do { if(stage == 0) GCM_LAUNCH_DIRECT(0, MB_, PF_); else if(stage == 1) GCM_LAUNCH_DIRECT(1, MB_, PF_); else GCM_LAUNCH_DIRECT(2, MB_, PF_); } while(0)
-#define GCM_LAUNCH_DIRECT_MB(MB_) do { if(s->direct_prefetch == 0) GCM_LAUNCH_DIRECT_S(MB_, 0); else GCM_LAUNCH_DIRECT_S(MB_, 2); } while(0)
-			// deep pass: the whole range minus the nodes flagged shell; shell pass: the listed shell nodes
-			const int* dlist = part == 2 ? s->ov_fast_shell.p : nullptr;
-			const int nbeg = (int)(z ? z->node_off : 0), nrange = part == 2 ? nf : (int)(z ? (size_t)z->hm.N : dm.N);
-			const dim3 dgrid((unsigned)((nrange + 127) / 128));
-			if(dx) {
-				CK(cudaMemsetAsync(dm.cold.p, 0, sizeof(int), s->stream));
-				// instantiated budgets: 4 (128 registers), 6 (80), 8 (64, the default); measured 3..8, see DESIGN.md
-				if(s->direct_min_blocks == 4) GCM_LAUNCH_DIRECT_MB(4);
-				else if(s->direct_min_blocks == 6) GCM_LAUNCH_DIRECT_MB(6);
-				else GCM_LAUNCH_DIRECT_MB(8);
-				// whatever the index could not settle: the literal routine, right behind
-				gcm::stage_deferred_kernel<<<296, 128, 0, s->stream>>>(m, dm.cold.p, stage, dm.unext(), s->d_err, zone, tap);
+			if(cached) {
+				// the contiguous node range of the zone (or of the whole device mesh); entries of other nodes are invalid
+				const int nbeg = (int)(z ? z->node_off : 0), nrange = (int)(z ? (size_t)z->hm.N : dm.N);
+				const dim3 grid((unsigned)((nrange + 255) / 256)), block(256);
+				const gcm::InnerCacheEntry* ce = dm.icache.p + (size_t)stage * dm.N;
+				const int* otap = (tap && dm.icache_owner.p) ? dm.icache_owner.p + (size_t)stage * 2 * dm.N : nullptr;
+				{
+					ProfScope ps(s, PROF_INNER, nf - dm.n_cold);
+#define GCM_LAUNCH_CACHED(S_, P_) gcm::stage_inner_cached_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), nbeg, nrange, dm.unext(), ce, tab, dm.n_mat, mid, yp, \
+						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N)
+					if(stage == 0) GCM_LAUNCH_CACHED(0, false);
+					else if(stage == 1) GCM_LAUNCH_CACHED(1, false);
+					else if(yp) GCM_LAUNCH_CACHED(2, true);
+					else GCM_LAUNCH_CACHED(2, false);
+#undef GCM_LAUNCH_CACHED
+					s->launches++;
+				}
+				if(dm.n_cold) {
+					// whatever the cache could not take: the literal routine, right behind (a per-zone call strides
+					// over the whole list; nodes of other zones are skipped by the range test below)
+					ProfScope ps(s, PROF_INNER_GENERIC, dm.n_cold);
+					gcm::stage_deferred_kernel<<<(dm.n_cold + 127) / 128 < 296 ? (dm.n_cold + 127) / 128 : 296, 128, 0, s->stream>>>(m, dm.cold.p, stage, dm.unext(), s->d_err, zone, tap, yp,
+						nbeg, nbeg + nrange);
+					s->launches++;
+				}
+			} else {
+				ProfScope ps(s, PROF_INNER, nf);
+				const int4* n2x = reinterpret_cast<const int4*>(dm.n2x.p);
+				const int* fl = dm.fast_list.p + (z ? z->fast_off : 0);
+				const dim3 grid((nf + 127) / 128), block(128);
+#define GCM_LAUNCH_INNER(S_, MB_) gcm::stage_inner_kernel<S_, MB_><<<grid, block, 0, s->stream>>>(m, fl, nf, dm.unext(), s->d_err, zone, tap, tab, dm.n_mat, mid, dm.w0.p, n2x, yp)
+				if(stage == 0) GCM_LAUNCH_INNER(0, 5);
+				else if(stage == 1) GCM_LAUNCH_INNER(1, 5);
+				else GCM_LAUNCH_INNER(2, 5);
+#undef GCM_LAUNCH_INNER
 				s->launches++;
 			}
-			else if(stage == 0) GCM_LAUNCH_INNER(0, 5);
-			else if(stage == 1) GCM_LAUNCH_INNER(1, 5);
-			else GCM_LAUNCH_INNER(2, 5);
-			s->launches++;
 		}
 	}
-	if((nb || nsh || fused_done) && s->concurrent) {
+	if(border_work && s->concurrent) {
 		CK(cudaEventRecord(s->ev_join, s->aux));
 		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
 	}
@@ -934,65 +970,6 @@ void comm_exchange(gcm_b200_set* s, cudaStream_t st)
 }
 
 
-// Classifies the local nodes for the overlapped stage and lays the kernel lists out (deep part first).
-void build_overlap_plan(gcm_b200_set* s)
-{
-	DeviceMesh& dm = s->dm;
-	const size_t N = dm.N;
-	std::vector<char> mark(N, 0);
-	for(auto& kv : s->peers) {
-		const PeerPlan& p = kv.second;
-		for(size_t k = 0; k < p.recv_node.size(); k++) mark[s->zones[p.recv_zone[k]]->node_off + p.recv_node[k]] = 1;
-	}
-	// two rings: a node reads the vertices of its first-ring tets, and the literal routine may go one ring further
-	for(int pass = 0; pass < 2; pass++) {
-		std::vector<char> nxt(mark);
-		for(int zi : s->local_zones) {
-			const Zone& z = *s->zones[zi];
-			const HostMesh& hm = z.hm;
-			for(int t = 0; t < hm.T; t++) {
-				const int* tv = &hm.tets[4 * (size_t)t];
-				if(mark[z.node_off + tv[0]] || mark[z.node_off + tv[1]] || mark[z.node_off + tv[2]] || mark[z.node_off + tv[3]])
-					for(int j = 0; j < 4; j++) nxt[z.node_off + tv[j]] = 1;
-			}
-		}
-		mark.swap(nxt);
-	}
-	std::vector<int> flat[2], sharp[2], generic[2], fast_shell;
-	for(int zi : s->local_zones) {
-		const Zone& z = *s->zones[zi];
-		const HostMesh& hm = z.hm;
-		for(size_t k = 0; k < hm.border_launch.size(); k++) {
-			const int g = (int)(z.node_off + hm.border_launch[k]);
-			((int)k < hm.n_sharp ? sharp : flat)[mark[g] ? 1 : 0].push_back(g);
-		}
-		for(int i : hm.inner_generic) generic[mark[z.node_off + i] ? 1 : 0].push_back((int)(z.node_off + i));
-		for(int i : hm.inner_fast) if(mark[z.node_off + i]) fast_shell.push_back((int)(z.node_off + i));
-	}
-	auto put2 = [&](DevBuf<int>& d, std::vector<int>* v, size_t& n_deep) {
-		n_deep = v[0].size();
-		std::vector<int> all(v[0]);
-		all.insert(all.end(), v[1].begin(), v[1].end());
-		d.upload(all, s->stream);
-	};
-	put2(s->ov_flat, flat, s->ov_flat_deep);
-	put2(s->ov_sharp, sharp, s->ov_sharp_deep);
-	put2(s->ov_generic, generic, s->ov_generic_deep);
-	s->ov_fast_shell.upload(fast_shell, s->stream);
-	if(!fast_shell.empty() && dm.didx.p) {
-		gcm::mark_shell_kernel<<<(int)((fast_shell.size() + 255) / 256), 256, 0, s->stream>>>(reinterpret_cast<uint4*>(dm.didx.p), N, s->ov_fast_shell.p, (int)fast_shell.size());
-		s->launches++;
-		CK(cudaGetLastError());
-	}
-	CK(cudaStreamSynchronize(s->stream));
-	if(!s->comm_stream) {
-		CK(cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking));
-		CK(cudaEventCreateWithFlags(&s->ev_comm_begin, cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&s->ev_comm_done, cudaEventDisableTiming));
-	}
-	s->ov_ready = true;
-}
-
 } // namespace
 
 #define GUARD_BEGIN try {
@@ -1042,22 +1019,15 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 		CK(cudaEventCreateWithFlags(&s->ev_step_mark, cudaEventDisableTiming));
 		CK(cudaMalloc(&s->d_err, 4 * sizeof(int)));
 		CK(cudaMemset(s->d_err, 0, 4 * sizeof(int)));
-		CK(cudaMallocHost(&s->h_err, 4 * sizeof(int)));
+		CK(cudaMallocHost(&s->h_err, 8 * sizeof(int)));
 	}
 	s->rng.seed(1);   // libc default when srand() was never called
 	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
 	if(const char* e = getenv("GCM_B200_FAST_INNER")) s->fast_inner = atoi(e) != 0;
-	if(const char* e = getenv("GCM_B200_COOP_BORDER")) s->coop_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_FUSED_BORDER")) s->fused_border = atoi(e) != 0;
-	if(const char* e = getenv("GCM_B200_BORDER_MB")) s->border_min_blocks = atoi(e);
-	if(const char* e = getenv("GCM_B200_BORDER_BLOCK")) { int b = atoi(e); if(b == 32 || b == 64 || b == 128) s->border_block = b; }
-	if(const char* e = getenv("GCM_B200_LEAN_BORDER")) s->lean_border = atoi(e) != 0;
-	if(const char* e = getenv("GCM_B200_OVERLAP")) s->overlap = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BASES_AHEAD")) s->bases_ahead = atoi(e) != 0;
-	if(const char* e = getenv("GCM_B200_DIR_INDEX")) s->dir_index = atoi(e) != 0;
-	if(const char* e = getenv("GCM_B200_DIRECT_MB")) s->direct_min_blocks = atoi(e);
-	if(const char* e = getenv("GCM_B200_DIRECT_PF")) s->direct_prefetch = atoi(e);
-	if(const char* e = getenv("GCM_B200_N2X_GENERIC")) s->use_n2x_generic = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_INNER_CACHE")) s->inner_cache = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_FUSE_PLASTIC")) s->fuse_plastic = atoi(e) != 0;
 	*out = s.release();
 	return 0;
 	GUARD_END
@@ -1071,7 +1041,6 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		if(s->stream) cudaStreamSynchronize(s->stream);
 		if(s->aux) cudaStreamSynchronize(s->aux);
 		if(s->rng_stream) cudaStreamSynchronize(s->rng_stream);
-		if(s->comm_stream) { cudaStreamSynchronize(s->comm_stream); cudaStreamDestroy(s->comm_stream); cudaEventDestroy(s->ev_comm_begin); cudaEventDestroy(s->ev_comm_done); }
 		if(s->nccl_comm) { nccl_api().CommDestroy(s->nccl_comm); s->nccl_comm = nullptr; }
 		prof_drain(s);
 		for(int k = 0; k < 2; k++) { if(s->h_basis[k]) cudaFreeHost(s->h_basis[k]); if(s->basis_ev[k]) cudaEventDestroy(s->basis_ev[k]); }
@@ -1398,7 +1367,6 @@ int gcm_b200_set_comm_init(gcm_b200_set* s, const void* id128, int rank, int n_r
 	memcpy(&id, id128, sizeof id);
 	nccl_check(nccl_api().CommInitRank(&s->nccl_comm, n_ranks, id, rank), "comm init");
 	s->comm_rank = rank; s->comm_size = n_ranks;
-	if(s->overlap && s->dir_index && s->fast_inner && !s->peers.empty()) build_overlap_plan(s);
 	return 0;
 	GUARD_END
 }
@@ -1413,24 +1381,6 @@ int gcm_b200_set_comm_sync_nodes(gcm_b200_set* s)
 	GUARD_END
 }
 
-// One axis stage with the cross-process exchange running beside the deep nodes: the halo slots the
-// exchange fills are read only by the shell nodes, which start when it has landed.
-static int overlapped_stage(gcm_b200_set* s, int stage)
-{
-	GUARD_BEGIN
-	NEED_DEVICE(s);
-	CK(cudaEventRecord(s->ev_comm_begin, s->stream));
-	CK(cudaStreamWaitEvent(s->comm_stream, s->ev_comm_begin, 0));
-	comm_exchange(s, s->comm_stream);
-	CK(cudaEventRecord(s->ev_comm_done, s->comm_stream));
-	run_stage(s, -1, s->time_step, stage, 1);
-	CK(cudaStreamWaitEvent(s->stream, s->ev_comm_done, 0));
-	run_stage(s, -1, s->time_step, stage, 2);
-	finish_axis_stage(s);
-	return 0;
-	GUARD_END
-}
-
 int gcm_b200_set_do_next_step(gcm_b200_set* s)
 {
 	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
@@ -1438,14 +1388,18 @@ int gcm_b200_set_do_next_step(gcm_b200_set* s)
 		return fail(gcmh::CONFIG_EXCEPTION, "multi-process set: call gcm_b200_set_comm_init, or drive the stages with gcm_b200_halo_* between them");
 	int rc = gcm_b200_set_begin_step(s);
 	if(rc) return rc;
-	for(int stage = 0; stage < 4; stage++) {
+	// Whole-step call: the plastic stage (per node, no neighbours) runs as the epilogue of the stage-2
+	// writers, and the halo refresh in front of it -- never read: stage 3 touches local nodes only and the
+	// next step's first refresh overwrites the same slots -- is not issued.
+	const bool fuse = s->fuse_plastic;
+	for(int stage = 0; stage < (fuse ? 3 : 4); stage++) {
 		if((rc = gcm_b200_set_sync_nodes(s))) return rc;
-		if(s->nccl_comm && s->ov_ready && stage < 3 && !s->contact_active) {
-			if((rc = overlapped_stage(s, stage))) return rc;
-			continue;
-		}
 		if(s->nccl_comm && (rc = gcm_b200_set_comm_sync_nodes(s))) return rc;
-		if((rc = gcm_b200_set_do_next_part_step(s, s->time_step, stage))) return rc;
+		GUARD_BEGIN
+		NEED_DEVICE(s);
+		run_stage(s, -1, s->time_step, stage, fuse);
+		if(stage < 3) finish_axis_stage(s);
+		GUARD_END
 	}
 	return gcm_b200_set_end_step(s);
 }

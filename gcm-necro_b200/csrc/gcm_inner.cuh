@@ -171,13 +171,14 @@ __device__ __forceinline__ void load_cand(Cand& c, const int4 x, const float4* _
 // candidate, or no owner in the first ring) goes through the literal per-node routine, which also
 // classifies the failure exactly as the reference does.
 __device__ __noinline__ void inner_node_generic(const MeshView& m, int node, int stage, float* __restrict__ un,
-                                                int* err, int zone, StageTap* tap)
+                                                int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane)
 {
 	float out[9];
 	StageTap t;
 	const int e = node_stage_nocontact(m, node, stage, out, tap ? &t : nullptr);
 	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
 	if(e) { report_error(err, e, zone, node, stage); return; }
+	if(yield_plane && !plastic_epilogue(out, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
 	const float* r = m.u + (size_t)node * GCM_REC;
 	float4* __restrict__ o = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
 	o[0] = make_float4(out[0], out[1], out[2], out[3]);
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(128, MB)
 stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
                    float* __restrict__ un, int* err, int zone, StageTap* tap,
                    const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
-                   const float* __restrict__ w0, const int4* __restrict__ n2x)
+                   const float* __restrict__ w0, const int4* __restrict__ n2x, const float* __restrict__ yield_plane)
 {
 	__shared__ float sU[GCM_MAX_MATERIALS][81];
 	__shared__ float sU1[GCM_MAX_MATERIALS][81];
@@ -295,7 +296,7 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 			if(v1 > 0) { owner = c.t; break; }
 		}
 		if(cold || owner < 0) {
-			inner_node_generic(m, node, S, un, err, zone, tap);
+			inner_node_generic(m, node, S, un, err, zone, tap, yield_plane);
 			return;
 		}
 		tp.owner[dir] = owner;
@@ -353,162 +354,108 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 			if((u1_pattern(S, i) >> j) & 1) o += U1[i * 9 + j] * omega[j];
 		res[i] = o;
 	}
+	if(yield_plane && !plastic_epilogue(res, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
 	float4* __restrict__ out = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
 	out[0] = make_float4(res[0], res[1], res[2], res[3]);
 	out[1] = make_float4(res[4], res[5], res[6], res[7]);
 	out[2] = make_float4(res[8], X.x, X.y, X.z);
 }
 
-// ---- angular candidate index ------------------------------------------------------------------
-// Built once on the device after the mesh upload.  The pre-filter's verdict for a candidate
-// depends on static data only (the vertex coordinates, h(tet) and the SIGN of the displacement
-// along axis S -- the length is rescaled away, see the file header), so the candidates it rejects
-// ("certainly fails") are the same on every step.  Per (node, axis, sign) the index keeps the
-// positions of the surviving candidates as a 32-bit mask over the node's list and, inline, the
-// expanded-CSR entry and (h, Vol) of the FIRST survivor -- with the rejects gone that one is the
-// owner almost always, and having it in the index saves the two scattered 64-byte DRAM accesses
-// (CSR entry, tet_hv) per direction that dominated the kernel's traffic.  The per-step search is
-// unchanged: survivors in list order through the same pre-filter / exact predicate, first pass
-// wins.  Same function, same inputs, same compiler flags at build and at step time -> the skipped
-// verdicts are exactly the -1 ones.  Entry of one (axis, node), 4 x uint4 = 64 bytes:
-//   q0 = first survivor, dksi < 0: (ia, ib, ic, t | k << 30)
-//   q1 = (its h, its Vol, survivors after it, min h over the whole list)
-//   q2, q3 = the same for dksi > 0, with w0 in the last word (sign bit: "shell", see the kernel)
-// so that each direction reads its own 32 bytes when it needs them.
-// min h == 0 marks "not a node of the fast inner path" (all-zero entry: border, halo, generic);
-// ia == -1 "no survivor".  The step-time guard  0 < delta < 0.99 * min h  implies the pre-filter's
-// own precondition delta < 0.99 h(tet) for every candidate (rounding of h * 0.99 is monotone in
-// h); a node that fails it, or has more than 32 candidates (min h stored as -1), takes the
-// literal per-node routine.
-#define GCM_DIDX_QUADS 4
-template<int S>
-__global__ void __launch_bounds__(128)
-build_dir_index_kernel(const float* __restrict__ u, const int* __restrict__ n2t_off, const float* __restrict__ tet_hv,
-                       const int* __restrict__ list, int n_list, const float* __restrict__ w0,
-                       const int4* __restrict__ n2x, uint4* __restrict__ didx)
-{
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_list) return;
-	const int node = list[idx];
-	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u);
-	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(tet_hv);
-	const float4 o2 = rec[3 * (size_t)node + 2];
-	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
-	const int e0 = n2t_off[node], e1 = n2t_off[node + 1];
-	unsigned mm = 0, mp = 0;
-	float hmin = -1.0f;
-	if(e1 - e0 <= 32) {
-		for(int e = e0; e < e1; e++) {
-			Cand c;
-			load_cand<S>(c, __ldg(n2x + e), rec, hv2);
-			hmin = (e == e0 || c.h < hmin) ? c.h : hmin;
-			const bool shaped = c.vol > 0;
-			if(!(shaped && prefilter<S>(c, X, -1.0f) < 0)) mm |= 1u << (e - e0);
-			if(!(shaped && prefilter<S>(c, X, 1.0f) < 0)) mp |= 1u << (e - e0);
-		}
-	}
-	int4 xm = make_int4(-1, -1, -1, 0), xp = make_int4(-1, -1, -1, 0);
-	float2 hm = make_float2(0.f, 0.f), hp = make_float2(0.f, 0.f);
-	if(mm) { xm = __ldg(n2x + e0 + __ffs(mm) - 1); hm = __ldg(hv2 + (xm.w & 0x3fffffff)); mm &= mm - 1; }
-	if(mp) { xp = __ldg(n2x + e0 + __ffs(mp) - 1); hp = __ldg(hv2 + (xp.w & 0x3fffffff)); mp &= mp - 1; }
-	uint4* __restrict__ o = didx + GCM_DIDX_QUADS * (size_t)node;
-	o[0] = make_uint4((unsigned)xm.x, (unsigned)xm.y, (unsigned)xm.z, (unsigned)xm.w);
-	o[1] = make_uint4(__float_as_uint(hm.x), __float_as_uint(hm.y), mm, __float_as_uint(hmin));
-	o[2] = make_uint4((unsigned)xp.x, (unsigned)xp.y, (unsigned)xp.z, (unsigned)xp.w);
-	o[3] = make_uint4(__float_as_uint(hp.x), __float_as_uint(hp.y), mp, __float_as_uint(w0[node]));
-}
+#endif // __CUDACC__ (index-free kernel)
 
-// Sets the "shell" bit (sign of w0) of the listed nodes in the three planes of the index.
-__global__ void mark_shell_kernel(uint4* __restrict__ didx, size_t n_nodes, const int* __restrict__ list, int n_list)
-{
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_list) return;
-	const int node = list[idx];
-	for(int sgl = 0; sgl < 3; sgl++) {
-		uint4* e = didx + GCM_DIDX_QUADS * ((size_t)sgl * n_nodes + node);
-		if(e[1].w != 0u) e[3].w |= 0x80000000u;
-	}
-}
-
-// ---- inner kernel, indexed -------------------------------------------------------------------
-// One thread per NODE of a contiguous node range (no list indirection): the node's index entry
-// says whether it is a fast inner node at all.  Two rounds of dependent loads per node-stage:
-// (index entry, own record) -> (records of the two first survivors' vertices: coordinates for the
-// predicate and values for the interpolation in one go).  A direction whose first survivor is not
-// the owner continues down its mask through the expanded CSR.  Arithmetic identical to
-// stage_inner_kernel.
-struct CandFull {
-	Cand c;
-	float4 a0, a1, b0, b1, c0, c1;     // first two record quads of A, B, C (the third is c.qa/qb/qc)
+// ---- step-invariant cache of the inner-node stage ------------------------------------------------
+// For an inner node nothing the stage computes before it touches the VALUES changes from step to step:
+// the basis is the identity, tau is fixed (TetrMeshSet.cpp:105-106), the mesh does not move
+// (move_coords is disabled, TetrMeshSet.cpp:170-171) and the material is static.  So the owner
+// tetrahedron of every characteristic foot and its four interpolation factors are functions of static
+// data -- the legal cache of SURVEY section 7.  It is built once per (tau, mesh) by the LITERAL per-node
+// routine of gcm_step.cuh (find_nodes_on_previous_time_layer: the reference's own search, predicate and
+// interpolate arithmetic, no pre-filter), one 96-byte entry per (axis, node):
+//   a0 b0 c0 | flags      dksi < 0: the owner's other three vertices in tet order; flags = k0 | k1 << 2 | valid << 31
+//   w10[4]                factors (own, A, B, C) of the foot  -c1 tau
+//   w20[4]                factors of the foot  -c2 tau
+//   a1 b1 c1 | w0         dksi > 0: the same; w0 = own factor of the zero-speed foot (inside elements[0])
+//   w11[4], w21[4]
+// k = position of the node in the owner's vertex list (decides the association of the 4-term sum).
+// An entry is valid only if the literal routine took its plainest path: one alpha try, all nine
+// characteristics inner, both feet of a direction in the same first-ring tetrahedron, the zero-speed
+// foot in elements[0] with all weight on the node.  Anything else (or any error) leaves the entry
+// invalid and the node on the `cold` list, advanced every stage by the literal routine itself.
+// The step-time kernel then is: entry + own record + six gathered records -> 12 interpolated values ->
+// sparse Omega rows -> sparse Omega^-1: ~250 instructions per node-stage, bounded by HBM.
+struct InnerCacheEntry {
+	int a0, b0, c0; unsigned flags;
+	float w10[4], w20[4];
+	int a1, b1, c1; float w0;
+	float w11[4], w21[4];
 };
+#define GCM_IC_VALID 0x80000000u
 
-__device__ __forceinline__ void load_value_quads(CandFull& f, const float4* __restrict__ rec)
-{
-	f.a0 = __ldg(rec + 3 * (size_t)f.c.ia); f.a1 = __ldg(rec + 3 * (size_t)f.c.ia + 1);
-	f.b0 = __ldg(rec + 3 * (size_t)f.c.ib); f.b1 = __ldg(rec + 3 * (size_t)f.c.ib + 1);
-	f.c0 = __ldg(rec + 3 * (size_t)f.c.ic); f.c1 = __ldg(rec + 3 * (size_t)f.c.ic + 1);
-}
+// components of a gathered record the stage reads at all: rows 0..5 of Omega
+GCM_CONSTEXPR_HD unsigned short gather_mask(int stage) { return u_pattern(stage, 0) | u_pattern(stage, 2) | u_pattern(stage, 4); }
 
-// values = false: only the coordinate quads (what the search and the interpolation factors need);
-// the value quads then follow in feet_of_dir<S, true>, when the factors are known
-__device__ __forceinline__ void load_records(CandFull& f, const float4* __restrict__ rec, bool values = true)
+// Builds the entry of (node, stage); returns true when it is valid.  owner_tets (optional, 2 ints):
+// the owner per direction, for the parity tap.
+GCM_HD bool build_inner_cache_entry(const MeshView& m, int node, int stage, InnerCacheEntry& e, int* owner_tets)
 {
-	f.c.qa = __ldg(rec + 3 * (size_t)f.c.ia + 2);
-	f.c.qb = __ldg(rec + 3 * (size_t)f.c.ib + 2);
-	f.c.qc = __ldg(rec + 3 * (size_t)f.c.ic + 2);
-	if(values) load_value_quads(f, rec);
-}
-
-__device__ __forceinline__ void set_entry(CandFull& f, const uint4 x, float h, float vol)
-{
-	f.c.ia = (int)x.x; f.c.ib = (int)x.y; f.c.ic = (int)x.z;
-	f.c.t = (int)(x.w & 0x3fffffffu); f.c.k = (int)(x.w >> 30);
-	f.c.h = h; f.c.vol = vol;
-}
-
-// Owner search of one direction starting from the (already loaded) first survivor; `rest` = the
-// later survivors.  Returns false when the node must take the literal routine.
-template<int S, bool LATE>
-__device__ __forceinline__ bool settle_dir(CandFull& f, unsigned rest, int node, const int* __restrict__ n2t_off, const F3& X, float sgn,
-                                           float dk1, float de1, float dk2, float de2,
-                                           const int4* __restrict__ n2x, const float4* __restrict__ rec, const float2* __restrict__ hv2)
-{
-	for(;;) {
-		const Cand& c = f.c;
-		int v1 = 0;
-		if(c.vol > 0) v1 = prefilter<S>(c, X, sgn);
-		if(v1 == 0) return false;   // within 1e-3 of a face: the literal routine decides (deferred)
-		if(v1 > 0) return true;
-		if(!rest) return false;
-		const int4 x = __ldg(n2x + n2t_off[node] + __ffs(rest) - 1);
-		rest &= rest - 1;
-		const float2 hv = __ldg(hv2 + (x.w & 0x3fffffff));
-		set_entry(f, make_uint4((unsigned)x.x, (unsigned)x.y, (unsigned)x.z, (unsigned)x.w), hv.x, hv.y);
-		load_records(f, rec, !LATE);
+	e.a0 = e.b0 = e.c0 = e.a1 = e.b1 = e.c1 = 0; e.flags = 0; e.w0 = 0;
+	for(int k = 0; k < 4; k++) { e.w10[k] = e.w20[k] = e.w11[k] = e.w21[k] = 0; }
+	if(owner_tets) { owner_tets[0] = -1; owner_tets[1] = -1; }
+	if(m.flags[node] & NF_BORDER) return false;
+	CurNode cur;
+	cur.base = node;
+	cur.pos = load_xyz(m, node);
+	for(int k = 0; k < 9; k++) cur.val[k] = 0.f;      // values do not enter the search or the factors
+	cur.la = m.mat[node]; cur.mu = m.mat[m.stride + node]; cur.rho = m.mat[2*m.stride + node];
+	cur.is_border = false; cur.has_contact_data = false;
+	for(int k = 0; k < 3; k++) { cur.axis_plus[k] = -1; cur.axis_minus[k] = -1; }
+	float ksi[3] = {0.f, 0.f, 0.f};
+	ksi[stage] = 1.f;                                   // create_random_axis: basis := E (:712-722)
+	float L[9];
+	if(elastic_matrix(cur.la, cur.mu, cur.rho, ksi[0], ksi[1], ksi[2], L, nullptr, nullptr)) return false;
+	float dksi[9];
+	for(int i = 0; i < 9; i++) dksi[i] = - L[i] * m.tau;
+	FeetOut feet;
+	FootGeom fg[5];
+	for(int p = 0; p < 5; p++) for(int k = 0; k < 4; k++) { fg[p].v[k] = -1; fg[p].f[k] = 0; }
+	const int outer = find_nodes_on_previous_time_layer(m, cur, stage, 0.0f, dksi, ksi, feet, false, fg);
+	if(outer != 0 || feet.n_points != 5) return false;
+	const int want[9] = {0, 1, 2, 3, 2, 3, 4, 4, 4};
+	for(int i = 0; i < 9; i++) if(feet.ppoint[i] != want[i]) return false;
+	for(int p = 0; p < 5; p++) if(feet.owner[p] < 0) return false;
+	if(feet.owner[0] != feet.owner[2] || feet.owner[1] != feet.owner[3]) return false;
+	if(feet.owner[4] != m.n2t[m.n2t_off[node]]) return false;
+	// zero-speed foot: all weight on the node itself
+	int k4 = -1;
+	for(int k = 0; k < 4; k++) { if(fg[4].v[k] == node) k4 = k; else if(fg[4].f[k] != 0.0f) return false; }
+	if(k4 < 0) return false;
+	e.w0 = fg[4].f[k4];
+	int kk[2];
+	for(int d = 0; d < 2; d++) {
+		const FootGeom& f1 = fg[d];        // foot -+ c1 tau
+		const FootGeom& f2 = fg[2 + d];    // foot -+ c2 tau (same tetrahedron)
+		int k = -1;
+		for(int j = 0; j < 4; j++) {
+			if(f1.v[j] != f2.v[j]) return false;
+			if(f1.v[j] == node && k < 0) k = j;
+		}
+		if(k < 0) return false;            // an owner outside the first ring: the literal routine keeps this node
+		kk[d] = k;
+		const int ia = f1.v[k == 0 ? 1 : 0], ib = f1.v[k <= 1 ? 2 : 1], ic = f1.v[k == 3 ? 2 : 3];
+		float* w1 = d == 0 ? e.w10 : e.w11;
+		float* w2 = d == 0 ? e.w20 : e.w21;
+		w1[0] = f1.f[k]; w1[1] = f1.f[k == 0 ? 1 : 0]; w1[2] = f1.f[k <= 1 ? 2 : 1]; w1[3] = f1.f[k == 3 ? 2 : 3];
+		w2[0] = f2.f[k]; w2[1] = f2.f[k == 0 ? 1 : 0]; w2[2] = f2.f[k <= 1 ? 2 : 1]; w2[3] = f2.f[k == 3 ? 2 : 3];
+		if(d == 0) { e.a0 = ia; e.b0 = ib; e.c0 = ic; } else { e.a1 = ia; e.b1 = ib; e.c1 = ic; }
+		if(owner_tets) owner_tets[d] = feet.owner[d];
 	}
-}
-
-// Interpolation factors of the foot X + dks e_S inside candidate c, as (own, A, B, C)
-// (TetrMesh_1stOrder.cpp:1764-1857).  Returns false when the reference throws.
-template<int S>
-__device__ __forceinline__ bool axis_factors(const Cand& c, const F3& X, float dks, float w[4])
-{
-	F3 Fp = X;
-	if(S == 0) Fp.x = X.x + dks; else if(S == 1) Fp.y = X.y + dks; else Fp.z = X.z + dks;
-	F3 p0, p1, p2, p3;
-	tet_order(c, X, p0, p1, p2, p3);
-	float f[4];
-	if(!interp_factors(to_vec3(p0), to_vec3(p1), to_vec3(p2), to_vec3(p3), Fp.x, Fp.y, Fp.z, c.vol, f))
-		return false;
-	w[0] = c.k == 0 ? f[0] : (c.k == 1 ? f[1] : (c.k == 2 ? f[2] : f[3]));
-	w[1] = c.k == 0 ? f[1] : f[0];
-	w[2] = c.k <= 1 ? f[2] : f[1];
-	w[3] = c.k == 3 ? f[2] : f[3];
+	e.flags = (unsigned)kk[0] | ((unsigned)kk[1] << 2) | GCM_IC_VALID;
 	return true;
 }
 
-// ((v0 f0 + v1 f1) + v2 f2) + v3 f3 in tet order (:1858-1871); a + b == b + a, so k = 0 and k = 1 coincide
-__device__ __forceinline__ float axis_value(int k, const float w[4], float own, float a, float b, float c)
+// ((v0 f0 + v1 f1) + v2 f2) + v3 f3 in tet order (TetrMesh_1stOrder.cpp:1864-1877) with the node at
+// position k; w = (own, A, B, C).  a + b == b + a, so k = 0 and k = 1 coincide.
+GCM_HD float cached_value(int k, const float w[4], float own, float a, float b, float c)
 {
 	const float tA = a * w[1], tB = b * w[2], tC = c * w[3], tX = own * w[0];
 	const float s1 = tA + (k <= 1 ? tX : tB);
@@ -516,29 +463,36 @@ __device__ __forceinline__ float axis_value(int k, const float w[4], float own, 
 	return s2 + (k == 3 ? tX : tC);
 }
 
-// The two feet of one direction inside its owner and their three Riemann invariants
-// (rows dir, 2 + dir, 4 + dir of Omega).  Returns false when the reference throws.
-// LATE: the value quads of the owner's vertices are requested here, after the factors of both feet
-// (they are 24 registers that need not be live during the search and the determinants).
-template<int S, bool LATE>
-__device__ __forceinline__ bool feet_of_dir(CandFull& f, int dir, const F3& X, float dk1, float dk2,
-                                            const float own[9], const float* __restrict__ U, float omega[9],
-                                            const float4* __restrict__ rec)
+// the components of record i the stage reads (the others are left untouched)
+template<int S>
+GCM_HD void gather_record(const float* __restrict__ u, int i, float v[9])
 {
-	float w1[4], w2[4];
-	if(!axis_factors<S>(f.c, X, dk1, w1)) return false;
-	if(!axis_factors<S>(f.c, X, dk2, w2)) return false;
-	if(LATE) load_value_quads(f, rec);
-	const float va[9] = {f.a0.x, f.a0.y, f.a0.z, f.a0.w, f.a1.x, f.a1.y, f.a1.z, f.a1.w, f.c.qa.x};
-	const float vb[9] = {f.b0.x, f.b0.y, f.b0.z, f.b0.w, f.b1.x, f.b1.y, f.b1.z, f.b1.w, f.c.qb.x};
-	const float vc[9] = {f.c0.x, f.c0.y, f.c0.z, f.c0.w, f.c1.x, f.c1.y, f.c1.z, f.c1.w, f.c.qc.x};
+#if defined(__CUDA_ARCH__)
+	const float4* q = reinterpret_cast<const float4*>(u) + 3 * (size_t)i;
+	const float4 a = __ldg(q), b = __ldg(q + 1);
+	v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+	if((gather_mask(S) >> 8) & 1) v[8] = __ldg(q + 2).x; else v[8] = 0.f;
+#else
+	for(int k = 0; k < 9; k++) v[k] = u[(size_t)i * GCM_REC + k];
+#endif
+}
+
+// The two feet of one direction and their three Riemann invariants (rows dir, 2 + dir, 4 + dir of Omega).
+template<int S>
+GCM_HD void cached_dir(const float* __restrict__ u, int dir, int k, int ia, int ib, int ic, const float w1[4], const float w2[4],
+                       const float own[9], const float* __restrict__ U, float omega[9])
+{
+	float va[9], vb[9], vc[9];
+	gather_record<S>(u, ia, va);
+	gather_record<S>(u, ib, vb);
+	gather_record<S>(u, ic, vc);
 	// omega_i = Omega(i,:) . u(foot of i)  (SimpleVolumeCalculator.cpp:14-23); ppoint_num = (0,1,2,3,2,3,4,4,4)
 	float om = 0, om2 = 0, om4 = 0;
 	#pragma unroll
 	for(int j = 0; j < 9; j++) {
-		if((u_pattern(S, 0) >> j) & 1) om += U[dir * 9 + j] * axis_value(f.c.k, w1, own[j], va[j], vb[j], vc[j]);
+		if((u_pattern(S, 0) >> j) & 1) om += U[dir * 9 + j] * cached_value(k, w1, own[j], va[j], vb[j], vc[j]);
 		if(((u_pattern(S, 2) | u_pattern(S, 4)) >> j) & 1) {
-			const float v2 = axis_value(f.c.k, w2, own[j], va[j], vb[j], vc[j]);
+			const float v2 = cached_value(k, w2, own[j], va[j], vb[j], vc[j]);
 			if((u_pattern(S, 2) >> j) & 1) om2 += U[(2 + dir) * 9 + j] * v2;
 			if((u_pattern(S, 4) >> j) & 1) om4 += U[(4 + dir) * 9 + j] * v2;
 		}
@@ -546,114 +500,26 @@ __device__ __forceinline__ bool feet_of_dir(CandFull& f, int dir, const F3& X, f
 	omega[dir] = om;
 	omega[2 + dir] = om2;
 	omega[4 + dir] = om4;
-	return true;
 }
 
-// PF: 1 = the records of both directions' first survivors are requested together, 0 = the second
-// direction's after the first direction's search, 2 = after the first direction's interpolation
-// (fewest live registers).
-// list / skip_shell: see the body.
-// A node the index cannot settle (guard, disagreeing feet, no owner in the first ring) is appended to
-// `cold` (cold[0] = count) and advanced by stage_deferred_kernel right after this launch: keeping the
-// literal routine out of this kernel leaves its hot path spill-free at 128 registers (-7 % time).
-template<int S, int MB, int PF>
-__global__ void __launch_bounds__(128, MB)
-stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, int n_range,
-                          float* __restrict__ un, int* err, int zone, StageTap* tap,
-                          const MatTab* __restrict__ tab, int n_mat, const unsigned char* __restrict__ mat_id,
-                          const int4* __restrict__ n2x, const uint4* __restrict__ didx, int* __restrict__ cold,
-                          const int* __restrict__ list, int skip_shell)
+// One inner node, axis stage S, from its cache entry: the volume update of
+// SimpleVolumeCalculator.cpp:7-32 with the structural zeros of Omega / Omega^-1 skipped.
+template<int S>
+GCM_HD void inner_cached_stage(const float* __restrict__ u, const InnerCacheEntry& e, const float own[9],
+                               const float* __restrict__ U, const float* __restrict__ U1, float res[9])
 {
 	static_assert(u_pattern(S, 0) == u_pattern(S, 1) && u_pattern(S, 2) == u_pattern(S, 3) && u_pattern(S, 4) == u_pattern(S, 5),
 	              "rows 2q and 2q+1 of Omega must share their sparsity pattern");
-	__shared__ float sU[GCM_MAX_MATERIALS][81];
-	__shared__ float sU1[GCM_MAX_MATERIALS][81];
-	__shared__ float sL[GCM_MAX_MATERIALS][4];
-	for(int i = threadIdx.x; i < n_mat * 81; i += blockDim.x) {
-		const MatTab& mt = tab[(i / 81) * 3 + S];
-		sU[i / 81][i % 81] = mt.U[i % 81];
-		sU1[i / 81][i % 81] = mt.U1[i % 81];
-	}
-	for(int i = threadIdx.x; i < n_mat * 4; i += blockDim.x) sL[i / 4][i % 4] = tab[(i / 4) * 3 + S].L[i % 4];
-	__syncthreads();
-
-	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_range) return;
-	// list == NULL: the contiguous range; else the listed nodes (the shell pass of the overlapped stage)
-	const int node = list ? list[idx] : node_begin + idx;
-	const uint4* __restrict__ ent = didx + GCM_DIDX_QUADS * (size_t)node;
-	const uint4 e0q = __ldg(ent), e1q = __ldg(ent + 1);
-	if(e1q.w == 0u) return;                       // min h == 0: not a node of the fast inner path
-	uint4 e2q = make_uint4(0u, 0u, 0u, 0u), e3q = e2q;
-	if(PF != 2 || skip_shell) { e2q = __ldg(ent + 2); e3q = __ldg(ent + 3); }
-	// sign bit of w0 (a weight, >= 0) = "shell": within two rings of a halo node owned by another process;
-	// the deep pass leaves those to the pass that runs after the exchange
-	if(skip_shell && (e3q.w & 0x80000000u)) return;
-	const float4* __restrict__ rec = reinterpret_cast<const float4*>(m.u);
-	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(m.tet_hv);
-	const float4 o0 = rec[3 * (size_t)node], o1 = rec[3 * (size_t)node + 1], o2 = rec[3 * (size_t)node + 2];
-	const bool have = (int)e0q.x >= 0 && (PF == 2 || (int)e2q.x >= 0);
-	CandFull f0, f1;
-	set_entry(f0, e0q, __uint_as_float(e1q.x), __uint_as_float(e1q.y));
-	if(PF != 2) set_entry(f1, e2q, __uint_as_float(e3q.x), __uint_as_float(e3q.y));
-	if(have) load_records(f0, rec, PF != 2);
-	if(PF == 1 && have) load_records(f1, rec);
-
-	const int mid = mat_id ? mat_id[node] : 0;
-	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
-	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
-	bool bad = false;
-	#pragma unroll
-	for(int k = 0; k < 9; k++) bad |= !(fabsf(own[k]) <= 3.4028235e38f);   // NaN or Inf (TetrMethod_Plastic_1stOrder.cpp:192-194): one compare
-	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
-	const float* U = sU[mid];
-	const float* U1 = sU1[mid];
-	float dk[4], de[4];
-	{
-		// all four displacements must be rescaled by every candidate (then the index is valid)
-		const double h99 = (double)__uint_as_float(e1q.w) * 0.99;
-		bool ok = have;
-		#pragma unroll
-		for(int q = 0; q < 4; q++) {
-			dk[q] = - sL[mid][q] * m.tau;             // dksi[i] = - L(i,i) * time_step
-			de[q] = sqrtf(dk[q] * dk[q]);             // delta; off-axis components are +-0
-			ok = ok && de[q] > 0 && (double)de[q] < h99;
-		}
-		if(!ok) { cold[1 + atomicAdd(&cold[0], 1)] = node; return; }
-	}
 	float omega[9];
-	// dir 0: dksi < 0 (characteristics 0 and 2: -c1 tau, -c2 tau); dir 1: dksi > 0 (1 and 3)
-	if(!settle_dir<S, PF == 2>(f0, e1q.z, node, m.n2t_off, X, -1.0f, dk[0], de[0], dk[2], de[2], n2x, rec, hv2)) {
-		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
-	}
-	if(PF == 0) load_records(f1, rec);
-	if(!feet_of_dir<S, PF == 2>(f0, 0, X, dk[0], dk[2], own, U, omega, rec)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
-	if(PF == 2) {
-		// nothing of the second direction is live while the first one is interpolated: its entry is
-		// read again (the line is in L1) and its records are requested only now
-		e2q = __ldg(ent + 2); e3q = __ldg(ent + 3);
-		if((int)e2q.x < 0) { cold[1 + atomicAdd(&cold[0], 1)] = node; return; }   // no survivor on this side
-		set_entry(f1, e2q, __uint_as_float(e3q.x), __uint_as_float(e3q.y));
-		load_records(f1, rec, false);
-	}
-	if(!settle_dir<S, PF == 2>(f1, e3q.z, node, m.n2t_off, X, 1.0f, dk[1], de[1], dk[3], de[3], n2x, rec, hv2)) {
-		cold[1 + atomicAdd(&cold[0], 1)] = node; return;
-	}
-	if(!feet_of_dir<S, PF == 2>(f1, 1, X, dk[1], dk[3], own, U, omega, rec)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
-
-	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every
-	// factor but the node's own is exactly 0, the own one is the static weight w0
+	// dir 0: dksi < 0 (characteristics 0, 2, 4); dir 1: dksi > 0 (1, 3, 5)
+	cached_dir<S>(u, 0, (int)(e.flags & 3u), e.a0, e.b0, e.c0, e.w10, e.w20, own, U, omega);
+	cached_dir<S>(u, 1, (int)((e.flags >> 2) & 3u), e.a1, e.b1, e.c1, e.w11, e.w21, own, U, omega);
+	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every factor
+	// but the node's own is exactly 0 (their products are signed zeros, absorbed by the sums below,
+	// which start from +0), the own one is w0
 	float vz[9];
-	const float wz = __uint_as_float(e3q.w & 0x7fffffffu);
 	#pragma unroll
-	for(int k = 0; k < 9; k++) vz[k] = own[k] * wz;
-	if(tap) {
-		StageTap tp;
-		tp.owner[0] = f0.c.t; tp.owner[2] = f0.c.t; tp.owner[1] = f1.c.t; tp.owner[3] = f1.c.t;
-		tp.owner[4] = m.n2t[m.n2t_off[node]];
-		tp.outer_count = 0; tp.tries = 1;
-		tap[(size_t)S * m.n_nodes + node] = tp;
-	}
+	for(int k = 0; k < 9; k++) vz[k] = own[k] * e.w0;
 	#pragma unroll
 	for(int i = 6; i < 9; i++) {
 		float om = 0;
@@ -663,7 +529,6 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 		omega[i] = om;
 	}
 	// u' = Omega^-1 * omega (SimpleVolumeCalculator.cpp:24-31), skipping the structural zeros
-	float res[9];
 	#pragma unroll
 	for(int i = 0; i < 9; i++) {
 		float o = 0;
@@ -672,10 +537,99 @@ stage_inner_direct_kernel(const __grid_constant__ MeshView m, int node_begin, in
 			if((u1_pattern(S, i) >> j) & 1) o += U1[i * 9 + j] * omega[j];
 		res[i] = o;
 	}
+}
+
+#if defined(__CUDACC__)
+
+// One thread per listed inner node: the literal routine once, its outcome into the cache
+// (and into `cold`, cold[0] = count, when the node has to stay with the literal routine).
+__global__ void __launch_bounds__(128)
+build_inner_cache_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
+                         InnerCacheEntry* __restrict__ cache, int* __restrict__ cold, int* __restrict__ owner_tap)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	InnerCacheEntry e;
+	int own2[2];
+	const bool ok = build_inner_cache_entry(m, node, stage, e, own2);
+	uint4* o = reinterpret_cast<uint4*>(cache + node);
+	const uint4* src = reinterpret_cast<const uint4*>(&e);
+	#pragma unroll
+	for(int q = 0; q < 6; q++) o[q] = src[q];
+	if(owner_tap) { owner_tap[2 * (size_t)node] = own2[0]; owner_tap[2 * (size_t)node + 1] = own2[1]; }
+	if(!ok && stage == 0) cold[1 + atomicAdd(&cold[0], 1)] = node;
+}
+
+// stage > 0: a node invalid on this axis only joins the list too (once)
+__global__ void __launch_bounds__(256)
+merge_cold_kernel(const InnerCacheEntry* __restrict__ c0, const InnerCacheEntry* __restrict__ c1, const InnerCacheEntry* __restrict__ c2,
+                  const int* __restrict__ list, int n_list, int* __restrict__ cold)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	const bool v0 = (c0[node].flags & GCM_IC_VALID) != 0, v1 = (c1[node].flags & GCM_IC_VALID) != 0, v2 = (c2[node].flags & GCM_IC_VALID) != 0;
+	if(v0 && !(v1 && v2)) cold[1 + atomicAdd(&cold[0], 1)] = node;   // !v0: already listed by the stage-0 build
+}
+
+// The hot kernel.  One thread per node of a contiguous range; the entry says whether the node is
+// an inner node of the cached path at all (all-zero entries: border, halo, generic, cold).
+// PLASTIC: stage 3 folded in (only instantiated for S == 2).
+template<int S, bool PLASTIC>
+__global__ void __launch_bounds__(256)
+stage_inner_cached_kernel(const float* __restrict__ u, int node_begin, int n_range, float* __restrict__ un,
+                          const InnerCacheEntry* __restrict__ cache, const MatTab* __restrict__ tab, int n_mat,
+                          const unsigned char* __restrict__ mat_id, const float* __restrict__ yield_plane,
+                          int* err, int zone, StageTap* tap, const int* __restrict__ owner_tap,
+                          const int* __restrict__ n2t_off, const int* __restrict__ n2t, int n_nodes)
+{
+	__shared__ float sU[GCM_MAX_MATERIALS][81];
+	__shared__ float sU1[GCM_MAX_MATERIALS][81];
+	for(int i = threadIdx.x; i < n_mat * 81; i += blockDim.x) {
+		const MatTab& mt = tab[(i / 81) * 3 + S];
+		sU[i / 81][i % 81] = mt.U[i % 81];
+		sU1[i / 81][i % 81] = mt.U1[i % 81];
+	}
+	__syncthreads();
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_range) return;
+	const int node = node_begin + idx;
+	InnerCacheEntry e;
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(cache + node);
+		uint4* dst = reinterpret_cast<uint4*>(&e);
+		const uint4 q0 = __ldg(src);
+		if(!(q0.w & GCM_IC_VALID)) return;
+		dst[0] = q0;
+		#pragma unroll
+		for(int q = 1; q < 6; q++) dst[q] = __ldg(src + q);
+	}
+	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u) + 3 * (size_t)node;
+	const float4 o0 = rec[0], o1 = rec[1], o2 = rec[2];
+	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
+	bool bad = false;
+	#pragma unroll
+	for(int k = 0; k < 9; k++) bad |= !(fabsf(own[k]) <= 3.4028235e38f);   // NaN or Inf (TetrMethod_Plastic_1stOrder.cpp:192-194)
+	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
+	const int mid = mat_id ? mat_id[node] : 0;
+	float res[9];
+	inner_cached_stage<S>(u, e, own, sU[mid], sU1[mid], res);
+	if(tap) {
+		StageTap tp;
+		tp.owner[0] = tp.owner[2] = owner_tap ? owner_tap[2 * (size_t)node] : -2;
+		tp.owner[1] = tp.owner[3] = owner_tap ? owner_tap[2 * (size_t)node + 1] : -2;
+		tp.owner[4] = n2t[n2t_off[node]];
+		tp.outer_count = 0; tp.tries = 1;
+		tap[(size_t)S * n_nodes + node] = tp;
+	}
+	if(PLASTIC) {
+		if(!plastic_epilogue(res, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
+	}
 	float4* __restrict__ out = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
 	out[0] = make_float4(res[0], res[1], res[2], res[3]);
 	out[1] = make_float4(res[4], res[5], res[6], res[7]);
-	out[2] = make_float4(res[8], X.x, X.y, X.z);
+	out[2] = make_float4(res[8], o2.y, o2.z, o2.w);
 }
 
 #endif // __CUDACC__

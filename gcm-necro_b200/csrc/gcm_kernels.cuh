@@ -13,15 +13,25 @@ __device__ __forceinline__ void report_error(int* err, int code, int zone, int n
 
 } // namespace gcm
 #include "gcm_inner.cuh"
-#include "gcm_border_coop.cuh"
 namespace gcm {
+
+// Writes one node's stage result: the 9 values into the next layer; with yield_plane != NULL the
+// plastic stage is folded in (whole-step calls run stage 3 as the epilogue of stage 2).
+__device__ __forceinline__ void store_node(float* __restrict__ un, int node, float out[9], const float* __restrict__ yield_plane,
+                                           int* err, int zone)
+{
+	if(yield_plane && !plastic_epilogue(out, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
+	#pragma unroll
+	for(int k = 0; k < 9; k++)
+		un[(size_t)node * GCM_REC + k] = out[k];
+}
 
 // One thread per listed node, one axis stage: TetrMesh_1stOrder::do_next_part_step's two
 // node loops (gcm/meshtypes/TetrMesh_1stOrder.cpp:1906-1923); the copy-back loop (:1925-1932)
 // is the caller's buffer swap.
 __global__ void __launch_bounds__(128)
 stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
-                     int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
+                     int stage, float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane)
 {
 	int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if(idx >= n_list) return;
@@ -31,67 +41,28 @@ stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 	int e = node_stage_nocontact(m, node, stage, out, tap ? &t : nullptr);
 	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
 	if(e) { report_error(err, e, zone, node, stage); return; }
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		un[(size_t)node * GCM_REC + k] = out[k];
+	store_node(un, node, out, yield_plane, err, zone);
 }
 
-// The nodes the indexed inner kernel could not settle (cold[0] = how many, cold[1..] = which), through
+// The nodes a specialised kernel could not settle (cold[0] = how many, cold[1..] = which), through
 // the literal per-node routine; a small fixed grid strides over the list (it is empty on regular
-// meshes, a handful of nodes on jittered ones, every inner node if tau were too large for the index).
+// meshes, a handful of nodes on irregular ones).
 __global__ void __launch_bounds__(128)
 stage_deferred_kernel(const __grid_constant__ MeshView m, const int* __restrict__ cold, int stage,
-                      float* __restrict__ un, int* err, int zone, StageTap* tap)
+                      float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane,
+                      int node_begin, int node_end)
 {
 	const int n = cold[0];
 	for(int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
 		const int node = cold[1 + idx];
+		if(node < node_begin || node >= node_end) continue;   // a per-zone call: the list covers every local zone
 		float out[9];
 		StageTap t;
 		const int e = node_stage_nocontact_cold(m, node, stage, out, tap ? &t : nullptr);
 		if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
 		if(e) { report_error(err, e, zone, node, stage); continue; }
-		#pragma unroll
-		for(int k = 0; k < 9; k++)
-			un[(size_t)node * GCM_REC + k] = out[k];
+		store_node(un, node, out, yield_plane, err, zone);
 	}
-}
-
-// Same kernel with a register budget for MB resident blocks per SM (occupancy vs spills).
-template<int MB>
-__global__ void __launch_bounds__(128, MB)
-stage_generic_kernel_mb(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
-                        int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
-{
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_list) return;
-	int node = list[idx];
-	float out[9];
-	StageTap t;
-	int e = node_stage_nocontact(m, node, stage, out, tap ? &t : nullptr);
-	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
-	if(e) { report_error(err, e, zone, node, stage); return; }
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		un[(size_t)node * GCM_REC + k] = out[k];
-}
-
-// Border nodes, one thread per node, small-footprint routine (node_stage_border_lean).
-__global__ void __launch_bounds__(128, 4)
-stage_border_lean_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
-                         int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
-{
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_list) return;
-	int node = list[idx];
-	float out[9];
-	StageTap t;
-	int e = node_stage_border_lean(m, node, stage, out, tap ? &t : nullptr);
-	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
-	if(e) { report_error(err, e, zone, node, stage); return; }
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		un[(size_t)node * GCM_REC + k] = out[k];
 }
 
 // Border nodes on sharp edges / corners usually burn all 11 alpha tries of prepare_node
@@ -114,7 +85,7 @@ struct SharpDecide {
 
 __global__ void __launch_bounds__(64)
 stage_sharp_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
-                   int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
+                   int stage, float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane)
 {
 	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int idx = gid >> 4;
@@ -128,9 +99,7 @@ stage_sharp_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	if(e == -1000) return;                  // another lane's try decides this node
 	if(tap) tap[(size_t)stage * m.n_nodes + node] = tp;
 	if(e) { report_error(err, e, zone, node, stage); return; }
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		un[(size_t)node * GCM_REC + k] = out[k];
+	store_node(un, node, out, yield_plane, err, zone);
 }
 
 // Sharp and flat border nodes in ONE launch: the first blocks take the sharp nodes (16 lanes per
@@ -140,7 +109,7 @@ stage_sharp_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 __global__ void __launch_bounds__(128, 4)
 stage_border_fused_kernel(const __grid_constant__ MeshView m, const int* __restrict__ sharp_list, int n_sharp,
                           const int* __restrict__ flat_list, int n_flat,
-                          int stage, float* __restrict__ un, int* err, int zone, StageTap* tap)
+                          int stage, float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane)
 {
 	const int sharp_blocks = (n_sharp * 16 + 127) / 128;
 	float out[9];
@@ -163,9 +132,7 @@ stage_border_fused_kernel(const __grid_constant__ MeshView m, const int* __restr
 	}
 	if(tap) tap[(size_t)stage * m.n_nodes + node] = tp;
 	if(e) { report_error(err, e, zone, node, stage); return; }
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		un[(size_t)node * GCM_REC + k] = out[k];
+	store_node(un, node, out, yield_plane, err, zone);
 }
 
 // Border nodes in contact on axis `stage` (only axis 0 can be: BruteforceCollisionDetector.cpp:58-60):
@@ -247,17 +214,18 @@ plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* 
 	}
 }
 
-// DataBus::sync_nodes, same-process branch (gcm/system/DataBus.cpp:64-79): halo node values
-// of one zone copied from the owner zone's nodes.  Only the 9 evolving values move per stage.
-__global__ void halo_copy_kernel(float* __restrict__ dst_u, const int* __restrict__ dst_idx,
-                                 const float* __restrict__ src_u, const int* __restrict__ src_idx, int n)
+// DataBus::sync_nodes, same-process branch (gcm/system/DataBus.cpp:64-79): halo node records of one
+// zone copied from the owner zone's nodes, three threads per node, one 16-byte quad each (the third
+// quad carries the coordinates, which are equal on both sides since the start-up sync).
+__global__ void __launch_bounds__(256)
+halo_copy_kernel(float* __restrict__ dst_u, const int* __restrict__ dst_idx,
+                 const float* __restrict__ src_u, const int* __restrict__ src_idx, int n)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	const int g = blockIdx.x * blockDim.x + threadIdx.x;
+	const int i = g / 3, q = g - 3 * i;
 	if(i >= n) return;
-	int d = dst_idx[i], s = src_idx[i];
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		dst_u[(size_t)d * GCM_REC + k] = src_u[(size_t)s * GCM_REC + k];
+	const int d = dst_idx[i], s = src_idx[i];
+	reinterpret_cast<float4*>(dst_u)[3 * (size_t)d + q] = reinterpret_cast<const float4*>(src_u)[3 * (size_t)s + q];
 }
 
 // Cross-process halo: gather into / scatter from a plane-major [9][n] exchange buffer.

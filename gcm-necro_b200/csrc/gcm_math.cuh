@@ -467,6 +467,17 @@ GCM_HD bool drop_deviator(float v[9], float yield_limit)
 	return false;
 }
 
+// Stage 3 folded into the writers of stage 2 (TetrMethod_Plastic_1stOrder.cpp:192-199 on the values
+// stage 2 just produced: the NaN guard of the stage-3 call, then drop_deviator).  Returns false on NaN/Inf.
+GCM_HD bool plastic_epilogue(float v[9], float yield_limit)
+{
+	bool bad = false;
+	for(int k = 0; k < 9; k++) bad |= !(fabsf(v[k]) <= 3.4028235e38f);
+	if(bad) return false;
+	drop_deviator(v, yield_limit);
+	return true;
+}
+
 // ---- dense LU in double (GSL gsl_linalg_LU_decomp / gsl_linalg_LU_solve semantics) --------
 // GSL is a third-party dependency of the reference, absent from /root/reference and unpinned
 // (gcm/CMakeLists.txt:88).  Published GSL 1.x algorithm: Gaussian elimination with partial

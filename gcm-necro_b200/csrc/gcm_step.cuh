@@ -53,6 +53,13 @@ struct MeshView {
 	const int* cond_id;      // [n_border]   index into conds[] or -1 = default
 	const int* contact;      // [n_border][6] axis_plus[3], axis_minus[3] (virt node ids) or NULL
 	int* ring_ws;            // NULL, or GCM_RING_WS ints per thread of the launch: workspace of find_owner_general
+	// Thresholds of the conservative owner pre-filter (barycentric units, both negative): a candidate
+	// certainly fails below pf_fail and certainly passes above pf_pass.  They depend on how much the
+	// reference's own float evaluation of the tested point is perturbed, i.e. on max|coordinate| / min h
+	// (gcm_capi.cu: prefilter_thresholds); exact_only != 0 switches the pre-filter off altogether
+	// (huge coordinates, and the one-time build of the inner cache, where speed does not matter).
+	float pf_fail, pf_pass;
+	int exact_only;
 	float tau;
 	float time;
 	float min_h;
@@ -102,7 +109,8 @@ GCM_HD void load_tet(const MeshView& m, int t, TetGeom& g)
 //   -1  some coordinate < -1e-3        -> the predicate certainly fails
 //   +1  all four coordinates > -1e-4   -> it certainly passes
 //    0  anything else (or tet / displacement outside the filter's assumptions) -> evaluate it
-GCM_HD int owner_prefilter(const TetGeom& g, int base, const Vec3& X, float dx, float dy, float dz, float delta)
+GCM_HD int owner_prefilter(const TetGeom& g, int base, const Vec3& X, float dx, float dy, float dz, float delta,
+                           float pf_fail, float pf_pass)
 {
 	if(!(g.vol > 0) || !(delta > 0) || !((double)delta < (double)g.h * 0.99)) return 0;
 	const int k = (g.v[0] == base) ? 0 : (g.v[1] == base) ? 1 : (g.v[2] == base) ? 2 : (g.v[3] == base) ? 3 : -1;
@@ -123,7 +131,7 @@ GCM_HD int owner_prefilter(const TetGeom& g, int base, const Vec3& X, float dx, 
 	const float D2 = D * D;
 	const float lx = D2 - (la + lb + lc);
 	const float mn = fminf(fminf(la, lb), fminf(lc, lx));
-	return mn < -1e-3f * D2 ? -1 : (mn > -1e-4f * D2 ? 1 : 0);
+	return mn < pf_fail * D2 ? -1 : (mn > pf_pass * D2 ? 1 : 0);
 }
 
 // First ring of gcm/meshtypes/TetrMesh_1stOrder.cpp:1468-1602: the candidates are the base
@@ -164,7 +172,7 @@ GCM_HD int find_owner_first_ring(const MeshView& m, int base, const Vec3& node_p
 			t = m.n2t[e];
 			load_tet(m, t, g);
 		}
-		int verdict = owner_prefilter(g, base, X, dx, dy, dz, delta);
+		int verdict = m.exact_only ? 0 : owner_prefilter(g, base, X, dx, dy, dz, delta, m.pf_fail, m.pf_pass);
 		if(verdict == 0)
 			verdict = point_in_tetr(X, dx, dy, dz, delta, g.p[0], g.p[1], g.p[2], g.p[3], g.h, g.vol) ? 1 : -1;
 		if(verdict > 0)
@@ -330,12 +338,17 @@ int find_owner_general(const MeshView& m, int base, const Vec3& node_pos,
 
 // Interpolated state at a foot (gcm/meshtypes/TetrMesh_1stOrder.cpp:1764-1880).
 // out[0..8] = values, out[9..11] = la, mu, rho (only virtual nodes read those).
+// What a foot's interpolation is made of: the owner's vertices (tet order) and their factors.  Filled
+// on request (the step-invariant cache of the inner kernel is built from it, gcm_inner.cuh).
+struct FootGeom { int v[4]; float f[4]; };
+
 GCM_HD int interpolate_foot(const MeshView& m, const TetGeom& g, float x, float y, float z,
-                            float out[12], bool with_material)
+                            float out[12], bool with_material, FootGeom* fg = nullptr)
 {
 	float f[4];
 	if(!interp_factors(g.p[0], g.p[1], g.p[2], g.p[3], x, y, z, g.vol, f))
 		return ERR_INTERP_SUM;
+	if(fg) for(int k = 0; k < 4; k++) { fg->v[k] = g.v[k]; fg->f[k] = f[k]; }
 #if defined(__CUDA_ARCH__)
 	// three 16-byte loads per vertex record instead of nine 4-byte ones
 	float r0[12], r1[12], r2[12], r3[12];
@@ -466,8 +479,8 @@ GCM_HD void scan_ring_both_senses(const MeshView& m, int base, const Vec3& X, co
 			const float sum = la + lb + lc;
 			const float mn1 = fminf(fminf(la, lb), fminf(lc, D2 - sum));
 			const float mn0 = fminf(fminf(-la, -lb), fminf(-lc, D2 + sum));
-			v1 = mn1 < -1e-3f * D2 ? -1 : (mn1 > -1e-4f * D2 ? 1 : 0);
-			v0 = mn0 < -1e-3f * D2 ? -1 : (mn0 > -1e-4f * D2 ? 1 : 0);
+			v1 = mn1 < m.pf_fail * D2 ? -1 : (mn1 > m.pf_pass * D2 ? 1 : 0);
+			v0 = mn0 < m.pf_fail * D2 ? -1 : (mn0 > m.pf_pass * D2 ? 1 : 0);
 		}
 		if(open0) { if(v0 > 0) { rs.own[0] = t; open0 = false; } else if(v0 == 0) { rs.amb[0] = true; open0 = false; } }
 		if(open1) { if(v1 > 0) { rs.own[1] = t; open1 = false; } else if(v1 == 0) { rs.amb[1] = true; open1 = false; } }
@@ -489,7 +502,7 @@ GCM_HD void scan_ring_both_senses(const MeshView& m, int base, const Vec3& X, co
 // on its base node (not a virtual node).
 GCM_HD int foot_point(const MeshView& m, const CurNode& cur, int stage, float alpha, float dks, const float ksi[3],
                       const float Xc[3], const float curc[3], const float tetr_center[3], bool with_material,
-                      bool* inner, int* owner_out, float val[12], const RingScan* rs = nullptr)
+                      bool* inner, int* owner_out, float val[12], const RingScan* rs = nullptr, FootGeom* fg = nullptr)
 {
 	float dx[3], dx_ksi[3];
 	float safe_direction[3];
@@ -569,7 +582,7 @@ GCM_HD int foot_point(const MeshView& m, const CurNode& cur, int stage, float al
 	} else if( cur.has_contact_data && (cur.axis_minus[stage] != -1) && (dks < 0) ) {
 		*inner = false;
 	} else if(owner >= 0) {
-		int e = interpolate_foot(m, g, fc[0], fc[1], fc[2], val, with_material);
+		int e = interpolate_foot(m, g, fc[0], fc[1], fc[2], val, with_material, fg);
 		if(e) return e;
 		*inner = true;
 	} else if(dks == 0) {
@@ -585,7 +598,7 @@ GCM_HD int foot_point(const MeshView& m, const CurNode& cur, int stage, float al
 // gcm/methods/TetrMethod_Plastic_1stOrder.cpp:430-681.  ksi = random_axis[basis_num].ksi[stage].
 // Returns the outer count, or -(StepError) on a condition the reference throws on.
 GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& cur, int stage,
-	float alpha, const float dksi[9], const float ksi[3], FeetOut& out, bool with_material)
+	float alpha, const float dksi[9], const float ksi[3], FeetOut& out, bool with_material, FootGeom* fgs = nullptr)
 {
 	Vec3 X = load_xyz(m, cur.base);
 	float Xc[3] = {X.x, X.y, X.z};
@@ -610,7 +623,7 @@ GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& c
 	// first try of a real node: one shared walk over the first ring serves all moving feet
 	RingScan rs;
 	rs.valid = false;
-	if(alpha == 0.0f && curc[0] == Xc[0] && curc[1] == Xc[1] && curc[2] == Xc[2])
+	if(alpha == 0.0f && !m.exact_only && curc[0] == Xc[0] && curc[1] == Xc[1] && curc[2] == Xc[2])
 		scan_ring_both_senses(m, cur.base, X, ksi, rs);
 
 	int count = 0;
@@ -634,7 +647,7 @@ GCM_HD int find_nodes_on_previous_time_layer(const MeshView& m, const CurNode& c
 
 		bool inn = false;
 		int own = -1;
-		int fe = foot_point(m, cur, stage, alpha, dksi[i], ksi, Xc, curc, tetr_center, with_material, &inn, &own, out.val[count], &rs);
+		int fe = foot_point(m, cur, stage, alpha, dksi[i], ksi, Xc, curc, tetr_center, with_material, &inn, &own, out.val[count], &rs, fgs ? fgs + count : nullptr);
 		if(fe) return -fe;
 		out.inner[i] = inn;
 		out.owner[count] = own;

@@ -14,6 +14,7 @@
 
 #include "../../gcm-necro_b200/csrc/gcm_host.h"
 #include "../../gcm-necro_b200/csrc/gcm_step.cuh"
+#include "../../gcm-necro_b200/csrc/gcm_inner.cuh"
 
 using gcmh::HostMesh;
 using std::string;
@@ -33,6 +34,8 @@ struct Z {
 	size_t stride;
 	vector<float> xyz, u[2], mat;
 	int cur = 0;
+	vector<gcm::InnerCacheEntry> icache[3];   // the step-invariant cache of the inner kernel (gcm_inner.cuh)
+	vector<int> icache_owner[3];
 };
 struct Cond { gcm::BorderCond bc; float start, dur, box[6]; };
 
@@ -87,6 +90,7 @@ int main(int argc, char** argv)
 	}
 	const int NZ = (int)mesh_files.size();
 	const bool lean_border = !(getenv("GCM_EMUL_LEAN_BORDER") && atoi(getenv("GCM_EMUL_LEAN_BORDER")) == 0);
+	const bool inner_cache = !(getenv("GCM_EMUL_INNER_CACHE") && atoi(getenv("GCM_EMUL_INNER_CACHE")) == 0);
 	vector<std::unique_ptr<Z>> zs;
 	for(int z = 0; z < NZ; z++) {
 		FILE* f = fopen(mesh_files[z].c_str(), "rb"); if(!f) die("cannot open mesh");
@@ -154,6 +158,29 @@ int main(int argc, char** argv)
 			for(int k = 0; k < 9; k++) z.u[0][GCM_REC*(size_t)i+k] = hm.values[9*(size_t)i+k];
 		}
 		z.u[1] = z.u[0];
+	}
+	long n_cached = 0, n_cold = 0;
+	if(inner_cache) {
+		// exactly what build_inner_cache_kernel does on the device
+		for(auto& zp : zs) {
+			Z& z = *zp; HostMesh& hm = z.hm;
+			gcm::MeshView m; memset(&m, 0, sizeof m);
+			m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
+			m.u = z.u[0].data(); m.mat = z.mat.data(); m.flags = hm.flags.data();
+			m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = nullptr; m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
+			m.border_slot = hm.border_slot.data();
+			m.tau = 0.002f; m.time = 0; m.min_h = hm.min_h;
+			for(int st = 0; st < 3; st++) {
+				z.icache[st].assign(hm.N, gcm::InnerCacheEntry());
+				memset(z.icache[st].data(), 0, hm.N * sizeof(gcm::InnerCacheEntry));
+				z.icache_owner[st].assign(2*(size_t)hm.N, -1);
+				#pragma omp parallel for schedule(dynamic, 1024) reduction(+:n_cached,n_cold)
+				for(size_t q = 0; q < hm.inner_fast.size(); q++) {
+					const int i = hm.inner_fast[q];
+					if(gcm::build_inner_cache_entry(m, i, st, z.icache[st][i], &z.icache_owner[st][2*(size_t)i])) n_cached++; else n_cold++;
+				}
+			}
+		}
 	}
 	if(ring_check > 0) {
 		// --ring-check N: the list-building device search (gcm::find_owner_general, what the deep contact
@@ -284,7 +311,25 @@ int main(int argc, char** argv)
 						if(vw) for(int k = 0; k < 9; k++) vh.values[k] = vo[k];
 					} else if(slot >= 0 && lean_border)
 						e = gcm::node_stage_border_lean(m, i, stage, o, &t);
-					else
+					else if(inner_cache && slot < 0 && (z.icache[stage][i].flags & GCM_IC_VALID)
+					        && (z.icache[0][i].flags & z.icache[1][i].flags & z.icache[2][i].flags & GCM_IC_VALID)) {
+						// stage_inner_cached_kernel
+						const gcm::InnerCacheEntry& ce = z.icache[stage][i];
+						const gcmh::MaterialRegistry& reg = hm.registry ? *hm.registry : hm.own_registry;
+						const gcm::MatTab* tab = reinterpret_cast<const gcm::MatTab*>(reg.table.data()) + 3 * (size_t)hm.mat_id[i] + stage;
+						float own[9]; bool bad = false;
+						for(int k = 0; k < 9; k++) { own[k] = ucur[GCM_REC*(size_t)i+k]; bad |= !(fabsf(own[k]) <= 3.4028235e38f); }
+						e = bad ? gcm::ERR_NAN : 0;
+						if(!e) {
+							if(stage == 0) gcm::inner_cached_stage<0>(ucur, ce, own, tab->U, tab->U1, o);
+							else if(stage == 1) gcm::inner_cached_stage<1>(ucur, ce, own, tab->U, tab->U1, o);
+							else gcm::inner_cached_stage<2>(ucur, ce, own, tab->U, tab->U1, o);
+						}
+						t.owner[0] = t.owner[2] = z.icache_owner[stage][2*(size_t)i];
+						t.owner[1] = t.owner[3] = z.icache_owner[stage][2*(size_t)i+1];
+						t.owner[4] = hm.n2t[hm.n2t_off[i]];
+						t.outer_count = 0; t.tries = 1;
+					} else
 						e = gcm::node_stage_nocontact(m, i, stage, o, &t);
 					if(e) {
 						#pragma omp critical
@@ -325,6 +370,6 @@ int main(int argc, char** argv)
 		}
 		if(tap_step >= 0) write_file(out + ".tap.i32", tap);
 	}
-	printf("{\"impl\": \"emul\", \"steps\": %d, \"rc\": %d}\n", steps, rc);
+	printf("{\"impl\": \"emul\", \"steps\": %d, \"rc\": %d, \"inner_cached\": %ld, \"inner_cold\": %ld}\n", steps, rc, n_cached, n_cold);
 	return rc;
 }

@@ -583,7 +583,7 @@ void sync_nodes_device(gcm_b200_set* s)
 	const int n = (int)dm.n_halo;
 	if(!n) return;
 	ProfScope ps(s, PROF_HALO, n);
-	gcm::halo_copy_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.halo_dst.p, dm.ucur(), dm.halo_src.p, n);
+	gcm::halo_copy_kernel<<<(3 * n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.halo_dst.p, dm.ucur(), dm.halo_src.p, n);
 	s->launches++;
 }
 

@@ -2,6 +2,7 @@
 #include "gcm_host.h"
 #include "gcm_math.cuh"
 #include "gcm_inner.cuh"
+#include "gcm_border.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -501,6 +502,94 @@ void HostMesh::build_fast_path_tables()
 			n2x[4*(size_t)e] = o[0]; n2x[4*(size_t)e+1] = o[1]; n2x[4*(size_t)e+2] = o[2];
 			n2x[4*(size_t)e+3] = (int)((unsigned)t | ((unsigned)k << 30));
 		}
+}
+
+// Static inputs of gcm_border.cuh: per flat border node its candidate list with the barycentric
+// gradients of the other three vertices scaled by 0.99 h(tet) (the point point_in_tetr tests for a
+// direction q^ is X + 0.99 h q^, so a candidate's barycentric coordinates there are q^ . G), computed in
+// double from the float coordinates, plus what the search needs to know when it finds nothing.
+void build_border_flat_tables(const std::vector<BorderFlatZone>& zones, std::vector<int>& slot_static8, std::vector<float>& cand_quads)
+{
+	size_t NB = 0, NF = 0;
+	for(const auto& z : zones) { NB += z.hm->border_nodes.size(); NF += z.hm->border_launch.size() - z.hm->n_sharp; }
+	slot_static8.assign(8 * NB, 0);
+	gcm::BndSlotStatic* st = reinterpret_cast<gcm::BndSlotStatic*>(slot_static8.data());
+	static_assert(sizeof(gcm::BndSlotStatic) == 32, "BndSlotStatic is 8 words");
+	// flat nodes in launch order
+	struct Ref { const BorderFlatZone* z; int node; };
+	std::vector<Ref> flat; flat.reserve(NF);
+	for(const auto& z : zones)
+		for(size_t q = z.hm->n_sharp; q < z.hm->border_launch.size(); q++) flat.push_back(Ref{&z, z.hm->border_launch[q]});
+	const size_t NW = (NF + GCM_BND_LANES - 1) / GCM_BND_LANES;
+	std::vector<size_t> warp_off(NW + 1, 0);
+	for(size_t w = 0; w < NW; w++) {
+		int dmax = 0;
+		for(size_t p = w * GCM_BND_LANES; p < std::min(NF, (w + 1) * GCM_BND_LANES); p++) {
+			const HostMesh& hm = *flat[p].z->hm; const int i = flat[p].node;
+			dmax = std::max(dmax, hm.n2t_off[i+1] - hm.n2t_off[i]);
+		}
+		warp_off[w+1] = warp_off[w] + (size_t)3 * dmax * GCM_BND_LANES;
+	}
+	if(warp_off[NW] >= 0x7fffffffull) throw HostError{CONFIG_EXCEPTION, "border candidate table too large for 32-bit offsets"};
+	cand_quads.assign(4 * warp_off[NW], 0.f);
+	#pragma omp parallel for schedule(dynamic, 256)
+	for(long p = 0; p < (long)NF; p++) {
+		const BorderFlatZone& z = *flat[p].z;
+		const HostMesh& hm = *z.hm;
+		const int i = flat[p].node;
+		gcm::BndSlotStatic& s = st[z.slot_off + hm.border_slot[i]];
+		const int e0 = hm.n2t_off[i], e1 = hm.n2t_off[i+1];
+		const Vec3 X = P(hm.coords, i);
+		// zero-speed foot: elements[0] must pass the literal predicate at the node itself with all weight on it
+		{
+			const int t = hm.n2t[e0];
+			const int* tv = &hm.tets[4*(size_t)t];
+			const Vec3 pp[4] = { P(hm.coords, tv[0]), P(hm.coords, tv[1]), P(hm.coords, tv[2]), P(hm.coords, tv[3]) };
+			const float h = hm.tet_hv[2*(size_t)t], vol = hm.tet_hv[2*(size_t)t+1];
+			if(!gcm::point_in_tetr(X, 0.f, 0.f, 0.f, 0.f, pp[0], pp[1], pp[2], pp[3], h, vol)) continue;
+			float f[4];
+			if(!gcm::interp_factors(pp[0], pp[1], pp[2], pp[3], X.x, X.y, X.z, vol, f)) continue;
+			int k = -1; bool ok = true;
+			for(int j = 0; j < 4; j++) { if(tv[j] == i && k < 0) k = j; else if(f[j] != 0) ok = false; }
+			if(k < 0 || !ok) continue;
+			s.w0 = f[k];
+		}
+		const size_t base = warp_off[p / GCM_BND_LANES] + (size_t)(p % GCM_BND_LANES);
+		float hmin = 3.4e38f, dmin2 = 3.4e38f;
+		for(int e = e0; e < e1; e++) {
+			const int c = e - e0;
+			const int* x = &hm.n2x[4*(size_t)e];
+			const int t = (int)((unsigned)x[3] & 0x3fffffffu), k = (int)((unsigned)x[3] >> 30);
+			const Vec3 A = P(hm.coords, x[0]), B = P(hm.coords, x[1]), C = P(hm.coords, x[2]);
+			const float h = hm.tet_hv[2*(size_t)t], vflag = hm.tet_hv[2*(size_t)t+1];
+			hmin = std::min(hmin, h);
+			// the reference measures only the vertices BEFORE the node in tet order (`break`, :1544-1545)
+			for(int j = 0; j < 3 && j < k; j++) {
+				const Vec3& Q = j == 0 ? A : (j == 1 ? B : C);
+				const float d2 = (X.x - Q.x) * (X.x - Q.x) + (X.y - Q.y) * (X.y - Q.y) + (X.z - Q.z) * (X.z - Q.z);
+				dmin2 = std::min(dmin2, d2);
+			}
+			const double ea[3] = {(double)A.x - X.x, (double)A.y - X.y, (double)A.z - X.z};
+			const double eb[3] = {(double)B.x - X.x, (double)B.y - X.y, (double)B.z - X.z};
+			const double ec[3] = {(double)C.x - X.x, (double)C.y - X.y, (double)C.z - X.z};
+			const double bc[3] = {eb[1]*ec[2] - eb[2]*ec[1], eb[2]*ec[0] - eb[0]*ec[2], eb[0]*ec[1] - eb[1]*ec[0]};
+			const double ca[3] = {ec[1]*ea[2] - ec[2]*ea[1], ec[2]*ea[0] - ec[0]*ea[2], ec[0]*ea[1] - ec[1]*ea[0]};
+			const double ab[3] = {ea[1]*eb[2] - ea[2]*eb[1], ea[2]*eb[0] - ea[0]*eb[2], ea[0]*eb[1] - ea[1]*eb[0]};
+			const double D = ea[0]*bc[0] + ea[1]*bc[1] + ea[2]*bc[2];
+			// the node must be a vertex of the candidate (it is: the list is the node's own) and the tet well shaped
+			const bool usable = vflag > 0 && D != 0 && x[0] != i && x[1] != i && x[2] != i;
+			const double sc = usable ? 0.99 * (double)h / D : 0.0;
+			float* q = &cand_quads[4 * (base + (size_t)(3 * c) * GCM_BND_LANES)];
+			float* q1 = q + 4 * GCM_BND_LANES; float* q2 = q1 + 4 * GCM_BND_LANES;
+			q[0] = (float)(sc * bc[0]); q[1] = (float)(sc * bc[1]); q[2] = (float)(sc * bc[2]); q[3] = (float)(sc * ca[0]);
+			q1[0] = (float)(sc * ca[1]); q1[1] = (float)(sc * ca[2]); q1[2] = (float)(sc * ab[0]); q1[3] = (float)(sc * ab[1]);
+			q2[0] = (float)(sc * ab[2]); q2[1] = usable ? 1.f : 0.f; q2[2] = 0.f; q2[3] = 0.f;
+		}
+		s.deg = e1 - e0;
+		s.e0 = (int)(z.entry_off + e0);
+		s.hmin = hmin; s.dmin2 = dmin2;
+		s.cand_off = (int)base;
+	}
 }
 
 // create_rotation_matrix_with_normal + the rand() bookkeeping of create_random_axis,

@@ -170,6 +170,7 @@ int main(int argc, char** argv)
 			m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = nullptr; m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 			m.border_slot = hm.border_slot.data();
 			m.tau = 0.002f; m.time = 0; m.min_h = hm.min_h;
+			m.pf_fail = -1e-3f; m.pf_pass = -1e-4f; m.exact_only = 1;   // as ensure_inner_cache (gcm_capi.cu)
 			for(int st = 0; st < 3; st++) {
 				z.icache[st].assign(hm.N, gcm::InnerCacheEntry());
 				memset(z.icache[st].data(), 0, hm.N * sizeof(gcm::InnerCacheEntry));
@@ -236,6 +237,7 @@ int main(int argc, char** argv)
 		m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 		m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 		m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
+		m.pf_fail = -1e-3f; m.pf_pass = -1e-4f; m.exact_only = 0;
 		return m;
 	};
 	for(int step = 0; step < steps && !rc; step++) {
@@ -278,6 +280,7 @@ int main(int argc, char** argv)
 				m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 				m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 				m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
+				m.pf_fail = -1e-3f; m.pf_pass = -1e-4f; m.exact_only = 0;
 				m.n_conds = (int)conds.size();
 				for(size_t c = 0; c < conds.size(); c++) {
 					m.conds[c] = conds[c].bc;

@@ -1,6 +1,6 @@
 # usage: r2_round.sh <tag> [bench args...]  -- parity tests, then serial + concurrent bench lines
 TAG=$1; shift
-timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; tail -3 gpurun_out/pytest_$TAG.log
+timeout 1200 python -m pytest tests -m gpu -q --maxfail=8 > gpurun_out/pytest_$TAG.log 2>&1; tail -3 gpurun_out/pytest_$TAG.log
 GCM_B200_CONCURRENT=0 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e "$@" 2>gpurun_out/bench_serial_$TAG.err | tail -1 > gpurun_out/bench_serial_$TAG.json
 python - <<PY
 import json

@@ -44,6 +44,12 @@ struct BndSlotStatic {
 };
 #define GCM_BND_LANES 32      // candidates of one warp of flat nodes are interleaved: quad (c, q) of lane l at off + (3 c + q) * 32 + l
 #define GCM_BND_DEFER (-1)
+#if defined(GCM_BND_STATS) && !defined(__CUDA_ARCH__)
+static long g_bnd_defer_reason[16];
+#define GCM_BND_DEFER_R(r) (__sync_fetch_and_add(&g_bnd_defer_reason[r], 1), GCM_BND_DEFER)
+#else
+#define GCM_BND_DEFER_R(r) GCM_BND_DEFER
+#endif
 
 // 9x9 double system in caller-provided storage
 struct LocalMat9 { double a[81]; GCM_HD double& at(int i, int j) { return a[i * 9 + j]; } };
@@ -286,7 +292,7 @@ template<class Mat>
 GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, const gcm_f4* __restrict__ cand,
                                   int node, int stage, float out[9], StageTap* tap, Mat* A)
 {
-	if(bs.deg <= 0 || m.exact_only) return GCM_BND_DEFER;
+	if(bs.deg <= 0 || m.exact_only) return GCM_BND_DEFER_R(1);
 	float own[9];
 	Vec3 X;
 #if defined(__CUDA_ARCH__)
@@ -333,7 +339,7 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 			#pragma unroll
 			for(int q = 0; q < p; q++)
 				if( (double)fabsf(dk[p] - dk[q]) <= 0.01 * (double)fabsf(dk[p] + dk[q]) ) usual = false;
-		if(!usual) return GCM_BND_DEFER;
+		if(!usual) return GCM_BND_DEFER_R(2);
 	}
 	// displacements and feet of the four moving points (real node, no contact, alpha == 0: :553-558)
 	float fc[4][3], R2[4];
@@ -348,7 +354,7 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 		R2[p] = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
 		const float delta = sqrtf(R2[p]);
 		// the shared scan answers only for feet every candidate rescales
-		if(!(delta > 0) || !((double)delta < (double)bs.hmin * 0.99)) return GCM_BND_DEFER;
+		if(!(delta > 0) || !((double)delta < (double)bs.hmin * 0.99)) return GCM_BND_DEFER_R(3);
 	}
 
 	// ---- one walk over the first ring, both senses (0: -q, 1: +q) ----
@@ -360,7 +366,7 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 		bool open0 = true, open1 = true;
 		for(int c = 0; c < bs.deg && (open0 || open1); c++) {
 			const gcm_f4 g0 = cand[(3 * c) * GCM_BND_LANES], g1 = cand[(3 * c + 1) * GCM_BND_LANES], g2 = cand[(3 * c + 2) * GCM_BND_LANES];
-			if(!(g2.y > 0)) return GCM_BND_DEFER;    // ill-shaped tetrahedron: only the literal predicate may judge it
+			if(!(g2.y > 0)) return GCM_BND_DEFER_R(4);    // ill-shaped tetrahedron: only the literal predicate may judge it
 			// barycentric coordinates of X + 0.99 h q^ w.r.t. A, B, C; those of the opposite sense are the negatives
 			const float la = qx * g0.x + qy * g0.y + qz * g0.z;
 			const float lb = qx * g0.w + qy * g1.x + qz * g1.y;
@@ -370,8 +376,8 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 			const float mn0 = fminf(fminf(-la, -lb), fminf(-lc, 1.0f + sum));
 			const int v1 = mn1 < m.pf_fail ? -1 : (mn1 > m.pf_pass ? 1 : 0);
 			const int v0 = mn0 < m.pf_fail ? -1 : (mn0 > m.pf_pass ? 1 : 0);
-			if(open0) { if(v0 > 0) { own_c[0] = c; open0 = false; } else if(v0 == 0) return GCM_BND_DEFER; }
-			if(open1) { if(v1 > 0) { own_c[1] = c; open1 = false; } else if(v1 == 0) return GCM_BND_DEFER; }
+			if(open0) { if(v0 > 0) { own_c[0] = c; open0 = false; } else if(v0 == 0) return GCM_BND_DEFER_R(5); }
+			if(open1) { if(v1 > 0) { own_c[1] = c; open1 = false; } else if(v1 == 0) return GCM_BND_DEFER_R(6); }
 		}
 	}
 	// a sense without owner: NULL only if no candidate vertex lies within |dx| (else the reference expands the ring)
@@ -380,12 +386,12 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 	for(int p = 0; p < 4; p++) {
 		const int sgn = dk[p] < 0 ? 0 : 1;
 		inn[p] = own_c[sgn] >= 0;
-		if(!inn[p] && bs.dmin2 < R2[p]) return GCM_BND_DEFER;
+		if(!inn[p] && bs.dmin2 < R2[p]) return GCM_BND_DEFER_R(7);
 	}
 	inn[4] = true;     // dksi == 0: the node itself (interpolated inside elements[0], weight w0)
 	const int outer_count = (inn[0] ? 0 : 1) + (inn[1] ? 0 : 1) + (inn[2] ? 0 : 2) + (inn[3] ? 0 : 2);
-	if(outer_count != 0 && outer_count != 3) return GCM_BND_DEFER;      // the alpha-retry loop: literal routine
-	if(outer_count == 3 && !A) return GCM_BND_DEFER;
+	if(outer_count != 0 && outer_count != 3) return GCM_BND_DEFER_R(8);      // the alpha-retry loop: literal routine
+	if(outer_count == 3 && !A) return GCM_BND_DEFER_R(9);
 	// points 0 and 2 share a sense (dksi < 0), so do 1 and 3: a sense is inner or outer as a whole
 	int xs[2][4];
 	#pragma unroll

@@ -103,6 +103,9 @@ struct DeviceMesh {
 	float icache_tau = -1.f;
 	bool icache_ready = false;
 	int n_cold = 0;                  // inner nodes that stay with the literal routine (cold[0] on the device)
+	// static tables of the flat-border kernel (gcm_border.cuh) and the list of nodes it defers per launch
+	DevBuf<int> bnd_static, bnd_defer;
+	DevBuf<float> bnd_cand;
 	float pf_fail = -1e-3f, pf_pass = -1e-4f;   // thresholds of the conservative owner pre-filter (prefilter_thresholds)
 	int exact_only = 0;
 	DevBuf<int> sharp_list, flat_list, fast_list, generic_list, inner_list;
@@ -130,8 +133,8 @@ struct gcm_b200_set {
 	gcmh::GlibcRand rng;
 	gcmh::MaterialRegistry materials;
 	DeviceMesh dm;
-	cudaStream_t stream = nullptr, aux = nullptr, rng_stream = nullptr;
-	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_rng_done = nullptr, ev_step_mark = nullptr;
+	cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, rng_stream = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_rng_done = nullptr, ev_step_mark = nullptr;
 	bool bases_ahead = true;     // device generator: the NEXT step's bases are produced on rng_stream during this step
 	bool ahead_valid = false;    // dm.basis_next holds the bases of the coming step
 	int* d_err = nullptr;
@@ -150,7 +153,8 @@ struct gcm_b200_set {
 	float time_step = 0.002f;
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
-	bool fused_border = true;    // sharp and flat border nodes in one launch (stage_border_fused_kernel)
+	bool fused_border = true;    // literal border path: sharp and flat border nodes in one launch (stage_border_fused_kernel)
+	bool flat_border = true;     // flat border nodes through gcm_border.cuh (0 = the literal per-node routine for every border node)
 	bool inner_cache = true;     // inner nodes through the step-invariant owner/factor cache (gcm_inner.cuh); 0 = index-free scan kernel
 	bool fuse_plastic = true;    // whole-step calls: stage 3 as the epilogue of the stage-2 writers (and no exchange before it)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
@@ -424,6 +428,16 @@ void upload_mesh(gcm_b200_set* s)
 	dm.cur = 0;
 	dm.ready = true;
 	dm.cold.alloc(N + 1);   // inner nodes the cache could not take: count, then node ids
+	if(NB) {
+		std::vector<gcmh::BorderFlatZone> bz;
+		for(int zi : s->local_zones) { Zone& z = *s->zones[zi]; bz.push_back(gcmh::BorderFlatZone{&z.hm, z.node_off, z.entry_off, z.slot_off}); }
+		std::vector<int> st8; std::vector<float> cq;
+		gcmh::build_border_flat_tables(bz, st8, cq);
+		dm.bnd_static.upload(st8, st);
+		if(cq.empty()) cq.assign(4, 0.f);
+		dm.bnd_cand.upload(cq, st);
+		dm.bnd_defer.alloc(NB + 1);
+	}
 	dm.icache_ready = false;
 	prefilter_thresholds(s);
 	for(int zi : s->local_zones) upload_values(s, *s->zones[zi]);
@@ -663,7 +677,25 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 			CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
 		}
 		ProfScope ps(s, PROF_BORDER, nb + nsh, bst);
-		if(nsh && nb && s->fused_border) {
+		if(s->flat_border && nb) {
+			// flat nodes: the redesigned kernel, then the literal routine for what it deferred; sharp nodes
+			// (16 lanes per node, speculative alpha tries) beside them on their own stream
+			if(nsh) {
+				cudaStream_t sst = s->concurrent ? s->aux2 : bst;
+				if(s->concurrent) CK(cudaStreamWaitEvent(s->aux2, s->ev_fork, 0));
+				gcm::stage_sharp_kernel<<<(nsh * 16 + 63) / 64, 64, 0, sst>>>(m, shl, nsh, stage, dm.unext(), s->d_err, zone, tap, yp);
+				if(s->concurrent) CK(cudaEventRecord(s->ev_join2, s->aux2));
+				s->launches++;
+			}
+			CK(cudaMemsetAsync(dm.bnd_defer.p, 0, sizeof(int), bst));
+			const gcm::BndSlotStatic* bstat = reinterpret_cast<const gcm::BndSlotStatic*>(dm.bnd_static.p);
+			const float4* cq = reinterpret_cast<const float4*>(dm.bnd_cand.p);
+			if(stage == 0) gcm::stage_border_flat_kernel<true, 64><<<(nb + 63) / 64, 64, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
+			else gcm::stage_border_flat_kernel<false, 128><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
+			gcm::stage_deferred_kernel<<<64, 128, 0, bst>>>(m, dm.bnd_defer.p, stage, dm.unext(), s->d_err, zone, tap, yp, 0, 0x7fffffff);
+			s->launches += 2;
+			if(nsh && s->concurrent) CK(cudaStreamWaitEvent(bst, s->ev_join2, 0));
+		} else if(nsh && nb && s->fused_border) {
 			const int blocks = (nsh * 16 + 127) / 128 + (nb + 127) / 128;
 			gcm::stage_border_fused_kernel<<<blocks, 128, 0, bst>>>(m, shl, nsh, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp);
 			s->launches++;
@@ -1012,6 +1044,8 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(device >= 0) {
 		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->aux2, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 		CK(cudaStreamCreateWithFlags(&s->rng_stream, cudaStreamNonBlocking));
@@ -1025,6 +1059,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
 	if(const char* e = getenv("GCM_B200_FAST_INNER")) s->fast_inner = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_FUSED_BORDER")) s->fused_border = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_FLAT_BORDER")) s->flat_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BASES_AHEAD")) s->bases_ahead = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_CACHE")) s->inner_cache = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_FUSE_PLASTIC")) s->fuse_plastic = atoi(e) != 0;
@@ -1040,6 +1075,8 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		cudaSetDevice(s->device);
 		if(s->stream) cudaStreamSynchronize(s->stream);
 		if(s->aux) cudaStreamSynchronize(s->aux);
+		if(s->aux2) { cudaStreamSynchronize(s->aux2); cudaStreamDestroy(s->aux2); }
+		if(s->ev_join2) cudaEventDestroy(s->ev_join2);
 		if(s->rng_stream) cudaStreamSynchronize(s->rng_stream);
 		if(s->nccl_comm) { nccl_api().CommDestroy(s->nccl_comm); s->nccl_comm = nullptr; }
 		prof_drain(s);

@@ -13,6 +13,7 @@ __device__ __forceinline__ void report_error(int* err, int code, int zone, int n
 
 } // namespace gcm
 #include "gcm_inner.cuh"
+#include "gcm_border.cuh"
 namespace gcm {
 
 // Writes one node's stage result: the 9 values into the next layer; with yield_plane != NULL the
@@ -63,6 +64,39 @@ stage_deferred_kernel(const __grid_constant__ MeshView m, const int* __restrict_
 		if(e) { report_error(err, e, zone, node, stage); continue; }
 		store_node(un, node, out, yield_plane, err, zone);
 	}
+}
+
+// Flat border nodes (gcm_border.cuh), one thread per node.  LU: the launch provides the shared-memory
+// 9x9 double systems (element-major across the block: thread t owns column t of an [81][BLOCK] array),
+// needed on the normal axis (stage 0) where three characteristics leave the body; the tangential
+// stages run without it at full occupancy.  Whatever the routine defers (ambiguous candidate, alpha
+// retries, ...) is appended to `defer` (defer[0] = count) for the literal routine right behind.
+template<bool LU, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+stage_border_flat_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
+                         float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane,
+                         const BndSlotStatic* __restrict__ bstat, const float4* __restrict__ cand, int* __restrict__ defer)
+{
+	__shared__ double sA[LU ? 81 * BLOCK : 1];
+	const int idx = blockIdx.x * BLOCK + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	BndSlotStatic bs;
+	{
+		const uint4* q = reinterpret_cast<const uint4*>(bstat + m.border_slot[node]);
+		const uint4 a = __ldg(q), b = __ldg(q + 1);
+		bs.deg = (int)a.x; bs.e0 = (int)a.y; bs.hmin = __uint_as_float(a.z); bs.dmin2 = __uint_as_float(a.w);
+		bs.w0 = __uint_as_float(b.x); bs.cand_off = (int)b.y; bs.pad0 = 0; bs.pad1 = 0;
+	}
+	StridedMat9<BLOCK> A;
+	A.base = sA + threadIdx.x;
+	float out[9];
+	StageTap tp;
+	const int e = node_stage_border_flat(m, bs, cand + bs.cand_off, node, stage, out, tap ? &tp : nullptr, LU ? &A : (StridedMat9<BLOCK>*)nullptr);
+	if(e == GCM_BND_DEFER) { defer[1 + atomicAdd(&defer[0], 1)] = node; return; }
+	if(tap) tap[(size_t)stage * m.n_nodes + node] = tp;
+	if(e) { report_error(err, e, zone, node, stage); return; }
+	store_node(un, node, out, yield_plane, err, zone);
 }
 
 // Border nodes on sharp edges / corners usually burn all 11 alpha tries of prepare_node

@@ -12,9 +12,11 @@
 #include <vector>
 #include <memory>
 
+#define GCM_BND_STATS 1
 #include "../../gcm-necro_b200/csrc/gcm_host.h"
 #include "../../gcm-necro_b200/csrc/gcm_step.cuh"
 #include "../../gcm-necro_b200/csrc/gcm_inner.cuh"
+#include "../../gcm-necro_b200/csrc/gcm_border.cuh"
 
 using gcmh::HostMesh;
 using std::string;
@@ -36,6 +38,8 @@ struct Z {
 	int cur = 0;
 	vector<gcm::InnerCacheEntry> icache[3];   // the step-invariant cache of the inner kernel (gcm_inner.cuh)
 	vector<int> icache_owner[3];
+	vector<int> bnd_static;                   // flat-border tables (gcm_border.cuh), as build_border_flat_tables makes them
+	vector<float> bnd_cand;
 };
 struct Cond { gcm::BorderCond bc; float start, dur, box[6]; };
 
@@ -158,6 +162,12 @@ int main(int argc, char** argv)
 			for(int k = 0; k < 9; k++) z.u[0][GCM_REC*(size_t)i+k] = hm.values[9*(size_t)i+k];
 		}
 		z.u[1] = z.u[0];
+	}
+	const int border_mode = getenv("GCM_EMUL_BORDER") ? atoi(getenv("GCM_EMUL_BORDER")) : 2;   // 0 literal, 1 lean, 2 flat (+ literal for what it defers)
+	long n_flat_done = 0, n_flat_deferred = 0;
+	for(auto& zp : zs) {
+		std::vector<gcmh::BorderFlatZone> one(1, gcmh::BorderFlatZone{&zp->hm, 0, 0, 0});
+		gcmh::build_border_flat_tables(one, zp->bnd_static, zp->bnd_cand);
 	}
 	long n_cached = 0, n_cold = 0;
 	if(inner_cache) {
@@ -312,7 +322,20 @@ int main(int argc, char** argv)
 						mc.ring_ws = ring_ws.data(); mv.ring_ws = ring_ws.data();
 						e = gcm::node_stage_contact(mc, mv, i, vn, vidx, stage, &hm.normals[3*(size_t)slot], contact_calc == "friction" ? 1 : 0, o, &t, vo, &vw, step == 0);
 						if(vw) for(int k = 0; k < 9; k++) vh.values[k] = vo[k];
-					} else if(slot >= 0 && lean_border)
+					} else if(slot >= 0 && border_mode == 2) {
+						// stage_border_flat_kernel, then the literal routine for what it defers
+						const gcm::BndSlotStatic& bs = reinterpret_cast<const gcm::BndSlotStatic*>(z.bnd_static.data())[slot];
+						gcm::LocalMat9 A;
+						e = gcm::node_stage_border_flat(m, bs, reinterpret_cast<const gcm::gcm_f4*>(z.bnd_cand.data()) + bs.cand_off, i, stage, o, &t, &A);
+						if(e == GCM_BND_DEFER) {
+							e = gcm::node_stage_nocontact(m, i, stage, o, &t);
+							#pragma omp atomic
+							n_flat_deferred++;
+						} else {
+							#pragma omp atomic
+							n_flat_done++;
+						}
+					} else if(slot >= 0 && border_mode == 1 && lean_border)
 						e = gcm::node_stage_border_lean(m, i, stage, o, &t);
 					else if(inner_cache && slot < 0 && (z.icache[stage][i].flags & GCM_IC_VALID)
 					        && (z.icache[0][i].flags & z.icache[1][i].flags & z.icache[2][i].flags & GCM_IC_VALID)) {
@@ -373,6 +396,7 @@ int main(int argc, char** argv)
 		}
 		if(tap_step >= 0) write_file(out + ".tap.i32", tap);
 	}
-	printf("{\"impl\": \"emul\", \"steps\": %d, \"rc\": %d, \"inner_cached\": %ld, \"inner_cold\": %ld}\n", steps, rc, n_cached, n_cold);
+	if(getenv("GCM_EMUL_BND_STATS")) { fprintf(stderr, "flat defer reasons:"); for(int r = 1; r < 10; r++) fprintf(stderr, " %d:%ld", r, gcm::g_bnd_defer_reason[r]); fprintf(stderr, "\n"); }
+	printf("{\"impl\": \"emul\", \"steps\": %d, \"rc\": %d, \"inner_cached\": %ld, \"inner_cold\": %ld, \"flat_done\": %ld, \"flat_deferred\": %ld}\n", steps, rc, n_cached, n_cold, n_flat_done, n_flat_deferred);
 	return rc;
 }

@@ -100,6 +100,11 @@ struct DeviceMesh {
 	// step-invariant cache of the inner kernel (gcm_inner.cuh): 3 planes of N entries, built lazily for a tau
 	DevBuf<gcm::InnerCacheEntry> icache;
 	DevBuf<int> icache_owner;        // [3][N][2] owner tets per direction, only kept when the parity tap is on
+	// the cache de-duplicated into patterns (per axis; pattern_ok[axis] says whether the axis compressed)
+	DevBuf<unsigned> ic_pat_idx;     // [3][N] pattern id per node or GCM_IC_NO_PATTERN
+	DevBuf<gcm::InnerCacheEntry> ic_patterns;   // [3][GCM_IC_MAX_PATTERNS]
+	bool pattern_ok[3] = {false, false, false};
+	int n_patterns[3] = {0, 0, 0};
 	float icache_tau = -1.f;
 	bool icache_ready = false;
 	int n_cold = 0;                  // inner nodes that stay with the literal routine (cold[0] on the device)
@@ -156,6 +161,7 @@ struct gcm_b200_set {
 	bool fused_border = true;    // literal border path: sharp and flat border nodes in one launch (stage_border_fused_kernel)
 	bool flat_border = true;     // flat border nodes through gcm_border.cuh (0 = the literal per-node routine for every border node)
 	bool inner_cache = true;     // inner nodes through the step-invariant owner/factor cache (gcm_inner.cuh); 0 = index-free scan kernel
+	bool inner_patterns = true;  // de-duplicate the cache into a pattern table where an axis has few distinct entries
 	bool fuse_plastic = true;    // whole-step calls: stage 3 as the epilogue of the stage-2 writers (and no exchange before it)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
@@ -629,6 +635,32 @@ void ensure_inner_cache(gcm_b200_set* s, float tau)
 		CK(cudaMemcpyAsync(s->h_err + 4, dm.cold.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
 		dm.n_cold = s->h_err[4];
+		for(int st = 0; st < 3; st++) { dm.pattern_ok[st] = false; dm.n_patterns[st] = 0; }
+		if(s->inner_patterns) {
+			// de-duplicate each axis: hash insert -> exact comparison with the representative + numbering -> ids
+			const unsigned cap = 1u << 18;
+			DevBuf<unsigned long long> keys; DevBuf<int> rep, slot_of, slot_pid, stats;
+			keys.alloc(cap); rep.alloc(cap); slot_pid.alloc(cap); slot_of.alloc(N); stats.alloc(4);
+			if(!dm.ic_pat_idx.p) { dm.ic_pat_idx.alloc(3 * N); dm.ic_patterns.alloc(3 * (size_t)GCM_IC_MAX_PATTERNS); }
+			CK(cudaMemsetAsync(dm.ic_pat_idx.p, 0xff, 3 * N * sizeof(unsigned), s->stream));
+			const int g256 = (nf + 255) / 256;
+			for(int st = 0; st < 3; st++) {
+				CK(cudaMemsetAsync(keys.p, 0, cap * sizeof(unsigned long long), s->stream));
+				CK(cudaMemsetAsync(rep.p, 0x7f, cap * sizeof(int), s->stream));
+				CK(cudaMemsetAsync(stats.p, 0, 4 * sizeof(int), s->stream));
+				const gcm::InnerCacheEntry* ce = dm.icache.p + (size_t)st * N;
+				gcm::ic_dedup_insert_kernel<<<g256, 256, 0, s->stream>>>(ce, dm.fast_list.p, nf, keys.p, rep.p, cap, slot_of.p, stats.p);
+				gcm::ic_dedup_number_kernel<<<g256, 256, 0, s->stream>>>(ce, dm.fast_list.p, nf, rep.p, slot_of.p, slot_pid.p,
+					dm.ic_patterns.p + (size_t)st * GCM_IC_MAX_PATTERNS, GCM_IC_MAX_PATTERNS, stats.p);
+				gcm::ic_dedup_assign_kernel<<<g256, 256, 0, s->stream>>>(dm.fast_list.p, nf, slot_of.p, slot_pid.p, dm.ic_pat_idx.p + (size_t)st * N);
+				s->launches += 3;
+				CK(cudaGetLastError());
+				CK(cudaMemcpyAsync(s->h_err + 4, stats.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+				CK(cudaStreamSynchronize(s->stream));
+				dm.pattern_ok[st] = s->h_err[5] == 0 && s->h_err[6] <= GCM_IC_MAX_PATTERNS;
+				dm.n_patterns[st] = s->h_err[6];
+			}
+		}
 	}
 	dm.icache_tau = tau;
 	dm.icache_ready = true;
@@ -736,8 +768,13 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 				const int* otap = (tap && dm.icache_owner.p) ? dm.icache_owner.p + (size_t)stage * 2 * dm.N : nullptr;
 				{
 					ProfScope ps(s, PROF_INNER, nf - dm.n_cold);
-#define GCM_LAUNCH_CACHED(S_, P_) gcm::stage_inner_cached_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), nbeg, nrange, dm.unext(), ce, tab, dm.n_mat, mid, yp, \
-						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N)
+					const unsigned* pidx = dm.ic_pat_idx.p + (size_t)stage * dm.N;
+					const gcm::InnerCacheEntry* pats = dm.ic_patterns.p + (size_t)stage * GCM_IC_MAX_PATTERNS;
+					const bool pat = dm.pattern_ok[stage];
+#define GCM_LAUNCH_CACHED(S_, P_) do { if(pat) gcm::stage_inner_pattern_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), nbeg, nrange, dm.unext(), pidx, pats, tab, dm.n_mat, mid, yp, \
+						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N); \
+					else gcm::stage_inner_cached_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), nbeg, nrange, dm.unext(), ce, tab, dm.n_mat, mid, yp, \
+						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N); } while(0)
 					if(stage == 0) GCM_LAUNCH_CACHED(0, false);
 					else if(stage == 1) GCM_LAUNCH_CACHED(1, false);
 					else if(yp) GCM_LAUNCH_CACHED(2, true);
@@ -1042,9 +1079,14 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 			s->local_zones.push_back(z);
 		}
 	if(device >= 0) {
-		CK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-		CK(cudaStreamCreateWithFlags(&s->aux, cudaStreamNonBlocking));
-		CK(cudaStreamCreateWithFlags(&s->aux2, cudaStreamNonBlocking));
+		// the border kernels are short and latency-bound: their streams outrank the inner kernel's, so their
+		// blocks are placed as soon as they are launched instead of queueing behind a 40 000-block grid
+		int prio_lo = 0, prio_hi = 0;
+		CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		if(const char* e = getenv("GCM_B200_AUX_PRIO")) if(atoi(e) == 0) prio_hi = prio_lo;
+		CK(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, prio_lo));
+		CK(cudaStreamCreateWithPriority(&s->aux, cudaStreamNonBlocking, prio_hi));
+		CK(cudaStreamCreateWithPriority(&s->aux2, cudaStreamNonBlocking, prio_hi));
 		CK(cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
@@ -1063,6 +1105,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_BASES_AHEAD")) s->bases_ahead = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_CACHE")) s->inner_cache = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_FUSE_PLASTIC")) s->fuse_plastic = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_INNER_PATTERNS")) s->inner_patterns = atoi(e) != 0;
 	*out = s.release();
 	return 0;
 	GUARD_END
@@ -1701,6 +1744,28 @@ int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long
 	if(launches) *launches = s->prof_launches[which];
 	if(units) *units = s->prof_units[which];
 	return 0;
+}
+
+int gcm_b200_set_kernel_stats(gcm_b200_set* s, long long* out16)
+{
+	GUARD_BEGIN
+	if(!s || !out16) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
+	for(int k = 0; k < 16; k++) out16[k] = 0;
+	DeviceMesh& dm = s->dm;
+	if(!dm.ready) return 0;
+	CK(cudaSetDevice(s->device));
+	out16[0] = dm.icache_ready ? (long long)dm.n_fast - dm.n_cold : 0;
+	out16[1] = dm.icache_ready ? dm.n_cold : (long long)dm.n_fast;
+	for(int k = 0; k < 3; k++) { out16[2 + k] = dm.n_patterns[k]; out16[5 + k] = dm.pattern_ok[k] ? 1 : 0; }
+	out16[8] = (long long)dm.n_flat; out16[9] = (long long)dm.n_sharp;
+	if(dm.bnd_defer.p) {
+		CK(cudaMemcpyAsync(s->h_err + 4, dm.bnd_defer.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		out16[10] = s->h_err[4];
+	}
+	out16[11] = dm.exact_only;
+	return 0;
+	GUARD_END
 }
 
 int gcm_b200_set_virt_count(gcm_b200_set* s) { return s ? (int)s->virt.size() : 0; }

@@ -539,6 +539,36 @@ GCM_HD void inner_cached_stage(const float* __restrict__ u, const InnerCacheEntr
 	}
 }
 
+// ---- pattern table: the cache without its redundancy ---------------------------------------------
+// On a mesh with translational regularity (create_cube's 6 tets per hex, extruded layers, ...) most
+// entries are equal once the six vertex ids are written relative to the node: same stencil, same
+// factors bit for bit.  After the build the entries of an axis are de-duplicated on the device (hash
+// table on the 24 relative words, then an exact word-by-word comparison with the pattern's
+// representative, so equal means EQUAL); when an axis has few patterns the step kernel reads a 4-byte
+// pattern id per node and the 96-byte pattern from a table that lives in L1/L2 -- 100 instead of 192
+// bytes of DRAM traffic per node-stage, same arithmetic on the same numbers.  An irregular mesh (more
+// than GCM_IC_MAX_PATTERNS distinct entries on an axis) keeps the per-node entries.
+#define GCM_IC_WORDS 24
+#define GCM_IC_MAX_PATTERNS 32768
+#define GCM_IC_NO_PATTERN 0xffffffffu
+
+// entry -> the 24 words of its pattern (ids relative to the node)
+GCM_HD void ic_relative(const InnerCacheEntry& e, int node, unsigned w[GCM_IC_WORDS])
+{
+	const unsigned* src = reinterpret_cast<const unsigned*>(&e);
+	for(int k = 0; k < GCM_IC_WORDS; k++) w[k] = src[k];
+	w[0] = (unsigned)(e.a0 - node); w[1] = (unsigned)(e.b0 - node); w[2] = (unsigned)(e.c0 - node);
+	w[12] = (unsigned)(e.a1 - node); w[13] = (unsigned)(e.b1 - node); w[14] = (unsigned)(e.c1 - node);
+}
+
+// pattern + node -> entry
+GCM_HD void ic_absolute(const InnerCacheEntry& pat, int node, InnerCacheEntry& e)
+{
+	e = pat;
+	e.a0 = pat.a0 + node; e.b0 = pat.b0 + node; e.c0 = pat.c0 + node;
+	e.a1 = pat.a1 + node; e.b1 = pat.b1 + node; e.c1 = pat.c1 + node;
+}
+
 #if defined(__CUDACC__)
 
 // One thread per listed inner node: the literal routine once, its outcome into the cache
@@ -607,6 +637,145 @@ stage_inner_cached_kernel(const float* __restrict__ u, int node_begin, int n_ran
 	}
 	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u) + 3 * (size_t)node;
 	const float4 o0 = rec[0], o1 = rec[1], o2 = rec[2];
+	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
+	bool bad = false;
+	#pragma unroll
+	for(int k = 0; k < 9; k++) bad |= !(fabsf(own[k]) <= 3.4028235e38f);   // NaN or Inf (TetrMethod_Plastic_1stOrder.cpp:192-194)
+	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
+	const int mid = mat_id ? mat_id[node] : 0;
+	float res[9];
+	inner_cached_stage<S>(u, e, own, sU[mid], sU1[mid], res);
+	if(tap) {
+		StageTap tp;
+		tp.owner[0] = tp.owner[2] = owner_tap ? owner_tap[2 * (size_t)node] : -2;
+		tp.owner[1] = tp.owner[3] = owner_tap ? owner_tap[2 * (size_t)node + 1] : -2;
+		tp.owner[4] = n2t[n2t_off[node]];
+		tp.outer_count = 0; tp.tries = 1;
+		tap[(size_t)S * n_nodes + node] = tp;
+	}
+	if(PLASTIC) {
+		if(!plastic_epilogue(res, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
+	}
+	float4* __restrict__ out = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
+	out[0] = make_float4(res[0], res[1], res[2], res[3]);
+	out[1] = make_float4(res[4], res[5], res[6], res[7]);
+	out[2] = make_float4(res[8], o2.y, o2.z, o2.w);
+}
+
+// --- de-duplication of one axis of the cache (see "pattern table" above) ---
+// table: `cap` (power of two) slots of (64-bit key, representative node); stats[0] = distinct keys,
+// stats[1] = failure flag (table full / hash collision between different entries), stats[2] = patterns numbered.
+__device__ __forceinline__ unsigned long long ic_hash(const unsigned w[GCM_IC_WORDS])
+{
+	unsigned long long h = 0x9E3779B97F4A7C15ull;
+	#pragma unroll
+	for(int k = 0; k < GCM_IC_WORDS; k++) {
+		h ^= w[k];
+		h *= 0xBF58476D1CE4E5B9ull;
+		h ^= h >> 29;
+	}
+	return h | 1ull;        // 0 marks an empty slot
+}
+
+__global__ void __launch_bounds__(256)
+ic_dedup_insert_kernel(const InnerCacheEntry* __restrict__ cache, const int* __restrict__ list, int n_list,
+                       unsigned long long* __restrict__ keys, int* __restrict__ rep, unsigned cap, int* __restrict__ slot_of, int* __restrict__ stats)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	const InnerCacheEntry e = cache[node];
+	if(!(e.flags & GCM_IC_VALID)) { slot_of[node] = -1; return; }
+	unsigned w[GCM_IC_WORDS];
+	ic_relative(e, node, w);
+	const unsigned long long key = ic_hash(w);
+	unsigned h = (unsigned)(key >> 20) & (cap - 1);
+	for(unsigned probe = 0; probe < cap; probe++) {
+		const unsigned long long old = atomicCAS(&keys[h], 0ull, key);
+		if(old == 0ull) { atomicAdd(&stats[0], 1); }
+		if(old == 0ull || old == key) { atomicMin(&rep[h], node); slot_of[node] = (int)h; return; }
+		h = (h + 1) & (cap - 1);
+		if(probe > 4096) break;
+	}
+	slot_of[node] = -1;
+	atomicExch(&stats[1], 1);
+}
+
+__global__ void __launch_bounds__(256)
+ic_dedup_number_kernel(const InnerCacheEntry* __restrict__ cache, const int* __restrict__ list, int n_list,
+                       const int* __restrict__ rep, const int* __restrict__ slot_of, int* __restrict__ slot_pid,
+                       InnerCacheEntry* __restrict__ patterns, int max_patterns, int* __restrict__ stats)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	const int slot = slot_of[node];
+	if(slot < 0) return;
+	const int r = rep[slot];
+	unsigned w[GCM_IC_WORDS], wr[GCM_IC_WORDS];
+	ic_relative(cache[node], node, w);
+	if(r != node) {
+		// equal hash is not enough: the entry must equal its pattern word for word
+		ic_relative(cache[r], r, wr);
+		bool same = true;
+		#pragma unroll
+		for(int k = 0; k < GCM_IC_WORDS; k++) same = same && (w[k] == wr[k]);
+		if(!same) atomicExch(&stats[1], 1);
+		return;
+	}
+	const int pid = atomicAdd(&stats[2], 1);
+	if(pid >= max_patterns) { atomicExch(&stats[1], 1); return; }
+	slot_pid[slot] = pid;
+	unsigned* dst = reinterpret_cast<unsigned*>(patterns + pid);
+	#pragma unroll
+	for(int k = 0; k < GCM_IC_WORDS; k++) dst[k] = w[k];
+}
+
+__global__ void __launch_bounds__(256)
+ic_dedup_assign_kernel(const int* __restrict__ list, int n_list, const int* __restrict__ slot_of, const int* __restrict__ slot_pid,
+                       unsigned* __restrict__ pat_idx)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	const int slot = slot_of[node];
+	pat_idx[node] = slot < 0 ? GCM_IC_NO_PATTERN : (unsigned)slot_pid[slot];
+}
+
+// The hot kernel over the pattern table: identical to stage_inner_cached_kernel but for where the
+// entry comes from (pattern id -> pattern -> absolute vertex ids).
+template<int S, bool PLASTIC>
+__global__ void __launch_bounds__(256)
+stage_inner_pattern_kernel(const float* __restrict__ u, int node_begin, int n_range, float* __restrict__ un,
+                           const unsigned* __restrict__ pat_idx, const InnerCacheEntry* __restrict__ patterns,
+                           const MatTab* __restrict__ tab, int n_mat,
+                           const unsigned char* __restrict__ mat_id, const float* __restrict__ yield_plane,
+                           int* err, int zone, StageTap* tap, const int* __restrict__ owner_tap,
+                           const int* __restrict__ n2t_off, const int* __restrict__ n2t, int n_nodes)
+{
+	__shared__ float sU[GCM_MAX_MATERIALS][81];
+	__shared__ float sU1[GCM_MAX_MATERIALS][81];
+	for(int i = threadIdx.x; i < n_mat * 81; i += blockDim.x) {
+		const MatTab& mt = tab[(i / 81) * 3 + S];
+		sU[i / 81][i % 81] = mt.U[i % 81];
+		sU1[i / 81][i % 81] = mt.U1[i % 81];
+	}
+	__syncthreads();
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_range) return;
+	const int node = node_begin + idx;
+	const unsigned pid = __ldg(pat_idx + node);
+	if(pid == GCM_IC_NO_PATTERN) return;
+	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u) + 3 * (size_t)node;
+	const float4 o0 = rec[0], o1 = rec[1], o2 = rec[2];
+	InnerCacheEntry e;
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(patterns + pid);
+		uint4* dst = reinterpret_cast<uint4*>(&e);
+		#pragma unroll
+		for(int q = 0; q < 6; q++) dst[q] = __ldg(src + q);
+		e.a0 += node; e.b0 += node; e.c0 += node; e.a1 += node; e.b1 += node; e.c1 += node;
+	}
 	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
 	bool bad = false;
 	#pragma unroll

@@ -94,6 +94,7 @@ SIGNATURES = {
     "gcm_b200_set_enable_tap": (_i, [_p, _i]),
     "gcm_b200_zone_get_tap": (_i, [_p, _i, _ip, _ip, _ip]),
     "gcm_b200_set_launch_count": (C.c_longlong, [_p]),
+    "gcm_b200_set_kernel_stats": (_i, [_p, C.POINTER(C.c_longlong)]),
     "gcm_b200_set_virt_count": (_i, [_p]),
     "gcm_b200_set_get_virt": (_i, [_p, _fp]),
     "gcm_b200_set_profile": (_i, [_p, _i]),
@@ -318,6 +319,13 @@ class TetrMeshSet:
 
     def launch_count(self):
         return self.lib.gcm_b200_set_launch_count(self.h)
+
+    def kernel_stats(self):
+        """Coverage of the specialised kernels (include/gcm_b200.h: gcm_b200_set_kernel_stats)."""
+        a = (C.c_longlong * 16)()
+        self._ck(self.lib.gcm_b200_set_kernel_stats(self.h, a))
+        return dict(inner_cached=a[0], inner_cold=a[1], patterns=[a[2], a[3], a[4]], pattern_axes=[a[5], a[6], a[7]],
+                    border_flat=a[8], border_sharp=a[9], flat_deferred_last=a[10], exact_only=a[11])
 
     def profile(self, on=True):
         self._ck(self.lib.gcm_b200_set_profile(self.h, int(on)))

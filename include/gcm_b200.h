@@ -153,6 +153,12 @@ long long gcm_b200_set_launch_count(gcm_b200_set* s);
  * is bracketed by events on the set's stream; read returns summed ms, launches and nodes. */
 int gcm_b200_set_profile(gcm_b200_set* s, int on);
 int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long long* launches, long long* units);
+/* What the specialised kernels cover (tests, bench.py): out[0] inner nodes on the cached path,
+ * [1] inner nodes left to the literal routine, [2..4] patterns per axis of the de-duplicated cache,
+ * [5..7] 1 where that axis runs from the pattern table, [8] flat border nodes, [9] sharp border nodes,
+ * [10] flat border nodes the last border launch deferred to the literal routine, [11] 1 when the
+ * conservative owner pre-filter is switched off for this mesh (huge coordinates), [12..15] 0. */
+int gcm_b200_set_kernel_stats(gcm_b200_set* s, long long* out16);
 /* Virtual (contact) nodes of the last collision pass: n and [16] floats each (coords, values). */
 int gcm_b200_set_virt_count(gcm_b200_set* s);
 int gcm_b200_set_get_virt(gcm_b200_set* s, float* out16);

@@ -1,6 +1,5 @@
-// gcm_border.cuh -- one axis stage of a FLAT border node (a node whose incident border faces are
-// coplanar: 97-99 % of the border of the benchmark meshes), the B200-first replacement of the literal
-// per-node routine for that class.
+// gcm_border.cuh -- one axis stage of a border node without contact, the B200-first replacement of
+// the literal per-node routine (which stays as the fallback for whatever this one declines).
 //
 // What the reference computes for such a node (gcm/methods/TetrMethod_Plastic_1stOrder.cpp:190-297,
 // first alpha try) is kept operation for operation wherever a value is produced; what is redesigned is
@@ -11,8 +10,13 @@
 //     short displacement to 0.99 h (TetrMesh_1stOrder.cpp:1304-1307), so a candidate's verdict for the
 //     direction q is three dot products q^ . G -- one walk over the list serves both senses and all
 //     four moving feet.  The verdict is conservative (certainly fails / certainly passes / don't know,
-//     thresholds MeshView::pf_fail / pf_pass); "don't know", a foot the rescale does not cover, a ring
-//     expansion or a second alpha try hand the node to the literal routine (returns -1).
+//     thresholds MeshView::pf_fail / pf_pass); "don't know", a foot the rescale does not cover or a ring
+//     expansion hand the node to the literal routine (returns -1).
+//   * the alpha-retry loop of prepare_node (:99-108) collapses: tries 1..9 only shorten the bent feet
+//     along the same direction, which the rescale undoes, so their verdicts are those of try 0 and none
+//     of them can decide the node; a node try 0 does not decide (edges and corners on their tangential
+//     axes) is decided by the 11th try, whose bent feet all sit at the centre of elements[0] (:569-584).
+//     Two evaluations instead of eleven, tries reported as the reference counts them.
 //   * no 81-float Omega / Omega^-1 per thread: the rows are generated from the three direction vectors
 //     where they are consumed (same expressions as ElasticMatrix3D.cpp:371-517, rows 2q / 2q+1 differ
 //     by sign only), the Riemann invariants are accumulated straight from the interpolated values.
@@ -40,7 +44,8 @@ struct BndSlotStatic {
 	float dmin2;    // min squared distance node <-> candidate vertex under the reference's scan rule (:1541-1545)
 	float w0;       // own factor of the zero-speed foot
 	int cand_off;   // index (in quads) of candidate 0, quad 0 of this node in the transposed table
-	int pad0, pad1;
+	float h0;       // h(elements[0]): the last-chance foot (centre of elements[0]) is rescaled to 0.99 h0 when nearer
+	int pad1;
 };
 #define GCM_BND_LANES 32      // candidates of one warp of flat nodes are interleaved: quad (c, q) of lane l at off + (3 c + q) * 32 + l
 #define GCM_BND_DEFER (-1)
@@ -153,6 +158,30 @@ GCM_HD void bnd_U_row(const BndDirs& d, int i, float row[9])
 	}
 }
 
+// Rows 0..5 of Omega come in pairs that differ by the sign of their stress part (-x / y == -(x / y) in
+// IEEE arithmetic): the 18 quotients are made once per (node, axis).
+struct BndRows { float s[3][6]; };
+GCM_HD void bnd_rows_prepare(const BndDirs& d, BndRows& R)
+{
+	const float w[6] = {1, 2, 2, 1, 2, 1};
+	#pragma unroll
+	for(int q = 0; q < 6; q++) {
+		R.s[0][q] = div_z(w[q] * bnd_N(d, 0, 0, q), d.c1 * d.ro);
+		R.s[1][q] = div_z(w[q] * bnd_N(d, 0, 1, q), d.c2 * d.ro);
+		R.s[2][q] = div_z(w[q] * bnd_N(d, 0, 2, q), d.c2 * d.ro);
+	}
+}
+// Row i of Omega from the prepared quotients (bitwise the row bnd_U_row gives)
+GCM_HD void bnd_U_row_p(const BndDirs& d, const BndRows& R, int i, float row[9])
+{
+	if(i >= 6) { bnd_U_row(d, i, row); return; }
+	const int a = i >> 1;
+	#pragma unroll
+	for(int k = 0; k < 3; k++) row[k] = d.n[a][k];
+	#pragma unroll
+	for(int q = 0; q < 6; q++) row[3 + q] = (i & 1) ? R.s[a][q] : -R.s[a][q];
+}
+
 // Row r of Omega^-1 (U1), ElasticMatrix3D.cpp:371-427
 GCM_HD void bnd_U1_row(const BndDirs& d, int r, float row[9])
 {
@@ -245,22 +274,9 @@ GCM_HD int bnd_feet_values(const MeshView& m, int node, const Vec3& X, const flo
 	const int k = (int)((unsigned)x[3] >> 30);
 	const int t = x[3] & 0x3fffffff;
 	float ra[12], rb[12], rc[12];
-#if defined(__CUDA_ARCH__)
-	{
-		const float4* q = reinterpret_cast<const float4*>(m.u);
-		#pragma unroll
-		for(int w = 0; w < 3; w++) {
-			const float4 a = q[3 * (size_t)ia + w], b = q[3 * (size_t)ib + w], c = q[3 * (size_t)ic + w];
-			ra[4*w] = a.x; ra[4*w+1] = a.y; ra[4*w+2] = a.z; ra[4*w+3] = a.w;
-			rb[4*w] = b.x; rb[4*w+1] = b.y; rb[4*w+2] = b.z; rb[4*w+3] = b.w;
-			rc[4*w] = c.x; rc[4*w+1] = c.y; rc[4*w+2] = c.z; rc[4*w+3] = c.w;
-		}
-	}
-#else
-	for(int w = 0; w < 12; w++) {
-		ra[w] = m.u[(size_t)ia * GCM_REC + w]; rb[w] = m.u[(size_t)ib * GCM_REC + w]; rc[w] = m.u[(size_t)ic * GCM_REC + w];
-	}
-#endif
+	rec_load12(m.u, m.rs, ia, ra);
+	rec_load12(m.u, m.rs, ib, rb);
+	rec_load12(m.u, m.rs, ic, rc);
 	Vec3 A, B, C;
 	A.x = ra[9]; A.y = ra[10]; A.z = ra[11];
 	B.x = rb[9]; B.y = rb[10]; B.z = rb[11];
@@ -285,28 +301,39 @@ GCM_HD int bnd_feet_values(const MeshView& m, int node, const Vec3& X, const flo
 	return ERR_NONE;
 }
 
-// One flat border node without contact, axis `stage`.  cand = the node's candidate quads (already
-// offset to its lane; quad (c, q) at cand[(3 c + q) * GCM_BND_LANES]).  A = storage of the 9x9 system
-// or NULL (then a node that needs a border solve is deferred).  Returns a StepError, or GCM_BND_DEFER.
+// Conservative verdict of candidate quads (g0, g1, g2) for the unit direction (qx, qy, qz):
+// v1 for the sense +q, v0 for -q (-1 certainly fails, +1 certainly passes, 0 don't know).
+GCM_HD void bnd_verdicts(const gcm_f4& g0, const gcm_f4& g1, const gcm_f4& g2, float qx, float qy, float qz,
+                         float pf_fail, float pf_pass, int& v0, int& v1)
+{
+	// barycentric coordinates of X + 0.99 h q^ w.r.t. A, B, C; those of the opposite sense are the negatives
+	const float la = qx * g0.x + qy * g0.y + qz * g0.z;
+	const float lb = qx * g0.w + qy * g1.x + qz * g1.y;
+	const float lc = qx * g1.z + qy * g1.w + qz * g2.x;
+	const float sum = la + lb + lc;
+	const float mn1 = fminf(fminf(la, lb), fminf(lc, 1.0f - sum));
+	const float mn0 = fminf(fminf(-la, -lb), fminf(-lc, 1.0f + sum));
+	v1 = mn1 < pf_fail ? -1 : (mn1 > pf_pass ? 1 : 0);
+	v0 = mn0 < pf_fail ? -1 : (mn0 > pf_pass ? 1 : 0);
+}
+
+// One border node without contact, axis `stage`.  cand = the node's candidate quads (already offset to
+// its lane; quad (c, q) at cand[(3 c + q) * GCM_BND_LANES]).  A = storage of the 9x9 system or NULL
+// (then a node that needs a border solve is deferred).  Returns a StepError, or GCM_BND_DEFER.
 template<class Mat>
-GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, const gcm_f4* __restrict__ cand,
+GCM_HD int node_stage_border_fast(const MeshView& m, const BndSlotStatic& bs, const gcm_f4* __restrict__ cand,
                                   int node, int stage, float out[9], StageTap* tap, Mat* A)
 {
 	if(bs.deg <= 0 || m.exact_only) return GCM_BND_DEFER_R(1);
 	float own[9];
 	Vec3 X;
-#if defined(__CUDA_ARCH__)
 	{
-		const float4* q = reinterpret_cast<const float4*>(m.u) + 3 * (size_t)node;
-		const float4 a = q[0], b = q[1], c = q[2];
-		own[0] = a.x; own[1] = a.y; own[2] = a.z; own[3] = a.w;
-		own[4] = b.x; own[5] = b.y; own[6] = b.z; own[7] = b.w; own[8] = c.x;
-		X.x = c.y; X.y = c.z; X.z = c.w;
+		float r[12];
+		rec_load12(m.u, m.rs, node, r);
+		#pragma unroll
+		for(int k = 0; k < 9; k++) own[k] = r[k];
+		X.x = r[9]; X.y = r[10]; X.z = r[11];
 	}
-#else
-	for(int k = 0; k < 9; k++) own[k] = m.u[(size_t)node * GCM_REC + k];
-	X = load_xyz(m, node);
-#endif
 	{
 		bool bad = false;
 		#pragma unroll
@@ -339,9 +366,9 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 			#pragma unroll
 			for(int q = 0; q < p; q++)
 				if( (double)fabsf(dk[p] - dk[q]) <= 0.01 * (double)fabsf(dk[p] + dk[q]) ) usual = false;
-		if(!usual) return GCM_BND_DEFER_R(2);
+		if(!usual || !(dk[0] < 0) || !(dk[2] < 0) || !(dk[1] > 0) || !(dk[3] > 0)) return GCM_BND_DEFER_R(2);
 	}
-	// displacements and feet of the four moving points (real node, no contact, alpha == 0: :553-558)
+	// displacements and feet of the four moving points on the first try (real node, no contact, alpha == 0: :553-558)
 	float fc[4][3], R2[4];
 	#pragma unroll
 	for(int p = 0; p < 4; p++) {
@@ -353,86 +380,149 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 		}
 		R2[p] = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
 		const float delta = sqrtf(R2[p]);
-		// the shared scan answers only for feet every candidate rescales
-		if(!(delta > 0) || !((double)delta < (double)bs.hmin * 0.99)) return GCM_BND_DEFER_R(3);
+		// the shared scan answers only for feet every candidate rescales (the bent feet of tries 1..9 are
+		// shorter still, and longer than 0 down to alpha = 0.9)
+		if(!(delta > 0) || !((double)delta < (double)bs.hmin * 0.99) || !(0.05f * delta > 0)) return GCM_BND_DEFER_R(3);
 	}
 
-	// ---- one walk over the first ring, both senses (0: -q, 1: +q) ----
+	// ---- one walk over the first ring, both senses (0: -q, 1: +q); four candidates' quads in flight ----
 	int own_c[2] = {-1, -1};
 	{
 		const float qn = sqrtf(ksi[0]*ksi[0] + ksi[1]*ksi[1] + ksi[2]*ksi[2]);
 		const float iq = 1.0f / qn;                 // the filter is conservative: its rounding is free
 		const float qx = ksi[0] * iq, qy = ksi[1] * iq, qz = ksi[2] * iq;
 		bool open0 = true, open1 = true;
-		for(int c = 0; c < bs.deg && (open0 || open1); c++) {
-			const gcm_f4 g0 = cand[(3 * c) * GCM_BND_LANES], g1 = cand[(3 * c + 1) * GCM_BND_LANES], g2 = cand[(3 * c + 2) * GCM_BND_LANES];
-			if(!(g2.y > 0)) return GCM_BND_DEFER_R(4);    // ill-shaped tetrahedron: only the literal predicate may judge it
-			// barycentric coordinates of X + 0.99 h q^ w.r.t. A, B, C; those of the opposite sense are the negatives
-			const float la = qx * g0.x + qy * g0.y + qz * g0.z;
-			const float lb = qx * g0.w + qy * g1.x + qz * g1.y;
-			const float lc = qx * g1.z + qy * g1.w + qz * g2.x;
-			const float sum = la + lb + lc;
-			const float mn1 = fminf(fminf(la, lb), fminf(lc, 1.0f - sum));
-			const float mn0 = fminf(fminf(-la, -lb), fminf(-lc, 1.0f + sum));
-			const int v1 = mn1 < m.pf_fail ? -1 : (mn1 > m.pf_pass ? 1 : 0);
-			const int v0 = mn0 < m.pf_fail ? -1 : (mn0 > m.pf_pass ? 1 : 0);
-			if(open0) { if(v0 > 0) { own_c[0] = c; open0 = false; } else if(v0 == 0) return GCM_BND_DEFER_R(5); }
-			if(open1) { if(v1 > 0) { own_c[1] = c; open1 = false; } else if(v1 == 0) return GCM_BND_DEFER_R(6); }
+		for(int c0 = 0; c0 < bs.deg && (open0 || open1); c0 += 4) {
+			gcm_f4 g[4][3];
+			#pragma unroll
+			for(int j = 0; j < 4; j++)        // the table is padded: reading up to 3 candidates past the list is in bounds
+				#pragma unroll
+				for(int q = 0; q < 3; q++) g[j][q] = cand[(3 * (c0 + j) + q) * GCM_BND_LANES];
+			#pragma unroll
+			for(int j = 0; j < 4; j++) {
+				if(c0 + j >= bs.deg || !(open0 || open1)) break;
+				if(!(g[j][2].y > 0)) return GCM_BND_DEFER_R(4);    // ill-shaped tetrahedron: only the literal predicate may judge it
+				int v0, v1;
+				bnd_verdicts(g[j][0], g[j][1], g[j][2], qx, qy, qz, m.pf_fail, m.pf_pass, v0, v1);
+				if(open0) { if(v0 > 0) { own_c[0] = c0 + j; open0 = false; } else if(v0 == 0) return GCM_BND_DEFER_R(5); }
+				if(open1) { if(v1 > 0) { own_c[1] = c0 + j; open1 = false; } else if(v1 == 0) return GCM_BND_DEFER_R(6); }
+			}
 		}
 	}
 	// a sense without owner: NULL only if no candidate vertex lies within |dx| (else the reference expands the ring)
 	bool inn[5];
 	#pragma unroll
 	for(int p = 0; p < 4; p++) {
-		const int sgn = dk[p] < 0 ? 0 : 1;
-		inn[p] = own_c[sgn] >= 0;
+		inn[p] = own_c[p & 1] >= 0;
 		if(!inn[p] && bs.dmin2 < R2[p]) return GCM_BND_DEFER_R(7);
 	}
 	inn[4] = true;     // dksi == 0: the node itself (interpolated inside elements[0], weight w0)
-	const int outer_count = (inn[0] ? 0 : 1) + (inn[1] ? 0 : 1) + (inn[2] ? 0 : 2) + (inn[3] ? 0 : 2);
-	if(outer_count != 0 && outer_count != 3) return GCM_BND_DEFER_R(8);      // the alpha-retry loop: literal routine
-	if(outer_count == 3 && !A) return GCM_BND_DEFER_R(9);
-	// points 0 and 2 share a sense (dksi < 0), so do 1 and 3: a sense is inner or outer as a whole
-	int xs[2][4];
-	#pragma unroll
-	for(int sgn = 0; sgn < 2; sgn++) {
-		if(own_c[sgn] < 0) { xs[sgn][0] = xs[sgn][1] = xs[sgn][2] = 0; xs[sgn][3] = -1; continue; }
-		const int* x = m.n2x_scan + 4*(size_t)(bs.e0 + own_c[sgn]);
+	int outer_count = (inn[0] ? 0 : 1) + (inn[1] ? 0 : 1) + (inn[2] ? 0 : 2) + (inn[3] ? 0 : 2);
+	int tries = 1;
+	// ---- the retry loop (:99-108).  Tries 1..9 move the bent feet (dksi < 0) to dksi (1 - alpha) ksi: same
+	// direction, rescaled by point_in_tetr to the same tested point, so the same verdicts and the same
+	// outer count as the first try.  The 11th (alpha = 1) puts every foot but the outward ones of the
+	// normal axis at the centre of elements[0] (:569-584).
+	bool centre[2] = {false, false};       // per sense: its feet sit at the centre of elements[0]
+	float fcc[3] = {0.f, 0.f, 0.f};
+	int x0[4] = {0, 0, 0, 0};
+	if(outer_count != 0 && outer_count != 3) {
+		tries = 11;
+		{
+			const int* x = m.n2x_scan + 4*(size_t)bs.e0;
 #if defined(__CUDA_ARCH__)
-		const int4 q4 = *reinterpret_cast<const int4*>(x);
-		xs[sgn][0] = q4.x; xs[sgn][1] = q4.y; xs[sgn][2] = q4.z; xs[sgn][3] = q4.w;
+			const int4 q4 = *reinterpret_cast<const int4*>(x);
+			x0[0] = q4.x; x0[1] = q4.y; x0[2] = q4.z; x0[3] = q4.w;
 #else
-		xs[sgn][0] = x[0]; xs[sgn][1] = x[1]; xs[sgn][2] = x[2]; xs[sgn][3] = x[3];
+			x0[0] = x[0]; x0[1] = x[1]; x0[2] = x[2]; x0[3] = x[3];
 #endif
+		}
+		const int k = (int)((unsigned)x0[3] >> 30);
+		const Vec3 Pa = load_xyz(m, x0[0]), Pb = load_xyz(m, x0[1]), Pc = load_xyz(m, x0[2]);
+		const Vec3 p0 = k == 0 ? X : Pa, p1 = k == 0 ? Pa : (k == 1 ? X : Pb), p2 = k <= 1 ? Pb : (k == 2 ? X : Pc), p3 = k == 3 ? X : Pc;
+		float dxc[3];
+		dxc[0] = ( p0.x + p1.x + p2.x + p3.x ) / 4 - X.x;
+		dxc[1] = ( p0.y + p1.y + p2.y + p3.y ) / 4 - X.y;
+		dxc[2] = ( p0.z + p1.z + p2.z + p3.z ) / 4 - X.z;
+		fcc[0] = X.x + dxc[0]; fcc[1] = X.y + dxc[1]; fcc[2] = X.z + dxc[2];
+		// the search from X along dxc must stop at elements[0] (candidate 0) with certainty
+		const float dl = sqrtf(dxc[0]*dxc[0] + dxc[1]*dxc[1] + dxc[2]*dxc[2]);
+		if(!(dl > 0)) return GCM_BND_DEFER_R(8);
+		const gcm_f4 g0 = cand[0], g1 = cand[GCM_BND_LANES], g2 = cand[2 * GCM_BND_LANES];
+		if(!(g2.y > 0)) return GCM_BND_DEFER_R(8);
+		// tested point: X + 0.99 h0 dxc/|dxc| when |dxc| < 0.99 h0, else X + dxc itself; G = 0.99 h0 grad
+		const bool resc = (double)dl < (double)bs.h0 * 0.99;
+		const float sc = resc ? 1.0f / dl : 1.0f / (0.99f * bs.h0);
+		int v0, v1;
+		bnd_verdicts(g0, g1, g2, dxc[0] * sc, dxc[1] * sc, dxc[2] * sc, m.pf_fail, m.pf_pass, v0, v1);
+		if(v1 <= 0) return GCM_BND_DEFER_R(8);
+		centre[0] = true;                   // dksi < 0: always
+		centre[1] = stage != 0;             // dksi > 0: unless border node on its normal axis (:569)
+		#pragma unroll
+		for(int p = 0; p < 4; p++) if(centre[p & 1]) inn[p] = true;
+		outer_count = (inn[0] ? 0 : 1) + (inn[1] ? 0 : 1) + (inn[2] ? 0 : 2) + (inn[3] ? 0 : 2);
 	}
 	if(tap) {
-		const int t0 = own_c[0] >= 0 ? (xs[0][3] & 0x3fffffff) : -1, t1 = own_c[1] >= 0 ? (xs[1][3] & 0x3fffffff) : -1;
-		// dk[0], dk[2] < 0 -> sense 0; dk[1], dk[3] > 0 -> sense 1 (l > 0)
-		tap->owner[0] = t0; tap->owner[1] = t1; tap->owner[2] = t0; tap->owner[3] = t1;
+		// owners of the last try
+		#pragma unroll
+		for(int sgn = 0; sgn < 2; sgn++) {
+			int t = -1;
+			if(centre[sgn]) t = x0[3] & 0x3fffffff;
+			else if(own_c[sgn] >= 0) t = m.n2x_scan[4*(size_t)(bs.e0 + own_c[sgn]) + 3] & 0x3fffffff;
+			tap->owner[sgn] = t; tap->owner[2 + sgn] = t;
+		}
 		tap->owner[4] = m.n2t[m.n2t_off[node]];
-		tap->outer_count = outer_count; tap->tries = 1;
+		tap->outer_count = outer_count; tap->tries = tries;
 	}
+	if(outer_count != 0 && outer_count != 3) return ERR_OUTER_COUNT;     // :234-239, after the last try
+	if(outer_count == 3 && !A) return GCM_BND_DEFER_R(9);
 
 	// ---- Riemann invariants omega_i = Omega(i,:) . u(foot of i), ppoint_num = (0,1,2,3,2,3,4,4,4) ----
+	BndRows R;
+	bnd_rows_prepare(d, R);
 	float omega[9];
 	float row[9];
+	// the 11th try: the zero-speed foot (dksi = -0, not > 0) moves to the centre of elements[0] as well (:569-584)
+	float vz[9];
+	if(tries == 11) {
+		float vdup[9];
+		const int e = bnd_feet_values(m, node, X, own, x0, fcc, fcc, vz, vdup);
+		if(e) return e;
+	} else {
+		#pragma unroll
+		for(int k = 0; k < 9; k++) vz[k] = own[k] * bs.w0;
+	}
 	#pragma unroll
 	for(int sgn = 0; sgn < 2; sgn++) {
 		omega[sgn] = 0; omega[2 + sgn] = 0; omega[4 + sgn] = 0;
-		if(own_c[sgn] < 0) continue;
+		if(!inn[sgn]) continue;
+		if(centre[sgn]) {
+			bnd_U_row_p(d, R, sgn, row);
+			omega[sgn] = omega_row(row, 0, vz);
+			bnd_U_row_p(d, R, 2 + sgn, row);
+			omega[2 + sgn] = omega_row(row, 0, vz);
+			bnd_U_row_p(d, R, 4 + sgn, row);
+			omega[4 + sgn] = omega_row(row, 0, vz);
+			continue;
+		}
 		float v1[9], v2[9];
-		const int e = bnd_feet_values(m, node, X, own, xs[sgn], fc[sgn], fc[2 + sgn], v1, v2);
+		int xs[4];
+		const int* x = m.n2x_scan + 4*(size_t)(bs.e0 + own_c[sgn]);
+#if defined(__CUDA_ARCH__)
+		const int4 q4 = *reinterpret_cast<const int4*>(x);
+		xs[0] = q4.x; xs[1] = q4.y; xs[2] = q4.z; xs[3] = q4.w;
+#else
+		xs[0] = x[0]; xs[1] = x[1]; xs[2] = x[2]; xs[3] = x[3];
+#endif
+		const int e = bnd_feet_values(m, node, X, own, xs, fc[sgn], fc[2 + sgn], v1, v2);
 		if(e) return e;
-		bnd_U_row(d, sgn, row);
+		bnd_U_row_p(d, R, sgn, row);
 		omega[sgn] = omega_row(row, 0, v1);
-		bnd_U_row(d, 2 + sgn, row);
+		bnd_U_row_p(d, R, 2 + sgn, row);
 		omega[2 + sgn] = omega_row(row, 0, v2);
-		bnd_U_row(d, 4 + sgn, row);
+		bnd_U_row_p(d, R, 4 + sgn, row);
 		omega[4 + sgn] = omega_row(row, 0, v2);
 	}
-	float vz[9];
-	#pragma unroll
-	for(int k = 0; k < 9; k++) vz[k] = own[k] * bs.w0;
 	#pragma unroll
 	for(int i = 6; i < 9; i++) {
 		bnd_U_row(d, i, row);
@@ -469,7 +559,7 @@ GCM_HD int node_stage_border_flat(const MeshView& m, const BndSlotStatic& bs, co
 	#pragma unroll
 	for(int i = 0; i < 9; i++) {
 		if(inn[pp[i]]) {
-			bnd_U_row(d, i, row);
+			bnd_U_row_p(d, R, i, row);
 			b[i] = (double)omega[i];
 			#pragma unroll
 			for(int j = 0; j < 9; j++) A->at(i, j) = (double)row[j];

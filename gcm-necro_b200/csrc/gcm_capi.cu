@@ -86,14 +86,13 @@ struct Zone {
 	size_t node_off = 0, tet_off = 0, entry_off = 0, slot_off = 0;
 	size_t fast_off = 0, generic_off = 0, inner_off = 0;   // ranges of this zone in the merged node lists
 	size_t st0_off = 0, st0_n = 0, c0_off = 0, c0_n = 0, c1_off = 0, c1_n = 0;   // contact launch lists
-	size_t sharp_off = 0, flat_off = 0;          // ranges in the merged sharp / flat border lists
-	size_t st0s_off = 0, st0s_n = 0;             // stage-0 sharp border nodes not in contact
+	size_t border_off = 0;                       // range in the merged border list
 	bool stage_done = false;
 };
 
 // The merged device mesh of every local zone.
 struct DeviceMesh {
-	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0;
+	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0, rs = 0;   // rs: quads per plane of the node records (gcm_step.cuh)
 	size_t n_fast = 0, n_generic = 0, n_inner = 0;
 	DevBuf<float> u0, u1, mat, tet_hv, basis, basis_next, normals, w0, aos, mat_tab;
 	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, cold;
@@ -113,7 +112,7 @@ struct DeviceMesh {
 	DevBuf<float> bnd_cand;
 	float pf_fail = -1e-3f, pf_pass = -1e-4f;   // thresholds of the conservative owner pre-filter (prefilter_thresholds)
 	int exact_only = 0;
-	DevBuf<int> sharp_list, flat_list, fast_list, generic_list, inner_list;
+	DevBuf<int> border_list, fast_list, generic_list, inner_list;
 	size_t n_sharp = 0, n_flat = 0;
 	DevBuf<unsigned char> mat_id;
 	DevBuf<gcm::StageTap> tap;
@@ -158,8 +157,7 @@ struct gcm_b200_set {
 	float time_step = 0.002f;
 	bool fast_inner = true;     // specialised inner-node kernel (gcm_inner.cuh)
 	bool concurrent = true;     // border kernel on a second stream, next to the inner kernel
-	bool fused_border = true;    // literal border path: sharp and flat border nodes in one launch (stage_border_fused_kernel)
-	bool flat_border = true;     // flat border nodes through gcm_border.cuh (0 = the literal per-node routine for every border node)
+	bool flat_border = true;     // border nodes through gcm_border.cuh (0 = the literal per-node routine for every border node)
 	bool inner_cache = true;     // inner nodes through the step-invariant owner/factor cache (gcm_inner.cuh); 0 = index-free scan kernel
 	bool inner_patterns = true;  // de-duplicate the cache into a pattern table where an axis has few distinct entries
 	bool fuse_plastic = true;    // whole-step calls: stage 3 as the epilogue of the stage-2 writers (and no exchange before it)
@@ -167,9 +165,8 @@ struct gcm_b200_set {
 	std::vector<gcmh::VirtNodeHost> virt;
 	std::vector<std::vector<int> > axis_plus0;   // per local zone (local_meshes order), per border slot
 	DevBuf<gcm::VirtNode> d_virt;
-	DevBuf<int> d_axis_plus0, d_border_stage0, d_sharp_stage0, d_contact_nodes, d_border_by_slot;
+	DevBuf<int> d_axis_plus0, d_border_stage0, d_contact_nodes, d_border_by_slot;
 	DevBuf<int> d_deep, d_ring_ws;   // contact nodes deferred to the list-building owner search, and its workspaces
-	size_t st0s_total = 0;
 	DevBuf<float> d_gather;
 	size_t st0_total = 0, c0_total = 0;
 	bool contact_active = false;
@@ -302,7 +299,7 @@ void upload_values(gcm_b200_set* s, Zone& z)
 	if(!n) return;
 	float* stage = dm.aos.p + 9 * z.node_off;
 	CK(cudaMemcpyAsync(stage, z.hm.values.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.u0.p + GCM_REC * z.node_off, dm.u1.p + GCM_REC * z.node_off,
+	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.u0.p + 4 * z.node_off, dm.u1.p + 4 * z.node_off, dm.rs,
 		stage, dm.flags.p + z.node_off, n, 0);
 	s->launches++;
 	CK(cudaStreamSynchronize(s->stream));
@@ -352,7 +349,7 @@ void upload_mesh(gcm_b200_set* s)
 	size_t N = 0, T = 0, E = 0, NB = 0, nf = 0, ng = 0, ni = 0, nsh = 0, nfl = 0;
 	for(int zi : s->local_zones) {
 		Zone& z = *s->zones[zi];
-		z.fast_off = nf; z.generic_off = ng; z.inner_off = ni; z.sharp_off = nsh; z.flat_off = nfl;
+		z.fast_off = nf; z.generic_off = ng; z.inner_off = ni; z.border_off = nsh + nfl;
 		nsh += z.hm.n_sharp; nfl += z.hm.border_launch.size() - z.hm.n_sharp;
 		N += z.hm.N; T += z.hm.T; E += z.hm.n2t.size(); NB += z.hm.border_nodes.size();
 		nf += z.hm.inner_fast.size(); ng += z.hm.inner_generic.size(); ni += z.hm.inner_nodes.size();
@@ -360,13 +357,14 @@ void upload_mesh(gcm_b200_set* s)
 	if(T >= (1u << 30) || E >= 0x7fffffffull || N >= 0x7fffffffull / GCM_REC * 4) throw HostError{gcmh::CONFIG_EXCEPTION, "mesh too large for 32-bit device indices"};
 	dm.N = N; dm.T = T; dm.E = E; dm.NB = NB; dm.n_fast = nf; dm.n_generic = ng; dm.n_inner = ni; dm.n_sharp = nsh; dm.n_flat = nfl;
 	dm.stride = (N + 31) / 32 * 32;
+	dm.rs = N + 1;
 	dm.u0.alloc(GCM_REC * (N + 1)); dm.u1.alloc(GCM_REC * (N + 1));
 	CK(cudaMemsetAsync(dm.u0.p, 0, GCM_REC * (N + 1) * sizeof(float), st));
 	CK(cudaMemsetAsync(dm.u1.p, 0, GCM_REC * (N + 1) * sizeof(float), st));
 	dm.mat.alloc(4 * dm.stride); dm.tet_hv.alloc(2 * T); dm.basis.alloc(9 * NB); dm.normals.alloc(3 * NB);
 	dm.w0.alloc(N); dm.aos.alloc(9 * N); dm.flags.alloc(N); dm.n2t_off.alloc(N + 1); dm.n2t.alloc(E); dm.tets.alloc(4 * T);
 	dm.border_slot.alloc(N); dm.cond_id.alloc(NB); dm.n2x.alloc(4 * E); dm.mat_id.alloc(N);
-	dm.sharp_list.alloc(nsh); dm.flat_list.alloc(nfl); dm.fast_list.alloc(nf); dm.generic_list.alloc(ng); dm.inner_list.alloc(ni);
+	dm.border_list.alloc(nsh + nfl); dm.fast_list.alloc(nf); dm.generic_list.alloc(ng); dm.inner_list.alloc(ni);
 	if(dm.basis.p) CK(cudaMemsetAsync(dm.basis.p, 0, 9 * NB * sizeof(float), st));
 	for(int zi : s->local_zones) {
 		Zone& z = *s->zones[zi];
@@ -376,7 +374,7 @@ void upload_mesh(gcm_b200_set* s)
 		{
 			DevBuf<float> xyz; xyz.upload(hm.coords, st);
 			if(n) {
-				gcm::coords_to_records_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(dm.u0.p + GCM_REC * z.node_off, dm.u1.p + GCM_REC * z.node_off, xyz.p, (int)n);
+				gcm::coords_to_records_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(dm.u0.p + 4 * z.node_off, dm.u1.p + 4 * z.node_off, dm.rs, xyz.p, (int)n);
 				s->launches++;
 			}
 			CK(cudaStreamSynchronize(st));
@@ -412,12 +410,7 @@ void upload_mesh(gcm_b200_set* s)
 		dm.w0.put(hm.w0, z.node_off, st);
 		dm.mat_id.put(hm.mat_id, z.node_off, st);
 		dm.normals.put(hm.normals, 3 * z.slot_off, st);
-		{
-			std::vector<int> sh(hm.border_launch.begin(), hm.border_launch.begin() + hm.n_sharp);
-			std::vector<int> fl(hm.border_launch.begin() + hm.n_sharp, hm.border_launch.end());
-			dm.sharp_list.put(shifted(sh, (long long)z.node_off), z.sharp_off, st);
-			dm.flat_list.put(shifted(fl, (long long)z.node_off), z.flat_off, st);
-		}
+		dm.border_list.put(shifted(hm.border_launch, (long long)z.node_off), z.border_off, st);
 		dm.fast_list.put(shifted(hm.inner_fast, (long long)z.node_off), z.fast_off, st);
 		dm.generic_list.put(shifted(hm.inner_generic, (long long)z.node_off), z.generic_off, st);
 		dm.inner_list.put(shifted(hm.inner_nodes, (long long)z.node_off), z.inner_off, st);
@@ -455,7 +448,7 @@ gcm::MeshView make_view(gcm_b200_set* s, float tau)
 	gcm::MeshView m;
 	memset(&m, 0, sizeof(m));
 	m.n_nodes = (int)dm.N; m.n_tets = (int)dm.T; m.stride = dm.stride;
-	m.u = dm.ucur(); m.mat = dm.mat.p; m.flags = dm.flags.p;
+	m.u = dm.ucur(); m.rs = dm.rs; m.mat = dm.mat.p; m.flags = dm.flags.p;
 	m.n2t_off = dm.n2t_off.p; m.n2t = dm.n2t.p; m.tets = dm.tets.p; m.tet_hv = dm.tet_hv.p;
 	m.n2x = nullptr;
 	m.pf_fail = dm.pf_fail; m.pf_pass = dm.pf_pass; m.exact_only = dm.exact_only;
@@ -603,7 +596,7 @@ void sync_nodes_device(gcm_b200_set* s)
 	const int n = (int)dm.n_halo;
 	if(!n) return;
 	ProfScope ps(s, PROF_HALO, n);
-	gcm::halo_copy_kernel<<<(3 * n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.halo_dst.p, dm.ucur(), dm.halo_src.p, n);
+	gcm::halo_copy_kernel<<<(3 * n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.halo_dst.p, dm.ucur(), dm.halo_src.p, n, dm.rs);
 	s->launches++;
 }
 
@@ -677,7 +670,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 		const int n = (int)(z ? (size_t)z->hm.N : dm.N);
 		if(n) {
 			ProfScope ps(s, PROF_PLASTIC, n);
-			gcm::plastic_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.mat.p, dm.flags.p, (int)off, n, dm.stride, s->d_err, zone);
+			gcm::plastic_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur(), dm.rs, dm.mat.p, dm.flags.p, (int)off, n, dm.stride, s->d_err, zone);
 			s->launches++;
 		}
 		return;
@@ -688,58 +681,35 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 	const float* yp = (fuse && stage == 2) ? dm.mat.p + 3 * dm.stride : nullptr;
 	if(s->tap_on && !dm.tap.p) { dm.tap.alloc(3 * dm.N); CK(cudaMemsetAsync(dm.tap.p, 0xff, 3 * dm.N * sizeof(gcm::StageTap), s->stream)); }
 	gcm::StageTap* tap = s->tap_on ? dm.tap.p : nullptr;
-	// border nodes: flat ones one thread per node, sharp ones 16 lanes per node (speculative alpha tries)
-	int nb = (int)(z ? z->hm.border_launch.size() - z->hm.n_sharp : dm.n_flat);
-	const int* bl = dm.flat_list.p + (z ? z->flat_off : 0);
-	int nsh = (int)(z ? (size_t)z->hm.n_sharp : dm.n_sharp);
-	const int* shl = dm.sharp_list.p + (z ? z->sharp_off : 0);
+	// border nodes: one thread per node
+	int nb = (int)(z ? z->hm.border_launch.size() : dm.NB);
+	const int* bl = dm.border_list.p + (z ? z->border_off : 0);
 	const bool contact = stage == 0 && s->contact_active;
 	if(contact) {   // border nodes in contact on axis 0 take the contact kernel instead
 		nb = (int)(z ? z->st0_n : s->st0_total);
 		bl = s->d_border_stage0.p + (z ? z->st0_off : 0);
-		nsh = (int)(z ? z->st0s_n : s->st0s_total);
-		shl = s->d_sharp_stage0.p + (z ? z->st0s_off : 0);
 	}
 	cudaStream_t bst = s->stream;
-	const bool border_work = nb || nsh;
+	const bool border_work = nb > 0;
 	if(border_work) {
 		if(s->concurrent) {
 			bst = s->aux;
 			CK(cudaEventRecord(s->ev_fork, s->stream));
 			CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
 		}
-		ProfScope ps(s, PROF_BORDER, nb + nsh, bst);
-		if(s->flat_border && nb) {
-			// flat nodes: the redesigned kernel, then the literal routine for what it deferred; sharp nodes
-			// (16 lanes per node, speculative alpha tries) beside them on their own stream
-			if(nsh) {
-				cudaStream_t sst = s->concurrent ? s->aux2 : bst;
-				if(s->concurrent) CK(cudaStreamWaitEvent(s->aux2, s->ev_fork, 0));
-				gcm::stage_sharp_kernel<<<(nsh * 16 + 63) / 64, 64, 0, sst>>>(m, shl, nsh, stage, dm.unext(), s->d_err, zone, tap, yp);
-				if(s->concurrent) CK(cudaEventRecord(s->ev_join2, s->aux2));
-				s->launches++;
-			}
+		ProfScope ps(s, PROF_BORDER, nb, bst);
+		if(s->flat_border) {
+			// the redesigned kernel (gcm_border.cuh), then the literal routine for what it deferred
 			CK(cudaMemsetAsync(dm.bnd_defer.p, 0, sizeof(int), bst));
 			const gcm::BndSlotStatic* bstat = reinterpret_cast<const gcm::BndSlotStatic*>(dm.bnd_static.p);
 			const float4* cq = reinterpret_cast<const float4*>(dm.bnd_cand.p);
-			if(stage == 0) gcm::stage_border_flat_kernel<true, 64><<<(nb + 63) / 64, 64, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
-			else gcm::stage_border_flat_kernel<false, 128><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
+			if(stage == 0) gcm::stage_border_fast_kernel<true, 64><<<(nb + 63) / 64, 64, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
+			else gcm::stage_border_fast_kernel<false, 128><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
 			gcm::stage_deferred_kernel<<<64, 128, 0, bst>>>(m, dm.bnd_defer.p, stage, dm.unext(), s->d_err, zone, tap, yp, 0, 0x7fffffff);
 			s->launches += 2;
-			if(nsh && s->concurrent) CK(cudaStreamWaitEvent(bst, s->ev_join2, 0));
-		} else if(nsh && nb && s->fused_border) {
-			const int blocks = (nsh * 16 + 127) / 128 + (nb + 127) / 128;
-			gcm::stage_border_fused_kernel<<<blocks, 128, 0, bst>>>(m, shl, nsh, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp);
-			s->launches++;
 		} else {
-			if(nsh) {
-				gcm::stage_sharp_kernel<<<(nsh * 16 + 63) / 64, 64, 0, bst>>>(m, shl, nsh, stage, dm.unext(), s->d_err, zone, tap, yp);
-				s->launches++;
-			}
-			if(nb) {
-				gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp);
-				s->launches++;
-			}
+			gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp);
+			s->launches++;
 		}
 	}
 	if(!s->fast_inner) {
@@ -771,9 +741,9 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 					const unsigned* pidx = dm.ic_pat_idx.p + (size_t)stage * dm.N;
 					const gcm::InnerCacheEntry* pats = dm.ic_patterns.p + (size_t)stage * GCM_IC_MAX_PATTERNS;
 					const bool pat = dm.pattern_ok[stage];
-#define GCM_LAUNCH_CACHED(S_, P_) do { if(pat) gcm::stage_inner_pattern_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), nbeg, nrange, dm.unext(), pidx, pats, tab, dm.n_mat, mid, yp, \
+#define GCM_LAUNCH_CACHED(S_, P_) do { if(pat) gcm::stage_inner_pattern_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), dm.rs, nbeg, nrange, dm.unext(), pidx, pats, tab, dm.n_mat, mid, yp, \
 						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N); \
-					else gcm::stage_inner_cached_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), nbeg, nrange, dm.unext(), ce, tab, dm.n_mat, mid, yp, \
+					else gcm::stage_inner_cached_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), dm.rs, nbeg, nrange, dm.unext(), ce, tab, dm.n_mat, mid, yp, \
 						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N); } while(0)
 					if(stage == 0) GCM_LAUNCH_CACHED(0, false);
 					else if(stage == 1) GCM_LAUNCH_CACHED(1, false);
@@ -858,7 +828,7 @@ void run_collision_detection(gcm_b200_set* s)
 			s->d_border_by_slot.upload(bys, s->stream);
 			s->d_gather.alloc(9 * dm.NB);
 		}
-		gcm::gather_records_kernel<<<(int)((dm.NB + 255) / 256), 256, 0, s->stream>>>(s->d_gather.p, dm.ucur(), s->d_border_by_slot.p, (int)dm.NB);
+		gcm::gather_records_kernel<<<(int)((dm.NB + 255) / 256), 256, 0, s->stream>>>(s->d_gather.p, dm.ucur(), dm.rs, s->d_border_by_slot.p, (int)dm.NB);
 		s->launches++;
 		std::vector<float> g(9 * dm.NB), bs(9 * dm.NB);
 		CK(cudaMemcpyAsync(g.data(), s->d_gather.p, g.size() * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
@@ -887,7 +857,7 @@ void run_collision_detection(gcm_b200_set* s)
 		v.real = (int)(s->zones[h.real_zone]->node_off + h.real_node);
 		v.phase = order[h.remote_zone] < order[h.real_zone] ? 1 : 0;
 	}
-	std::vector<int> axis(dm.NB, -1), st0, st0s, c0, c1;
+	std::vector<int> axis(dm.NB, -1), st0, c0, c1;
 	for(size_t a = 0; a < s->local_zones.size(); a++) {
 		Zone& z = *s->zones[s->local_zones[a]];
 		for(size_t b = 0; b < z.hm.border_nodes.size(); b++) axis[z.slot_off + b] = s->axis_plus0[a][b];
@@ -895,14 +865,14 @@ void run_collision_detection(gcm_b200_set* s)
 	// lists: stage-0 border nodes not in contact (sharp / flat, launch order), contact nodes by phase
 	for(size_t a = 0; a < s->local_zones.size(); a++) {
 		Zone& z = *s->zones[s->local_zones[a]];
-		z.st0_off = st0.size(); z.st0s_off = st0s.size(); z.c0_off = c0.size();
+		z.st0_off = st0.size(); z.c0_off = c0.size();
 		for(size_t q = 0; q < z.hm.border_launch.size(); q++) {
 			const int node = z.hm.border_launch[q];
 			const int v = s->axis_plus0[a][z.hm.border_slot[node]];
-			if(v < 0) ((int)q < z.hm.n_sharp ? st0s : st0).push_back((int)(z.node_off + node));
+			if(v < 0) st0.push_back((int)(z.node_off + node));
 			else if(dv[v].phase == 0) c0.push_back((int)(z.node_off + node));
 		}
-		z.st0_n = st0.size() - z.st0_off; z.st0s_n = st0s.size() - z.st0s_off; z.c0_n = c0.size() - z.c0_off;
+		z.st0_n = st0.size() - z.st0_off; z.c0_n = c0.size() - z.c0_off;
 	}
 	for(size_t a = 0; a < s->local_zones.size(); a++) {
 		Zone& z = *s->zones[s->local_zones[a]];
@@ -913,12 +883,11 @@ void run_collision_detection(gcm_b200_set* s)
 		}
 		z.c1_n = c0.size() + c1.size() - z.c1_off;
 	}
-	s->st0_total = st0.size(); s->st0s_total = st0s.size(); s->c0_total = c0.size();
+	s->st0_total = st0.size(); s->c0_total = c0.size();
 	std::vector<int> cn(c0); cn.insert(cn.end(), c1.begin(), c1.end());
 	s->d_virt.upload(dv, s->stream);
 	s->d_axis_plus0.upload(axis, s->stream);
 	s->d_border_stage0.upload(st0, s->stream);
-	s->d_sharp_stage0.upload(st0s, s->stream);
 	s->d_contact_nodes.upload(cn, s->stream);
 	s->contact_active = !s->virt.empty();
 }
@@ -1015,7 +984,7 @@ void comm_exchange(gcm_b200_set* s, cudaStream_t st)
 		if(!n) continue;
 		if(!p.send_buf.p) p.send_buf.alloc(9 * (size_t)n);
 		ProfScope ps(s, PROF_HALO, n, st);
-		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.send_buf.p, s->dm.ucur(), p.d_send.p, n, n, 0);
+		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, st>>>(p.send_buf.p, s->dm.ucur(), s->dm.rs, p.d_send.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
@@ -1032,7 +1001,7 @@ void comm_exchange(gcm_b200_set* s, cudaStream_t st)
 		const int n = (int)p.recv_node.size();
 		if(!n) continue;
 		ProfScope ps(s, PROF_HALO, n, st);
-		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(s->dm.ucur(), p.recv_buf.p, p.d_recv.p, n, n, 0);
+		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(s->dm.ucur(), s->dm.rs, p.recv_buf.p, p.d_recv.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
@@ -1100,7 +1069,6 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	s->rng.seed(1);   // libc default when srand() was never called
 	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
 	if(const char* e = getenv("GCM_B200_FAST_INNER")) s->fast_inner = atoi(e) != 0;
-	if(const char* e = getenv("GCM_B200_FUSED_BORDER")) s->fused_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_FLAT_BORDER")) s->flat_border = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BASES_AHEAD")) s->bases_ahead = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_CACHE")) s->inner_cache = atoi(e) != 0;
@@ -1255,7 +1223,7 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values)
 		DeviceMesh& dm = s->dm;
 		const int n = hm.N;
 		float* stage = dm.aos.p + 9 * z->node_off;
-		gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + GCM_REC * z->node_off, n);
+		gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + 4 * z->node_off, dm.rs, n);
 		s->launches++;
 		CK(cudaMemcpyAsync(hm.values.data(), stage, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 		CK(cudaStreamSynchronize(s->stream));
@@ -1276,7 +1244,7 @@ int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* ho
 	if(!n) return 0;
 	float* stage = dm.aos.p + 9 * z->node_off;
 	CK(cudaMemcpyAsync(stage, host_values, 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur() + GCM_REC * z->node_off, nullptr, stage, dm.flags.p + z->node_off, n, 1);
+	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur() + 4 * z->node_off, nullptr, dm.rs, stage, dm.flags.p + z->node_off, n, 1);
 	s->launches++;
 	CK(cudaGetLastError());
 	return 0;
@@ -1293,7 +1261,7 @@ int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_v
 	const int n = z->hm.N;
 	if(!n) return 0;
 	float* stage = dm.aos.p + 9 * z->node_off;
-	gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + GCM_REC * z->node_off, n);
+	gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + 4 * z->node_off, dm.rs, n);
 	s->launches++;
 	CK(cudaMemcpyAsync(host_values, stage, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 	return 0;
@@ -1611,7 +1579,7 @@ int gcm_b200_halo_pack(gcm_b200_set* s, int peer_rank, float* dev_buf)
 	const int n = (int)p.send_node.size();
 	if(n) {
 		ProfScope ps(s, PROF_HALO, n);
-		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dev_buf, s->dm.ucur(), p.d_send.p, n, n, 0);
+		gcm::halo_pack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dev_buf, s->dm.ucur(), s->dm.rs, p.d_send.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());
@@ -1630,7 +1598,7 @@ int gcm_b200_halo_unpack(gcm_b200_set* s, int peer_rank, const float* dev_buf)
 	const int n = (int)p.recv_node.size();
 	if(n) {
 		ProfScope ps(s, PROF_HALO, n);
-		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->dm.ucur(), dev_buf, p.d_recv.p, n, n, 0);
+		gcm::halo_unpack_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(s->dm.ucur(), s->dm.rs, dev_buf, p.d_recv.p, n, n, 0);
 		s->launches++;
 	}
 	CK(cudaGetLastError());

@@ -511,15 +511,15 @@ void HostMesh::build_fast_path_tables()
 void build_border_flat_tables(const std::vector<BorderFlatZone>& zones, std::vector<int>& slot_static8, std::vector<float>& cand_quads)
 {
 	size_t NB = 0, NF = 0;
-	for(const auto& z : zones) { NB += z.hm->border_nodes.size(); NF += z.hm->border_launch.size() - z.hm->n_sharp; }
+	for(const auto& z : zones) { NB += z.hm->border_nodes.size(); NF += z.hm->border_launch.size(); }
 	slot_static8.assign(8 * NB, 0);
 	gcm::BndSlotStatic* st = reinterpret_cast<gcm::BndSlotStatic*>(slot_static8.data());
 	static_assert(sizeof(gcm::BndSlotStatic) == 32, "BndSlotStatic is 8 words");
-	// flat nodes in launch order
+	// border nodes in launch order
 	struct Ref { const BorderFlatZone* z; int node; };
 	std::vector<Ref> flat; flat.reserve(NF);
 	for(const auto& z : zones)
-		for(size_t q = z.hm->n_sharp; q < z.hm->border_launch.size(); q++) flat.push_back(Ref{&z, z.hm->border_launch[q]});
+		for(size_t q = 0; q < z.hm->border_launch.size(); q++) flat.push_back(Ref{&z, z.hm->border_launch[q]});
 	const size_t NW = (NF + GCM_BND_LANES - 1) / GCM_BND_LANES;
 	std::vector<size_t> warp_off(NW + 1, 0);
 	for(size_t w = 0; w < NW; w++) {
@@ -531,7 +531,7 @@ void build_border_flat_tables(const std::vector<BorderFlatZone>& zones, std::vec
 		warp_off[w+1] = warp_off[w] + (size_t)3 * dmax * GCM_BND_LANES;
 	}
 	if(warp_off[NW] >= 0x7fffffffull) throw HostError{CONFIG_EXCEPTION, "border candidate table too large for 32-bit offsets"};
-	cand_quads.assign(4 * warp_off[NW], 0.f);
+	cand_quads.assign(4 * (warp_off[NW] + (size_t)3 * 4 * GCM_BND_LANES), 0.f);   // + 4 candidates of padding: the kernel loads them four at a time
 	#pragma omp parallel for schedule(dynamic, 256)
 	for(long p = 0; p < (long)NF; p++) {
 		const BorderFlatZone& z = *flat[p].z;
@@ -588,6 +588,7 @@ void build_border_flat_tables(const std::vector<BorderFlatZone>& zones, std::vec
 		s.deg = e1 - e0;
 		s.e0 = (int)(z.entry_off + e0);
 		s.hmin = hmin; s.dmin2 = dmin2;
+		s.h0 = hm.tet_hv[2*(size_t)hm.n2t[e0]];
 		s.cand_off = (int)base;
 	}
 }

@@ -103,10 +103,10 @@ struct HostMesh {
 	void translate(float dx, float dy, float dz);
 };
 
-// Static tables of the flat-border-node kernel (gcm_border.cuh), over the zones of one process in
+// Static tables of the border-node kernel (gcm_border.cuh), over the zones of one process in
 // local_meshes order: one BndSlotStatic per border slot (merged numbering, laid out as 8 ints), and the
-// warp-transposed candidate quads.  The flat nodes are taken in launch order (border_launch after the
-// sharp ones, zone after zone) = the order of the device's flat list.
+// warp-transposed candidate quads.  The nodes are taken in launch order (border_launch, zone after
+// zone) = the order of the device's border list.
 struct BorderFlatZone { const HostMesh* hm; size_t node_off, entry_off, slot_off; };
 void build_border_flat_tables(const std::vector<BorderFlatZone>& zones, std::vector<int>& slot_static8, std::vector<float>& cand_quads);
 

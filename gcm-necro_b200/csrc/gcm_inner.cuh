@@ -156,13 +156,13 @@ __device__ __forceinline__ int prefilter(const Cand& c, const F3& X, float sgn)
 }
 
 template<int S>
-__device__ __forceinline__ void load_cand(Cand& c, const int4 x, const float4* __restrict__ rec, const float2* __restrict__ hv2)
+__device__ __forceinline__ void load_cand(Cand& c, const int4 x, const float* __restrict__ rec, size_t rs, const float2* __restrict__ hv2)
 {
 	c.ia = x.x; c.ib = x.y; c.ic = x.z;
 	c.t = x.w & 0x3fffffff; c.k = (unsigned)x.w >> 30;
-	c.qa = __ldg(rec + 3 * (size_t)c.ia + 2);
-	c.qb = __ldg(rec + 3 * (size_t)c.ib + 2);
-	c.qc = __ldg(rec + 3 * (size_t)c.ic + 2);
+	c.qa = rec_quad_ldg(rec, rs, c.ia, 2);
+	c.qb = rec_quad_ldg(rec, rs, c.ib, 2);
+	c.qc = rec_quad_ldg(rec, rs, c.ic, 2);
 	const float2 hv = __ldg(hv2 + c.t);
 	c.h = hv.x; c.vol = hv.y;
 }
@@ -179,11 +179,10 @@ __device__ __noinline__ void inner_node_generic(const MeshView& m, int node, int
 	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
 	if(e) { report_error(err, e, zone, node, stage); return; }
 	if(yield_plane && !plastic_epilogue(out, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
-	const float* r = m.u + (size_t)node * GCM_REC;
-	float4* __restrict__ o = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
-	o[0] = make_float4(out[0], out[1], out[2], out[3]);
-	o[1] = make_float4(out[4], out[5], out[6], out[7]);
-	o[2] = make_float4(out[8], r[9], r[10], r[11]);
+	const float4 c = rec_quad(m.u, m.rs, node, 2);
+	rec_quad_store(un, m.rs, node, 0, make_float4(out[0], out[1], out[2], out[3]));
+	rec_quad_store(un, m.rs, node, 1, make_float4(out[4], out[5], out[6], out[7]));
+	rec_quad_store(un, m.rs, node, 2, make_float4(out[8], c.y, c.z, c.w));
 }
 
 // Interpolated state at the foot X + dks e_S inside candidate c (TetrMesh_1stOrder.cpp:1764-1880).
@@ -214,11 +213,11 @@ __device__ __forceinline__ bool interp_axis(const Cand& c, const F3& X, float dk
 	return true;
 }
 
-__device__ __forceinline__ void load_values(const Cand& c, const float4* __restrict__ rec, float va[9], float vb[9], float vc[9])
+__device__ __forceinline__ void load_values(const Cand& c, const float* __restrict__ rec, size_t rs, float va[9], float vb[9], float vc[9])
 {
-	const float4 a0 = __ldg(rec + 3 * (size_t)c.ia), a1 = __ldg(rec + 3 * (size_t)c.ia + 1);
-	const float4 b0 = __ldg(rec + 3 * (size_t)c.ib), b1 = __ldg(rec + 3 * (size_t)c.ib + 1);
-	const float4 c0 = __ldg(rec + 3 * (size_t)c.ic), c1 = __ldg(rec + 3 * (size_t)c.ic + 1);
+	const float4 a0 = rec_quad_ldg(rec, rs, c.ia, 0), a1 = rec_quad_ldg(rec, rs, c.ia, 1);
+	const float4 b0 = rec_quad_ldg(rec, rs, c.ib, 0), b1 = rec_quad_ldg(rec, rs, c.ib, 1);
+	const float4 c0 = rec_quad_ldg(rec, rs, c.ic, 0), c1 = rec_quad_ldg(rec, rs, c.ic, 1);
 	va[0] = a0.x; va[1] = a0.y; va[2] = a0.z; va[3] = a0.w; va[4] = a1.x; va[5] = a1.y; va[6] = a1.z; va[7] = a1.w; va[8] = c.qa.x;
 	vb[0] = b0.x; vb[1] = b0.y; vb[2] = b0.z; vb[3] = b0.w; vb[4] = b1.x; vb[5] = b1.y; vb[6] = b1.z; vb[7] = b1.w; vb[8] = c.qb.x;
 	vc[0] = c0.x; vc[1] = c0.y; vc[2] = c0.z; vc[3] = c0.w; vc[4] = c1.x; vc[5] = c1.y; vc[6] = c1.z; vc[7] = c1.w; vc[8] = c.qc.x;
@@ -250,9 +249,10 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 	if(idx >= n_list) return;
 	const int node = list[idx];
 	const int mid = mat_id ? mat_id[node] : 0;
-	const float4* __restrict__ rec = reinterpret_cast<const float4*>(m.u);
+	const float* __restrict__ rec = m.u;
+	const size_t rs = m.rs;
 	const float2* __restrict__ hv2 = reinterpret_cast<const float2*>(m.tet_hv);
-	const float4 o0 = rec[3 * (size_t)node], o1 = rec[3 * (size_t)node + 1], o2 = rec[3 * (size_t)node + 2];
+	const float4 o0 = rec_quad(rec, rs, node, 0), o1 = rec_quad(rec, rs, node, 1), o2 = rec_quad(rec, rs, node, 2);
 	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
 	F3 X; X.x = o2.y; X.y = o2.z; X.z = o2.w;
 	bool bad = false;
@@ -280,7 +280,7 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		for(int e = e0; e < e1; e++) {
 			const int4 x = xn;
 			if(e + 1 < e1) xn = __ldg(n2x + e + 1);
-			load_cand<S>(c, x, rec, hv2);
+			load_cand<S>(c, x, rec, rs, hv2);
 			const double h99 = (double)c.h * 0.99;
 			int v1 = 0;
 			if(c.vol > 0 && de1 > 0 && de2 > 0 && (double)de1 < h99 && (double)de2 < h99)
@@ -303,7 +303,7 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		tp.owner[2 + dir] = owner;
 
 		float va[9], vb[9], vc[9], v[9];
-		load_values(c, rec, va, vb, vc);
+		load_values(c, rec, rs, va, vb, vc);
 		if(!interp_axis<S>(c, X, dk1, own, va, vb, vc, v)) { report_error(err, ERR_INTERP_SUM, zone, node, S); return; }
 		// omega_i = Omega(i,:) . u(foot of i)  (SimpleVolumeCalculator.cpp:14-23); ppoint_num = (0,1,2,3,2,3,4,4,4)
 		{
@@ -355,10 +355,9 @@ stage_inner_kernel(const __grid_constant__ MeshView m, const int* __restrict__ l
 		res[i] = o;
 	}
 	if(yield_plane && !plastic_epilogue(res, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
-	float4* __restrict__ out = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
-	out[0] = make_float4(res[0], res[1], res[2], res[3]);
-	out[1] = make_float4(res[4], res[5], res[6], res[7]);
-	out[2] = make_float4(res[8], X.x, X.y, X.z);
+	rec_quad_store(un, rs, node, 0, make_float4(res[0], res[1], res[2], res[3]));
+	rec_quad_store(un, rs, node, 1, make_float4(res[4], res[5], res[6], res[7]));
+	rec_quad_store(un, rs, node, 2, make_float4(res[8], X.x, X.y, X.z));
 }
 
 #endif // __CUDACC__ (index-free kernel)
@@ -465,27 +464,26 @@ GCM_HD float cached_value(int k, const float w[4], float own, float a, float b, 
 
 // the components of record i the stage reads (the others are left untouched)
 template<int S>
-GCM_HD void gather_record(const float* __restrict__ u, int i, float v[9])
+GCM_HD void gather_record(const float* __restrict__ u, size_t rs, int i, float v[9])
 {
 #if defined(__CUDA_ARCH__)
-	const float4* q = reinterpret_cast<const float4*>(u) + 3 * (size_t)i;
-	const float4 a = __ldg(q), b = __ldg(q + 1);
+	const float4 a = rec_quad_ldg(u, rs, i, 0), b = rec_quad_ldg(u, rs, i, 1);
 	v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-	if((gather_mask(S) >> 8) & 1) v[8] = __ldg(q + 2).x; else v[8] = 0.f;
+	if((gather_mask(S) >> 8) & 1) v[8] = rec_quad_ldg(u, rs, i, 2).x; else v[8] = 0.f;
 #else
-	for(int k = 0; k < 9; k++) v[k] = u[(size_t)i * GCM_REC + k];
+	for(int k = 0; k < 9; k++) v[k] = rec_get(u, rs, i, k);
 #endif
 }
 
 // The two feet of one direction and their three Riemann invariants (rows dir, 2 + dir, 4 + dir of Omega).
 template<int S>
-GCM_HD void cached_dir(const float* __restrict__ u, int dir, int k, int ia, int ib, int ic, const float w1[4], const float w2[4],
+GCM_HD void cached_dir(const float* __restrict__ u, size_t rs, int dir, int k, int ia, int ib, int ic, const float w1[4], const float w2[4],
                        const float own[9], const float* __restrict__ U, float omega[9])
 {
 	float va[9], vb[9], vc[9];
-	gather_record<S>(u, ia, va);
-	gather_record<S>(u, ib, vb);
-	gather_record<S>(u, ic, vc);
+	gather_record<S>(u, rs, ia, va);
+	gather_record<S>(u, rs, ib, vb);
+	gather_record<S>(u, rs, ic, vc);
 	// omega_i = Omega(i,:) . u(foot of i)  (SimpleVolumeCalculator.cpp:14-23); ppoint_num = (0,1,2,3,2,3,4,4,4)
 	float om = 0, om2 = 0, om4 = 0;
 	#pragma unroll
@@ -505,15 +503,15 @@ GCM_HD void cached_dir(const float* __restrict__ u, int dir, int k, int ia, int 
 // One inner node, axis stage S, from its cache entry: the volume update of
 // SimpleVolumeCalculator.cpp:7-32 with the structural zeros of Omega / Omega^-1 skipped.
 template<int S>
-GCM_HD void inner_cached_stage(const float* __restrict__ u, const InnerCacheEntry& e, const float own[9],
+GCM_HD void inner_cached_stage(const float* __restrict__ u, size_t rs, const InnerCacheEntry& e, const float own[9],
                                const float* __restrict__ U, const float* __restrict__ U1, float res[9])
 {
 	static_assert(u_pattern(S, 0) == u_pattern(S, 1) && u_pattern(S, 2) == u_pattern(S, 3) && u_pattern(S, 4) == u_pattern(S, 5),
 	              "rows 2q and 2q+1 of Omega must share their sparsity pattern");
 	float omega[9];
 	// dir 0: dksi < 0 (characteristics 0, 2, 4); dir 1: dksi > 0 (1, 3, 5)
-	cached_dir<S>(u, 0, (int)(e.flags & 3u), e.a0, e.b0, e.c0, e.w10, e.w20, own, U, omega);
-	cached_dir<S>(u, 1, (int)((e.flags >> 2) & 3u), e.a1, e.b1, e.c1, e.w11, e.w21, own, U, omega);
+	cached_dir<S>(u, rs, 0, (int)(e.flags & 3u), e.a0, e.b0, e.c0, e.w10, e.w20, own, U, omega);
+	cached_dir<S>(u, rs, 1, (int)((e.flags >> 2) & 3u), e.a1, e.b1, e.c1, e.w11, e.w21, own, U, omega);
 	// zero-speed characteristics: interpolation at the node itself inside elements[0]; every factor
 	// but the node's own is exactly 0 (their products are signed zeros, absorbed by the sums below,
 	// which start from +0), the own one is w0
@@ -608,7 +606,7 @@ merge_cold_kernel(const InnerCacheEntry* __restrict__ c0, const InnerCacheEntry*
 // PLASTIC: stage 3 folded in (only instantiated for S == 2).
 template<int S, bool PLASTIC>
 __global__ void __launch_bounds__(256)
-stage_inner_cached_kernel(const float* __restrict__ u, int node_begin, int n_range, float* __restrict__ un,
+stage_inner_cached_kernel(const float* __restrict__ u, size_t rs, int node_begin, int n_range, float* __restrict__ un,
                           const InnerCacheEntry* __restrict__ cache, const MatTab* __restrict__ tab, int n_mat,
                           const unsigned char* __restrict__ mat_id, const float* __restrict__ yield_plane,
                           int* err, int zone, StageTap* tap, const int* __restrict__ owner_tap,
@@ -635,8 +633,7 @@ stage_inner_cached_kernel(const float* __restrict__ u, int node_begin, int n_ran
 		#pragma unroll
 		for(int q = 1; q < 6; q++) dst[q] = __ldg(src + q);
 	}
-	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u) + 3 * (size_t)node;
-	const float4 o0 = rec[0], o1 = rec[1], o2 = rec[2];
+	const float4 o0 = rec_quad(u, rs, node, 0), o1 = rec_quad(u, rs, node, 1), o2 = rec_quad(u, rs, node, 2);
 	const float own[9] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w, o2.x};
 	bool bad = false;
 	#pragma unroll
@@ -644,7 +641,7 @@ stage_inner_cached_kernel(const float* __restrict__ u, int node_begin, int n_ran
 	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
 	const int mid = mat_id ? mat_id[node] : 0;
 	float res[9];
-	inner_cached_stage<S>(u, e, own, sU[mid], sU1[mid], res);
+	inner_cached_stage<S>(u, rs, e, own, sU[mid], sU1[mid], res);
 	if(tap) {
 		StageTap tp;
 		tp.owner[0] = tp.owner[2] = owner_tap ? owner_tap[2 * (size_t)node] : -2;
@@ -656,10 +653,9 @@ stage_inner_cached_kernel(const float* __restrict__ u, int node_begin, int n_ran
 	if(PLASTIC) {
 		if(!plastic_epilogue(res, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
 	}
-	float4* __restrict__ out = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
-	out[0] = make_float4(res[0], res[1], res[2], res[3]);
-	out[1] = make_float4(res[4], res[5], res[6], res[7]);
-	out[2] = make_float4(res[8], o2.y, o2.z, o2.w);
+	rec_quad_store(un, rs, node, 0, make_float4(res[0], res[1], res[2], res[3]));
+	rec_quad_store(un, rs, node, 1, make_float4(res[4], res[5], res[6], res[7]));
+	rec_quad_store(un, rs, node, 2, make_float4(res[8], o2.y, o2.z, o2.w));
 }
 
 // --- de-duplication of one axis of the cache (see "pattern table" above) ---
@@ -746,7 +742,7 @@ ic_dedup_assign_kernel(const int* __restrict__ list, int n_list, const int* __re
 // entry comes from (pattern id -> pattern -> absolute vertex ids).
 template<int S, bool PLASTIC>
 __global__ void __launch_bounds__(256)
-stage_inner_pattern_kernel(const float* __restrict__ u, int node_begin, int n_range, float* __restrict__ un,
+stage_inner_pattern_kernel(const float* __restrict__ u, size_t rs, int node_begin, int n_range, float* __restrict__ un,
                            const unsigned* __restrict__ pat_idx, const InnerCacheEntry* __restrict__ patterns,
                            const MatTab* __restrict__ tab, int n_mat,
                            const unsigned char* __restrict__ mat_id, const float* __restrict__ yield_plane,
@@ -766,8 +762,7 @@ stage_inner_pattern_kernel(const float* __restrict__ u, int node_begin, int n_ra
 	const int node = node_begin + idx;
 	const unsigned pid = __ldg(pat_idx + node);
 	if(pid == GCM_IC_NO_PATTERN) return;
-	const float4* __restrict__ rec = reinterpret_cast<const float4*>(u) + 3 * (size_t)node;
-	const float4 o0 = rec[0], o1 = rec[1], o2 = rec[2];
+	const float4 o0 = rec_quad(u, rs, node, 0), o1 = rec_quad(u, rs, node, 1), o2 = rec_quad(u, rs, node, 2);
 	InnerCacheEntry e;
 	{
 		const uint4* src = reinterpret_cast<const uint4*>(patterns + pid);
@@ -783,7 +778,7 @@ stage_inner_pattern_kernel(const float* __restrict__ u, int node_begin, int n_ra
 	if(bad) { report_error(err, ERR_NAN, zone, node, S); return; }
 	const int mid = mat_id ? mat_id[node] : 0;
 	float res[9];
-	inner_cached_stage<S>(u, e, own, sU[mid], sU1[mid], res);
+	inner_cached_stage<S>(u, rs, e, own, sU[mid], sU1[mid], res);
 	if(tap) {
 		StageTap tp;
 		tp.owner[0] = tp.owner[2] = owner_tap ? owner_tap[2 * (size_t)node] : -2;
@@ -795,10 +790,9 @@ stage_inner_pattern_kernel(const float* __restrict__ u, int node_begin, int n_ra
 	if(PLASTIC) {
 		if(!plastic_epilogue(res, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
 	}
-	float4* __restrict__ out = reinterpret_cast<float4*>(un) + 3 * (size_t)node;
-	out[0] = make_float4(res[0], res[1], res[2], res[3]);
-	out[1] = make_float4(res[4], res[5], res[6], res[7]);
-	out[2] = make_float4(res[8], o2.y, o2.z, o2.w);
+	rec_quad_store(un, rs, node, 0, make_float4(res[0], res[1], res[2], res[3]));
+	rec_quad_store(un, rs, node, 1, make_float4(res[4], res[5], res[6], res[7]));
+	rec_quad_store(un, rs, node, 2, make_float4(res[8], o2.y, o2.z, o2.w));
 }
 
 #endif // __CUDACC__

@@ -18,13 +18,13 @@ namespace gcm {
 
 // Writes one node's stage result: the 9 values into the next layer; with yield_plane != NULL the
 // plastic stage is folded in (whole-step calls run stage 3 as the epilogue of stage 2).
-__device__ __forceinline__ void store_node(float* __restrict__ un, int node, float out[9], const float* __restrict__ yield_plane,
+__device__ __forceinline__ void store_node(float* __restrict__ un, size_t rs, int node, float out[9], const float* __restrict__ yield_plane,
                                            int* err, int zone)
 {
 	if(yield_plane && !plastic_epilogue(out, yield_plane[node])) { report_error(err, ERR_NAN, zone, node, 3); return; }
-	#pragma unroll
-	for(int k = 0; k < 9; k++)
-		un[(size_t)node * GCM_REC + k] = out[k];
+	rec_quad_store(un, rs, node, 0, make_float4(out[0], out[1], out[2], out[3]));
+	rec_quad_store(un, rs, node, 1, make_float4(out[4], out[5], out[6], out[7]));
+	un[rec_index(rs, node, 8)] = out[8];      // the coordinates in the rest of the third quad are static
 }
 
 // One thread per listed node, one axis stage: TetrMesh_1stOrder::do_next_part_step's two
@@ -42,7 +42,7 @@ stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 	int e = node_stage_nocontact(m, node, stage, out, tap ? &t : nullptr);
 	if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
 	if(e) { report_error(err, e, zone, node, stage); return; }
-	store_node(un, node, out, yield_plane, err, zone);
+	store_node(un, m.rs, node, out, yield_plane, err, zone);
 }
 
 // The nodes a specialised kernel could not settle (cold[0] = how many, cold[1..] = which), through
@@ -62,18 +62,18 @@ stage_deferred_kernel(const __grid_constant__ MeshView m, const int* __restrict_
 		const int e = node_stage_nocontact_cold(m, node, stage, out, tap ? &t : nullptr);
 		if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
 		if(e) { report_error(err, e, zone, node, stage); continue; }
-		store_node(un, node, out, yield_plane, err, zone);
+		store_node(un, m.rs, node, out, yield_plane, err, zone);
 	}
 }
 
-// Flat border nodes (gcm_border.cuh), one thread per node.  LU: the launch provides the shared-memory
+// Border nodes without contact (gcm_border.cuh), one thread per node.  LU: the launch provides the shared-memory
 // 9x9 double systems (element-major across the block: thread t owns column t of an [81][BLOCK] array),
 // needed on the normal axis (stage 0) where three characteristics leave the body; the tangential
 // stages run without it at full occupancy.  Whatever the routine defers (ambiguous candidate, alpha
 // retries, ...) is appended to `defer` (defer[0] = count) for the literal routine right behind.
 template<bool LU, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-stage_border_flat_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
+stage_border_fast_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
                          float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane,
                          const BndSlotStatic* __restrict__ bstat, const float4* __restrict__ cand, int* __restrict__ defer)
 {
@@ -86,87 +86,17 @@ stage_border_flat_kernel(const __grid_constant__ MeshView m, const int* __restri
 		const uint4* q = reinterpret_cast<const uint4*>(bstat + m.border_slot[node]);
 		const uint4 a = __ldg(q), b = __ldg(q + 1);
 		bs.deg = (int)a.x; bs.e0 = (int)a.y; bs.hmin = __uint_as_float(a.z); bs.dmin2 = __uint_as_float(a.w);
-		bs.w0 = __uint_as_float(b.x); bs.cand_off = (int)b.y; bs.pad0 = 0; bs.pad1 = 0;
+		bs.w0 = __uint_as_float(b.x); bs.cand_off = (int)b.y; bs.h0 = __uint_as_float(b.z); bs.pad1 = 0;
 	}
 	StridedMat9<BLOCK> A;
 	A.base = sA + threadIdx.x;
 	float out[9];
 	StageTap tp;
-	const int e = node_stage_border_flat(m, bs, cand + bs.cand_off, node, stage, out, tap ? &tp : nullptr, LU ? &A : (StridedMat9<BLOCK>*)nullptr);
+	const int e = node_stage_border_fast(m, bs, cand + bs.cand_off, node, stage, out, tap ? &tp : nullptr, LU ? &A : (StridedMat9<BLOCK>*)nullptr);
 	if(e == GCM_BND_DEFER) { defer[1 + atomicAdd(&defer[0], 1)] = node; return; }
 	if(tap) tap[(size_t)stage * m.n_nodes + node] = tp;
 	if(e) { report_error(err, e, zone, node, stage); return; }
-	store_node(un, node, out, yield_plane, err, zone);
-}
-
-// Border nodes on sharp edges / corners usually burn all 11 alpha tries of prepare_node
-// (TetrMethod_Plastic_1stOrder.cpp:105-108) on their tangential axes -- one thread doing them in
-// sequence is the longest thread of the whole stage by an order of magnitude.  The tries are
-// independent given alpha, so 16 lanes serve one node: lane t evaluates try t (t = 0..10), the
-// lanes vote, and the lane of the first deciding try (legal outer count, or an error the reference
-// would have thrown there; else the last try) finishes the node.  Same result, 1/11 the latency.
-struct SharpDecide {
-	__device__ __forceinline__ bool operator()(int outer, int t, void*) const
-	{
-		const bool hit = (outer == 0 || outer == 3 || outer < 0);
-		const unsigned mask = __ballot_sync(0xffffffffu, hit);
-		const int g = (threadIdx.x & 31) >> 4;
-		const unsigned gm = (mask >> (16 * g)) & 0x7ffu;
-		const int winner = gm ? (__ffs(gm) - 1) : 10;
-		return t == winner;
-	}
-};
-
-__global__ void __launch_bounds__(64)
-stage_sharp_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
-                   int stage, float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane)
-{
-	const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-	const int idx = gid >> 4;
-	int t = threadIdx.x & 15;
-	const bool real = idx < n_list && t < 11;
-	const int node = list[real ? idx : 0];
-	if(!real) t = 11;                       // padding lane: goes through the same vote, never wins
-	float out[9];
-	StageTap tp;
-	const int e = node_stage_nocontact_t(m, node, stage, out, tap ? &tp : nullptr, t, SharpDecide(), nullptr);
-	if(e == -1000) return;                  // another lane's try decides this node
-	if(tap) tap[(size_t)stage * m.n_nodes + node] = tp;
-	if(e) { report_error(err, e, zone, node, stage); return; }
-	store_node(un, node, out, yield_plane, err, zone);
-}
-
-// Sharp and flat border nodes in ONE launch: the first blocks take the sharp nodes (16 lanes per
-// node, as stage_sharp_kernel), the rest the flat ones (one thread per node, as
-// stage_generic_kernel).  Both are long, latency-bound threads and the sharp launch is tiny, so
-// back to back on one stream the two cost the sum of their latencies; fused they cost the maximum.
-__global__ void __launch_bounds__(128, 4)
-stage_border_fused_kernel(const __grid_constant__ MeshView m, const int* __restrict__ sharp_list, int n_sharp,
-                          const int* __restrict__ flat_list, int n_flat,
-                          int stage, float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane)
-{
-	const int sharp_blocks = (n_sharp * 16 + 127) / 128;
-	float out[9];
-	StageTap tp;
-	int node, e;
-	if((int)blockIdx.x < sharp_blocks) {
-		const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-		const int idx = gid >> 4;
-		int t = threadIdx.x & 15;
-		const bool real = idx < n_sharp && t < 11;
-		node = sharp_list[real ? idx : 0];
-		if(!real) t = 11;                       // padding lane: goes through the same vote, never wins
-		e = node_stage_nocontact_t(m, node, stage, out, tap ? &tp : nullptr, t, SharpDecide(), nullptr);
-		if(e == -1000) return;                  // another lane's try decides this node
-	} else {
-		const int idx = (blockIdx.x - sharp_blocks) * blockDim.x + threadIdx.x;
-		if(idx >= n_flat) return;
-		node = flat_list[idx];
-		e = node_stage_nocontact(m, node, stage, out, tap ? &tp : nullptr);
-	}
-	if(tap) tap[(size_t)stage * m.n_nodes + node] = tp;
-	if(e) { report_error(err, e, zone, node, stage); return; }
-	store_node(un, node, out, yield_plane, err, zone);
+	store_node(un, m.rs, node, out, yield_plane, err, zone);
 }
 
 // Border nodes in contact on axis `stage` (only axis 0 can be: BruteforceCollisionDetector.cpp:58-60):
@@ -205,27 +135,25 @@ stage_contact_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 		if(e == ERR_RING_OVERFLOW && !deep_pass && deep) { deep[1 + atomicAdd(&deep[0], 1)] = node; continue; }
 		if(tap) tap[(size_t)stage * m.n_nodes + node] = t;
 		if(e) { report_error(err, e, zone, node, stage); continue; }
-		#pragma unroll
-		for(int k = 0; k < 9; k++)
-			un[(size_t)node * GCM_REC + k] = out[k];
+		store_node(un, m.rs, node, out, nullptr, err, zone);
 		if(vw) for(int k = 0; k < 9; k++) virt[vidx].val[k] = vout[k];
 	}
 }
 
 // Gather the records of listed nodes (collision discovery reads border-node values on the host).
-__global__ void gather_records_kernel(float* __restrict__ out9, const float* __restrict__ u, const int* __restrict__ list, int n)
+__global__ void gather_records_kernel(float* __restrict__ out9, const float* __restrict__ u, size_t rs, const int* __restrict__ list, int n)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n) return;
 	const int node = list[i];
 	#pragma unroll
-	for(int k = 0; k < 9; k++) out9[9 * (size_t)i + k] = u[(size_t)node * GCM_REC + k];
+	for(int k = 0; k < 9; k++) out9[9 * (size_t)i + k] = rec_get(u, rs, node, k);
 }
 
 // Stage 3: the plastic corrector drop_deviator (TetrMethod_Plastic_1stOrder.cpp:51-71,192-199),
 // in place on the current layer for every local node.
 __global__ void __launch_bounds__(256)
-plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* __restrict__ flags,
+plastic_kernel(float* __restrict__ u, size_t rs, const float* __restrict__ mat, const int* __restrict__ flags,
                int first, int n_nodes, size_t stride, int* err, int zone)   // u: node records, mat: planes
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,7 +164,7 @@ plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* 
 	bool bad = false;
 	#pragma unroll
 	for(int k = 0; k < 9; k++) {
-		v[k] = u[(size_t)i * GCM_REC + k];
+		v[k] = rec_get(u, rs, i, k);
 		bad |= (isnan(v[k]) || isinf(v[k]));
 	}
 	if(bad) { report_error(err, ERR_NAN, zone, i, 3); return; }
@@ -244,7 +172,7 @@ plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* 
 	if(drop_deviator(v, yield_limit)) {
 		#pragma unroll
 		for(int k = 3; k < 9; k++)
-			u[(size_t)i * GCM_REC + k] = v[k];
+			rec_set(u, rs, i, k, v[k]);
 	}
 }
 
@@ -253,17 +181,17 @@ plastic_kernel(float* __restrict__ u, const float* __restrict__ mat, const int* 
 // quad carries the coordinates, which are equal on both sides since the start-up sync).
 __global__ void __launch_bounds__(256)
 halo_copy_kernel(float* __restrict__ dst_u, const int* __restrict__ dst_idx,
-                 const float* __restrict__ src_u, const int* __restrict__ src_idx, int n)
+                 const float* __restrict__ src_u, const int* __restrict__ src_idx, int n, size_t rs)
 {
 	const int g = blockIdx.x * blockDim.x + threadIdx.x;
-	const int i = g / 3, q = g - 3 * i;
-	if(i >= n) return;
+	const int q = g / n, i = g - q * n;        // plane-major: consecutive threads, consecutive list entries
+	if(q >= 3) return;
 	const int d = dst_idx[i], s = src_idx[i];
-	reinterpret_cast<float4*>(dst_u)[3 * (size_t)d + q] = reinterpret_cast<const float4*>(src_u)[3 * (size_t)s + q];
+	rec_quad_store(dst_u, rs, d, q, rec_quad(src_u, rs, s, q));
 }
 
 // Cross-process halo: gather into / scatter from a plane-major [9][n] exchange buffer.
-__global__ void halo_pack_kernel(float* __restrict__ buf, const float* __restrict__ u,
+__global__ void halo_pack_kernel(float* __restrict__ buf, const float* __restrict__ u, size_t rs,
                                  const int* __restrict__ idx, int n, int n_total, int offset)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,10 +199,10 @@ __global__ void halo_pack_kernel(float* __restrict__ buf, const float* __restric
 	int s = idx[i];
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		buf[(size_t)k * n_total + offset + i] = u[(size_t)s * GCM_REC + k];
+		buf[(size_t)k * n_total + offset + i] = rec_get(u, rs, s, k);
 }
 
-__global__ void halo_unpack_kernel(float* __restrict__ u, const float* __restrict__ buf,
+__global__ void halo_unpack_kernel(float* __restrict__ u, size_t rs, const float* __restrict__ buf,
                                    const int* __restrict__ idx, int n, int n_total, int offset)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,7 +210,7 @@ __global__ void halo_unpack_kernel(float* __restrict__ u, const float* __restric
 	int d = idx[i];
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		u[(size_t)d * GCM_REC + k] = buf[(size_t)k * n_total + offset + i];
+		rec_set(u, rs, d, k, buf[(size_t)k * n_total + offset + i]);
 }
 
 // ---- the per-step random local bases, generated on the device ------------------------------
@@ -353,7 +281,7 @@ __global__ void basis_kernel(float* __restrict__ basis, const float* __restrict_
 // Host-facing state layout is the reference's node-major values[9] (ElasticNode.h:28-44); the
 // device keeps 12-float node records.  These kernels sit on either side of a pinned-memory copy;
 // values_to_records with local_only writes local nodes only (halo slots belong to sync_nodes).
-__global__ void values_to_records_kernel(float* __restrict__ u0, float* __restrict__ u1,
+__global__ void values_to_records_kernel(float* __restrict__ u0, float* __restrict__ u1, size_t rs,
                                          const float* __restrict__ aos, const int* __restrict__ flags, int n, int local_only)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -362,30 +290,30 @@ __global__ void values_to_records_kernel(float* __restrict__ u0, float* __restri
 	#pragma unroll
 	for(int k = 0; k < 9; k++) {
 		float v = aos[9 * (size_t)i + k];
-		u0[(size_t)i * GCM_REC + k] = v;
-		if(u1) u1[(size_t)i * GCM_REC + k] = v;
+		rec_set(u0, rs, i, k, v);
+		if(u1) rec_set(u1, rs, i, k, v);
 	}
 }
 
-__global__ void records_to_values_kernel(float* __restrict__ aos, const float* __restrict__ u, int n)
+__global__ void records_to_values_kernel(float* __restrict__ aos, const float* __restrict__ u, size_t rs, int n)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n) return;
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
-		aos[9 * (size_t)i + k] = u[(size_t)i * GCM_REC + k];
+		aos[9 * (size_t)i + k] = rec_get(u, rs, i, k);
 }
 
 // Static coordinates into the xyz slots of both layers' records (once, at upload).
-__global__ void coords_to_records_kernel(float* __restrict__ u0, float* __restrict__ u1, const float* __restrict__ xyz, int n)
+__global__ void coords_to_records_kernel(float* __restrict__ u0, float* __restrict__ u1, size_t rs, const float* __restrict__ xyz, int n)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if(i >= n) return;
 	#pragma unroll
 	for(int k = 0; k < 3; k++) {
 		float v = xyz[3 * (size_t)i + k];
-		u0[(size_t)i * GCM_REC + 9 + k] = v;
-		u1[(size_t)i * GCM_REC + 9 + k] = v;
+		rec_set(u0, rs, i, 9 + k, v);
+		rec_set(u1, rs, i, 9 + k, v);
 	}
 }
 

@@ -33,7 +33,7 @@ template<class T> static void write_file(const string& name, const vector<T>& v)
 
 struct Z {
 	HostMesh hm;
-	size_t stride;
+	size_t stride, rs = 0;                    // rs: quads per plane of the node records (gcm_step.cuh)
 	vector<float> xyz, u[2], mat;
 	int cur = 0;
 	vector<gcm::InnerCacheEntry> icache[3];   // the step-invariant cache of the inner kernel (gcm_inner.cuh)
@@ -155,11 +155,12 @@ int main(int argc, char** argv)
 	for(auto& zp : zs) {
 		Z& z = *zp; HostMesh& hm = z.hm;
 		z.stride = (hm.N + 31) / 32 * 32;
+		z.rs = hm.N;
 		z.mat.assign(4*z.stride, 0); z.u[0].assign(GCM_REC*(size_t)hm.N, 0);
 		for(int i = 0; i < hm.N; i++) {
-			for(int k = 0; k < 3; k++) z.u[0][GCM_REC*(size_t)i+9+k] = hm.coords[3*(size_t)i+k];
+			for(int k = 0; k < 3; k++) z.u[0][gcm::rec_index(z.rs, i, 9+k)] = hm.coords[3*(size_t)i+k];
 			for(int k = 0; k < 4; k++) z.mat[k*z.stride+i] = hm.mat[4*(size_t)i+k];
-			for(int k = 0; k < 9; k++) z.u[0][GCM_REC*(size_t)i+k] = hm.values[9*(size_t)i+k];
+			for(int k = 0; k < 9; k++) z.u[0][gcm::rec_index(z.rs, i, k)] = hm.values[9*(size_t)i+k];
 		}
 		z.u[1] = z.u[0];
 	}
@@ -176,7 +177,7 @@ int main(int argc, char** argv)
 			Z& z = *zp; HostMesh& hm = z.hm;
 			gcm::MeshView m; memset(&m, 0, sizeof m);
 			m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
-			m.u = z.u[0].data(); m.mat = z.mat.data(); m.flags = hm.flags.data();
+			m.u = z.u[0].data(); m.rs = z.rs; m.mat = z.mat.data(); m.flags = hm.flags.data();
 			m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = nullptr; m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 			m.border_slot = hm.border_slot.data();
 			m.tau = 0.002f; m.time = 0; m.min_h = hm.min_h;
@@ -206,7 +207,7 @@ int main(int argc, char** argv)
 			Z& z = *zp; HostMesh& hm = z.hm;
 			gcm::MeshView m; memset(&m, 0, sizeof m);
 			m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
-			m.u = z.u[0].data(); m.mat = z.mat.data(); m.flags = hm.flags.data();
+			m.u = z.u[0].data(); m.rs = z.rs; m.mat = z.mat.data(); m.flags = hm.flags.data();
 			m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 			for(int k = 0; k < ring_check; k++) {
 				const int node = (int)(rr.next() % (unsigned)hm.N);
@@ -243,7 +244,7 @@ int main(int argc, char** argv)
 		HostMesh& hm = z.hm;
 		gcm::MeshView m; memset(&m, 0, sizeof m);
 		m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
-		m.u = z.u[z.cur].data(); m.mat = z.mat.data(); m.flags = hm.flags.data();
+		m.u = z.u[z.cur].data(); m.rs = z.rs; m.mat = z.mat.data(); m.flags = hm.flags.data();
 		m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 		m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 		m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
@@ -257,7 +258,7 @@ int main(int argc, char** argv)
 			vector<HostMesh*> ms;
 			for(auto& zp : zs) {
 				Z& z = *zp;
-				for(int i = 0; i < z.hm.N; i++) for(int k = 0; k < 9; k++) z.hm.values[9*(size_t)i+k] = z.u[z.cur][GCM_REC*(size_t)i+k];
+				for(int i = 0; i < z.hm.N; i++) for(int k = 0; k < 9; k++) z.hm.values[9*(size_t)i+k] = z.u[z.cur][gcm::rec_index(z.rs, i, k)];
 				ms.push_back(&z.hm);
 			}
 			try { gcmh::find_collisions(ms, 1.0f, virt, axis_plus0); }
@@ -270,7 +271,7 @@ int main(int argc, char** argv)
 				for(int i = 0; i < d.hm.N; i++) {
 					if(d.hm.flags[i] & 2) continue;
 					Z& o = *zs[d.hm.remote_zone[i]]; int si = d.hm.remote_num[i];
-					for(int k = 0; k < 9; k++) d.u[d.cur][GCM_REC*(size_t)i+k] = o.u[o.cur][GCM_REC*(size_t)si+k];
+					for(int k = 0; k < 9; k++) d.u[d.cur][gcm::rec_index(d.rs, i, k)] = o.u[o.cur][gcm::rec_index(o.rs, si, k)];
 				}
 			}
 			for(int zi = 0; zi < NZ && !rc; zi++) {
@@ -279,14 +280,14 @@ int main(int argc, char** argv)
 				if(stage == 3) {
 					for(int i = 0; i < hm.N; i++) {
 						if(!hm.is_local(i)) continue;
-						float v[9]; for(int k = 0; k < 9; k++) v[k] = ucur[GCM_REC*(size_t)i+k];
-						if(gcm::drop_deviator(v, z.mat[3*z.stride+i])) for(int k = 3; k < 9; k++) ucur[GCM_REC*(size_t)i+k] = v[k];
+						float v[9]; for(int k = 0; k < 9; k++) v[k] = ucur[gcm::rec_index(z.rs, i, k)];
+						if(gcm::drop_deviator(v, z.mat[3*z.stride+i])) for(int k = 3; k < 9; k++) ucur[gcm::rec_index(z.rs, i, k)] = v[k];
 					}
 					continue;
 				}
 				gcm::MeshView m; memset(&m, 0, sizeof m);
 				m.n_nodes = hm.N; m.n_tets = hm.T; m.stride = z.stride;
-				m.u = ucur; m.mat = z.mat.data(); m.flags = hm.flags.data();
+				m.u = ucur; m.rs = z.rs; m.mat = z.mat.data(); m.flags = hm.flags.data();
 				m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 				m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 				m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
@@ -326,7 +327,7 @@ int main(int argc, char** argv)
 						// stage_border_flat_kernel, then the literal routine for what it defers
 						const gcm::BndSlotStatic& bs = reinterpret_cast<const gcm::BndSlotStatic*>(z.bnd_static.data())[slot];
 						gcm::LocalMat9 A;
-						e = gcm::node_stage_border_flat(m, bs, reinterpret_cast<const gcm::gcm_f4*>(z.bnd_cand.data()) + bs.cand_off, i, stage, o, &t, &A);
+						e = gcm::node_stage_border_fast(m, bs, reinterpret_cast<const gcm::gcm_f4*>(z.bnd_cand.data()) + bs.cand_off, i, stage, o, &t, &A);
 						if(e == GCM_BND_DEFER) {
 							e = gcm::node_stage_nocontact(m, i, stage, o, &t);
 							#pragma omp atomic
@@ -344,12 +345,12 @@ int main(int argc, char** argv)
 						const gcmh::MaterialRegistry& reg = hm.registry ? *hm.registry : hm.own_registry;
 						const gcm::MatTab* tab = reinterpret_cast<const gcm::MatTab*>(reg.table.data()) + 3 * (size_t)hm.mat_id[i] + stage;
 						float own[9]; bool bad = false;
-						for(int k = 0; k < 9; k++) { own[k] = ucur[GCM_REC*(size_t)i+k]; bad |= !(fabsf(own[k]) <= 3.4028235e38f); }
+						for(int k = 0; k < 9; k++) { own[k] = ucur[gcm::rec_index(z.rs, i, k)]; bad |= !(fabsf(own[k]) <= 3.4028235e38f); }
 						e = bad ? gcm::ERR_NAN : 0;
 						if(!e) {
-							if(stage == 0) gcm::inner_cached_stage<0>(ucur, ce, own, tab->U, tab->U1, o);
-							else if(stage == 1) gcm::inner_cached_stage<1>(ucur, ce, own, tab->U, tab->U1, o);
-							else gcm::inner_cached_stage<2>(ucur, ce, own, tab->U, tab->U1, o);
+							if(stage == 0) gcm::inner_cached_stage<0>(ucur, z.rs, ce, own, tab->U, tab->U1, o);
+							else if(stage == 1) gcm::inner_cached_stage<1>(ucur, z.rs, ce, own, tab->U, tab->U1, o);
+							else gcm::inner_cached_stage<2>(ucur, z.rs, ce, own, tab->U, tab->U1, o);
 						}
 						t.owner[0] = t.owner[2] = z.icache_owner[stage][2*(size_t)i];
 						t.owner[1] = t.owner[3] = z.icache_owner[stage][2*(size_t)i+1];
@@ -362,7 +363,7 @@ int main(int argc, char** argv)
 						{ if(!err) { err = e; fprintf(stderr, "gcm_emul: error %d zone %d node %d stage %d\n", e, zi, i, stage); } }
 						continue;
 					}
-					for(int k = 0; k < 9; k++) un[GCM_REC*(size_t)i+k] = o[k];
+					for(int k = 0; k < 9; k++) un[gcm::rec_index(z.rs, i, k)] = o[k];
 					if(step == tap_step) {
 						#pragma omp critical
 						{ tap.push_back(zi); tap.push_back(i); tap.push_back(stage); for(int k = 0; k < 5; k++) tap.push_back(t.owner[k]); tap.push_back(t.outer_count); tap.push_back(t.tries); }
@@ -379,7 +380,7 @@ int main(int argc, char** argv)
 			Z& z = *zs[zi]; HostMesh& hm = z.hm;
 			vector<float> vals(9*(size_t)hm.N), bases(9*(size_t)hm.N, 0.f);
 			for(int i = 0; i < hm.N; i++) {
-				for(int k = 0; k < 9; k++) vals[9*(size_t)i+k] = z.u[z.cur][GCM_REC*(size_t)i+k];
+				for(int k = 0; k < 9; k++) vals[9*(size_t)i+k] = z.u[z.cur][gcm::rec_index(z.rs, i, k)];
 				if(hm.is_local(i)) {
 					int b = hm.border_slot[i];
 					const float E[9] = {1,0,0,0,1,0,0,0,1};

@@ -504,6 +504,33 @@ void HostMesh::build_fast_path_tables()
 		}
 }
 
+// The reference evaluates point_in_tetr at P = X + d rounded to float: each coordinate of P is off by up
+// to ulp(|coordinate|)/2, i.e. each barycentric coordinate by up to  n = sqrt(3) ulp(Cmax) / (2 min h).
+// The predicate passes iff the negative barycentric coordinates sum to less than 5e-4 (sum|s| < 1.001
+// Vol); with at most three of them negative, "all > -t_p" is certain to pass while 3 t_p + 3 n + 1e-5 <
+// 5e-4, and "one < -t_f" certain to fail once t_f > 5e-4 + 3 n + 1e-5.  2e-5 of each is left to the
+// filter's own float rounding.  At the benchmark scale (|coordinates| < 256, h = 0.577) this gives the
+// 1e-4 / 1e-3 the filter was validated with; a body far from the origin gets tighter values and, when
+// no positive t_p is left (|coordinate| / h beyond ~2000), no pre-filter at all: every candidate through
+// the literal predicate.
+void prefilter_thresholds(const std::vector<const HostMesh*>& meshes, float* pf_fail, float* pf_pass, int* exact_only)
+{
+	float cmax = 0, hmin = -1;
+	for(const HostMesh* hm : meshes) {
+		for(size_t k = 0; k < hm->coords.size(); k++) cmax = fmaxf(cmax, fabsf(hm->coords[k]));
+		if(hm->min_h > 0 && (hmin < 0 || hm->min_h < hmin)) hmin = hm->min_h;
+	}
+	*pf_fail = -1e-3f; *pf_pass = -1e-4f; *exact_only = 0;
+	if(!(hmin > 0) || !std::isfinite(cmax)) { *exact_only = 1; return; }
+	cmax += 2 * hmin;                                         // the tested point is up to 0.99 h away from a node
+	const float ulp = nextafterf(cmax, INFINITY) - cmax;
+	const float n = 0.8660254f * ulp / hmin;
+	const float tp = fminf(1e-4f, (4.9e-4f - 3 * n) / 3 * 0.9f - 2e-5f);
+	const float tf = fmaxf(1e-3f, 1.1f * (5.1e-4f + 3 * n) + 2e-5f);
+	if(!(tp >= 2e-5f)) { *exact_only = 1; return; }
+	*pf_pass = -tp; *pf_fail = -tf;
+}
+
 // Static inputs of gcm_border.cuh: per flat border node its candidate list with the barycentric
 // gradients of the other three vertices scaled by 0.99 h(tet) (the point point_in_tetr tests for a
 // direction q^ is X + 0.99 h q^, so a candidate's barycentric coordinates there are q^ . G), computed in

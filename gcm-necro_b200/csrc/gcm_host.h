@@ -103,6 +103,10 @@ struct HostMesh {
 	void translate(float dx, float dy, float dz);
 };
 
+// Thresholds of the conservative owner pre-filter (MeshView::pf_fail / pf_pass / exact_only) for the
+// meshes of one process; see the definition for the error budget behind them.
+void prefilter_thresholds(const std::vector<const HostMesh*>& meshes, float* pf_fail, float* pf_pass, int* exact_only);
+
 // Static tables of the border-node kernel (gcm_border.cuh), over the zones of one process in
 // local_meshes order: one BndSlotStatic per border slot (merged numbering, laid out as 8 ints), and the
 // warp-transposed candidate quads.  The nodes are taken in launch order (border_launch, zone after

@@ -11,7 +11,8 @@
 #   (gcm/methods/TetrMethod_Plastic_1stOrder.cpp:590), compiled in ONLY with -DGCM_ORACLE_TAP
 # - the reference's build system (cmake + VTK/GSL/TinyXML/MPI, all absent) is not used;
 #   stubs/ provides the headers, databus_stub.cpp the one-rank DataBus, driver.cpp main().
-# Outputs: oracle/_ref/gcm3d_ref (timed build, no tap) and oracle/_ref/gcm3d_ref_tap.
+# Outputs: oracle/_ref/gcm3d_ref (timed build, no tap), oracle/_ref/gcm3d_ref_tap and
+# oracle/_ref/gcm3d_ref_kat (known-answer driver, ref_build/kat_driver.cpp).
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${GCM_REFERENCE:-/root/reference}"
@@ -87,5 +88,9 @@ $CXX $OWNFLAGS -c "$HERE/ref_build/driver.cpp" -o "$OUT/obj/driver.o"
 $CXX $OWNFLAGS -DGCM_ORACLE_TAP -c "$HERE/ref_build/driver.cpp" -o "$OUT/obj_tap/driver.o"
 $CXX -O2 "$OUT"/obj/*.o -o "$OUT/gcm3d_ref"
 $CXX -O2 "$OUT"/obj_tap/*.o -o "$OUT/gcm3d_ref_tap"
+# known-answer driver: the same reference objects behind kat_driver.cpp's main()
+$CXX $OWNFLAGS -c "$HERE/ref_build/kat_driver.cpp" -o "$OUT/kat_driver.o"
+$CXX -O2 $(ls "$OUT"/obj/*.o | grep -v '/driver.o$') "$OUT/kat_driver.o" -o "$OUT/gcm3d_ref_kat"
+rm -f "$OUT/kat_driver.o"
 rm -rf "$OUT/obj" "$OUT/obj_tap"
 echo "built $OUT/gcm3d_ref and $OUT/gcm3d_ref_tap"

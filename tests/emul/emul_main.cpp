@@ -164,6 +164,12 @@ int main(int argc, char** argv)
 		}
 		z.u[1] = z.u[0];
 	}
+	float pf_fail = -1e-3f, pf_pass = -1e-4f; int exact_only = 0;     // as the product computes them (gcm_capi.cu)
+	{
+		std::vector<const HostMesh*> hms;
+		for(auto& zp : zs) hms.push_back(&zp->hm);
+		gcmh::prefilter_thresholds(hms, &pf_fail, &pf_pass, &exact_only);
+	}
 	const int border_mode = getenv("GCM_EMUL_BORDER") ? atoi(getenv("GCM_EMUL_BORDER")) : 2;   // 0 literal, 1 lean, 2 flat (+ literal for what it defers)
 	long n_flat_done = 0, n_flat_deferred = 0;
 	for(auto& zp : zs) {
@@ -181,7 +187,7 @@ int main(int argc, char** argv)
 			m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = nullptr; m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 			m.border_slot = hm.border_slot.data();
 			m.tau = 0.002f; m.time = 0; m.min_h = hm.min_h;
-			m.pf_fail = -1e-3f; m.pf_pass = -1e-4f; m.exact_only = 1;   // as ensure_inner_cache (gcm_capi.cu)
+			m.pf_fail = pf_fail; m.pf_pass = pf_pass; m.exact_only = 1;   // as ensure_inner_cache (gcm_capi.cu)
 			for(int st = 0; st < 3; st++) {
 				z.icache[st].assign(hm.N, gcm::InnerCacheEntry());
 				memset(z.icache[st].data(), 0, hm.N * sizeof(gcm::InnerCacheEntry));
@@ -248,7 +254,7 @@ int main(int argc, char** argv)
 		m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 		m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 		m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
-		m.pf_fail = -1e-3f; m.pf_pass = -1e-4f; m.exact_only = 0;
+		m.pf_fail = pf_fail; m.pf_pass = pf_pass; m.exact_only = exact_only;
 		return m;
 	};
 	for(int step = 0; step < steps && !rc; step++) {
@@ -291,7 +297,7 @@ int main(int argc, char** argv)
 				m.n2t_off = hm.n2t_off.data(); m.n2t = hm.n2t.data(); m.n2x = hm.n2x.data(); m.n2x_scan = hm.n2x.data(); m.tets = hm.tets.data(); m.tet_hv = hm.tet_hv.data();
 				m.border_slot = hm.border_slot.data(); m.basis = hm.basis.data(); m.cond_id = hm.cond_id.data();
 				m.tau = tau; m.time = hm.current_time; m.min_h = hm.min_h;
-				m.pf_fail = -1e-3f; m.pf_pass = -1e-4f; m.exact_only = 0;
+				m.pf_fail = pf_fail; m.pf_pass = pf_pass; m.exact_only = exact_only;
 				m.n_conds = (int)conds.size();
 				for(size_t c = 0; c < conds.size(); c++) {
 					m.conds[c] = conds[c].bc;
@@ -398,6 +404,6 @@ int main(int argc, char** argv)
 		if(tap_step >= 0) write_file(out + ".tap.i32", tap);
 	}
 	if(getenv("GCM_EMUL_BND_STATS")) { fprintf(stderr, "flat defer reasons:"); for(int r = 1; r < 10; r++) fprintf(stderr, " %d:%ld", r, gcm::g_bnd_defer_reason[r]); fprintf(stderr, "\n"); }
-	printf("{\"impl\": \"emul\", \"steps\": %d, \"rc\": %d, \"inner_cached\": %ld, \"inner_cold\": %ld, \"flat_done\": %ld, \"flat_deferred\": %ld}\n", steps, rc, n_cached, n_cold, n_flat_done, n_flat_deferred);
+	printf("{\"impl\": \"emul\", \"steps\": %d, \"rc\": %d, \"inner_cached\": %ld, \"inner_cold\": %ld, \"flat_done\": %ld, \"flat_deferred\": %ld, \"exact_only\": %d, \"pf_pass\": %g}\n", steps, rc, n_cached, n_cold, n_flat_done, n_flat_deferred, exact_only, pf_pass);
 	return rc;
 }

@@ -19,7 +19,7 @@ import util_parity as up  # noqa: E402
 
 
 def main():
-    for name in (sys.argv[1:] or up.CASE_NAMES + up.CPU_ONLY_CASE_NAMES):
+    for name in (sys.argv[1:] or up.CASE_NAMES):
         case = up.make_case(name)
         res = up.run_oracle(case, tap=True)
         d = dict(n_zones=len(res))

@@ -10,7 +10,7 @@ import pytest
 import util_parity as up
 
 
-@pytest.mark.parametrize("name", up.CASE_NAMES + up.CPU_ONLY_CASE_NAMES)
+@pytest.mark.parametrize("name", up.CASE_NAMES)
 def test_emulation_matches_golden(built, name):
     case = up.make_case(name)
     got = up.run_emul(case)

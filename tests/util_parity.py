@@ -106,6 +106,30 @@ def make_case(name):
         m[z.coords[:, 0] > 3.5] = (3e9, 2e9, 2.7e6, 1e16)
         c["materials"] = [m]
         c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=19)]
+    elif name == "far_jitter12":
+        # a jittered body far from the origin: coordinates ~1000 leave ulp(1000)/h ~ 1e-4 of the pre-filter's
+        # 5e-4 margin to the reference's own rounding of the tested point (gcm_capi.cu: prefilter_thresholds)
+        z = meshgen.make_cube(12, jitter=0.2, seed=31)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=32)]
+        c["translates"] = [(0, 1000.0, -500.0, 215.0)]
+        c["seed"] = 77
+    elif name == "far_cube10":
+        # the same translation of a regular (slightly jittered inside) cube: h = 0.5 keeps a positive pass
+        # threshold (4e-5 instead of 1e-4), so the pre-filtered paths run with the tightened margins
+        z = meshgen.make_cube(10, jitter=0.05, seed=33)
+        c["zones"] = [z]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=34)]
+        c["translates"] = [(0, 1000.0, -500.0, 215.0)]
+        c["seed"] = 79
+    elif name == "fine_spacing8":
+        # spacing 1e-2 with a material slow enough that c1 tau stays below the altitude (tau is fixed at 0.002):
+        # every margin of the search is relative to the element size, nothing may depend on a unit spacing
+        z = meshgen.make_cube(8, spacing=(0.01, 0.01, 0.01), jitter=0.2, seed=41)
+        c["zones"] = [z]
+        c["material"] = (LA, MU, 7.8e10, 1e16)
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, 7.8e10, seed=42)]
+        c["seed"] = 78
     elif name == "extvalues8":
         # ExternalValuesCalculator: the three outer rows pin v = (0.5, -0.25, 1.0) on the z = 7 face,
         # and sigma_xz, sigma_yz, sigma_zz on the z = 0 face (vars 5, 7, 8)
@@ -155,12 +179,11 @@ def make_case(name):
     return c
 
 
-# cases checked against the reference through the CPU emulation only so far (no GPU run of them yet)
-CPU_ONLY_CASE_NAMES = ["twomat8", "delaunay7", "delaunay_contact", "delaunay_friction"]
-
 CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zones3_jitter", "plastic8",
               "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static",
-              "contact_offset", "readme_contact", "extvalues8"]
+              "contact_offset", "readme_contact", "extvalues8",
+              "twomat8", "delaunay7", "delaunay_contact", "delaunay_friction",
+              "far_jitter12", "far_cube10", "fine_spacing8"]
 
 
 def _write_inputs(case, d):

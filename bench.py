@@ -9,8 +9,15 @@ Workload (BASELINE.json configs[2], the one the metric is quoted on): elastic cu
 8 z-slab zones with one halo layer, material la=7e9 mu=1e9 rho=7.8e6, plane P-wave initial state,
 tau = 0.002, srand(12345).  One *step* = TetrMeshSet::do_next_step = 3 axis stages + plastic
 stage on every local node, with the halo exchange before each stage.  Strong scaling: the 8 zones
-are dealt to the N ranks (8/N zones per GPU); the cross-rank halo goes over NCCL send/recv.
-One JSON line is printed by rank 0 (see the task contract for the keys).
+are dealt to the N ranks (8/N zones per GPU); the cross-rank halo goes over NVLink (direct peer
+stores into the neighbour's halo slots, NCCL send/recv as the fallback).  The two end slabs carry a
+whole 216^2 face of border nodes each, and a border node costs several inner nodes, so by default
+the slabs are cut for equal work (--layers auto: 24,28,28,28,28,28,28,24 layers) instead of
+equal thickness (--layers equal); config.layers says which.
+One JSON line is printed by rank 0 (see the task contract for the keys).  state_digest = a checksum of
+the values of the nodes >= 80 cells away from the cube's surface after all the steps of the run: it
+does not depend on how the zones are dealt to ranks (the border bases do: every rank owns a rand()
+stream, as every MPI rank of the reference does), so runs at 1/2/4/8 GPUs must print the same one.
 """
 from __future__ import annotations
 
@@ -94,13 +101,44 @@ def zone_owner(n_zones, world):
     return [z * world // n_zones for z in range(n_zones)]
 
 
+def slab_layers(spec, nz_layers, n_zones, border_weight):
+    """Per-zone owned layers.  auto: an end slab's extra face of border nodes costs about
+    `border_weight` layers of inner nodes, so end = mid - border_weight (sum preserved)."""
+    if spec == "equal" or n_zones < 3:
+        if nz_layers % n_zones:
+            raise SystemExit("--size must be divisible by --zones for equal slabs")
+        return [nz_layers // n_zones] * n_zones
+    if spec != "auto":
+        v = [int(x) for x in spec.split(",")]
+        if len(v) != n_zones or sum(v) != nz_layers:
+            raise SystemExit("--layers must list %d values summing to %d" % (n_zones, nz_layers))
+        return v
+    mid = int(round((nz_layers + 2.0 * border_weight) / n_zones))
+    end = (nz_layers - (n_zones - 2) * mid) // 2
+    v = [end] + [mid] * (n_zones - 2) + [nz_layers - (n_zones - 2) * mid - end]
+    if min(v) < 2:
+        return slab_layers("equal", nz_layers, n_zones, border_weight)
+    return v
+
+
+def kernel_source_hash():
+    """sha256 over the kernel sources: stamps measurements that were taken outside this run (ncu)."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "gcm-necro_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cuh", ".cu", ".cpp", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def run_reference(args, rank):
     """The reference's own CPU implementation (oracle/_ref = its sources compiled here), timed on
     the box's host cores on a bounded sample of the same workload."""
     if rank != 0:
         return
     from gcm_b200 import meshgen
-    size, nz = args.ref_size, args.zones
+    size, nz = args.ref_size, args.ref_zones
     if not os.path.exists(ORACLE):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/gcm3d_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
         return
@@ -112,8 +150,8 @@ def run_reference(args, rank):
             meshgen.write_gcmb(mp, z)
             meshgen.pwave_state(z.coords, LA, MU, RHO, z_c=size / 2.0).tofile(sp)
             meshes.append(mp); states.append(sp)
-        cmd = [ORACLE, "--mesh"] + meshes + ["--state"] + states + ["--steps", str(args.steps + args.warmup),
-                                                                      "--warmup", str(args.warmup), "--seed", "12345"]
+        k, w = max(1, min(args.steps, args.ref_steps)), min(args.warmup, 1)
+        cmd = [ORACLE, "--mesh"] + meshes + ["--state"] + states + ["--steps", str(k + w), "--warmup", str(w), "--seed", "12345"]
         r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         print(json.dumps({"impl": "reference", "unavailable": "oracle run failed: " + r.stderr[-200:].replace("\n", " ")}))
@@ -121,11 +159,14 @@ def run_reference(args, rank):
     j = json.loads(r.stdout.strip().splitlines()[-1])
     n_nodes = j["local_nodes"]
     v = n_nodes * j["timed_steps"] / j["seconds"]
-    sample = "%d^3 = %d-node cube in %d zones on one rank, %d steps (same mesh family / material / IC as the 216^3 workload)" % (size, n_nodes, nz, j["timed_steps"])
+    sample = ("%d^3 = %d-node cube in %d zone(s) on one rank, %d timed step(s) of the reference's own do_next_step (same mesh family / "
+              "material / initial state as the 216^3 workload, which needs ~8 GB and ~4 min per step on this path; "
+              "node-updates/s is per node, so the figure carries over)" % (size, n_nodes, nz, j["timed_steps"]))
     line = {"impl": "reference", "metric": "tet node-updates/sec", "value": v, "unit": "node-updates/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * j["seconds"] / j["timed_steps"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "elastic cube 216^3 nodes in 8 zones (BASELINE configs[2]); reference timed on a bounded sample", "sample": sample},
+            "config": {"workload": "elastic cube 216^3 nodes in 8 zones (BASELINE configs[2]); reference timed on a bounded sample", "sample": sample,
+                       "same_mesh_size": False},
             "cpu_baseline": {"value": v, "unit": "node-updates/s", "cores": 1, "kind": "reference", "sample": sample},
             "e2e": {"value": v, "unit": "node-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -161,7 +202,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=216, help="cube side in nodes (216 -> 10 077 696 nodes)")
     ap.add_argument("--zones", type=int, default=8)
-    ap.add_argument("--ref-size", type=int, default=48, help="cube side of the bounded sample of --impl reference")
+    ap.add_argument("--ref-size", type=int, default=100, help="cube side of the bounded sample of --impl reference (100 -> 10^6 nodes, BASELINE configs[1] size)")
+    ap.add_argument("--ref-zones", type=int, default=1)
+    ap.add_argument("--ref-steps", type=int, default=2, help="timed steps of the reference arm (about 11 s each at 10^6 nodes)")
+    ap.add_argument("--layers", default="auto", help="auto | equal | comma list of owned z-layers per zone")
+    ap.add_argument("--border-weight", type=float, default=4.0, help="cost of a face of border nodes in layers of inner nodes (--layers auto)")
     ap.add_argument("--cpu-size", type=int, default=64, help="cube side of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -191,7 +236,8 @@ def main():
     owner = zone_owner(nz, world)
     mine = [z for z in range(nz) if owner[z] == rank]
     t0 = time.time()
-    zones = meshgen.make_box_zones(size, size, size, nz, only=set(mine))
+    layers = slab_layers(args.layers, size, nz, args.border_weight)
+    zones = meshgen.make_box_zones(size, size, size, nz, only=set(mine), layers=layers)
     ms = gcm_b200.TetrMeshSet(n_zones=nz, zone_rank=owner, my_rank=rank, device=local_rank)
     ms.srand(12345)
     for z in mine:
@@ -204,12 +250,18 @@ def main():
     ms.pre_process_meshes()
     n_local = 0
     host = {}
+    deep = {}
     for z in mine:
         m = ms.get_mesh_by_zone_num(z)
         st = meshgen.pwave_state(zones[z].coords, LA, MU, RHO, z_c=size / 2.0)
         m.set_values(st)
         n_local += m.counts()["local_nodes"]
         host[z] = torch.from_numpy(st.copy()).pin_memory()
+        c = zones[z].coords
+        margin = min(80, size // 3)
+        sel = np.all((c >= margin) & (c <= size - 1 - margin), axis=1) & (zones[z].placement == 1)
+        gid = (np.rint(c[sel, 2]).astype(np.int64) * size + np.rint(c[sel, 1]).astype(np.int64)) * size + np.rint(c[sel, 0]).astype(np.int64)
+        deep[z] = (np.nonzero(sel)[0], gid)
     zones = None
     t_setup = time.time() - t0
     stream = torch.cuda.ExternalStream(ms.stream())
@@ -279,7 +331,8 @@ def main():
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the inner kernel on this workload,
         # from the committed ncu --set full capture (profiles/README.md says which)
         t = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-        if args.size == t.get("size") and args.zones == t.get("zones") and world == 1:
+        # only when it was captured from exactly these kernel sources on this workload: a stale figure is worse than none
+        if args.size == t.get("size") and args.zones == t.get("zones") and world == 1 and t.get("kernel_sha") == kernel_source_hash():
             traffic = t["bytes_per_launch"]
     except Exception:
         pass
@@ -289,7 +342,8 @@ def main():
                 "nodes_per_launch": in_units / max(in_launches, 1),
                 "step_frac": value / world * B_STEP / 1e9 / peak,
                 "kernel_timing": "CUDA events around each launch, in a pass with the border stream serialised behind the inner kernel",
-                "kernel_ms_share": {k: v[0] for k, v in prof.items()}}
+                "kernel_ms_share": {k: v[0] for k, v in prof.items()},
+                "kernel_sha": kernel_source_hash(), "coverage": ms.kernel_stats()}
 
     # ---- end to end through the C ABI with HOST buffers ---------------------------------------
     e2e = None
@@ -309,6 +363,21 @@ def main():
                "h2d_bytes_per_step": bytes_io, "d2h_bytes_per_step": bytes_io,
                "note": "per rank: pinned host values[9N] -> device (H2D + transpose), do_next_step, device -> pinned host"}
 
+    # ---- state digest: nodes >= 80 cells from the surface (rank-independent, see the module docstring) ----
+    ms.synchronize()
+    dig = np.zeros(2, np.int64)
+    for z in mine:
+        idx, gid = deep[z]
+        if len(idx):
+            v = ms.get_mesh_by_zone_num(z).get_values()[idx].view(np.uint32).astype(np.int64)
+            wts = (gid % 1000003 + 1)[:, None] * (np.arange(9, dtype=np.int64) + 1)[None, :]
+            dig[0] += int((v * wts % 2147483647).sum() % 2147483647)
+            dig[1] += len(idx)
+    digt = torch.from_numpy(dig).cuda()
+    if world > 1:
+        dist.all_reduce(digt)
+    state_digest = "%d:%d" % (int(digt[1].item()), int(digt[0].item()) % 2147483647)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
@@ -320,10 +389,12 @@ def main():
                 "config": {"workload": "elastic cube %d^3 = %d nodes, 6 tets/hex, %d z-slab zones (BASELINE configs[2]%s)"
                                        % (size, n_total, nz, "; yield 1e7 = configs[3]" if args.yield_limit < 1e15 else ""),
                            "zones_per_gpu": nz // world if nz % world == 0 else [owner.count(r) for r in range(world)],
+                           "layers": layers, "layers_rule": args.layers,
                            "tau": 0.002, "material": [LA, MU, RHO, args.yield_limit], "seed": 12345,
                            "l2": "inputs larger than L2 (state %.0f MB + mesh > 126 MB per GPU)" % (n_total / world * 72 / 1e6),
                            "setup_s": t_setup},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "state_digest": state_digest, "steps_total_before_digest": int(round(ms.current_time() / 0.002))}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -63,6 +63,9 @@ struct PeerPlan {   // exchange with one other process
 	DevBuf<int> d_recv, d_send;                  // merged-mesh indices
 	DevBuf<float> send_buf, recv_buf;            // [9][n] staging of the library-driven (NCCL) exchange
 	bool dev_ready = false;
+	// direct peer stores: the neighbour's mapped buffers and where my send nodes live in its arrays
+	void* map_u0 = nullptr; void* map_u1 = nullptr; void* map_flags = nullptr;
+	unsigned long long peer_rs = 0;
 };
 
 // NCCL entry points, resolved at run time (the library has no link-time dependency on NCCL and
@@ -77,6 +80,7 @@ struct NcclApi {
 	int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
+	int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
 	const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -148,6 +152,13 @@ struct gcm_b200_set {
 	std::map<int, PeerPlan> peers;
 	void* nccl_comm = nullptr;   // library-driven halo exchange (gcm_b200_set_comm_init); NULL = the host moves the halos
 	int comm_rank = -1, comm_size = 0;
+	// direct peer-store exchange (gcm_kernels.cuh: halo_push_kernel / halo_wait_kernel), set up by comm_init
+	bool p2p = true, p2p_ready = false;
+	int p2p_seq = 0;
+	DevBuf<int> p2p_flags, p2p_send_node, p2p_remote_slot, p2p_peer_ranks;
+	DevBuf<unsigned> p2p_counter;
+	DevBuf<gcm::PeerTarget> p2p_more;
+	std::vector<gcm::PeerTarget> p2p_targets;
 	bool plan_built = false;
 	bool preprocessed = false;
 	bool tap_on = false;
@@ -893,6 +904,7 @@ const char* step_error_text(int code)
 	case gcm::ERR_BAD_Q: return "Bad vector q";
 	case gcm::ERR_ZERO_VOLUME: return "Tetr volume is zero";
 	case gcm::ERR_FOOT_PATTERN: return "More than 5 distinct characteristic feet";
+	case gcm::ERR_PEER_TIMEOUT: return "A neighbour process did not deliver its halo nodes";
 	default: return "Unknown device error";
 	}
 }
@@ -903,6 +915,7 @@ int step_error_exc(int code)
 	case gcm::ERR_INTERP_SUM: case gcm::ERR_ZERO_VOLUME: return gcmh::MESH_EXCEPTION;
 	case gcm::ERR_BAD_RHEOLOGY: case gcm::ERR_BAD_Q: return gcmh::CONFIG_EXCEPTION;
 	case gcm::ERR_INNER_NO_OWNER: case gcm::ERR_RING_OVERFLOW: return gcmh::UNIMPLEMENTED_EXCEPTION;
+	case gcm::ERR_PEER_TIMEOUT: return gcmh::SYNC_EXCEPTION;
 	default: return gcmh::METHOD_EXCEPTION;
 	}
 }
@@ -936,6 +949,7 @@ NcclApi& nccl_api()
 	GCM_NCCL_SYM(Recv, "ncclRecv");
 	GCM_NCCL_SYM(GroupStart, "ncclGroupStart");
 	GCM_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+	GCM_NCCL_SYM(AllGather, "ncclAllGather");
 	GCM_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef GCM_NCCL_SYM
 	api.lib = h;
@@ -947,12 +961,127 @@ void nccl_check(int rc, const char* what)
 	if(rc != 0) throw HostError{gcmh::CONFIG_EXCEPTION, std::string("NCCL ") + what + ": " + nccl_api().GetErrorString(rc)};
 }
 
+// Maps every neighbour's record layers and flag array into this process and learns where its send
+// nodes live in the neighbour's arrays.  Collective over the communicator.  Leaves p2p_ready false
+// (the NCCL exchange stays in charge) when anything about it is not available.
+void p2p_setup(gcm_b200_set* s)
+{
+	if(!s->p2p || s->peers.empty() || s->peers.size() > GCM_MAX_PEERS) return;
+	NcclApi& nc = nccl_api();
+	DeviceMesh& dm = s->dm;
+	cudaStream_t st = s->stream;
+	const int R = s->comm_size, me = s->comm_rank;
+	s->p2p_flags.alloc((size_t)R);
+	CK(cudaMemsetAsync(s->p2p_flags.p, 0, R * sizeof(int), st));
+	// 1. everybody's handles: u0, u1, flags (64 bytes each) + rs + ok marker
+	struct Blob { cudaIpcMemHandle_t h[3]; unsigned long long rs; unsigned long long ok; };
+	Blob mine; memset(&mine, 0, sizeof mine);
+	bool ok = cudaIpcGetMemHandle(&mine.h[0], dm.u0.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.h[1], dm.u1.p) == cudaSuccess
+	       && cudaIpcGetMemHandle(&mine.h[2], s->p2p_flags.p) == cudaSuccess;
+	cudaGetLastError();
+	mine.rs = dm.rs; mine.ok = ok ? 1 : 0;
+	DevBuf<char> d_mine, d_all;
+	d_mine.alloc(sizeof(Blob)); d_all.alloc(sizeof(Blob) * (size_t)R);
+	CK(cudaMemcpyAsync(d_mine.p, &mine, sizeof(Blob), cudaMemcpyHostToDevice, st));
+	nccl_check(nc.AllGather(d_mine.p, d_all.p, sizeof(Blob), 0 /* ncclInt8 */, s->nccl_comm, st), "all gather");
+	std::vector<Blob> all((size_t)R);
+	CK(cudaMemcpyAsync(all.data(), d_all.p, sizeof(Blob) * (size_t)R, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	bool all_ok = true;
+	for(int r = 0; r < R; r++) all_ok = all_ok && all[r].ok;
+	// 2. my send nodes' slots in each neighbour's arrays = the neighbour's recv list, in the agreed order
+	std::map<int, DevBuf<int> > remote;
+	for(auto& kv : s->peers) { peer_dev_prepare(s, kv.second); if(!kv.second.send_node.empty()) remote[kv.first].alloc(kv.second.send_node.size()); }
+	nccl_check(nc.GroupStart(), "group start");
+	for(auto& kv : s->peers) {
+		PeerPlan& p = kv.second;
+		if(!p.recv_node.empty()) nccl_check(nc.Send(p.d_recv.p, p.recv_node.size(), 2 /* ncclInt32 */, kv.first, s->nccl_comm, st), "send");
+		if(!p.send_node.empty()) nccl_check(nc.Recv(remote[kv.first].p, p.send_node.size(), 2, kv.first, s->nccl_comm, st), "recv");
+	}
+	nccl_check(nc.GroupEnd(), "group end");
+	CK(cudaStreamSynchronize(st));
+	if(!all_ok) return;
+	// 3. map the neighbours' buffers
+	for(auto& kv : s->peers) {
+		PeerPlan& p = kv.second;
+		const Blob& b = all[kv.first];
+		if(cudaIpcOpenMemHandle(&p.map_u0, b.h[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+		   cudaIpcOpenMemHandle(&p.map_u1, b.h[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+		   cudaIpcOpenMemHandle(&p.map_flags, b.h[2], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = false; }
+		p.peer_rs = b.rs;
+	}
+	// every process must take the same decision: agree on it
+	{
+		int flag = all_ok ? 1 : 0;
+		DevBuf<int> d1, dR; d1.alloc(1); dR.alloc((size_t)R);
+		CK(cudaMemcpyAsync(d1.p, &flag, sizeof(int), cudaMemcpyHostToDevice, st));
+		nccl_check(nc.AllGather(d1.p, dR.p, 1, 2, s->nccl_comm, st), "all gather");
+		std::vector<int> f((size_t)R);
+		CK(cudaMemcpyAsync(f.data(), dR.p, R * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for(int r = 0; r < R; r++) all_ok = all_ok && f[r];
+	}
+	if(!all_ok) return;
+	// 4. concatenated send list + per-neighbour targets
+	std::vector<int> send_all, peer_ranks;
+	size_t n_total = 0;
+	for(auto& kv : s->peers) n_total += kv.second.send_node.size();
+	s->p2p_send_node.alloc(n_total); s->p2p_remote_slot.alloc(n_total);
+	s->p2p_targets.clear();
+	size_t off = 0;
+	for(auto& kv : s->peers) {
+		PeerPlan& p = kv.second;
+		gcm::PeerTarget t;
+		t.u[0] = (float*)p.map_u0; t.u[1] = (float*)p.map_u1; t.rs = p.peer_rs; t.flag = (int*)p.map_flags;
+		t.begin = (int)off; t.end = (int)(off + p.send_node.size());
+		if(!p.send_node.empty()) {
+			CK(cudaMemcpyAsync(s->p2p_send_node.p + off, p.d_send.p, p.send_node.size() * sizeof(int), cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(s->p2p_remote_slot.p + off, remote[kv.first].p, p.send_node.size() * sizeof(int), cudaMemcpyDeviceToDevice, st));
+		}
+		off += p.send_node.size();
+		s->p2p_targets.push_back(t);
+		peer_ranks.push_back(kv.first);
+	}
+	s->p2p_peer_ranks.upload(peer_ranks, st);
+	s->p2p_more.upload(s->p2p_targets, st);
+	s->p2p_counter.alloc(1);
+	CK(cudaMemsetAsync(s->p2p_counter.p, 0, sizeof(unsigned), st));
+	CK(cudaStreamSynchronize(st));
+	(void)me;
+	s->p2p_seq = 0;
+	s->p2p_ready = true;
+}
+
+// The exchange before a stage by peer stores: push my nodes into the neighbours' current layer, raise my
+// flag there, wait for theirs.  A neighbour's current layer is safe to write: nothing of it but local
+// nodes is written by the neighbour's own kernels, and its halo slots were last read two stages ago
+// (the neighbour cannot be further behind than that: I needed its previous push to get here).
+void p2p_exchange(gcm_b200_set* s, cudaStream_t st)
+{
+	DeviceMesh& dm = s->dm;
+	const int np = (int)s->p2p_targets.size();
+	const int n_total = (int)s->p2p_send_node.n;
+	const int seq = ++s->p2p_seq;
+	if(n_total) {
+		ProfScope ps(s, PROF_HALO, n_total, st);
+		const gcm::PeerTarget& t0 = s->p2p_targets[0];
+		const gcm::PeerTarget& t1 = s->p2p_targets[np > 1 ? 1 : 0];
+		gcm::halo_push_kernel<<<(3 * n_total + 255) / 256, 256, 0, st>>>(dm.ucur(), dm.rs, s->p2p_send_node.p, s->p2p_remote_slot.p, n_total,
+			t0, t1, s->p2p_more.p, np, dm.cur, s->comm_rank, seq, s->p2p_counter.p);
+		s->launches++;
+	}
+	gcm::halo_wait_kernel<<<1, 32, 0, st>>>(s->p2p_flags.p, s->p2p_peer_ranks.p, np, seq, s->d_err);
+	s->launches++;
+	CK(cudaGetLastError());
+}
+
 // DataBus::sync_nodes across processes (gcm/system/DataBus.cpp:81-115), all on the set's stream:
 // gather the nodes every neighbour asked for, one grouped ncclSend/ncclRecv per neighbour over
 // NVLink, scatter what arrived into the halo slots.
 void comm_exchange(gcm_b200_set* s, cudaStream_t st)
 {
 	if(s->peers.empty()) return;
+	if(s->p2p_ready) { p2p_exchange(s, st); return; }
 	NcclApi& nc = nccl_api();
 	for(auto& kv : s->peers) {
 		PeerPlan& p = kv.second;
@@ -1052,6 +1181,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_INNER_CACHE")) s->inner_cache = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_FUSE_PLASTIC")) s->fuse_plastic = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_PATTERNS")) s->inner_patterns = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_P2P")) s->p2p = atoi(e) != 0;
 	*out = s.release();
 	return 0;
 	GUARD_END
@@ -1067,6 +1197,13 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		if(s->aux2) { cudaStreamSynchronize(s->aux2); cudaStreamDestroy(s->aux2); }
 		if(s->ev_join2) cudaEventDestroy(s->ev_join2);
 		if(s->rng_stream) cudaStreamSynchronize(s->rng_stream);
+		for(auto& kv : s->peers) {
+			PeerPlan& p = kv.second;
+			if(p.map_u0) cudaIpcCloseMemHandle(p.map_u0);
+			if(p.map_u1) cudaIpcCloseMemHandle(p.map_u1);
+			if(p.map_flags) cudaIpcCloseMemHandle(p.map_flags);
+			p.map_u0 = p.map_u1 = p.map_flags = nullptr;
+		}
 		if(s->nccl_comm) { nccl_api().CommDestroy(s->nccl_comm); s->nccl_comm = nullptr; }
 		prof_drain(s);
 		for(int k = 0; k < 2; k++) { if(s->h_basis[k]) cudaFreeHost(s->h_basis[k]); if(s->basis_ev[k]) cudaEventDestroy(s->basis_ev[k]); }
@@ -1393,6 +1530,7 @@ int gcm_b200_set_comm_init(gcm_b200_set* s, const void* id128, int rank, int n_r
 	memcpy(&id, id128, sizeof id);
 	nccl_check(nccl_api().CommInitRank(&s->nccl_comm, n_ranks, id, rank), "comm init");
 	s->comm_rank = rank; s->comm_size = n_ranks;
+	p2p_setup(s);
 	return 0;
 	GUARD_END
 }

@@ -404,10 +404,22 @@ void HostMesh::pre_process_mesh()
 				if(!(fnr[0]*nn[0] + fnr[1]*nn[1] + fnr[2]*nn[2] > 0.999f)) sharp[s] = 1;
 			}
 		}
+		// flat nodes are grouped by the direction of their normal (26 sectors), node order inside a group:
+		// the 32 nodes of a warp then walk candidate lists of the same shape and take the same branches
+		// (on a box every face is one group; nothing but the launch order depends on this)
+		auto sector = [&](int s) {
+			const float* nn = &normals[3*(size_t)s];
+			int code = 0;
+			for(int k = 0; k < 3; k++) code = code * 3 + (nn[k] > 0.38f ? 2 : (nn[k] < -0.38f ? 0 : 1));
+			return code;
+		};
 		border_launch.clear();
 		for(int s = 0; s < NB; s++) if(sharp[s]) border_launch.push_back(border_nodes[s]);
 		n_sharp = (int)border_launch.size();
-		for(int s = 0; s < NB; s++) if(!sharp[s]) border_launch.push_back(border_nodes[s]);
+		std::vector<std::pair<int, int> > keyed;
+		for(int s = 0; s < NB; s++) if(!sharp[s]) keyed.push_back(std::make_pair(sector(s), border_nodes[s]));
+		std::sort(keyed.begin(), keyed.end());
+		for(size_t q = 0; q < keyed.size(); q++) border_launch.push_back(keyed[q].second);
 	}
 	build_fast_path_tables();
 	preprocessed = true;

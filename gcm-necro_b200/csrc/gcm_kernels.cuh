@@ -72,7 +72,7 @@ stage_deferred_kernel(const __grid_constant__ MeshView m, const int* __restrict_
 // stages run without it at full occupancy.  Whatever the routine defers (ambiguous candidate, alpha
 // retries, ...) is appended to `defer` (defer[0] = count) for the literal routine right behind.
 template<bool LU, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, LU ? 5 : 4)
 stage_border_fast_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
                          float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane,
                          const BndSlotStatic* __restrict__ bstat, const float4* __restrict__ cand, int* __restrict__ defer)
@@ -211,6 +211,63 @@ __global__ void halo_unpack_kernel(float* __restrict__ u, size_t rs, const float
 	#pragma unroll
 	for(int k = 0; k < 9; k++)
 		rec_set(u, rs, d, k, buf[(size_t)k * n_total + offset + i]);
+}
+
+// ---- cross-process halo by direct peer stores (DataBus::sync_nodes, gcm/system/DataBus.cpp:81-115) -------
+// The record buffers and a small flag array of every neighbour process are mapped into this process
+// (cudaIpcOpenMemHandle, once); before a stage each process WRITES the records of the nodes its
+// neighbours asked for straight into their halo slots over NVLink and then raises its flag in the
+// neighbour's flag array; the neighbour waits for the flag before its stage kernels start.  One small
+// kernel on either side instead of pack -> ncclSend/ncclRecv -> unpack.
+struct PeerTarget {
+	float* u[2];                 // the neighbour's two record layers (mapped)
+	unsigned long long rs;       // its quads per plane
+	int* flag;                   // its flag array (mapped); entry [my rank] is mine to raise
+	int begin, end;              // my range in the concatenated send list
+};
+#define GCM_MAX_PEERS 8
+
+// entries [begin, end) of peer k: quad q of my node send_node[i] -> quad q of the peer's node remote_slot[i].
+// The last block to finish (all stores fenced system-wide) raises the flags.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const float* __restrict__ u, size_t rs, const int* __restrict__ send_node, const int* __restrict__ remote_slot,
+                 int n_total, const __grid_constant__ PeerTarget t0, const __grid_constant__ PeerTarget t1,
+                 const PeerTarget* __restrict__ more, int n_peers, int layer, int my_rank, int seq, unsigned* __restrict__ done_counter)
+{
+	const int g = blockIdx.x * blockDim.x + threadIdx.x;
+	const int q = g / n_total, i = g - q * n_total;
+	if(q < 3) {
+		PeerTarget t = t0;
+		if(n_peers > 1 && i >= t1.begin && i < t1.end) t = t1;
+		for(int k = 2; k < n_peers; k++) if(i >= more[k].begin && i < more[k].end) t = more[k];
+		const float4 v = rec_quad(u, rs, send_node[i], q);
+		reinterpret_cast<float4*>(t.u[layer])[(size_t)q * t.rs + (size_t)remote_slot[i]] = v;
+	}
+	__threadfence_system();
+	__shared__ bool last;
+	__syncthreads();
+	if(threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+	__syncthreads();
+	if(last && threadIdx.x < n_peers) {
+		const PeerTarget& t = threadIdx.x == 0 ? t0 : (threadIdx.x == 1 ? t1 : more[threadIdx.x]);
+		__threadfence_system();
+		*reinterpret_cast<volatile int*>(t.flag + my_rank) = seq;
+		if(threadIdx.x == 0) *done_counter = 0;
+	}
+}
+
+// One thread per neighbour: wait until its flag reaches seq.  A neighbour that never arrives is reported
+// (SYNC error) after ~2 s instead of hanging the device.
+__global__ void halo_wait_kernel(const int* __restrict__ flags, const int* __restrict__ peer_ranks, int n_peers, int seq, int* err)
+{
+	const int k = threadIdx.x;
+	if(k >= n_peers) return;
+	const volatile int* f = flags + peer_ranks[k];
+	const long long t0 = clock64();
+	while(*f < seq) {
+		__nanosleep(200);
+		if(clock64() - t0 > 4000000000ll) { if(atomicCAS(&err[0], 0, ERR_PEER_TIMEOUT) == 0) { err[1] = -1; err[2] = peer_ranks[k]; err[3] = seq; } break; }
+	}
 }
 
 // ---- the per-step random local bases, generated on the device ------------------------------

@@ -59,7 +59,7 @@ def _slab_tets(nx: int, ny: int, nlayers: int) -> np.ndarray:
 
 def make_box_zones(nx: int, ny: int, nz: int, n_zones: int = 1, spacing=(1.0, 1.0, 1.0),
                    origin=(0.0, 0.0, 0.0), jitter: float = 0.0, jitter_border: bool = False,
-                   seed: int = 0, only=None) -> list[ZoneMesh]:
+                   seed: int = 0, only=None, layers=None) -> list[ZoneMesh]:
     """nx x ny x nz node box split into n_zones z-slabs, create_cube.c semantics.
 
     With nx == ny == nz == N*M and n_zones == N this is exactly ``create_cube`` with
@@ -68,10 +68,19 @@ def make_box_zones(nx: int, ny: int, nz: int, n_zones: int = 1, spacing=(1.0, 1.
     the offset is a function of the GLOBAL node id, so every zone sees the same coordinates.
     ``only`` = iterable of zone numbers to build (others are returned as None): a rank of a
     multi-process run builds only the zones it owns.
+    ``layers`` = per-zone number of owned z-layers (sum = nz) for slabs of unequal thickness (the end
+    slabs carry a whole face of border nodes: thinner end slabs balance the work per zone).
     """
-    if nz % n_zones:
-        raise ValueError("nz must be divisible by n_zones")
-    m = nz // n_zones
+    if layers is None:
+        if nz % n_zones:
+            raise ValueError("nz must be divisible by n_zones")
+        layers = [nz // n_zones] * n_zones
+    layers = [int(x) for x in layers]
+    if len(layers) != n_zones or sum(layers) != nz or min(layers) < 2:
+        raise ValueError("layers must give every zone >= 2 layers and sum to nz")
+    start = [0]
+    for x in layers:
+        start.append(start[-1] + x)
     sp = np.asarray(spacing, np.float64); org = np.asarray(origin, np.float64)
     kk, jj, ii = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     ijk = np.stack([ii.ravel(), jj.ravel(), kk.ravel()], 1)
@@ -90,24 +99,24 @@ def make_box_zones(nx: int, ny: int, nz: int, n_zones: int = 1, spacing=(1.0, 1.
         if only is not None and n not in only:
             zones.append(None)
             continue
-        k_lo = n * m - (1 if n > 0 else 0)
-        k_hi = (n + 1) * m + (1 if n < n_zones - 1 else 0)   # exclusive
+        k_lo = start[n] - (1 if n > 0 else 0)
+        k_hi = start[n + 1] + (1 if n < n_zones - 1 else 0)   # exclusive
         nl = k_hi - k_lo
         gid = np.arange(k_lo * layer, k_hi * layer)
         coords = xyz[gid].copy()
         placement = np.ones(nl * layer, np.int32)
         rz = np.full(nl * layer, -1, np.int32)
         rn = np.full(nl * layer, -1, np.int32)
-        if n > 0:   # low halo layer k = n*m-1, owned by zone n-1
-            lo_prev = (n - 1) * m - (1 if n - 1 > 0 else 0)
+        if n > 0:   # low halo layer k = start[n]-1, owned by zone n-1
+            lo_prev = start[n - 1] - (1 if n - 1 > 0 else 0)
             sl = slice(0, layer)
             placement[sl] = 0; rz[sl] = n - 1
-            rn[sl] = (n * m - 1 - lo_prev) * layer + np.arange(layer)
-        if n < n_zones - 1:  # top halo layer k = (n+1)*m, owned by zone n+1
-            lo_next = (n + 1) * m - 1
+            rn[sl] = (start[n] - 1 - lo_prev) * layer + np.arange(layer)
+        if n < n_zones - 1:  # top halo layer k = start[n+1], owned by zone n+1
+            lo_next = start[n + 1] - 1
             sl = slice((nl - 1) * layer, nl * layer)
             placement[sl] = 0; rz[sl] = n + 1
-            rn[sl] = ((n + 1) * m - lo_next) * layer + np.arange(layer)
+            rn[sl] = (start[n + 1] - lo_next) * layer + np.arange(layer)
         zones.append(ZoneMesh(n, coords, placement, rz, rn, _slab_tets(nx, ny, nl)))
     return zones
 

@@ -394,7 +394,7 @@ def main():
                            "l2": "inputs larger than L2 (state %.0f MB + mesh > 126 MB per GPU)" % (n_total / world * 72 / 1e6),
                            "setup_s": t_setup},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "state_digest": state_digest, "steps_total_before_digest": int(round(ms.current_time() / 0.002))}
+                "state_digest": state_digest, "steps_total_before_digest": int(round(ms.get_current_time() / 0.002))}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

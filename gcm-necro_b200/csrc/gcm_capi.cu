@@ -789,6 +789,14 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap, s->d_deep.p, 1);
 			s->launches += 2;
 		};
+		// a partner that was already advanced is read in its NEXT layer; its Remote (halo) entries are not written by
+		// a stage and keep the values synced before it (the copy-back loop, TetrMesh_1stOrder.cpp:1925-1932, touches
+		// local nodes only), so those slots are carried over from the current layer first
+		if(dm.n_halo && (z ? z->c1_n : s->virt.size())) {
+			const int n = (int)dm.n_halo;
+			gcm::halo_copy_kernel<<<(3 * n + 255) / 256, 256, 0, s->stream>>>(dm.unext(), dm.halo_dst.p, dm.ucur(), dm.halo_dst.p, n, dm.rs);
+			s->launches++;
+		}
 		if(z) { launch(z->c0_off, z->c0_n, 0, zone); launch(z->c1_off, z->c1_n, 1, zone); }
 		else {
 			launch(0, s->c0_total, 0, -1);

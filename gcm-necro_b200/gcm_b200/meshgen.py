@@ -76,8 +76,8 @@ def make_box_zones(nx: int, ny: int, nz: int, n_zones: int = 1, spacing=(1.0, 1.
             raise ValueError("nz must be divisible by n_zones")
         layers = [nz // n_zones] * n_zones
     layers = [int(x) for x in layers]
-    if len(layers) != n_zones or sum(layers) != nz or min(layers) < 2:
-        raise ValueError("layers must give every zone >= 2 layers and sum to nz")
+    if len(layers) != n_zones or sum(layers) != nz or min(layers) < 1:
+        raise ValueError("layers must give every zone >= 1 layer and sum to nz")
     start = [0]
     for x in layers:
         start.append(start[-1] + x)

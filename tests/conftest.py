@@ -19,7 +19,16 @@ def built():
     """Make sure the native pieces exist (library, emulation harness, oracle when possible)."""
     import util_parity as up
     import gcm_b200
-    if not (os.path.exists(gcm_b200.library_path()) and os.path.exists(up.EMUL)):
+    src = [os.path.join(ROOT, "tests", "emul", "emul_main.cpp")]
+    csrc = os.path.join(ROOT, "gcm-necro_b200", "csrc")
+    src += [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
+    newest = max(os.path.getmtime(f) for f in src)
+    built_files = [gcm_b200.library_path(), up.EMUL]
+    # a stale binary would silently validate old code: rebuild when any source is newer (a snapshot
+    # copied to another box keeps no useful mtimes, so there only missing files trigger a build)
+    stale = any(not os.path.exists(f) for f in built_files) or \
+        (os.path.isdir("/root/reference") and any(os.path.getmtime(f) < newest for f in built_files))
+    if stale:
         import __graft_entry__ as g
         g.build()
     return True

@@ -376,6 +376,10 @@ int main(int argc, char** argv)
 					}
 				}
 				if(err) rc = 10 + err;
+				// the copy-back loop (TetrMesh_1stOrder.cpp:1925-1932) touches local nodes only: a Remote entry keeps the
+				// value synced before the stage, and that is what a later mesh's virtual nodes read in this mesh
+				for(int i = 0; i < hm.N; i++)
+					if(!(hm.flags[i] & 2)) for(int k = 0; k < 9; k++) un[gcm::rec_index(z.rs, i, k)] = ucur[gcm::rec_index(z.rs, i, k)];
 				z.cur ^= 1;
 			}
 		}

@@ -154,6 +154,21 @@ def make_case(name):
         c["detector"] = "brute"
         c["static"] = name.endswith("_static")
         c["contact_calc"] = "friction" if name.startswith("friction") else "adhesion"
+    elif name in ("contact_zones2", "friction_zones2"):
+        # a contact body split into two zones of one process: the upper zone of body A owns ONE node layer (the
+        # contact face) over its halo layer, so every owner tetrahedron of a virtual node inside it has halo
+        # vertices; body B (zone 2, advanced after body A) must read those at the values synced before the
+        # stage, not what the owner zone wrote since (TetrMeshSet.cpp:148-167 advances the meshes in turn)
+        zs = meshgen.make_box_zones(6, 6, 6, 2, jitter=0.1, seed=51, layers=[5, 1])
+        zb = meshgen.make_cube(6)
+        zb.zone = 2
+        c["zones"] = zs + [zb]
+        c["translates"] = [(2, 0.0, 0.0, 5.01)]
+        c["states"] = [meshgen.generic_state(z.coords, LA, MU, RHO, seed=52) for z in zs] + [meshgen.generic_state(zb.coords, LA, MU, RHO, seed=53)]
+        c["detector"] = "brute"
+        c["static"] = False
+        c["contact_calc"] = "friction" if name.startswith("friction") else "adhesion"
+        c["tap_step"] = 2
     elif name == "readme_contact":
         # BASELINE configs[0]: tasks/friction-test.xml + basic-contact-task-1cpu-zones.xml.  gmsh is not
         # available, so the two bodies are structured boxes of the same extents and point spacing
@@ -183,7 +198,7 @@ CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zo
               "extforce8", "fixed_extvel8", "contact6", "contact6_static", "friction6", "friction6_static",
               "contact_offset", "readme_contact", "extvalues8",
               "twomat8", "delaunay7", "delaunay_contact", "delaunay_friction",
-              "far_jitter12", "far_cube10", "fine_spacing8"]
+              "far_jitter12", "far_cube10", "fine_spacing8", "contact_zones2", "friction_zones2"]
 
 
 def _write_inputs(case, d):

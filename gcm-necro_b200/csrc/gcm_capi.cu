@@ -12,6 +12,7 @@
 #include "gcm_kernels.cuh"
 
 #include <dlfcn.h>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -64,7 +65,8 @@ struct PeerPlan {   // exchange with one other process
 	DevBuf<float> send_buf, recv_buf;            // [9][n] staging of the library-driven (NCCL) exchange
 	bool dev_ready = false;
 	// direct peer stores: the neighbour's mapped buffers and where my send nodes live in its arrays
-	void* map_u0 = nullptr; void* map_u1 = nullptr; void* map_flags = nullptr;
+	void* map_u0 = nullptr; void* map_u1 = nullptr; void* map_flags = nullptr;    // what cudaIpcOpenMemHandle returned (to close)
+	float* peer_u[2] = {nullptr, nullptr}; int* peer_flags = nullptr;             // the neighbour's arrays inside those mappings
 	unsigned long long peer_rs = 0;
 };
 
@@ -119,6 +121,7 @@ struct DeviceMesh {
 	DevBuf<int> border_list, fast_list, generic_list, inner_list;
 	size_t n_sharp = 0, n_flat = 0;
 	DevBuf<unsigned char> mat_id;
+	DevBuf<float> destr_hist;        // [N] float4 running maxima of calc_destruction_criterias, when tracked
 	DevBuf<gcm::StageTap> tap;
 	DevBuf<int> halo_dst, halo_src;
 	size_t n_halo = 0;
@@ -171,6 +174,7 @@ struct gcm_b200_set {
 	bool flat_border = true;     // border nodes through gcm_border.cuh (0 = the literal per-node routine for every border node)
 	bool inner_cache = true;     // inner nodes through the step-invariant owner/factor cache (gcm_inner.cuh); 0 = index-free scan kernel
 	bool inner_patterns = true;  // de-duplicate the cache into a pattern table where an axis has few distinct entries
+	bool track_destruction = false;   // calc_destruction_criterias at the end of every step (its running maxima need every step)
 	bool fuse_plastic = true;    // whole-step calls: stage 3 as the epilogue of the stage-2 writers (and no exchange before it)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
@@ -969,6 +973,26 @@ void nccl_check(int rc, const char* what)
 	if(rc != 0) throw HostError{gcmh::CONFIG_EXCEPTION, std::string("NCCL ") + what + ": " + nccl_api().GetErrorString(rc)};
 }
 
+// Base address of the allocation p lies in (cuMemGetAddressRange through the runtime's driver entry points: the
+// library does not link libcuda).  An IPC handle always names a whole allocation, and cudaIpcOpenMemHandle returns
+// its base: a pointer the driver carved out of a larger block (small cudaMalloc's share 2 MiB blocks) must travel
+// as handle-of-base + offset.
+bool allocation_base(const void* p, char** base)
+{
+	typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+	static range_fn fn = nullptr;
+	if(!fn) {
+		void* f = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if(cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || !f) { cudaGetLastError(); return false; }
+		fn = (range_fn)f;
+	}
+	unsigned long long b = 0; size_t sz = 0;
+	if(fn(&b, &sz, (unsigned long long)(uintptr_t)p) != 0) return false;
+	*base = (char*)(uintptr_t)b;
+	return true;
+}
+
 // Maps every neighbour's record layers and flag array into this process and learns where its send
 // nodes live in the neighbour's arrays.  Collective over the communicator.  Leaves p2p_ready false
 // (the NCCL exchange stays in charge) when anything about it is not available.
@@ -979,14 +1003,24 @@ void p2p_setup(gcm_b200_set* s)
 	DeviceMesh& dm = s->dm;
 	cudaStream_t st = s->stream;
 	const int R = s->comm_size, me = s->comm_rank;
-	s->p2p_flags.alloc((size_t)R);
-	CK(cudaMemsetAsync(s->p2p_flags.p, 0, R * sizeof(int), st));
-	// 1. everybody's handles: u0, u1, flags (64 bytes each) + rs + ok marker
-	struct Blob { cudaIpcMemHandle_t h[3]; unsigned long long rs; unsigned long long ok; };
+	const bool dbg = getenv("GCM_B200_P2P_DEBUG") != nullptr;
+	// flags[r] = sequence number raised by rank r; flags[R + r] = scratch of the mapping check below.
+	// Its own 2 MiB allocation: nothing else of this process becomes visible to the neighbours through the handle.
+	s->p2p_flags.alloc((size_t)(2u << 20) / sizeof(int));
+	CK(cudaMemsetAsync(s->p2p_flags.p, 0, 2 * (size_t)R * sizeof(int), st));
+	// 1. everybody's handles: u0, u1, flags (handle of the allocation + offset inside it) + rs + ok marker
+	struct Blob { cudaIpcMemHandle_t h[3]; unsigned long long off[3]; unsigned long long rs; unsigned long long ok; };
 	Blob mine; memset(&mine, 0, sizeof mine);
-	bool ok = cudaIpcGetMemHandle(&mine.h[0], dm.u0.p) == cudaSuccess && cudaIpcGetMemHandle(&mine.h[1], dm.u1.p) == cudaSuccess
-	       && cudaIpcGetMemHandle(&mine.h[2], s->p2p_flags.p) == cudaSuccess;
-	cudaGetLastError();
+	bool ok = true;
+	{
+		const void* ptr[3] = {dm.u0.p, dm.u1.p, s->p2p_flags.p};
+		for(int k = 0; k < 3 && ok; k++) {
+			char* base = nullptr;
+			ok = allocation_base(ptr[k], &base) && cudaIpcGetMemHandle(&mine.h[k], base) == cudaSuccess;
+			if(ok) mine.off[k] = (unsigned long long)((const char*)ptr[k] - base);
+		}
+		cudaGetLastError();
+	}
 	mine.rs = dm.rs; mine.ok = ok ? 1 : 0;
 	DevBuf<char> d_mine, d_all;
 	d_mine.alloc(sizeof(Blob)); d_all.alloc(sizeof(Blob) * (size_t)R);
@@ -1008,7 +1042,20 @@ void p2p_setup(gcm_b200_set* s)
 	}
 	nccl_check(nc.GroupEnd(), "group end");
 	CK(cudaStreamSynchronize(st));
-	if(!all_ok) return;
+	// every process must take the same decision at every point it could give up: agree on it
+	auto agree = [&](bool mine_ok) {
+		int flag = mine_ok ? 1 : 0;
+		DevBuf<int> d1, dR; d1.alloc(1); dR.alloc((size_t)R);
+		CK(cudaMemcpyAsync(d1.p, &flag, sizeof(int), cudaMemcpyHostToDevice, st));
+		nccl_check(nc.AllGather(d1.p, dR.p, 1, 2, s->nccl_comm, st), "all gather");
+		std::vector<int> f((size_t)R);
+		CK(cudaMemcpyAsync(f.data(), dR.p, R * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		bool r = true;
+		for(int k = 0; k < R; k++) r = r && f[k];
+		return r;
+	};
+	if(!all_ok) { if(dbg) fprintf(stderr, "[gcm_b200 p2p %d] no IPC handles\n", me); return; }
 	// 3. map the neighbours' buffers
 	for(auto& kv : s->peers) {
 		PeerPlan& p = kv.second;
@@ -1017,20 +1064,46 @@ void p2p_setup(gcm_b200_set* s)
 		   cudaIpcOpenMemHandle(&p.map_u1, b.h[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
 		   cudaIpcOpenMemHandle(&p.map_flags, b.h[2], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = false; }
 		p.peer_rs = b.rs;
+		p.peer_u[0] = p.map_u0 ? (float*)((char*)p.map_u0 + b.off[0]) : nullptr;
+		p.peer_u[1] = p.map_u1 ? (float*)((char*)p.map_u1 + b.off[1]) : nullptr;
+		p.peer_flags = p.map_flags ? (int*)((char*)p.map_flags + b.off[2]) : nullptr;
+		if(dbg) fprintf(stderr, "[gcm_b200 p2p %d] peer %d: u0 %p+%llu u1 %p+%llu flags %p+%llu rs %llu send %zu recv %zu\n", me, kv.first,
+			p.map_u0, b.off[0], p.map_u1, b.off[1], p.map_flags, b.off[2], b.rs, p.send_node.size(), p.recv_node.size());
 	}
-	// every process must take the same decision: agree on it
+	if(!agree(all_ok)) { if(dbg) fprintf(stderr, "[gcm_b200 p2p %d] mapping failed somewhere\n", me); return; }
+	// 4. check the mapping end to end before trusting it with the state: a token into every neighbour's scratch
+	// flag and into the padding record (index N = rs - 1, never a node) of both its layers, then read back what arrived here
 	{
-		int flag = all_ok ? 1 : 0;
-		DevBuf<int> d1, dR; d1.alloc(1); dR.alloc((size_t)R);
-		CK(cudaMemcpyAsync(d1.p, &flag, sizeof(int), cudaMemcpyHostToDevice, st));
-		nccl_check(nc.AllGather(d1.p, dR.p, 1, 2, s->nccl_comm, st), "all gather");
-		std::vector<int> f((size_t)R);
-		CK(cudaMemcpyAsync(f.data(), dR.p, R * sizeof(int), cudaMemcpyDeviceToHost, st));
+		const int token = 0x5eed0000 + me;
+		for(auto& kv : s->peers) {
+			PeerPlan& p = kv.second;
+			CK(cudaMemcpyAsync(p.peer_flags + R + me, &token, sizeof(int), cudaMemcpyHostToDevice, st));
+			const float ft = (float)(1000 + me);
+			for(int l = 0; l < 2; l++)
+				CK(cudaMemcpyAsync(p.peer_u[l] + 4 * ((size_t)((me % 12) / 4) * p.peer_rs + (p.peer_rs - 1)) + me % 4, &ft, sizeof(float), cudaMemcpyHostToDevice, st));
+		}
 		CK(cudaStreamSynchronize(st));
-		for(int r = 0; r < R; r++) all_ok = all_ok && f[r];
+		agree(true);                       // barrier: every token is on its way before anybody looks
+		bool good = true;
+		std::vector<int> fl(2 * (size_t)R);
+		CK(cudaMemcpyAsync(fl.data(), s->p2p_flags.p, 2 * (size_t)R * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		for(auto& kv : s->peers) {
+			good = good && fl[R + kv.first] == 0x5eed0000 + kv.first;
+			// rank r writes float r % 12 of the padding record (two neighbours congruent mod 12: the check fails, NCCL stays)
+			for(int l = 0; l < 2; l++) {
+				float got = 0;
+				const float* src = (l ? dm.u1.p : dm.u0.p) + 4 * ((size_t)((kv.first % 12) / 4) * dm.rs + (dm.rs - 1)) + kv.first % 4;
+				CK(cudaMemcpy(&got, src, sizeof(float), cudaMemcpyDeviceToHost));
+				good = good && got == (float)(1000 + kv.first);
+				const float zero = 0;
+				CK(cudaMemcpy((void*)src, &zero, sizeof(float), cudaMemcpyHostToDevice));
+			}
+		}
+		if(dbg) fprintf(stderr, "[gcm_b200 p2p %d] mapping check %s\n", me, good ? "passed" : "FAILED");
+		if(!agree(good)) return;
 	}
-	if(!all_ok) return;
-	// 4. concatenated send list + per-neighbour targets
+	// 5. concatenated send list + per-neighbour targets
 	std::vector<int> send_all, peer_ranks;
 	size_t n_total = 0;
 	for(auto& kv : s->peers) n_total += kv.second.send_node.size();
@@ -1040,7 +1113,7 @@ void p2p_setup(gcm_b200_set* s)
 	for(auto& kv : s->peers) {
 		PeerPlan& p = kv.second;
 		gcm::PeerTarget t;
-		t.u[0] = (float*)p.map_u0; t.u[1] = (float*)p.map_u1; t.rs = p.peer_rs; t.flag = (int*)p.map_flags;
+		t.u[0] = p.peer_u[0]; t.u[1] = p.peer_u[1]; t.rs = p.peer_rs; t.flag = p.peer_flags;
 		t.begin = (int)off; t.end = (int)(off + p.send_node.size());
 		if(!p.send_node.empty()) {
 			CK(cudaMemcpyAsync(s->p2p_send_node.p + off, p.d_send.p, p.send_node.size() * sizeof(int), cudaMemcpyDeviceToDevice, st));
@@ -1050,12 +1123,30 @@ void p2p_setup(gcm_b200_set* s)
 		s->p2p_targets.push_back(t);
 		peer_ranks.push_back(kv.first);
 	}
+	{
+		// every slot must lie inside the neighbour's node range (a mismatch of the two lists would write anywhere)
+		std::vector<int> rs_host(n_total), sn_host(n_total);
+		if(n_total) {
+			CK(cudaMemcpyAsync(rs_host.data(), s->p2p_remote_slot.p, n_total * sizeof(int), cudaMemcpyDeviceToHost, st));
+			CK(cudaMemcpyAsync(sn_host.data(), s->p2p_send_node.p, n_total * sizeof(int), cudaMemcpyDeviceToHost, st));
+		}
+		CK(cudaStreamSynchronize(st));
+		bool good = true;
+		for(size_t k = 0; k < s->p2p_targets.size(); k++) {
+			const gcm::PeerTarget& t = s->p2p_targets[k];
+			int lo = 0x7fffffff, hi = -1;
+			for(int i = t.begin; i < t.end; i++) { lo = std::min(lo, rs_host[i]); hi = std::max(hi, rs_host[i]); }
+			if(t.end > t.begin && (lo < 0 || (unsigned long long)hi + 1 >= t.rs)) good = false;
+			if(dbg && t.end > t.begin) fprintf(stderr, "[gcm_b200 p2p %d] target %zu (rank %d): entries [%d, %d) my nodes %d..%d -> its slots %d..%d (range %d..%d) of rs %llu\n",
+				me, k, peer_ranks[k], t.begin, t.end, sn_host[t.begin], sn_host[t.end - 1], rs_host[t.begin], rs_host[t.end - 1], lo, hi, t.rs);
+		}
+		if(!agree(good)) { if(dbg) fprintf(stderr, "[gcm_b200 p2p %d] slot lists out of range somewhere\n", me); return; }
+	}
 	s->p2p_peer_ranks.upload(peer_ranks, st);
 	s->p2p_more.upload(s->p2p_targets, st);
 	s->p2p_counter.alloc(1);
 	CK(cudaMemsetAsync(s->p2p_counter.p, 0, sizeof(unsigned), st));
 	CK(cudaStreamSynchronize(st));
-	(void)me;
 	s->p2p_seq = 0;
 	s->p2p_ready = true;
 }
@@ -1512,9 +1603,55 @@ int gcm_b200_set_end_step(gcm_b200_set* s)
 	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed");
 	// proceed_rheology: VoidRheologyCalculator (no-op); calc_destruction_criterias: evaluated on
 	// download; update_current_time (TetrMesh_1stOrder.cpp:2403-2406)
+	if(s->track_destruction && s->dm.ready && s->dm.N) {
+		// calc_destruction_criterias (TetrMeshSet.cpp:177-178): the criteria of the current values are evaluated when
+		// they are read (gcm_b200_zone_get_destruction_criterias); the running maxima need every step
+		GUARD_BEGIN
+		CK(cudaSetDevice(s->device));
+		DeviceMesh& dm = s->dm;
+		gcm::destruction_history_kernel<<<(int)((dm.N + 255) / 256), 256, 0, s->stream>>>(dm.ucur(), dm.rs, dm.flags.p, (int)dm.N,
+			reinterpret_cast<float4*>(dm.destr_hist.p));
+		s->launches++;
+		CK(cudaGetLastError());
+		GUARD_END
+	}
 	for(int zi : s->local_zones) s->zones[zi]->hm.current_time += s->time_step;
 	s->step_count++;
 	return 0;
+}
+
+int gcm_b200_set_track_destruction(gcm_b200_set* s, int on)
+{
+	GUARD_BEGIN
+	NEED_DEVICE(s);
+	DeviceMesh& dm = s->dm;
+	if(on && !dm.destr_hist.p && dm.N) {
+		dm.destr_hist.alloc(4 * dm.N);
+		CK(cudaMemsetAsync(dm.destr_hist.p, 0, 4 * dm.N * sizeof(float), s->stream));
+	}
+	s->track_destruction = on != 0;
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_zone_get_destruction_criterias(gcm_b200_set* s, int zone, float* out8)
+{
+	GUARD_BEGIN
+	NEED_DEVICE(s);
+	Zone* z = get_zone(s, zone);
+	if(!z || !out8) return fail(gcmh::CONFIG_EXCEPTION, "zone is not local to this process");
+	DeviceMesh& dm = s->dm;
+	const int n = z->hm.N;
+	if(!n) return 0;
+	DevBuf<float> tmp; tmp.alloc(8 * (size_t)n);
+	// before the first step every criterion is 0 (load_msh_file zeroes them, TetrMesh_1stOrder.cpp:793)
+	gcm::destruction_gather_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(tmp.p, dm.ucur(), dm.rs, dm.flags.p,
+		reinterpret_cast<const float4*>(dm.destr_hist.p), (int)z->node_off, n, s->step_count > 0 ? 1 : 0);
+	s->launches++;
+	CK(cudaMemcpyAsync(out8, tmp.p, 8 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	return 0;
+	GUARD_END
 }
 
 int gcm_b200_comm_get_unique_id(void* id128)
@@ -1856,6 +1993,7 @@ int gcm_b200_set_kernel_stats(gcm_b200_set* s, long long* out16)
 		out16[10] = s->h_err[4];
 	}
 	out16[11] = dm.exact_only;
+	out16[12] = s->p2p_ready ? 1 : 0;
 	return 0;
 	GUARD_END
 }

@@ -176,6 +176,49 @@ plastic_kernel(float* __restrict__ u, size_t rs, const float* __restrict__ mat, 
 	}
 }
 
+// calc_destruction_criterias (TetrMesh_1stOrder.cpp:1957-1995), end of every step when tracking is on: the
+// running maxima hist[node] = (compression, tension, shear, deviator)_history of local nodes.
+__global__ void __launch_bounds__(256)
+destruction_history_kernel(const float* __restrict__ u, size_t rs, const int* __restrict__ flags, int n, float4* __restrict__ hist)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i >= n) return;
+	if((flags[i] & (NF_LOCAL | NF_USED)) != (NF_LOCAL | NF_USED)) return;
+	float v[9], c[4];
+	#pragma unroll
+	for(int k = 0; k < 9; k++) v[k] = rec_get(u, rs, i, k);
+	destruction_now(v, c);
+	float4 h = hist[i];
+	if(c[0] > h.x) h.x = c[0];
+	if(c[1] > h.y) h.y = c[1];
+	if(c[2] > h.z) h.z = c[2];
+	if(c[3] > h.w) h.w = c[3];
+	hist[i] = h;
+}
+
+// ElasticNode::destruction_criterias[8] of a node range, node-major: the four criteria of the current values, then
+// their running maxima (zeros when tracking was never switched on; remote nodes: zeros, as load_msh_file leaves them).
+__global__ void __launch_bounds__(256)
+destruction_gather_kernel(float* __restrict__ out8, const float* __restrict__ u, size_t rs, const int* __restrict__ flags,
+                          const float4* __restrict__ hist, int first, int n, int have_now)
+{
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if(k >= n) return;
+	const int i = first + k;
+	float c[4] = {0.f, 0.f, 0.f, 0.f};
+	float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+	if(have_now && (flags[i] & (NF_LOCAL | NF_USED)) == (NF_LOCAL | NF_USED)) {
+		float v[9];
+		#pragma unroll
+		for(int q = 0; q < 9; q++) v[q] = rec_get(u, rs, i, q);
+		destruction_now(v, c);
+		if(hist) h = hist[i];
+	}
+	float4* o = reinterpret_cast<float4*>(out8 + 8 * (size_t)k);
+	o[0] = make_float4(c[0], c[1], c[2], c[3]);
+	o[1] = h;
+}
+
 // DataBus::sync_nodes, same-process branch (gcm/system/DataBus.cpp:64-79): halo node records of one
 // zone copied from the owner zone's nodes, three threads per node, one 16-byte quad each (the third
 // quad carries the coordinates, which are equal on both sides since the start-up sync).

@@ -479,6 +479,29 @@ GCM_HD bool plastic_epilogue(float v[9], float yield_limit)
 	return true;
 }
 
+// TetrMesh_1stOrder::calc_destruction_criterias (gcm/meshtypes/TetrMesh_1stOrder.cpp:1957-1995), the part that
+// depends on the current values only: c = (max_compression, max_tension, max_shear, max_deviator).
+GCM_HD void destruction_now(const float v[9], float c[4])
+{
+	float ten = 0, com = 0, sh = 0;
+	if(v[3] > ten) ten = v[3];
+	if(v[3] < com) com = v[3];
+	if(v[6] > ten) ten = v[6];
+	if(v[6] < com) com = v[6];
+	if(v[8] > ten) ten = v[8];
+	if(v[8] < com) com = v[8];
+	com = fabsf(com);
+	if(fabsf(v[4]) > sh) sh = fabsf(v[4]);
+	if(fabsf(v[5]) > sh) sh = fabsf(v[5]);
+	if(fabsf(v[7]) > sh) sh = fabsf(v[7]);
+	const float dev = sqrtf( ( (v[3] - v[6]) * (v[3] - v[6])
+		+ (v[6] - v[8]) * (v[6] - v[8])
+		+ (v[3] - v[8]) * (v[3] - v[8])
+		+ 6 * ( (v[4]) * (v[4]) + (v[5]) * (v[5])
+		+ (v[7]) * (v[7])) ) / 6 );
+	c[0] = com; c[1] = ten; c[2] = sh; c[3] = dev;
+}
+
 // ---- dense LU in double (GSL gsl_linalg_LU_decomp / gsl_linalg_LU_solve semantics) --------
 // GSL is a third-party dependency of the reference, absent from /root/reference and unpinned
 // (gcm/CMakeLists.txt:88).  Published GSL 1.x algorithm: Gaussian elimination with partial

@@ -73,6 +73,8 @@ SIGNATURES = {
     "gcm_b200_set_do_next_part_step": (_i, [_p, _f, _i]),
     "gcm_b200_set_concurrency": (_i, [_p, _i]),
     "gcm_b200_set_end_step": (_i, [_p]),
+    "gcm_b200_set_track_destruction": (_i, [_p, _i]),
+    "gcm_b200_zone_get_destruction_criterias": (_i, [_p, _i, _fp]),
     "gcm_b200_set_synchronize": (_i, [_p]),
     "gcm_b200_set_current_time": (_f, [_p]),
     "gcm_b200_set_stream": (_p, [_p]),
@@ -168,6 +170,12 @@ class TetrMesh_1stOrder:
     def get_values(self):
         v = np.empty((self._n_nodes, 9), np.float32)
         self._ck(self.mesh_set.lib.gcm_b200_zone_get_values(self.mesh_set.h, self.zone_num, _fptr(v)))
+        return v
+
+    def get_destruction_criterias(self):
+        """[N, 8]: ElasticNode::destruction_criterias (4 of the current values + their running maxima)."""
+        v = np.empty((self._n_nodes, 8), np.float32)
+        self._ck(self.mesh_set.lib.gcm_b200_zone_get_destruction_criterias(self.mesh_set.h, self.zone_num, _fptr(v)))
         return v
 
     def upload_values_async(self, host_ptr):
@@ -297,6 +305,10 @@ class TetrMeshSet:
     def end_step(self):
         self._ck(self.lib.gcm_b200_set_end_step(self.h))
 
+    def track_destruction(self, on=True):
+        """Keep the running maxima of calc_destruction_criterias (after pre_process_meshes)."""
+        self._ck(self.lib.gcm_b200_set_track_destruction(self.h, int(on)))
+
     def synchronize(self):
         self._ck(self.lib.gcm_b200_set_synchronize(self.h))
 
@@ -325,7 +337,7 @@ class TetrMeshSet:
         a = (C.c_longlong * 16)()
         self._ck(self.lib.gcm_b200_set_kernel_stats(self.h, a))
         return dict(inner_cached=a[0], inner_cold=a[1], patterns=[a[2], a[3], a[4]], pattern_axes=[a[5], a[6], a[7]],
-                    border_flat=a[8], border_sharp=a[9], flat_deferred_last=a[10], exact_only=a[11])
+                    border_flat=a[8], border_sharp=a[9], flat_deferred_last=a[10], exact_only=a[11], peer_stores=a[12])
 
     def profile(self, on=True):
         self._ck(self.lib.gcm_b200_set_profile(self.h, int(on)))

@@ -100,6 +100,13 @@ int gcm_b200_zone_do_next_part_step(gcm_b200_set* s, int zone, float tau, int st
  * the next gcm_b200_set_sync_nodes (the layer swap happens when the last one has). */
 int gcm_b200_set_do_next_part_step(gcm_b200_set* s, float tau, int stage);
 int gcm_b200_set_end_step(gcm_b200_set* s);              /* :173-181 */
+/* TetrMesh_1stOrder::calc_destruction_criterias (TetrMesh_1stOrder.cpp:1957-1995, called by TetrMeshSet.cpp:177-178
+ * at the end of every step; consumed by the snapshot writers only).  The four criteria of the current values are
+ * evaluated when they are read; their running maxima need every step, so they are kept only while tracking is on
+ * (one extra pass of 56 B per node at the end of a step).  out8[8N] = ElasticNode::destruction_criterias per node:
+ * max_compression, max_tension, max_shear, max_deviator, then the four *_history (0 while never tracked). */
+int gcm_b200_set_track_destruction(gcm_b200_set* s, int on);
+int gcm_b200_zone_get_destruction_criterias(gcm_b200_set* s, int zone, float* out8);
 /* 1 (default): the border-node kernel runs on a second CUDA stream next to the inner-node kernel
  * of the same stage (they write disjoint nodes); 0: everything on the one stream. */
 int gcm_b200_set_concurrency(gcm_b200_set* s, int on);
@@ -157,7 +164,8 @@ int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long
  * [1] inner nodes left to the literal routine, [2..4] patterns per axis of the de-duplicated cache,
  * [5..7] 1 where that axis runs from the pattern table, [8] flat border nodes, [9] sharp border nodes,
  * [10] flat border nodes the last border launch deferred to the literal routine, [11] 1 when the
- * conservative owner pre-filter is switched off for this mesh (huge coordinates), [12..15] 0. */
+ * conservative owner pre-filter is switched off for this mesh (huge coordinates), [12] 1 when the cross-process
+ * halo exchange runs on direct peer stores (else NCCL send/recv, or none), [13..15] 0. */
 int gcm_b200_set_kernel_stats(gcm_b200_set* s, long long* out16);
 /* Virtual (contact) nodes of the last collision pass: n and [16] floats each (coords, values). */
 int gcm_b200_set_virt_count(gcm_b200_set* s);

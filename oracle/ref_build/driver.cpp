@@ -270,12 +270,13 @@ int main(int argc, char** argv)
 		for(int z = 0; z < Z; z++) {
 			TetrMesh_1stOrder* m = ms->get_mesh_by_zone_num(z);
 			const size_t N = m->nodes.size();
-			vector<float> vals(9 * N), crd(3 * N), bases(9 * N, 0.f);
+			vector<float> vals(9 * N), crd(3 * N), bases(9 * N, 0.f), destr(8 * N);
 			vector<int> flags(N), faces(3 * m->border.size()), contact(6 * N, -1);
 			for(size_t i = 0; i < N; i++) {
 				ElasticNode& n = m->nodes[i];
 				for(int k = 0; k < 9; k++) vals[9 * i + k] = n.values[k];
 				for(int k = 0; k < 3; k++) crd[3 * i + k] = n.coords[k];
+				for(int k = 0; k < 8; k++) destr[8 * i + k] = n.destruction_criterias[k];
 				flags[i] = (n.isInContact() ? 1 : 0) | (n.isLocal() ? 2 : 0) | (n.isUsed() ? 4 : 0) | (n.isBorder() ? 8 : 0);
 				if(n.local_basis) for(int k = 0; k < 9; k++) bases[9 * i + k] = n.local_basis->ksi[k / 3][k % 3];
 				if(n.contact_data) for(int k = 0; k < 3; k++) { contact[6*i+k] = n.contact_data->axis_plus[k]; contact[6*i+3+k] = n.contact_data->axis_minus[k]; }
@@ -285,6 +286,7 @@ int main(int argc, char** argv)
 			char zs[32]; snprintf(zs, sizeof zs, ".z%d", z);
 			write_file(out + zs + ".values.f32", vals);
 			write_file(out + zs + ".coords.f32", crd);
+			write_file(out + zs + ".destr.f32", destr);
 			write_file(out + zs + ".flags.i32", flags);
 			write_file(out + zs + ".faces.i32", faces);
 			write_file(out + zs + ".bases.f32", bases);

@@ -40,6 +40,7 @@ struct Z {
 	vector<int> icache_owner[3];
 	vector<int> bnd_static;                   // flat-border tables (gcm_border.cuh), as build_border_flat_tables makes them
 	vector<float> bnd_cand;
+	vector<float> destr_hist;                 // running maxima of calc_destruction_criterias, 4 per node
 };
 struct Cond { gcm::BorderCond bc; float start, dur, box[6]; };
 
@@ -383,6 +384,18 @@ int main(int argc, char** argv)
 				z.cur ^= 1;
 			}
 		}
+		// calc_destruction_criterias (TetrMeshSet.cpp:177-178): running maxima of every local node
+		for(auto& zp : zs) {
+			Z& z = *zp;
+			if(z.destr_hist.empty()) z.destr_hist.assign(4*(size_t)z.hm.N, 0.f);
+			for(int i = 0; i < z.hm.N; i++) {
+				if(!z.hm.is_local(i)) continue;
+				float v[9], c[4];
+				for(int k = 0; k < 9; k++) v[k] = z.u[z.cur][gcm::rec_index(z.rs, i, k)];
+				gcm::destruction_now(v, c);
+				for(int k = 0; k < 4; k++) if(c[k] > z.destr_hist[4*(size_t)i+k]) z.destr_hist[4*(size_t)i+k] = c[k];
+			}
+		}
 		for(auto& zp : zs) zp->hm.current_time += tau;
 	}
 	if(out.size()) {
@@ -404,6 +417,13 @@ int main(int argc, char** argv)
 			write_file(out + zs_ + ".flags.i32", fl);
 			write_file(out + zs_ + ".faces.i32", hm.faces);
 			write_file(out + zs_ + ".bases.f32", bases);
+			vector<float> destr(8*(size_t)hm.N, 0.f);
+			for(int i = 0; i < hm.N && steps > 0; i++) {
+				if(!hm.is_local(i)) continue;
+				gcm::destruction_now(&vals[9*(size_t)i], &destr[8*(size_t)i]);
+				for(int k = 0; k < 4; k++) destr[8*(size_t)i+4+k] = z.destr_hist[4*(size_t)i+k];
+			}
+			write_file(out + zs_ + ".destr.f32", destr);
 		}
 		if(tap_step >= 0) write_file(out + ".tap.i32", tap);
 	}

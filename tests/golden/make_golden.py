@@ -26,6 +26,8 @@ def main():
         for k, r in enumerate(res):
             for w in ("values", "flags", "faces", "bases", "owners", "tries"):
                 d["%s%d" % (w, k)] = r[w]
+            if name in up.DESTR_CASES:      # ElasticNode::destruction_criterias after the last step
+                d["destr%d" % k] = r["destr"]
         np.savez_compressed(up.golden_path(name), **d)
         print(name, [int(up.local_mask(r["flags"]).sum()) for r in res], "local nodes;",
               os.path.getsize(up.golden_path(name)), "bytes")

@@ -201,6 +201,10 @@ CASE_NAMES = ["cube8", "cube8_pwave", "jitter8", "jitter8_border", "zones2", "zo
               "far_jitter12", "far_cube10", "fine_spacing8", "contact_zones2", "friction_zones2"]
 
 
+# fixtures that also hold ElasticNode::destruction_criterias[8] per node (calc_destruction_criterias)
+DESTR_CASES = ["plastic8", "zones3_jitter"]
+
+
 def _write_inputs(case, d):
     meshes, states = [], []
     for k, (z, st) in enumerate(zip(case["zones"], case["states"])):
@@ -272,6 +276,8 @@ def run_oracle(case, tap=True):
                             faces=np.fromfile(pre + "faces.i32", np.int32).reshape(-1, 3),
                             bases=np.fromfile(pre + "bases.f32", np.float32).reshape(n, 9),
                             owners=owners[k] if tap else None, tries=tries[k] if tap else None))
+            if os.path.exists(pre + "destr.f32"):    # ElasticNode::destruction_criterias[8] after the last step
+                res[-1]["destr"] = np.fromfile(pre + "destr.f32", np.float32).reshape(n, 8)
         return res
 
 
@@ -297,11 +303,12 @@ def run_emul(case):
                             flags=np.fromfile(pre + "flags.i32", np.int32),
                             faces=np.fromfile(pre + "faces.i32", np.int32).reshape(-1, 3),
                             bases=np.fromfile(pre + "bases.f32", np.float32).reshape(n, 9),
+                            destr=np.fromfile(pre + "destr.f32", np.float32).reshape(n, 8),
                             owners=owners, tries=tries))
         return res
 
 
-def run_product(case, device=0, fast_inner=True):
+def run_product(case, device=0, fast_inner=True, track_destruction=False):
     """Run the case through the C ABI (libgcm_b200.so) on the GPU."""
     import gcm_b200
     la, mu, rho, yl = case["material"]
@@ -328,6 +335,8 @@ def run_product(case, device=0, fast_inner=True):
                 ms.add_border_condition(BORDER_TYPES[t], box, params=p, start=start, duration=dur)
         for k, st in enumerate(case["states"]):
             ms.get_mesh_by_zone_num(k).set_values(st)
+        if track_destruction:
+            ms.track_destruction(True)
         res = [dict() for _ in case["zones"]]
         for step in range(case["steps"]):
             ms.enable_tap(step == case["tap_step"])
@@ -340,6 +349,8 @@ def run_product(case, device=0, fast_inner=True):
         for k in range(len(case["zones"])):
             m = ms.get_mesh_by_zone_num(k)
             res[k].update(values=m.get_values(), flags=m.get_flags() & 15, faces=m.get_faces(), bases=m.get_bases())
+            if track_destruction:
+                res[k]["destr"] = m.get_destruction_criterias()
         return res
     finally:
         ms.close()
@@ -349,16 +360,16 @@ def local_mask(flags):
     return (flags & 6) == 6
 
 
-def compare(ref, got, what=("flags", "faces", "bases", "owners", "tries", "values")):
+def compare(ref, got, what=("flags", "faces", "bases", "owners", "tries", "values", "destr")):
     """Bit-exact comparison of a run against the reference run; returns list of mismatch strings."""
     bad = []
     for k, (r, g) in enumerate(zip(ref, got)):
         loc = local_mask(r["flags"])
         for w in what:
-            a, b = r[w], g[w]
+            a, b = r.get(w), g.get(w)
             if a is None or b is None:
                 continue
-            if w in ("values", "bases"):
+            if w in ("values", "bases", "destr"):
                 a, b = a[loc], b[loc]
                 same = a.shape == b.shape and np.array_equal(a.view(np.uint32) & 0x7fffffff == 0, b.view(np.uint32) & 0x7fffffff == 0) \
                     and np.array_equal(a, b)
@@ -384,5 +395,9 @@ def golden_path(name):
 def load_golden(name):
     g = np.load(golden_path(name))
     nz = int(g["n_zones"])
-    return [dict(values=g["values%d" % k], flags=g["flags%d" % k], faces=g["faces%d" % k], bases=g["bases%d" % k],
-                 owners=g["owners%d" % k], tries=g["tries%d" % k]) for k in range(nz)]
+    res = [dict(values=g["values%d" % k], flags=g["flags%d" % k], faces=g["faces%d" % k], bases=g["bases%d" % k],
+                owners=g["owners%d" % k], tries=g["tries%d" % k]) for k in range(nz)]
+    for k in range(nz):
+        if "destr%d" % k in g:
+            res[k]["destr"] = g["destr%d" % k]
+    return res

@@ -206,10 +206,11 @@ def main():
     ap.add_argument("--ref-zones", type=int, default=1)
     ap.add_argument("--ref-steps", type=int, default=2, help="timed steps of the reference arm (about 11 s each at 10^6 nodes)")
     ap.add_argument("--layers", default="auto", help="auto | equal | comma list of owned z-layers per zone")
-    ap.add_argument("--border-weight", type=float, default=4.0, help="cost of a face of border nodes in layers of inner nodes (--layers auto)")
+    ap.add_argument("--border-weight", type=float, default=20.0, help="cost of a face of border nodes in layers of inner nodes (--layers auto); measured: a border node costs ~20 inner nodes per step")
     ap.add_argument("--cpu-size", type=int, default=64, help="cube side of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the short configs[1] / configs[3] runs appended at 1 GPU")
     ap.add_argument("--yield-limit", type=float, default=YIELD, help="1e7 = BASELINE configs[3] (plastic corrector fires)")
     args = ap.parse_args()
 
@@ -232,7 +233,90 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    size, nz = args.size, args.zones
+    line = run_workload(args, rank, world, local_rank, args.size, args.zones, args.yield_limit, full=True)
+    if rank == 0 and world == 1 and not args.no_extra_configs:
+        # the other single-GPU configurations BASELINE.json names, as extra keys of the one line (short runs, device-timed)
+        extra = {}
+        extra["configs[1] single cube 100^3, 1 zone"] = run_workload(args, rank, world, local_rank, 100, 1, YIELD, full=False)
+        extra["configs[3] plastic corrector, yield 1e7, 216^3 in 8 zones"] = run_workload(args, rank, world, local_rank, args.size, args.zones, 1e7, full=False)
+        for calc, static in (("adhesion", True), ("friction", True), ("adhesion", False)):
+            extra["configs[4] two 126^3 cubes 0.01 apart, Bruteforce detector %s, %s contact"
+                  % ("static" if static else "every step", calc)] = run_contact(args, local_rank, 126, calc, static)
+        line["other_configs"] = extra
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_contact(args, local_rank, side, calc, static):
+    """BASELINE configs[4]: two bodies of side^3 nodes, the second translated by side - 1 + 0.01 along z, Bruteforce
+    collision detector (threshold 1), Adhesion or Friction contact on ~2 x (side-2)^2 nodes.  State: a compression
+    pulse across the interface, plus opposite shear velocities for the friction run (v_tau != 0)."""
+    import torch
+    import gcm_b200
+    from gcm_b200 import meshgen
+    t0 = time.time()
+    za, zb = meshgen.make_cube(side), meshgen.make_cube(side)
+    zb.zone = 1
+    ms = gcm_b200.TetrMeshSet(n_zones=2, device=local_rank)
+    ms.srand(12345)
+    ms.get_mesh_by_zone_num(0).load(za, la=LA, mu=MU, rho=RHO, yield_limit=YIELD)
+    ms.get_mesh_by_zone_num(1).load(zb, la=LA, mu=MU, rho=RHO, yield_limit=YIELD)
+    ms.get_mesh_by_zone_num(1).translate(0.0, 0.0, side - 1 + 0.01)
+    ms.set_collision_detector("brute", static=static, threshold=1.0)
+    ms.set_contact_calculator(calc)
+    ms.pre_process_meshes()
+    sa = meshgen.pwave_state(za.coords, LA, MU, RHO, z_c=side - 1.0)
+    sb = meshgen.pwave_state(zb.coords, LA, MU, RHO, z_c=0.0)
+    if calc == "friction":
+        sa[:, 0] += 0.3 * sa[:, 2]
+        sb[:, 0] -= 0.3 * sb[:, 2]
+    ms.get_mesh_by_zone_num(0).set_values(sa)
+    ms.get_mesh_by_zone_num(1).set_values(sb)
+    n_total = 2 * side ** 3
+    t_setup = time.time() - t0
+    stream = torch.cuda.ExternalStream(ms.stream())
+    for _ in range(args.warmup):
+        ms.do_next_step()
+    ms.synchronize()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ms.launch_count()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ms.do_next_step()
+    e1.record(stream)
+    ms.synchronize()
+    torch.cuda.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    launches = ms.launch_count() - l0
+    ms.set_concurrency(False)
+    ms.profile(True)
+    for _ in range(min(args.steps, 5)):
+        ms.do_next_step()
+    ms.synchronize()
+    prof = {k: ms.profile_read(i) for i, k in enumerate(["inner_stage", "border_stage", "plastic", "halo_copy", "rng_bases", "inner_generic"])}
+    ms.profile(False)
+    peak, _ = measured_peak_gbs()
+    value = n_total * args.steps / (total_ms * 1e-3)
+    out = {"nodes": n_total, "contact_nodes": ms.virt_count(), "ms_per_step": total_ms / args.steps, "value": value, "unit": "node-updates/s",
+           "step_frac": value * B_STEP / 1e9 / peak, "steps": args.steps, "gpu_launches": int(launches), "setup_s": t_setup,
+           "kernel_ms_per_5_steps_serialised": {k: v[0] for k, v in prof.items()}, "coverage": ms.kernel_stats()}
+    ms.close()
+    return out
+
+
+def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
+    """One workload on the current process group.  full: the whole JSON line (roofline pass, e2e, cpu baseline,
+    digest); else a short summary (ms/step, node-updates/s, step-level roofline fraction)."""
+    import torch
+    import torch.distributed as dist
+    import gcm_b200
+    from gcm_b200 import meshgen
+    from gcm_b200.distributed import DataBus
+
     owner = zone_owner(nz, world)
     mine = [z for z in range(nz) if owner[z] == rank]
     t0 = time.time()
@@ -241,7 +325,7 @@ def main():
     ms = gcm_b200.TetrMeshSet(n_zones=nz, zone_rank=owner, my_rank=rank, device=local_rank)
     ms.srand(12345)
     for z in mine:
-        ms.get_mesh_by_zone_num(z).load(zones[z], la=LA, mu=MU, rho=RHO, yield_limit=args.yield_limit)
+        ms.get_mesh_by_zone_num(z).load(zones[z], la=LA, mu=MU, rho=RHO, yield_limit=yield_limit)
     bus = None
     if world > 1:
         bus = DataBus(ms)
@@ -309,6 +393,13 @@ def main():
         dist.all_reduce(n_total)
     n_total = int(n_total.item())
     value = n_total * args.steps / (total_ms * 1e-3)
+    if not full:
+        peak, _ = measured_peak_gbs()
+        out = {"nodes": n_total, "zones": nz, "ms_per_step": total_ms / args.steps, "value": value, "unit": "node-updates/s",
+               "step_frac": value / world * B_STEP / 1e9 / peak, "steps": args.steps, "yield_limit": yield_limit,
+               "gpu_launches": int(launches), "coverage": ms.kernel_stats()}
+        ms.close()
+        return out
 
     # ---- per-kernel timing for the roofline (same steps, events around each launch) ----------
     # The timed loop above runs the border kernels on a second stream beside the inner kernel; for the
@@ -382,24 +473,22 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
 
+    line = None
     if rank == 0:
         line = {"metric": "tet node-updates/sec", "value": value, "unit": "node-updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "elastic cube %d^3 = %d nodes, 6 tets/hex, %d z-slab zones (BASELINE configs[2]%s)"
-                                       % (size, n_total, nz, "; yield 1e7 = configs[3]" if args.yield_limit < 1e15 else ""),
+                                       % (size, n_total, nz, "; yield 1e7 = configs[3]" if yield_limit < 1e15 else ""),
                            "zones_per_gpu": nz // world if nz % world == 0 else [owner.count(r) for r in range(world)],
                            "layers": layers, "layers_rule": args.layers,
-                           "tau": 0.002, "material": [LA, MU, RHO, args.yield_limit], "seed": 12345,
+                           "tau": 0.002, "material": [LA, MU, RHO, yield_limit], "seed": 12345,
                            "l2": "inputs larger than L2 (state %.0f MB + mesh > 126 MB per GPU)" % (n_total / world * 72 / 1e6),
                            "setup_s": t_setup},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "state_digest": state_digest, "steps_total_before_digest": int(round(ms.get_current_time() / 0.002))}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
     ms.close()
+    return line
 
 
 if __name__ == "__main__":

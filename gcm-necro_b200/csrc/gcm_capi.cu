@@ -1157,6 +1157,7 @@ void p2p_setup(gcm_b200_set* s)
 // (the neighbour cannot be further behind than that: I needed its previous push to get here).
 void p2p_exchange(gcm_b200_set* s, cudaStream_t st)
 {
+
 	DeviceMesh& dm = s->dm;
 	const int np = (int)s->p2p_targets.size();
 	const int n_total = (int)s->p2p_send_node.n;
@@ -1172,6 +1173,7 @@ void p2p_exchange(gcm_b200_set* s, cudaStream_t st)
 	gcm::halo_wait_kernel<<<1, 32, 0, st>>>(s->p2p_flags.p, s->p2p_peer_ranks.p, np, seq, s->d_err);
 	s->launches++;
 	CK(cudaGetLastError());
+
 }
 
 // DataBus::sync_nodes across processes (gcm/system/DataBus.cpp:81-115), all on the set's stream:
@@ -1482,14 +1484,15 @@ int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_v
 	GUARD_END
 }
 
-int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const float* params,
-                                      const int* vars, const float* vals,
-                                      float start, float duration, const float* box)
+// One BorderCondition without its area: calculator + StepPulseForm.  Returns its id through *id.
+static int define_border_condition(gcm_b200_set* s, int calc_type, const float* params, const int* vars, const float* vals,
+                                   float start, float duration, const float* box, int* id)
 {
-	GUARD_BEGIN
 	if(!s || !s->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "call gcm_b200_set_preprocess first");
 	if((int)s->conds.size() >= GCM_MAX_BORDER_CONDS) return fail(gcmh::CONFIG_EXCEPTION, "too many border conditions");
-	if(calc_type < 0 || calc_type > 4 || !box) return fail(gcmh::CONFIG_EXCEPTION, "bad border condition");
+	const bool dir_normalised = (calc_type & GCM_B200_DIR_NORMALISED) != 0;
+	calc_type &= ~GCM_B200_DIR_NORMALISED;
+	if(calc_type < 0 || calc_type > 4) return fail(gcmh::CONFIG_EXCEPTION, "bad border condition");
 	CondSpec cs;
 	memset(&cs, 0, sizeof(cs));
 	cs.bc.type = calc_type;
@@ -1497,7 +1500,7 @@ int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const floa
 		if(!params) return fail(gcmh::CONFIG_EXCEPTION, "missing calculator parameters");
 		// set_parameters, ExternalForceCalculator.cpp:19-27
 		cs.bc.p_normal = params[0]; cs.bc.p_tangential = params[1];
-		float dtmp = sqrtf(params[2]*params[2] + params[3]*params[3] + params[4]*params[4]);
+		float dtmp = dir_normalised ? 1.0f : sqrtf(params[2]*params[2] + params[3]*params[3] + params[4]*params[4]);
 		cs.bc.dir[0] = params[2] / dtmp; cs.bc.dir[1] = params[3] / dtmp; cs.bc.dir[2] = params[4] / dtmp;
 	}
 	if(calc_type == gcm::BC_EXT_VALUES) {
@@ -1508,9 +1511,20 @@ int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const floa
 		}
 	}
 	cs.start = start; cs.duration = duration;
-	memcpy(cs.box, box, 6 * sizeof(float));
-	int id = (int)s->conds.size();
+	if(box) memcpy(cs.box, box, 6 * sizeof(float));
+	*id = (int)s->conds.size();
 	s->conds.push_back(cs);
+	return 0;
+}
+
+int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const float* params,
+                                      const int* vars, const float* vals,
+                                      float start, float duration, const float* box)
+{
+	GUARD_BEGIN
+	if(!box) return fail(gcmh::CONFIG_EXCEPTION, "bad border condition");
+	int id = -1;
+	if(int rc = define_border_condition(s, calc_type, params, vars, vals, start, duration, box, &id)) return rc;
 	if(s->device >= 0) CK(cudaSetDevice(s->device));
 	// BoxArea::isInArea (areas/BoxArea.cpp:15-26) over every node of every local mesh; a later
 	// condition overrides an earlier one (TaskPreparator.cpp:432-438)
@@ -1524,6 +1538,31 @@ int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const floa
 		}
 		if(s->dm.ready) s->dm.cond_id.put(hm.cond_id, z.slot_off, s->stream);
 	}
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_set_define_border_condition(gcm_b200_set* s, int calc_type, const float* params,
+                                         const int* vars, const float* vals, float start, float duration, int* id)
+{
+	GUARD_BEGIN
+	if(!id) return fail(gcmh::CONFIG_EXCEPTION, "null id");
+	return define_border_condition(s, calc_type, params, vars, vals, start, duration, nullptr, id);
+	GUARD_END
+}
+
+int gcm_b200_zone_assign_border_conditions(gcm_b200_set* s, int zone, const int* cond_of_node)
+{
+	GUARD_BEGIN
+	Zone* z = get_zone(s, zone);
+	if(!z || !s->preprocessed || !cond_of_node) return fail(gcmh::CONFIG_EXCEPTION, "zone is not preprocessed");
+	HostMesh& hm = z->hm;
+	for(size_t b = 0; b < hm.border_nodes.size(); b++) {
+		const int id = cond_of_node[hm.border_nodes[b]];
+		if(id >= (int)s->conds.size()) return fail(gcmh::CONFIG_EXCEPTION, "unknown border condition id");
+		hm.cond_id[b] = id < 0 ? -1 : id;
+	}
+	if(s->dm.ready) { CK(cudaSetDevice(s->device)); s->dm.cond_id.put(hm.cond_id, z->slot_off, s->stream); }
 	return 0;
 	GUARD_END
 }

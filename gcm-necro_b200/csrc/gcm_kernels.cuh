@@ -280,11 +280,15 @@ halo_push_kernel(const float* __restrict__ u, size_t rs, const int* __restrict__
 	const int g = blockIdx.x * blockDim.x + threadIdx.x;
 	const int q = g / n_total, i = g - q * n_total;
 	if(q < 3) {
-		PeerTarget t = t0;
-		if(n_peers > 1 && i >= t1.begin && i < t1.end) t = t1;
-		for(int k = 2; k < n_peers; k++) if(i >= more[k].begin && i < more[k].end) t = more[k];
+		// field by field, no local PeerTarget copy indexed by `layer`: nvcc 12.9 lost the selection of such a copy
+		// on the n_peers == 2 path (the copy kept t1's pointers for t0's entries; seen in the SASS and on 4 GPUs)
+		const bool second = n_peers > 1 && i >= t1.begin && i < t1.end;
+		float* base = second ? (layer ? t1.u[1] : t1.u[0]) : (layer ? t0.u[1] : t0.u[0]);
+		unsigned long long prs = second ? t1.rs : t0.rs;
+		for(int k = 2; k < n_peers; k++)
+			if(i >= more[k].begin && i < more[k].end) { base = layer ? more[k].u[1] : more[k].u[0]; prs = more[k].rs; }
 		const float4 v = rec_quad(u, rs, send_node[i], q);
-		reinterpret_cast<float4*>(t.u[layer])[(size_t)q * t.rs + (size_t)remote_slot[i]] = v;
+		reinterpret_cast<float4*>(base)[(size_t)q * prs + (size_t)remote_slot[i]] = v;
 	}
 	__threadfence_system();
 	__shared__ bool last;
@@ -292,9 +296,9 @@ halo_push_kernel(const float* __restrict__ u, size_t rs, const int* __restrict__
 	if(threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
 	__syncthreads();
 	if(last && threadIdx.x < n_peers) {
-		const PeerTarget& t = threadIdx.x == 0 ? t0 : (threadIdx.x == 1 ? t1 : more[threadIdx.x]);
+		int* flag = threadIdx.x == 0 ? t0.flag : (threadIdx.x == 1 ? t1.flag : more[threadIdx.x].flag);
 		__threadfence_system();
-		*reinterpret_cast<volatile int*>(t.flag + my_rank) = seq;
+		*reinterpret_cast<volatile int*>(flag + my_rank) = seq;
 		if(threadIdx.x == 0) *done_counter = 0;
 	}
 }

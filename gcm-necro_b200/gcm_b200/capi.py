@@ -64,6 +64,8 @@ SIGNATURES = {
     "gcm_b200_zone_upload_values_async": (_i, [_p, _i, _p]),
     "gcm_b200_zone_download_values_async": (_i, [_p, _i, _p]),
     "gcm_b200_set_add_border_condition": (_i, [_p, _i, _fp, _ip, _fp, _f, _f, _fp]),
+    "gcm_b200_set_define_border_condition": (_i, [_p, _i, _fp, _ip, _fp, _f, _f, _ip]),
+    "gcm_b200_zone_assign_border_conditions": (_i, [_p, _i, _ip]),
     "gcm_b200_set_preprocess": (_i, [_p]),
     "gcm_b200_set_do_next_step": (_i, [_p]),
     "gcm_b200_set_do_steps": (_i, [_p, _i]),
@@ -320,6 +322,9 @@ class TetrMeshSet:
 
     def enable_tap(self, on=True):
         self._ck(self.lib.gcm_b200_set_enable_tap(self.h, int(on)))
+
+    def virt_count(self):
+        return self.lib.gcm_b200_set_virt_count(self.h)
 
     def get_virt_nodes(self):
         """Virtual (contact) nodes of the last collision pass: [n, 16] = coords(3) + values(13)."""

@@ -78,6 +78,16 @@ int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_v
 int gcm_b200_set_add_border_condition(gcm_b200_set* s, int calc_type, const float* params,
                                       const int* vars, const float* vals,
                                       float start, float duration, const float* box);
+/* The same for a host that keeps the reference's plugin objects and assigns them per node
+ * (nodes[i].border_condition = bc, as TaskPreparator.cpp:432-438 does after the area test): define a
+ * condition (calculator + StepPulseForm, no area; *id receives its number), then hand every node of a
+ * zone its condition id (cond_of_node[N]; -1 = the default Free border of TetrMeshSet.cpp:12,16-18;
+ * entries of non-border nodes are ignored).  After gcm_b200_set_preprocess. */
+#define GCM_B200_DIR_NORMALISED 0x100  /* or-ed into calc_type 2/3: params[2..4] is already the unit vector
+                                        * set_parameters stored (ExternalForceCalculator.cpp:23-26), do not divide again */
+int gcm_b200_set_define_border_condition(gcm_b200_set* s, int calc_type, const float* params,
+                                         const int* vars, const float* vals, float start, float duration, int* id);
+int gcm_b200_zone_assign_border_conditions(gcm_b200_set* s, int zone, const int* cond_of_node);
 
 /* main.cpp:124-130: DataBus::create_custom_types + sync_nodes (halo coordinates/material from
  * the owner zones of this process) + TetrMeshSet::pre_process_meshes, then the SoA upload.

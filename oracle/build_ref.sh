@@ -92,5 +92,23 @@ $CXX -O2 "$OUT"/obj_tap/*.o -o "$OUT/gcm3d_ref_tap"
 $CXX $OWNFLAGS -c "$HERE/ref_build/kat_driver.cpp" -o "$OUT/kat_driver.o"
 $CXX -O2 $(ls "$OUT"/obj/*.o | grep -v '/driver.o$') "$OUT/kat_driver.o" -o "$OUT/gcm3d_ref_kat"
 rm -f "$OUT/kat_driver.o"
+
+# gcm3d_b200: the same reference classes and the same driver, with TetrMeshSet::do_next_step and
+# TetrMesh_1stOrder::do_next_part_step replaced by the INTEGRATION.md shim (ref_build/shim/) and linked against
+# libgcm_b200.so -- the compiled drop-in proof.  The reference's own two bodies are kept under another name
+# (-D below renames them consistently in every reference TU; the shim and the driver see the real names).
+LIBDIR="$HERE/../gcm-necro_b200/gcm_b200"
+if [ -f "$LIBDIR/libgcm_b200.so" ]; then
+	mkdir -p "$OUT/obj_b200"
+	RENAME="-Ddo_next_step=do_next_step_host -Ddo_next_part_step=do_next_part_step_host"
+	echo $TUS | tr ' ' '\n' | xargs -P "$JOBS" -I{} bash -c "compile_one {} $OUT/obj_b200 '$RENAME'"
+	cp "$OUT/obj/databus_stub.o" "$OUT/obj/driver.o" "$OUT/obj_b200/"
+	$CXX $OWNFLAGS -I"$HERE/../include" -c "$HERE/ref_build/shim/tetrmeshset_b200.cpp" -o "$OUT/obj_b200/shim.o"
+	$CXX -O2 "$OUT"/obj_b200/*.o -L"$LIBDIR" -lgcm_b200 -ldl -Wl,-rpath,'$ORIGIN/../../gcm-necro_b200/gcm_b200' -o "$OUT/gcm3d_b200"
+	rm -rf "$OUT/obj_b200"
+	echo "built $OUT/gcm3d_b200 (reference classes + shim + libgcm_b200.so)"
+else
+	echo "build_ref.sh: libgcm_b200.so not built yet -- skipping gcm3d_b200" >&2
+fi
 rm -rf "$OUT/obj" "$OUT/obj_tap"
 echo "built $OUT/gcm3d_ref and $OUT/gcm3d_ref_tap"

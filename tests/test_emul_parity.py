@@ -87,3 +87,19 @@ def test_any_ring_search_matches_host_restatement(built):
     tested, found, bad = [int(x) for x in r.stdout.split(":")[1].split()]
     assert bad == 0
     assert tested > 3000 and 0.2 * tested < found < 0.95 * tested
+
+
+def test_reference_aborts_on_meshes_finer_than_c1_tau(built):
+    """Pins what `find_border_cross` means for parity: on a cube of spacing 0.05 (< c1 tau = 0.068) the reference
+    reaches TetrMethod_Plastic_1stOrder.cpp:619-643 and aborts (assert in Node::isOwnedBy, Node.h:132, or a smashed
+    stack in TetrMesh_1stOrder.cpp:1668-1675), with and without jitter.  There is no reference result for
+    such meshes; the product reports them (tests/test_gpu_parity.py)."""
+    if not os.path.exists(up.ORACLE_TAP):
+        pytest.skip("oracle/_ref not built")
+    from gcm_b200 import meshgen
+    for jit in (0.0, 0.2):
+        z = meshgen.make_cube(8, spacing=(0.05, 0.05, 0.05), jitter=jit, seed=41)
+        case = dict(name="fine", zones=[z], states=[meshgen.generic_state(z.coords, up.LA, up.MU, up.RHO, seed=42)],
+                    material=(up.LA, up.MU, up.RHO, 1e16), steps=1, seed=78, borders=[], tap_step=-1)
+        with pytest.raises(RuntimeError):
+            up.run_oracle(case)

@@ -257,9 +257,12 @@ def decode_oracle_tap(path, n_nodes_per_zone):
     return owners, tries
 
 
-def run_oracle(case, tap=True):
+SHIM = os.path.join(ROOT, "oracle", "_ref", "gcm3d_b200")   # reference classes + driver + INTEGRATION.md shim + libgcm_b200.so
+
+
+def run_oracle(case, tap=True, exe=None):
     """Run oracle/_ref on the case; returns per-zone dict of arrays."""
-    exe = ORACLE_TAP if tap else ORACLE
+    exe = exe or (ORACLE_TAP if tap else ORACLE)
     with tempfile.TemporaryDirectory() as d:
         meshes, states = _write_inputs(case, d)
         out = os.path.join(d, "o")
@@ -269,6 +272,7 @@ def run_oracle(case, tap=True):
         res = []
         ns = [z.n_nodes for z in case["zones"]]
         owners, tries = decode_oracle_tap(out + ".tap.bin", ns) if tap else (None, None)
+        virt = np.fromfile(out + ".virt.f32", np.float32).reshape(-1, 16) if os.path.exists(out + ".virt.f32") else None
         for k, n in enumerate(ns):
             pre = "%s.z%d." % (out, k)
             res.append(dict(values=np.fromfile(pre + "values.f32", np.float32).reshape(n, 9),
@@ -278,6 +282,8 @@ def run_oracle(case, tap=True):
                             owners=owners[k] if tap else None, tries=tries[k] if tap else None))
             if os.path.exists(pre + "destr.f32"):    # ElasticNode::destruction_criterias[8] after the last step
                 res[-1]["destr"] = np.fromfile(pre + "destr.f32", np.float32).reshape(n, 8)
+        if res:
+            res[0]["virt"] = virt
         return res
 
 

@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--ref-zones", type=int, default=1)
     ap.add_argument("--ref-steps", type=int, default=2, help="timed steps of the reference arm (about 11 s each at 10^6 nodes)")
     ap.add_argument("--layers", default="auto", help="auto | equal | comma list of owned z-layers per zone")
-    ap.add_argument("--border-weight", type=float, default=20.0, help="cost of a face of border nodes in layers of inner nodes (--layers auto); measured: a border node costs ~20 inner nodes per step")
+    ap.add_argument("--border-weight", type=float, default=28.0, help="cost of a face of border nodes in layers of inner nodes (--layers auto); a border node costs 20-30 inner nodes per step, and 28 keeps an end slab's border nodes (face + 6 layers of rim) within one wave of the stage-0 border kernel")
     ap.add_argument("--cpu-size", type=int, default=64, help="cube side of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -362,13 +362,17 @@ def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = [0.0]
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        t_host = time.perf_counter()
         for _ in range(k):
             fn()
         e1.record(stream)
+        host_issue[0] = (time.perf_counter() - t_host) * 1e3 / k    # host time to ISSUE a step (no waiting inside)
         ms.synchronize()
         barrier()
         ms_ = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -386,6 +390,7 @@ def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
     l0 = ms.launch_count()
     total_ms = timed(step, args.steps)
     launches = ms.launch_count() - l0
+    host_issue_ms = host_issue[0]
     clocks = sampler.stop() if rank == 0 else None
 
     n_total = torch.tensor([n_local], device="cuda", dtype=torch.int64)
@@ -485,7 +490,7 @@ def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
                            "tau": 0.002, "material": [LA, MU, RHO, yield_limit], "seed": 12345,
                            "l2": "inputs larger than L2 (state %.0f MB + mesh > 126 MB per GPU)" % (n_total / world * 72 / 1e6),
                            "setup_s": t_setup},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks,
                 "state_digest": state_digest, "steps_total_before_digest": int(round(ms.get_current_time() / 0.002))}
     ms.close()
     return line

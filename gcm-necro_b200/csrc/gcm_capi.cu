@@ -175,6 +175,8 @@ struct gcm_b200_set {
 	bool inner_cache = true;     // inner nodes through the step-invariant owner/factor cache (gcm_inner.cuh); 0 = index-free scan kernel
 	bool inner_patterns = true;  // de-duplicate the cache into a pattern table where an axis has few distinct entries
 	bool track_destruction = false;   // calc_destruction_criterias at the end of every step (its running maxima need every step)
+	int border_lu_block = 352;   // block size of the stage-0 border kernel (352: one block per SM, or 64: five)
+	int inner_mb = 5;            // register budget of the pattern kernel: resident 256-thread blocks per SM aimed at (4, 5, 6; anything else: 1 block, up to 255 registers); 5 = 48 registers measured fastest at 216^3 (1.47 vs 1.49 / 1.53 ms per step)
 	bool fuse_plastic = true;    // whole-step calls: stage 3 as the epilogue of the stage-2 writers (and no exchange before it)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
 	std::vector<gcmh::VirtNodeHost> virt;
@@ -696,7 +698,11 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 			CK(cudaMemsetAsync(dm.bnd_defer.p, 0, sizeof(int), bst));
 			const gcm::BndSlotStatic* bstat = reinterpret_cast<const gcm::BndSlotStatic*>(dm.bnd_static.p);
 			const float4* cq = reinterpret_cast<const float4*>(dm.bnd_cand.p);
-			if(stage == 0) gcm::stage_border_fast_kernel<true, 64><<<(nb + 63) / 64, 64, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
+			// stage 0 = the normal axis: every flat node needs the 9x9 solve, 648 bytes of shared memory per thread.
+			// One 352-thread block per SM on all of its shared memory keeps 352 systems resident against 5 x 64 = 320:
+			// 52 096 nodes per wave instead of 47 360 -- one wave for a rank that owns a whole 216^2 face
+			if(stage == 0 && s->border_lu_block == 352) gcm::stage_border_fast_kernel<true, 352><<<(nb + 351) / 352, 352, 81 * 352 * sizeof(double), bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
+			else if(stage == 0) gcm::stage_border_fast_kernel<true, 64><<<(nb + 63) / 64, 64, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
 			else gcm::stage_border_fast_kernel<false, 128><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
 			gcm::stage_deferred_kernel<<<64, 128, 0, bst>>>(m, dm.bnd_defer.p, stage, dm.unext(), s->d_err, zone, tap, yp, 0, 0x7fffffff);
 			s->launches += 2;
@@ -734,8 +740,10 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 					const unsigned* pidx = dm.ic_pat_idx.p + (size_t)stage * dm.N;
 					const gcm::InnerCacheEntry* pats = dm.ic_patterns.p + (size_t)stage * GCM_IC_MAX_PATTERNS;
 					const bool pat = dm.pattern_ok[stage];
-#define GCM_LAUNCH_CACHED(S_, P_) do { if(pat) gcm::stage_inner_pattern_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), dm.rs, nbeg, nrange, dm.unext(), pidx, pats, tab, dm.n_mat, mid, yp, \
-						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N); \
+#define GCM_LAUNCH_PATTERN(S_, P_, MB_) gcm::stage_inner_pattern_kernel<S_, P_, MB_><<<grid, block, 0, s->stream>>>(dm.ucur(), dm.rs, nbeg, nrange, dm.unext(), pidx, pats, tab, dm.n_mat, mid, yp, \
+						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N)
+#define GCM_LAUNCH_CACHED(S_, P_) do { if(pat) { if(s->inner_mb == 4) GCM_LAUNCH_PATTERN(S_, P_, 4); else if(s->inner_mb == 5) GCM_LAUNCH_PATTERN(S_, P_, 5); \
+						else if(s->inner_mb == 6) GCM_LAUNCH_PATTERN(S_, P_, 6); else GCM_LAUNCH_PATTERN(S_, P_, 1); } \
 					else gcm::stage_inner_cached_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), dm.rs, nbeg, nrange, dm.unext(), ce, tab, dm.n_mat, mid, yp, \
 						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N); } while(0)
 					if(stage == 0) GCM_LAUNCH_CACHED(0, false);
@@ -743,6 +751,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 					else if(yp) GCM_LAUNCH_CACHED(2, true);
 					else GCM_LAUNCH_CACHED(2, false);
 #undef GCM_LAUNCH_CACHED
+#undef GCM_LAUNCH_PATTERN
 					s->launches++;
 				}
 				if(dm.n_cold) {
@@ -1273,6 +1282,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 		CK(cudaMalloc(&s->d_err, 4 * sizeof(int)));
 		CK(cudaMemset(s->d_err, 0, 4 * sizeof(int)));
 		CK(cudaMallocHost(&s->h_err, 8 * sizeof(int)));
+		CK(cudaFuncSetAttribute(gcm::stage_border_fast_kernel<true, 352>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(81 * 352 * sizeof(double))));
 	}
 	s->rng.seed(1);   // libc default when srand() was never called
 	if(const char* e = getenv("GCM_B200_CONCURRENT")) s->concurrent = atoi(e) != 0;   // profiling aid
@@ -1283,6 +1293,8 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_FUSE_PLASTIC")) s->fuse_plastic = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_PATTERNS")) s->inner_patterns = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_P2P")) s->p2p = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_INNER_MB")) s->inner_mb = atoi(e);
+	if(const char* e = getenv("GCM_B200_BORDER_LU_BLOCK")) s->border_lu_block = atoi(e);
 	*out = s.release();
 	return 0;
 	GUARD_END
@@ -1400,6 +1412,72 @@ int gcm_b200_zone_load(gcm_b200_set* s, int zone, int n_nodes, int n_tets, const
 	hm.current_time = 0;
 	z->loaded = true;
 	s->plan_built = false;
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_zone_load_msh_file(gcm_b200_set* s, int zone, const char* path, float la, float mu, float rho, float yield_limit)
+{
+	GUARD_BEGIN
+	if(!path) return fail(gcmh::MESH_EXCEPTION, "Can not open msh file");
+	gcmh::MshData m;
+	gcmh::read_msh_file(path, m);
+	const int n = (int)m.placement.size();
+	std::vector<float> mat(4 * (size_t)n);
+	for(int i = 0; i < n; i++) { mat[4*(size_t)i] = la; mat[4*(size_t)i+1] = mu; mat[4*(size_t)i+2] = rho; mat[4*(size_t)i+3] = yield_limit; }
+	return gcm_b200_zone_load(s, zone, n, (int)(m.tets.size() / 4), m.coords.data(), m.placement.data(), m.remote_zone.data(),
+	                          m.remote_num.data(), m.tets.data(), mat.data());
+	GUARD_END
+}
+
+int gcm_b200_read_zones_map(const char* path, int* zone_rank, int capacity, int* n_zones)
+{
+	GUARD_BEGIN
+	if(!path || !n_zones) return fail(gcmh::CONFIG_EXCEPTION, "Can not open zone map file");
+	std::vector<int> z;
+	gcmh::read_zones_map(path, z);
+	*n_zones = (int)z.size();
+	if(zone_rank) for(int k = 0; k < (int)z.size() && k < capacity; k++) zone_rank[k] = z[k];
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_zone_dump_vtk(gcm_b200_set* s, int zone, const char* path)
+{
+	GUARD_BEGIN
+	Zone* z = get_zone(s, zone);
+	if(!z || !z->loaded || !path) return fail(gcmh::SNAP_EXCEPTION, "zone not loaded");
+	HostMesh& hm = z->hm;
+	gcmh::VtuData d;
+	d.coords = hm.coords; d.material = hm.mat; d.tets = hm.tets;
+	d.values.resize(9 * (size_t)hm.N);
+	if(int rc = gcm_b200_zone_get_values(s, zone, d.values.data())) return rc;
+	d.flags.resize(hm.N);
+	// Node::getFlags(): the reference's bit layout (Node.h:4-27) is the one the host mesh keeps
+	for(int i = 0; i < hm.N; i++) d.flags[i] = hm.flags[i];
+	if(s->dm.ready && s->device >= 0) {
+		d.destruction.resize(8 * (size_t)hm.N);
+		if(int rc = gcm_b200_zone_get_destruction_criterias(s, zone, d.destruction.data())) return rc;
+	}
+	gcmh::write_vtu_file(path, d);
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_zone_load_vtu_file(gcm_b200_set* s, int zone, const char* path)
+{
+	GUARD_BEGIN
+	Zone* z = get_zone(s, zone);
+	if(!z || !path) return fail(gcmh::CONFIG_EXCEPTION, "zone is not local to this process");
+	gcmh::VtuData d;
+	gcmh::read_vtu_file(path, d);
+	const int n = (int)d.flags.size();
+	// load_vtu_file keeps the stored flags: placement comes from them; a snapshot holds coordinates for every node
+	std::vector<int> placement(n), rz(n, -1), rn(n, -1);
+	for(int i = 0; i < n; i++) placement[i] = (d.flags[i] & gcm::NF_LOCAL) ? 1 : 0;
+	for(int i = 0; i < n; i++) if(!placement[i]) return fail(gcmh::UNIMPLEMENTED_EXCEPTION, "vtu restart of a zone with halo nodes (the snapshot does not store their owners)");
+	if(int rc = gcm_b200_zone_load(s, zone, n, (int)(d.tets.size() / 4), d.coords.data(), placement.data(), rz.data(), rn.data(), d.tets.data(), d.material.data())) return rc;
+	memcpy(z->hm.values.data(), d.values.data(), 9 * (size_t)n * sizeof(float));
 	return 0;
 	GUARD_END
 }
@@ -2041,12 +2119,24 @@ int gcm_b200_set_virt_count(gcm_b200_set* s) { return s ? (int)s->virt.size() : 
 
 int gcm_b200_set_get_virt(gcm_b200_set* s, float* out16)
 {
+	GUARD_BEGIN
 	if(!s || !out16) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
+	// the friction calculator writes into its virtual node (the swapped-argument Adhesion call of
+	// FrictionContactCalculator.cpp:123): the device copy is the current one
+	std::vector<gcm::VirtNode> dv;
+	if(s->d_virt.p && s->d_virt.n == s->virt.size() && !s->virt.empty() && s->device >= 0) {
+		CK(cudaSetDevice(s->device));
+		dv.resize(s->virt.size());
+		CK(cudaMemcpyAsync(dv.data(), s->d_virt.p, dv.size() * sizeof(gcm::VirtNode), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+	}
 	for(size_t k = 0; k < s->virt.size(); k++) {
 		memcpy(out16 + 16 * k, s->virt[k].coords, 3 * sizeof(float));
 		memcpy(out16 + 16 * k + 3, s->virt[k].values, 13 * sizeof(float));
+		if(!dv.empty()) memcpy(out16 + 16 * k + 3, dv[k].val, 9 * sizeof(float));
 	}
 	return 0;
+	GUARD_END
 }
 
 } // extern "C"

@@ -134,4 +134,19 @@ struct VirtNodeHost {
 void find_collisions(std::vector<HostMesh*>& meshes, float threshold, std::vector<VirtNodeHost>& virt,
                      std::vector<std::vector<int> >& axis_plus0);
 
+// ---- on-disk formats (gcm_io.cpp) ----------------------------------------------------------------
+struct MshData {           // what TetrMesh_1stOrder::load_msh_file leaves in nodes / tetrs
+	std::vector<float> coords;                       // [3N]; zeros for halo nodes
+	std::vector<int> placement, remote_zone, remote_num;   // [N]; 1 = Local; 0-based remote_num
+	std::vector<int> tets;                           // [4T], 0-based
+};
+void read_msh_file(const std::string& path, MshData& out);
+void read_zones_map(const std::string& path, std::vector<int>& zone_cpu);
+struct VtuData {           // one zone's snapshot: VTKSnapshotWriter::dump_vtk / TetrMesh_1stOrder::load_vtu_file
+	std::vector<float> coords, values, material, destruction;   // [3N] [9N] [4N] [8N or empty]
+	std::vector<int> flags, tets;                                 // [N] Node::getFlags(), [4T]
+};
+void write_vtu_file(const std::string& path, const VtuData& d);
+void read_vtu_file(const std::string& path, VtuData& d);
+
 } // namespace gcmh

@@ -740,8 +740,9 @@ ic_dedup_assign_kernel(const int* __restrict__ list, int n_list, const int* __re
 
 // The hot kernel over the pattern table: identical to stage_inner_cached_kernel but for where the
 // entry comes from (pattern id -> pattern -> absolute vertex ids).
-template<int S, bool PLASTIC>
-__global__ void __launch_bounds__(256)
+// MB = resident blocks per SM the register allocation aims at (1: unconstrained; occupancy against a few spilled words)
+template<int S, bool PLASTIC, int MB>
+__global__ void __launch_bounds__(256, MB)
 stage_inner_pattern_kernel(const float* __restrict__ u, size_t rs, int node_begin, int n_range, float* __restrict__ un,
                            const unsigned* __restrict__ pat_idx, const InnerCacheEntry* __restrict__ patterns,
                            const MatTab* __restrict__ tab, int n_mat,

@@ -72,12 +72,16 @@ stage_deferred_kernel(const __grid_constant__ MeshView m, const int* __restrict_
 // stages run without it at full occupancy.  Whatever the routine defers (ambiguous candidate, alpha
 // retries, ...) is appended to `defer` (defer[0] = count) for the literal routine right behind.
 template<bool LU, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, LU ? 5 : 4)
+__global__ void __launch_bounds__(BLOCK, LU ? (BLOCK > 64 ? 1 : 5) : 4)
 stage_border_fast_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
                          float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane,
                          const BndSlotStatic* __restrict__ bstat, const float4* __restrict__ cand, int* __restrict__ defer)
 {
-	__shared__ double sA[LU ? 81 * BLOCK : 1];
+	// BLOCK <= 64: static array, 5 blocks per SM; BLOCK = 352: one block per SM on 228 096 bytes of dynamic shared
+	// memory (the whole SM: 352 instead of 320 systems resident)
+	__shared__ double sA_static[(LU && BLOCK <= 64) ? 81 * BLOCK : 1];
+	extern __shared__ double sA_dynamic[];
+	double* sA = BLOCK > 64 ? sA_dynamic : sA_static;
 	const int idx = blockIdx.x * BLOCK + threadIdx.x;
 	if(idx >= n_list) return;
 	const int node = list[idx];
@@ -290,10 +294,14 @@ halo_push_kernel(const float* __restrict__ u, size_t rs, const int* __restrict__
 		const float4 v = rec_quad(u, rs, send_node[i], q);
 		reinterpret_cast<float4*>(base)[(size_t)q * prs + (size_t)remote_slot[i]] = v;
 	}
-	__threadfence_system();
+	// one system-wide fence per block, by the thread that then counts the block in: the barrier orders the block's
+	// stores before it, the fence is cumulative (every thread fencing on its own cost 20 us per exchange at 8 GPUs)
 	__shared__ bool last;
 	__syncthreads();
-	if(threadIdx.x == 0) last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+	if(threadIdx.x == 0) {
+		__threadfence_system();
+		last = atomicAdd(done_counter, 1u) == gridDim.x - 1;
+	}
 	__syncthreads();
 	if(last && threadIdx.x < n_peers) {
 		int* flag = threadIdx.x == 0 ? t0.flag : (threadIdx.x == 1 ? t1.flag : more[threadIdx.x].flag);

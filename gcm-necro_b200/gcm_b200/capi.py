@@ -59,6 +59,10 @@ SIGNATURES = {
     "gcm_b200_set_contact_calculator": (_i, [_p, _i]),
     "gcm_b200_zone_load": (_i, [_p, _i, _i, _i, _fp, _ip, _ip, _ip, _ip, _fp]),
     "gcm_b200_zone_translate": (_i, [_p, _i, _f, _f, _f]),
+    "gcm_b200_zone_load_msh_file": (_i, [_p, _i, C.c_char_p, _f, _f, _f, _f]),
+    "gcm_b200_read_zones_map": (_i, [C.c_char_p, _ip, _i, _ip]),
+    "gcm_b200_zone_dump_vtk": (_i, [_p, _i, C.c_char_p]),
+    "gcm_b200_zone_load_vtu_file": (_i, [_p, _i, C.c_char_p]),
     "gcm_b200_zone_set_values": (_i, [_p, _i, _fp]),
     "gcm_b200_zone_get_values": (_i, [_p, _i, _fp]),
     "gcm_b200_zone_upload_values_async": (_i, [_p, _i, _p]),
@@ -161,6 +165,20 @@ class TetrMesh_1stOrder:
                                                      _fptr(coords), _iptr(pl), _iptr(rz), _iptr(rn), _iptr(tets),
                                                      _fptr(material)))
         self._n_nodes = n
+
+    def load_msh_file(self, path, la, mu, rho, yield_limit=1e16):
+        """TetrMesh_1stOrder::load_msh_file + the rheology TaskPreparator gives every node."""
+        self._ck(self.mesh_set.lib.gcm_b200_zone_load_msh_file(self.mesh_set.h, self.zone_num, str(path).encode(), la, mu, rho, yield_limit))
+        self._n_nodes = self.counts()["nodes"]
+
+    def load_vtu_file(self, path):
+        """TetrMesh_1stOrder::load_vtu_file: mesh, material and state of a snapshot (restart)."""
+        self._ck(self.mesh_set.lib.gcm_b200_zone_load_vtu_file(self.mesh_set.h, self.zone_num, str(path).encode()))
+        self._n_nodes = self.counts()["nodes"]
+
+    def dump_vtk(self, path):
+        """VTKSnapshotWriter::dump_vtk for this zone."""
+        self._ck(self.mesh_set.lib.gcm_b200_zone_dump_vtk(self.mesh_set.h, self.zone_num, str(path).encode()))
 
     def translate(self, dx, dy, dz):
         self._ck(self.mesh_set.lib.gcm_b200_zone_translate(self.mesh_set.h, self.zone_num, dx, dy, dz))

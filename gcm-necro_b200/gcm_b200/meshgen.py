@@ -204,3 +204,28 @@ def make_delaunay_box(n_side: int, jitter: float = 0.3, seed: int = 0, min_quali
     tets = np.ascontiguousarray(tets[keep])
     n = xyz.shape[0]
     return ZoneMesh(0, xyz, np.ones(n, np.int32), np.full(n, -1, np.int32), np.full(n, -1, np.int32), tets)
+
+
+def write_msh(path: str, z: ZoneMesh, extra_elements: bool = True) -> None:
+    """gmsh-2 ASCII file as TetrMesh_1stOrder::load_msh_file reads it: local nodes ``id x y z``, halo nodes
+    ``-id remote_zone remote_id`` (1-based ids, the zone splitter's encoding, gcm/tools/create_cube.c:38-81),
+    tetrahedra ``num 4 2 0 1 v0 v1 v2 v3`` -- exactly three integers between the type and the vertices (two tags;
+    create_cube.c itself writes three tags and needs the sed of SURVEY fact 9).  ``extra_elements`` adds a few
+    non-tetrahedral elements (points, triangles), which the reader must skip."""
+    with open(path, "w") as f:
+        f.write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n%d\n" % z.n_nodes)
+        for i in range(z.n_nodes):
+            if z.placement[i]:
+                f.write("%d %s %s %s\n" % (i + 1, repr(float(z.coords[i, 0])), repr(float(z.coords[i, 1])), repr(float(z.coords[i, 2]))))
+            else:
+                f.write("%d %d %d\n" % (-(i + 1), z.remote_zone[i], z.remote_num[i] + 1))
+        extra = []
+        if extra_elements:
+            extra = ["%d 15 2 0 1 1" % 1, "%d 2 2 0 1 1 2 3" % 2]
+        f.write("$EndNodes\n$Elements\n%d\n" % (z.n_tets + len(extra)))
+        for e in extra:
+            f.write(e + "\n")
+        for t in range(z.n_tets):
+            v = z.tets[t]
+            f.write("%d 4 2 0 1 %d %d %d %d\n" % (t + 1 + len(extra), v[0] + 1, v[1] + 1, v[2] + 1, v[3] + 1))
+        f.write("$EndElements\n")

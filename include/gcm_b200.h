@@ -60,6 +60,19 @@ int gcm_b200_set_contact_calculator(gcm_b200_set* s, int type);
 int gcm_b200_zone_load(gcm_b200_set* s, int zone, int n_nodes, int n_tets, const float* coords,
                        const int* placement, const int* remote_zone, const int* remote_num,
                        const int* tets, const float* material);
+/* TetrMesh_1stOrder::load_msh_file (TetrMesh_1stOrder.cpp:735-866): the gmsh-2 ASCII subset it accepts, with the
+ * zone splitter's halo lines (-id remote_zone remote_id).  la/mu/rho/yield_limit: the rheology TaskPreparator
+ * assigns to every node of the mesh (TaskPreparator.cpp:335-386 with an unbounded area). */
+int gcm_b200_zone_load_msh_file(gcm_b200_set* s, int zone, const char* path, float la, float mu, float rho, float yield_limit);
+/* TaskPreparator::load_zones_info (TaskPreparator.cpp:65-99): <zones_map><zone num="i" cpu="r"/>...; *n_zones
+ * receives the number of zones, zone_rank[0..min(n, capacity)) their cpu.  Feeds gcm_b200_set_create. */
+int gcm_b200_read_zones_map(const char* path, int* zone_rank, int capacity, int* n_zones);
+/* VTKSnapshotWriter::dump_vtk (VTKSnapshotWriter.cpp:49-206) for one zone: .vtu UnstructuredGrid (ASCII arrays) with
+ * the same point arrays and names (velocity, sxx..szz, lambda, mu, rho, yieldLimit, contact, flags, max*),
+ * current device state; and the restart reader TetrMesh_1stOrder::load_vtu_file (:868-949) for such a file
+ * (instead of gcm_b200_zone_load; the stored values become the initial state). */
+int gcm_b200_zone_dump_vtk(gcm_b200_set* s, int zone, const char* path);
+int gcm_b200_zone_load_vtu_file(gcm_b200_set* s, int zone, const char* path);
 /* TetrMesh::translate (TetrMesh.cpp:29-45); before preprocess only. */
 int gcm_b200_zone_translate(gcm_b200_set* s, int zone, float dx, float dy, float dz);
 /* Initial state, written straight into nodes[i].values[0..8]; values[9N] node-major. */

@@ -2,7 +2,8 @@
 //
 // Reproduces gcm/main.cpp's call order without TaskPreparator (TinyXML is absent):
 //   srand(seed) -> TetrMeshSet/DataBus singletons -> per-zone mesh from a binary .gcmb file
-//   (same per-node initialisation as load_msh_file, TetrMesh_1stOrder.cpp:773-823) ->
+//   (same per-node initialisation as load_msh_file, TetrMesh_1stOrder.cpp:773-823) or, for a *.msh
+//   argument, through the reference's own load_msh_file ->
 //   sync_nodes -> pre_process_meshes -> initial state -> N x TetrMeshSet::do_next_step().
 // It dumps what the parity tests compare against: final values[9] per node, node flags,
 // border faces, border-node bases of the last step, and (tap build) one record per owner
@@ -143,6 +144,18 @@ int main(int argc, char** argv)
 	db->attach(cd);
 
 	for(int z = 0; z < Z; z++) {
+		if(mesh_files[z].size() > 4 && mesh_files[z].substr(mesh_files[z].size() - 4) == ".msh") {
+			// the reference's own reader (TetrMesh_1stOrder::load_msh_file, :735-866), then what TaskPreparator
+			// does with a loaded mesh: rheology for every node (TaskPreparator.cpp:335-386), method, attach
+			TetrMesh_1stOrder* m = ms->get_mesh_by_zone_num(z);
+			m->load_msh_file(const_cast<char*>(mesh_files[z].c_str()));
+			for(size_t i = 0; i < m->nodes.size(); i++) {
+				m->nodes[i].la = la; m->nodes[i].mu = mu; m->nodes[i].rho = rho; m->nodes[i].yield_limit = yield;
+			}
+			m->attach(new GCM_Tetr_Plastic_Interpolation_1stOrder_Rotate_Axis());
+			ms->attach(m);
+			continue;
+		}
 		FILE* f = fopen(mesh_files[z].c_str(), "rb");
 		if(!f) die("cannot open mesh file");
 		int hdr[5];

@@ -94,13 +94,15 @@ struct Zone {
 	size_t st0_off = 0, st0_n = 0, c0_off = 0, c0_n = 0, c1_off = 0, c1_n = 0;   // contact launch lists
 	size_t border_off = 0;                       // range in the merged border list
 	bool stage_done = false;
+	// pipelined host <-> device traffic of the *_async calls (see gcm_b200_zone_upload_values_async)
+	cudaEvent_t ev_h2d_done = nullptr, ev_in_consumed = nullptr, ev_out_ready = nullptr, ev_d2h_done = nullptr;
 };
 
 // The merged device mesh of every local zone.
 struct DeviceMesh {
 	size_t N = 0, T = 0, E = 0, NB = 0, stride = 0, rs = 0;   // rs: quads per plane of the node records (gcm_step.cuh)
 	size_t n_fast = 0, n_generic = 0, n_inner = 0;
-	DevBuf<float> u0, u1, mat, tet_hv, basis, basis_next, normals, w0, aos, mat_tab;
+	DevBuf<float> u0, u1, mat, tet_hv, basis, basis_next, normals, w0, aos, aos_out, mat_tab;
 	DevBuf<int> flags, n2t_off, n2t, tets, border_slot, cond_id, n2x, cold;
 	// step-invariant cache of the inner kernel (gcm_inner.cuh): 3 planes of N entries, built lazily for a tau
 	DevBuf<gcm::InnerCacheEntry> icache;
@@ -144,7 +146,7 @@ struct gcm_b200_set {
 	gcmh::GlibcRand rng;
 	gcmh::MaterialRegistry materials;
 	DeviceMesh dm;
-	cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, rng_stream = nullptr;
+	cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, rng_stream = nullptr, io_in = nullptr, io_out = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_rng_done = nullptr, ev_step_mark = nullptr;
 	bool bases_ahead = true;     // device generator: the NEXT step's bases are produced on rng_stream during this step
 	bool ahead_valid = false;    // dm.basis_next holds the bases of the coming step
@@ -157,6 +159,8 @@ struct gcm_b200_set {
 	int comm_rank = -1, comm_size = 0;
 	// direct peer-store exchange (gcm_kernels.cuh: halo_push_kernel / halo_wait_kernel), set up by comm_init
 	bool p2p = true, p2p_ready = false;
+	bool p2p_dma_wanted = false, p2p_dma = false;   // contiguous halo layers: records by cudaMemcpyAsync (copy engines) instead of the push kernel
+	std::vector<int> p2p_dma_ranges;              // per neighbour: first send node, first slot over there
 	int p2p_seq = 0;
 	DevBuf<int> p2p_flags, p2p_send_node, p2p_remote_slot, p2p_peer_ranks;
 	DevBuf<unsigned> p2p_counter;
@@ -175,7 +179,8 @@ struct gcm_b200_set {
 	bool inner_cache = true;     // inner nodes through the step-invariant owner/factor cache (gcm_inner.cuh); 0 = index-free scan kernel
 	bool inner_patterns = true;  // de-duplicate the cache into a pattern table where an axis has few distinct entries
 	bool track_destruction = false;   // calc_destruction_criterias at the end of every step (its running maxima need every step)
-	int border_lu_block = 352;   // block size of the stage-0 border kernel (352: one block per SM, or 64: five)
+	int border_lu_block = 64;    // block size of the stage-0 border kernel: 64 (five blocks per SM), or 352 (one block on all of an SM's
+	                             // shared memory: 10 % more systems per wave, but nothing else fits beside it -- slower at 8 GPUs, 0.333 vs 0.301 ms)
 	int inner_mb = 5;            // register budget of the pattern kernel: resident 256-thread blocks per SM aimed at (4, 5, 6; anything else: 1 block, up to 255 registers); 5 = 48 registers measured fastest at 216^3 (1.47 vs 1.49 / 1.53 ms per step)
 	bool fuse_plastic = true;    // whole-step calls: stage 3 as the epilogue of the stage-2 writers (and no exchange before it)
 	// contact: virtual nodes of the last collision pass and the launch lists derived from them
@@ -187,6 +192,14 @@ struct gcm_b200_set {
 	DevBuf<float> d_gather;
 	size_t st0_total = 0, c0_total = 0;
 	bool contact_active = false;
+	// collision discovery on the device (gcm_collide.cuh); the host detector stays as the A/B (GCM_B200_DEVICE_COLLISIONS=0)
+	bool coll_device = true, coll_ready = false, coll_host_stale = false;
+	int coll_n_cand = 0;
+	std::vector<int> coll_zone_off, coll_zone_n;     // per local zone (local_meshes order): its candidate range
+	DevBuf<gcm::CollPair> coll_pairs;
+	DevBuf<gcm::CollFace> coll_faces;
+	DevBuf<int> coll_cand_pair, coll_cand_node, coll_cand_slot, coll_cand_phase, coll_grid_start, coll_grid_items, coll_hit_l, coll_hit_virt, coll_n_virt;
+	DevBuf<float> coll_hit_p;
 	long long step_count = 0;
 	// device-side rand() stream + bases (rng_chunk_kernel / basis_kernel)
 	bool basis_on_device = true;
@@ -315,6 +328,7 @@ void upload_values(gcm_b200_set* s, Zone& z)
 	const int n = z.hm.N;
 	if(!n) return;
 	float* stage = dm.aos.p + 9 * z.node_off;
+	if(s->io_in) CK(cudaStreamSynchronize(s->io_in));
 	CK(cudaMemcpyAsync(stage, z.hm.values.data(), 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
 	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.u0.p + 4 * z.node_off, dm.u1.p + 4 * z.node_off, dm.rs,
 		stage, dm.flags.p + z.node_off, n, 0);
@@ -680,7 +694,9 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 	int nb = (int)(z ? z->hm.border_launch.size() : dm.NB);
 	const int* bl = dm.border_list.p + (z ? z->border_off : 0);
 	const bool contact = stage == 0 && s->contact_active;
-	if(contact) {   // border nodes in contact on axis 0 take the contact kernel instead
+	const bool dev_lists = contact && s->coll_ready;      // contact state built on the device: full lists + filters
+	const int* skip_contact = dev_lists ? s->d_axis_plus0.p : nullptr;
+	if(contact && !dev_lists) {   // border nodes in contact on axis 0 take the contact kernel instead
 		nb = (int)(z ? z->st0_n : s->st0_total);
 		bl = s->d_border_stage0.p + (z ? z->st0_off : 0);
 	}
@@ -701,13 +717,13 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 			// stage 0 = the normal axis: every flat node needs the 9x9 solve, 648 bytes of shared memory per thread.
 			// One 352-thread block per SM on all of its shared memory keeps 352 systems resident against 5 x 64 = 320:
 			// 52 096 nodes per wave instead of 47 360 -- one wave for a rank that owns a whole 216^2 face
-			if(stage == 0 && s->border_lu_block == 352) gcm::stage_border_fast_kernel<true, 352><<<(nb + 351) / 352, 352, 81 * 352 * sizeof(double), bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
-			else if(stage == 0) gcm::stage_border_fast_kernel<true, 64><<<(nb + 63) / 64, 64, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
+			if(stage == 0 && s->border_lu_block == 352) gcm::stage_border_fast_kernel<true, 352><<<(nb + 351) / 352, 352, 81 * 352 * sizeof(double), bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p, skip_contact);
+			else if(stage == 0) gcm::stage_border_fast_kernel<true, 64><<<(nb + 63) / 64, 64, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p, skip_contact);
 			else gcm::stage_border_fast_kernel<false, 128><<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, bstat, cq, dm.bnd_defer.p);
 			gcm::stage_deferred_kernel<<<64, 128, 0, bst>>>(m, dm.bnd_defer.p, stage, dm.unext(), s->d_err, zone, tap, yp, 0, 0x7fffffff);
 			s->launches += 2;
 		} else {
-			gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp);
+			gcm::stage_generic_kernel<<<(nb + 127) / 128, 128, 0, bst>>>(m, bl, nb, stage, dm.unext(), s->d_err, zone, tap, yp, skip_contact);
 			s->launches++;
 		}
 	}
@@ -794,23 +810,34 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 			if(s->d_deep.n < n + 1) s->d_deep.alloc(n + 1);
 			if(!s->d_ring_ws.p) s->d_ring_ws.alloc((size_t)deep_blocks * 64 * GCM_RING_WS);
 			CK(cudaMemsetAsync(s->d_deep.p, 0, sizeof(int), s->stream));
-			gcm::stage_contact_kernel<<<(int)((n + 63) / 64), 64, 0, s->stream>>>(m, s->d_contact_nodes.p + off, (int)n, stage, dm.unext(),
-				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap, s->d_deep.p, 0);
+			const int* list = (dev_lists ? s->coll_cand_node.p : s->d_contact_nodes.p) + off;
+			const int* sel = dev_lists ? s->coll_hit_virt.p + off : nullptr;
+			const int* sel_phase = dev_lists ? s->coll_cand_phase.p + off : nullptr;
+			gcm::stage_contact_kernel<<<(int)((n + 63) / 64), 64, 0, s->stream>>>(m, list, (int)n, stage, dm.unext(),
+				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap, s->d_deep.p, 0, sel, sel_phase, partner_next);
 			gcm::MeshView md = m;
 			md.ring_ws = s->d_ring_ws.p;
-			gcm::stage_contact_kernel<<<deep_blocks, 64, 0, s->stream>>>(md, s->d_contact_nodes.p + off, (int)n, stage, dm.unext(),
+			gcm::stage_contact_kernel<<<deep_blocks, 64, 0, s->stream>>>(md, list, (int)n, stage, dm.unext(),
 				s->d_virt.p, s->d_axis_plus0.p, dm.normals.p, s->contact_calc, partner_next, first, s->d_err, zn, tap, s->d_deep.p, 1);
 			s->launches += 2;
 		};
 		// a partner that was already advanced is read in its NEXT layer; its Remote (halo) entries are not written by
 		// a stage and keep the values synced before it (the copy-back loop, TetrMesh_1stOrder.cpp:1925-1932, touches
 		// local nodes only), so those slots are carried over from the current layer first
-		if(dm.n_halo && (z ? z->c1_n : s->virt.size())) {
+		if(dm.n_halo && (dev_lists ? (size_t)s->coll_n_cand : (z ? z->c1_n : s->virt.size()))) {
 			const int n = (int)dm.n_halo;
 			gcm::halo_copy_kernel<<<(3 * n + 255) / 256, 256, 0, s->stream>>>(dm.unext(), dm.halo_dst.p, dm.ucur(), dm.halo_dst.p, n, dm.rs);
 			s->launches++;
 		}
-		if(z) { launch(z->c0_off, z->c0_n, 0, zone); launch(z->c1_off, z->c1_n, 1, zone); }
+		if(dev_lists) {
+			// every candidate of the pass is listed (zone after zone); the kernel keeps those that hit, by phase
+			auto zpos = [&](int zn) { for(size_t a = 0; a < s->local_zones.size(); a++) if(s->local_zones[a] == zn) return a; return (size_t)0; };
+			if(z) { const size_t a = zpos(zone); launch(s->coll_zone_off[a], s->coll_zone_n[a], 0, zone); launch(s->coll_zone_off[a], s->coll_zone_n[a], 1, zone); }
+			else {
+				launch(0, s->coll_n_cand, 0, -1);
+				for(size_t a = 0; a < s->local_zones.size(); a++) launch(s->coll_zone_off[a], s->coll_zone_n[a], 1, s->local_zones[a]);
+			}
+		} else if(z) { launch(z->c0_off, z->c0_n, 0, zone); launch(z->c1_off, z->c1_n, 1, zone); }
 		else {
 			launch(0, s->c0_total, 0, -1);
 			for(int zi : s->local_zones) launch(s->zones[zi]->c1_off, s->zones[zi]->c1_n, 1, zi);
@@ -822,8 +849,104 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 // CollisionDetector::find_collisions + the bookkeeping around it in TetrMeshSet::do_next_step
 // (TetrMeshSet.cpp:111-120): runs on the host (gcmh::find_collisions) on the border nodes' current
 // values and bases, then lays the result out for stage_contact_kernel.
+// The device detector: static plan once, then four small launches per pass on the set's stream -- no host round trip.
+void run_collision_detection_device(gcm_b200_set* s)
+{
+	DeviceMesh& dm = s->dm;
+	cudaStream_t st = s->stream;
+	if(!s->coll_ready) {
+		std::vector<HostMesh*> meshes;
+		for(int zi : s->local_zones) meshes.push_back(&s->zones[zi]->hm);
+		gcmh::CollisionPlan plan;
+		gcmh::build_collision_plan(meshes, s->detector_threshold, plan);
+		// zone-local numbers -> the merged device mesh
+		std::vector<int> phase(plan.cand_node.size());
+		for(size_t g = 0; g < plan.cand_node.size(); g++) {
+			Zone& za = *s->zones[s->local_zones[plan.cand_mesh[g]]];
+			plan.cand_node[g] += (int)za.node_off;
+			plan.cand_slot[g] += (int)za.slot_off;
+			phase[g] = plan.pairs[plan.cand_pair[g]].phase;
+		}
+		for(size_t f = 0; f < plan.faces.size(); f++) {
+			const int off = (int)s->zones[s->local_zones[plan.face_mesh[f]]]->node_off;
+			plan.faces[f].v0 += off; plan.faces[f].v1 += off; plan.faces[f].v2 += off;
+		}
+		s->coll_n_cand = (int)plan.cand_node.size();
+		s->coll_zone_off.assign(plan.mesh_cand_off.begin(), plan.mesh_cand_off.end());
+		s->coll_zone_n.assign(plan.mesh_cand_n.begin(), plan.mesh_cand_n.end());
+		s->coll_pairs.upload(plan.pairs, st); s->coll_faces.upload(plan.faces, st);
+		s->coll_cand_pair.upload(plan.cand_pair, st); s->coll_cand_node.upload(plan.cand_node, st); s->coll_cand_slot.upload(plan.cand_slot, st);
+		s->coll_cand_phase.upload(phase, st);
+		if(plan.grid_start.empty()) plan.grid_start.push_back(0);
+		if(plan.grid_items.empty()) plan.grid_items.push_back(0);
+		s->coll_grid_start.upload(plan.grid_start, st); s->coll_grid_items.upload(plan.grid_items, st);
+		const size_t nc = (size_t)std::max(1, s->coll_n_cand);
+		s->coll_hit_l.alloc(nc); s->coll_hit_virt.alloc(nc); s->coll_hit_p.alloc(3 * nc); s->coll_n_virt.alloc(1);
+		s->d_virt.alloc(nc);
+		CK(cudaMemsetAsync(s->coll_n_virt.p, 0, sizeof(int), st));
+		if(!s->d_border_by_slot.p && dm.NB) {
+			std::vector<int> bys;
+			for(int zi : s->local_zones) {
+				Zone& z = *s->zones[zi];
+				for(int b : z.hm.border_nodes) bys.push_back((int)(z.node_off + b));
+			}
+			s->d_border_by_slot.upload(bys, st);
+			s->d_gather.alloc(9 * dm.NB);
+		}
+		s->d_axis_plus0.alloc(std::max<size_t>(1, dm.NB));
+		s->coll_ready = true;
+	}
+	const int nc = s->coll_n_cand;
+	if(dm.NB) {
+		gcm::collide_clear_kernel<<<(int)((dm.NB + 255) / 256), 256, 0, st>>>(dm.flags.p, s->d_border_by_slot.p, s->d_axis_plus0.p, (int)dm.NB);
+		s->launches++;
+	}
+	if(nc) {
+		ProfScope ps(s, PROF_BORDER, nc);
+		gcm::collide_find_kernel<<<(nc + 127) / 128, 128, 0, st>>>(dm.ucur(), dm.rs, dm.basis.p, s->coll_pairs.p, s->coll_cand_pair.p, s->coll_cand_node.p,
+			s->coll_cand_slot.p, nc, s->coll_faces.p, s->coll_grid_start.p, s->coll_grid_items.p, s->coll_hit_l.p, s->coll_hit_p.p, s->d_err);
+		gcm::collide_number_kernel<<<1, 1024, 0, st>>>(s->coll_hit_l.p, nc, s->coll_hit_virt.p, s->coll_n_virt.p);
+		gcm::collide_build_kernel<<<(nc + 127) / 128, 128, 0, st>>>(dm.ucur(), dm.rs, dm.mat.p, dm.stride, s->coll_pairs.p, s->coll_cand_pair.p, s->coll_cand_node.p,
+			s->coll_cand_slot.p, nc, s->coll_faces.p, s->coll_hit_l.p, s->coll_hit_p.p, s->coll_hit_virt.p, s->d_virt.p, s->d_axis_plus0.p, dm.flags.p, s->d_err);
+		s->launches += 3;
+	}
+	CK(cudaGetLastError());
+	s->contact_active = nc > 0;
+	s->coll_host_stale = true;
+}
+
+// Host mirrors of a device pass (virtual nodes, contact flags), fetched when somebody asks for them.
+void collisions_to_host(gcm_b200_set* s)
+{
+	if(!s->coll_ready || !s->coll_host_stale) return;
+	DeviceMesh& dm = s->dm;
+	CK(cudaSetDevice(s->device));
+	int n = 0;
+	CK(cudaMemcpyAsync(&n, s->coll_n_virt.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	std::vector<gcm::VirtNode> dv((size_t)n);
+	if(n) CK(cudaMemcpyAsync(dv.data(), s->d_virt.p, (size_t)n * sizeof(gcm::VirtNode), cudaMemcpyDeviceToHost, s->stream));
+	std::vector<int> fl(dm.N);
+	if(dm.N) CK(cudaMemcpyAsync(fl.data(), dm.flags.p, dm.N * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaStreamSynchronize(s->stream));
+	s->virt.assign((size_t)n, gcmh::VirtNodeHost());
+	for(int k = 0; k < n; k++) {
+		gcmh::VirtNodeHost& h = s->virt[k];
+		memset(&h, 0, sizeof h);
+		for(int q = 0; q < 3; q++) h.coords[q] = dv[k].pos[q];
+		for(int q = 0; q < 9; q++) h.values[q] = dv[k].val[q];
+		h.values[9] = dv[k].la; h.values[10] = dv[k].mu; h.values[11] = dv[k].rho; h.values[12] = dv[k].yield;
+	}
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		for(int i = 0; i < z.hm.N; i++) z.hm.flags[i] = (z.hm.flags[i] & ~1) | (fl[z.node_off + i] & 1);
+	}
+	s->coll_host_stale = false;
+}
+
 void run_collision_detection(gcm_b200_set* s)
 {
+	if(s->coll_device) { run_collision_detection_device(s); return; }
 	DeviceMesh& dm = s->dm;
 	std::vector<HostMesh*> meshes;
 	for(int zi : s->local_zones) meshes.push_back(&s->zones[zi]->hm);
@@ -862,7 +985,7 @@ void run_collision_detection(gcm_b200_set* s)
 		gcm::VirtNode& v = dv[k];
 		for(int q = 0; q < 3; q++) v.pos[q] = h.coords[q];
 		for(int q = 0; q < 9; q++) v.val[q] = h.values[q];
-		v.la = h.values[9]; v.mu = h.values[10]; v.rho = h.values[11];
+		v.la = h.values[9]; v.mu = h.values[10]; v.rho = h.values[11]; v.yield = h.values[12];
 		v.base = (int)(s->zones[h.remote_zone]->node_off + h.base_node);
 		v.real = (int)(s->zones[h.real_zone]->node_off + h.real_node);
 		v.phase = order[h.remote_zone] < order[h.real_zone] ? 1 : 0;
@@ -926,6 +1049,7 @@ const char* step_error_text(int code)
 	case gcm::ERR_ZERO_VOLUME: return "Tetr volume is zero";
 	case gcm::ERR_FOOT_PATTERN: return "More than 5 distinct characteristic feet";
 	case gcm::ERR_PEER_TIMEOUT: return "A neighbour process did not deliver its halo nodes";
+	case gcm::ERR_COLLISION_NAN: return "NAN or INF in collision detection (stage field: 1 p1, 2 p2, 3 p3, 4 p0, 5 v, 6 n, 7 virt node coords)";
 	default: return "Unknown device error";
 	}
 }
@@ -933,7 +1057,7 @@ const char* step_error_text(int code)
 int step_error_exc(int code)
 {
 	switch(code) {
-	case gcm::ERR_INTERP_SUM: case gcm::ERR_ZERO_VOLUME: return gcmh::MESH_EXCEPTION;
+	case gcm::ERR_INTERP_SUM: case gcm::ERR_ZERO_VOLUME: case gcm::ERR_COLLISION_NAN: return gcmh::MESH_EXCEPTION;
 	case gcm::ERR_BAD_RHEOLOGY: case gcm::ERR_BAD_Q: return gcmh::CONFIG_EXCEPTION;
 	case gcm::ERR_INNER_NO_OWNER: case gcm::ERR_RING_OVERFLOW: return gcmh::UNIMPLEMENTED_EXCEPTION;
 	case gcm::ERR_PEER_TIMEOUT: return gcmh::SYNC_EXCEPTION;
@@ -1150,6 +1274,18 @@ void p2p_setup(gcm_b200_set* s)
 				me, k, peer_ranks[k], t.begin, t.end, sn_host[t.begin], sn_host[t.end - 1], rs_host[t.begin], rs_host[t.end - 1], lo, hi, t.rs);
 		}
 		if(!agree(good)) { if(dbg) fprintf(stderr, "[gcm_b200 p2p %d] slot lists out of range somewhere\n", me); return; }
+		// halo layers that are contiguous node ranges on both sides (z-slab zones) can go through the copy engines
+		s->p2p_dma_ranges.clear();
+		bool contiguous = s->p2p_dma_wanted;
+		for(size_t k = 0; k < s->p2p_targets.size() && contiguous; k++) {
+			const gcm::PeerTarget& t = s->p2p_targets[k];
+			for(int i = t.begin; i < t.end && contiguous; i++)
+				contiguous = sn_host[i] == sn_host[t.begin] + (i - t.begin) && rs_host[i] == rs_host[t.begin] + (i - t.begin);
+			if(t.end > t.begin) { s->p2p_dma_ranges.push_back(sn_host[t.begin]); s->p2p_dma_ranges.push_back(rs_host[t.begin]); }
+			else { s->p2p_dma_ranges.push_back(0); s->p2p_dma_ranges.push_back(0); }
+		}
+		s->p2p_dma = contiguous;
+		if(dbg) fprintf(stderr, "[gcm_b200 p2p %d] copy-engine exchange: %s\n", me, s->p2p_dma ? "yes" : "no");
 	}
 	s->p2p_peer_ranks.upload(peer_ranks, st);
 	s->p2p_more.upload(s->p2p_targets, st);
@@ -1171,6 +1307,23 @@ void p2p_exchange(gcm_b200_set* s, cudaStream_t st)
 	const int np = (int)s->p2p_targets.size();
 	const int n_total = (int)s->p2p_send_node.n;
 	const int seq = ++s->p2p_seq;
+	if(s->p2p_dma) {
+		// three plane-wise peer copies per neighbour on the copy engines, then one small kernel: flags up, wait
+		ProfScope ps(s, PROF_HALO, n_total, st);
+		for(int k = 0; k < np; k++) {
+			const gcm::PeerTarget& t = s->p2p_targets[k];
+			const size_t cnt = (size_t)(t.end - t.begin);
+			if(!cnt) continue;
+			const size_t node0 = (size_t)s->p2p_dma_ranges[2 * k], slot0 = (size_t)s->p2p_dma_ranges[2 * k + 1];
+			for(int q = 0; q < 3; q++)
+				CK(cudaMemcpyAsync(t.u[dm.cur] + 4 * ((size_t)q * t.rs + slot0), dm.ucur() + 4 * ((size_t)q * dm.rs + node0),
+				                   cnt * 4 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+		}
+		gcm::halo_flag_wait_kernel<<<1, 32, 0, st>>>(s->p2p_more.p, s->p2p_flags.p, s->p2p_peer_ranks.p, np, s->comm_rank, seq, s->d_err);
+		s->launches++;
+		CK(cudaGetLastError());
+		return;
+	}
 	if(n_total) {
 		ProfScope ps(s, PROF_HALO, n_total, st);
 		const gcm::PeerTarget& t0 = s->p2p_targets[0];
@@ -1234,6 +1387,7 @@ void comm_exchange(gcm_b200_set* s, cudaStream_t st)
 
 #define NEED_SET(s) do { if(!(s)) return fail(gcmh::CONFIG_EXCEPTION, "null set"); } while(0)
 #define NEED_DEVICE(s) do { if(!(s) || !(s)->preprocessed) return fail(gcmh::CONFIG_EXCEPTION, "set is not preprocessed"); \
+	if((s)->local_zones.empty()) return fail(gcmh::CONFIG_EXCEPTION, "this process owns no zone (more processes than zones?): nothing to step"); \
 	if((s)->device < 0) return fail(gcmh::CONFIG_EXCEPTION, "host-only set (device -1): there is no CPU execution path for the step"); \
 	CK(cudaSetDevice((s)->device)); } while(0)
 
@@ -1277,6 +1431,8 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
 		CK(cudaStreamCreateWithFlags(&s->rng_stream, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->io_in, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&s->io_out, cudaStreamNonBlocking));
 		CK(cudaEventCreateWithFlags(&s->ev_rng_done, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_step_mark, cudaEventDisableTiming));
 		CK(cudaMalloc(&s->d_err, 4 * sizeof(int)));
@@ -1294,6 +1450,8 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_INNER_PATTERNS")) s->inner_patterns = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_P2P")) s->p2p = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_MB")) s->inner_mb = atoi(e);
+	if(const char* e = getenv("GCM_B200_DEVICE_COLLISIONS")) s->coll_device = atoi(e) != 0;
+	if(const char* e = getenv("GCM_B200_P2P_DMA")) s->p2p_dma_wanted = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_LU_BLOCK")) s->border_lu_block = atoi(e);
 	*out = s.release();
 	return 0;
@@ -1310,6 +1468,14 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		if(s->aux2) { cudaStreamSynchronize(s->aux2); cudaStreamDestroy(s->aux2); }
 		if(s->ev_join2) cudaEventDestroy(s->ev_join2);
 		if(s->rng_stream) cudaStreamSynchronize(s->rng_stream);
+		if(s->io_in) { cudaStreamSynchronize(s->io_in); cudaStreamDestroy(s->io_in); }
+		if(s->io_out) { cudaStreamSynchronize(s->io_out); cudaStreamDestroy(s->io_out); }
+		for(auto& zp : s->zones) if(zp) {
+			if(zp->ev_h2d_done) cudaEventDestroy(zp->ev_h2d_done);
+			if(zp->ev_in_consumed) cudaEventDestroy(zp->ev_in_consumed);
+			if(zp->ev_out_ready) cudaEventDestroy(zp->ev_out_ready);
+			if(zp->ev_d2h_done) cudaEventDestroy(zp->ev_d2h_done);
+		}
 		for(auto& kv : s->peers) {
 			PeerPlan& p = kv.second;
 			if(p.map_u0) cudaIpcCloseMemHandle(p.map_u0);
@@ -1517,6 +1683,7 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values)
 		DeviceMesh& dm = s->dm;
 		const int n = hm.N;
 		float* stage = dm.aos.p + 9 * z->node_off;
+		CK(cudaStreamSynchronize(s->io_in));      // an *_async upload may still be filling this staging slice
 		gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + 4 * z->node_off, dm.rs, n);
 		s->launches++;
 		CK(cudaMemcpyAsync(hm.values.data(), stage, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
@@ -1525,6 +1692,21 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values)
 	memcpy(values, hm.values.data(), 9*(size_t)hm.N * sizeof(float));
 	return 0;
 	GUARD_END
+}
+
+// The *_async pair is a three-stage pipeline over two extra streams, so that a caller who keeps the state in pinned
+// host memory and streams it through every step pays max(H2D, step + D2H) instead of their sum (PCIe is full duplex):
+//   io_in  : H2D copy of the zone's values into the input staging slice   (waits until the slice was consumed)
+//   stream : transpose into the records -- the step -- transpose into the output staging slice
+//   io_out : D2H copy of the output slice                                  (the next transpose-out waits for it)
+// Separate staging buffers for the two directions; one event per hand-over and zone.
+static void zone_io_events(Zone& z)
+{
+	if(z.ev_h2d_done) return;
+	CK(cudaEventCreateWithFlags(&z.ev_h2d_done, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&z.ev_in_consumed, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&z.ev_out_ready, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&z.ev_d2h_done, cudaEventDisableTiming));
 }
 
 int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* host_values)
@@ -1536,10 +1718,15 @@ int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* ho
 	DeviceMesh& dm = s->dm;
 	const int n = z->hm.N;
 	if(!n) return 0;
+	zone_io_events(*z);
 	float* stage = dm.aos.p + 9 * z->node_off;
-	CK(cudaMemcpyAsync(stage, host_values, 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+	CK(cudaStreamWaitEvent(s->io_in, z->ev_in_consumed, 0));      // the previous upload of this slice was transposed
+	CK(cudaMemcpyAsync(stage, host_values, 9 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->io_in));
+	CK(cudaEventRecord(z->ev_h2d_done, s->io_in));
+	CK(cudaStreamWaitEvent(s->stream, z->ev_h2d_done, 0));
 	gcm::values_to_records_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(dm.ucur() + 4 * z->node_off, nullptr, dm.rs, stage, dm.flags.p + z->node_off, n, 1);
 	s->launches++;
+	CK(cudaEventRecord(z->ev_in_consumed, s->stream));
 	CK(cudaGetLastError());
 	return 0;
 	GUARD_END
@@ -1554,10 +1741,28 @@ int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_v
 	DeviceMesh& dm = s->dm;
 	const int n = z->hm.N;
 	if(!n) return 0;
-	float* stage = dm.aos.p + 9 * z->node_off;
+	zone_io_events(*z);
+	if(!dm.aos_out.p) dm.aos_out.alloc(9 * dm.N);
+	float* stage = dm.aos_out.p + 9 * z->node_off;
+	CK(cudaStreamWaitEvent(s->stream, z->ev_d2h_done, 0));        // the previous download of this slice left the device
 	gcm::records_to_values_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(stage, dm.ucur() + 4 * z->node_off, dm.rs, n);
 	s->launches++;
-	CK(cudaMemcpyAsync(host_values, stage, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+	CK(cudaEventRecord(z->ev_out_ready, s->stream));
+	CK(cudaStreamWaitEvent(s->io_out, z->ev_out_ready, 0));
+	CK(cudaMemcpyAsync(host_values, stage, 9 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->io_out));
+	CK(cudaEventRecord(z->ev_d2h_done, s->io_out));
+	return 0;
+	GUARD_END
+}
+
+int gcm_b200_set_join_io(gcm_b200_set* s)
+{
+	GUARD_BEGIN
+	NEED_DEVICE(s);
+	for(int zi : s->local_zones) {
+		Zone& z = *s->zones[zi];
+		if(z.ev_d2h_done) CK(cudaStreamWaitEvent(s->stream, z.ev_d2h_done, 0));
+	}
 	return 0;
 	GUARD_END
 }
@@ -1792,6 +1997,31 @@ int gcm_b200_set_comm_init(gcm_b200_set* s, const void* id128, int rank, int n_r
 	memcpy(&id, id128, sizeof id);
 	nccl_check(nccl_api().CommInitRank(&s->nccl_comm, n_ranks, id, rank), "comm init");
 	s->comm_rank = rank; s->comm_size = n_ranks;
+	{
+		// Every pair of processes must agree on what travels between them, or the grouped send/recv of the first
+		// exchange would hang without a word: all-gather (nodes I send to r, nodes I expect from r) and compare.
+		NcclApi& nc = nccl_api();
+		const int R = n_ranks;
+		std::vector<int> mine(2 * (size_t)R, 0), all(2 * (size_t)R * R, 0);
+		for(auto& kv : s->peers) {
+			if(kv.first < 0 || kv.first >= R) return fail(gcmh::SYNC_EXCEPTION, "halo plan names a rank outside the communicator");
+			mine[kv.first] = (int)kv.second.send_node.size();
+			mine[R + kv.first] = (int)kv.second.recv_node.size();
+		}
+		DevBuf<int> d1, dall; d1.alloc(2 * (size_t)R); dall.alloc(2 * (size_t)R * R);
+		CK(cudaMemcpyAsync(d1.p, mine.data(), mine.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+		nccl_check(nc.AllGather(d1.p, dall.p, 2 * (size_t)R, 2 /* ncclInt32 */, s->nccl_comm, s->stream), "all gather");
+		CK(cudaMemcpyAsync(all.data(), dall.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		for(int a = 0; a < R; a++)
+			for(int b = 0; b < R; b++)
+				if(all[(size_t)a * 2 * R + b] != all[(size_t)b * 2 * R + R + a]) {
+					char buf[200];
+					snprintf(buf, sizeof buf, "halo plans disagree: rank %d sends %d nodes to rank %d, which expects %d (gcm_b200_halo_set_sends not called with the peer's requests?)",
+					         a, all[(size_t)a * 2 * R + b], b, all[(size_t)b * 2 * R + R + a]);
+					return fail(gcmh::SYNC_EXCEPTION, buf);
+				}
+	}
 	p2p_setup(s);
 	return 0;
 	GUARD_END
@@ -1842,6 +2072,8 @@ int gcm_b200_set_synchronize(gcm_b200_set* s)
 	NEED_DEVICE(s);
 	CK(cudaMemcpyAsync(s->h_err, s->d_err, 4 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
 	CK(cudaStreamSynchronize(s->stream));
+	CK(cudaStreamSynchronize(s->io_out));      // downloads of the *_async calls have landed
+	CK(cudaStreamSynchronize(s->io_in));
 	if(s->h_err[0]) {
 		char buf[256];
 		int zone = -1, node = s->h_err[2];   // kernels report merged node indices
@@ -2003,6 +2235,9 @@ int gcm_b200_zone_get_flags(gcm_b200_set* s, int zone, int* flags)
 {
 	Zone* z = get_zone(s, zone);
 	if(!z || !z->loaded || !flags) return fail(gcmh::CONFIG_EXCEPTION, "zone not loaded");
+	GUARD_BEGIN
+	collisions_to_host(s);      // the contact bit of a device collision pass
+	GUARD_END
 	memcpy(flags, z->hm.flags.data(), z->hm.N * sizeof(int));
 	return 0;
 }
@@ -2115,16 +2350,22 @@ int gcm_b200_set_kernel_stats(gcm_b200_set* s, long long* out16)
 	GUARD_END
 }
 
-int gcm_b200_set_virt_count(gcm_b200_set* s) { return s ? (int)s->virt.size() : 0; }
+int gcm_b200_set_virt_count(gcm_b200_set* s)
+{
+	if(!s) return 0;
+	try { collisions_to_host(s); } catch(...) { return 0; }
+	return (int)s->virt.size();
+}
 
 int gcm_b200_set_get_virt(gcm_b200_set* s, float* out16)
 {
 	GUARD_BEGIN
 	if(!s || !out16) return fail(gcmh::CONFIG_EXCEPTION, "bad arguments");
+	collisions_to_host(s);
 	// the friction calculator writes into its virtual node (the swapped-argument Adhesion call of
 	// FrictionContactCalculator.cpp:123): the device copy is the current one
 	std::vector<gcm::VirtNode> dv;
-	if(s->d_virt.p && s->d_virt.n == s->virt.size() && !s->virt.empty() && s->device >= 0) {
+	if(s->d_virt.p && s->d_virt.n >= s->virt.size() && !s->virt.empty() && s->device >= 0) {
 		CK(cudaSetDevice(s->device));
 		dv.resize(s->virt.size());
 		CK(cudaMemcpyAsync(dv.data(), s->d_virt.p, dv.size() * sizeof(gcm::VirtNode), cudaMemcpyDeviceToHost, s->stream));

@@ -1,5 +1,6 @@
 // gcm_host.cpp -- see gcm_host.h.  Compiled with  g++ -O2 -ffp-contract=off -fopenmp.
 #include "gcm_host.h"
+#include "gcm_collide.cuh"
 #include "gcm_math.cuh"
 #include "gcm_inner.cuh"
 #include "gcm_border.cuh"
@@ -702,53 +703,23 @@ void rng_teta_tables(float cos_t[360], float sin_t[360])
 }
 
 // ---- collision discovery (host; the per-step contact kernel consumes its output) ------------
-// TetrMesh_1stOrder::vector_intersects_triangle, gcm/meshtypes/TetrMesh_1stOrder.cpp:2194-2290.
-// As written there, the distance / direction test (t < 0 || t > l) and the three same_orientation
-// tests are overwritten before use: the answer is the area test alone (plus vn != 0).
+// TetrMesh_1stOrder::vector_intersects_triangle / interpolate_triangle (gcm/meshtypes/TetrMesh_1stOrder.cpp:2194-2311):
+// the arithmetic is gcm_collide.cuh's (shared with the device detector); here its error codes become the
+// reference's exceptions.
 static bool vector_intersects_triangle(const float* p1, const float* p2, const float* p3, const float* p0,
                                        const float* v, float /*l*/, float* p)
 {
-	const float* chk[5] = {p1, p2, p3, p0, v};
-	static const char* what[5] = {"NAN or INF in p1", "NAN or INF in p2", "NAN or INF in p3", "NAN or INF in p0", "NAN or INF in v"};
-	for(int a = 0; a < 5; a++)
-		for(int i = 0; i < 3; i++)
-			if(std::isnan(chk[a][i]) || std::isinf(chk[a][i])) throw HostError{MESH_EXCEPTION, what[a]};
-	float n[3];
-	Vec3 q1 = {p1[0], p1[1], p1[2]}, q2 = {p2[0], p2[1], p2[2]}, q3 = {p3[0], p3[1], p3[2]};
-	elem_normal(q1, q2, q3, n);
-	for(int i = 0; i < 3; i++)
-		if(std::isnan(n[i]) || std::isinf(n[i])) throw HostError{MESH_EXCEPTION, "NAN or INF in n"};
-	float vn = n[0]*v[0] + n[1]*v[1] + n[2]*v[2];
-	if(vn == 0) return false;
-	float d = - (n[0]*p1[0] + n[1]*p1[1] + n[2]*p1[2]);
-	float t = - ((n[0]*p0[0] + n[1]*p0[1] + n[2]*p0[2]) + d) / vn;
-	for(int i = 0; i < 3; i++) p[i] = p0[i] + t * v[i];
-	float area = fabsf( gcm::tri_area(p3[0] - p1[0], p3[1] - p1[1], p3[2] - p1[2], p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]) );
-	float areas[3];
-	areas[0] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
-	areas[1] = fabsf( gcm::tri_area(p1[0] - p[0], p1[1] - p[1], p1[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
-	areas[2] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p1[0] - p[0], p1[1] - p[1], p1[2] - p[2]) );
-	if( (double)fabsf(areas[0] + areas[1] + areas[2] - area) > (double)area * 0.0001 )
-		return false;
-	return true;
+	static const char* what[6] = {"NAN or INF in p1", "NAN or INF in p2", "NAN or INF in p3", "NAN or INF in p0", "NAN or INF in v", "NAN or INF in n"};
+	const int r = gcm::vector_intersects_triangle(p1, p2, p3, p0, v, p);
+	if(r < 0) throw HostError{MESH_EXCEPTION, what[-r - 1]};
+	return r != 0;
 }
 
-// TetrMesh_1stOrder::interpolate_triangle, :2292-2311
 static void interpolate_triangle(const float* p1, const float* p2, const float* p3, const float* p,
                                  const float* v1, const float* v2, const float* v3, float* v, int n)
 {
-	for(int i = 0; i < 3; i++)
-		if(std::isnan(p[i]) || std::isinf(p[i])) throw HostError{MESH_EXCEPTION, "NAN or INF in virt node coords"};
-	float areas[3];
-	areas[0] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
-	areas[1] = fabsf( gcm::tri_area(p1[0] - p[0], p1[1] - p[1], p1[2] - p[2], p2[0] - p[0], p2[1] - p[1], p2[2] - p[2]) );
-	areas[2] = fabsf( gcm::tri_area(p3[0] - p[0], p3[1] - p[1], p3[2] - p[2], p1[0] - p[0], p1[1] - p[1], p1[2] - p[2]) );
-	float l = areas[0] + areas[1] + areas[2];
-	float _l1 = areas[0] / l;
-	float _l2 = areas[2] / l;
-	float _l3 = areas[1] / l;
-	for(int i = 0; i < n; i++)
-		v[i] = _l1*v1[i] + _l2*v2[i] + _l3*v3[i];
+	if(!gcm::interpolate_triangle(p1, p2, p3, p, v1, v2, v3, v, n))
+		throw HostError{MESH_EXCEPTION, "NAN or INF in virt node coords"};
 }
 
 // 2-D bins over the faces that take part in one collision pass (see find_collisions).  Only a
@@ -965,6 +936,83 @@ void find_collisions(std::vector<HostMesh*>& meshes, float threshold, std::vecto
 				virt.push_back(vn);
 			}
 		}
+}
+
+// The static half of the device detector (gcm_collide.cuh): every ordered pair of local meshes whose outlines
+// intersect, with its candidate nodes, faces and face grid -- exactly the lists find_collisions builds per pass.
+void build_collision_plan(std::vector<HostMesh*>& meshes, float threshold, CollisionPlan& plan)
+{
+	const int M = (int)meshes.size();
+	plan = CollisionPlan();
+	plan.mesh_cand_off.assign(M, 0); plan.mesh_cand_n.assign(M, 0);
+	for(int a = 0; a < M; a++) {
+		plan.mesh_cand_off[a] = (int)plan.cand_node.size();
+		for(int b = 0; b < M; b++) {
+			if(a == b) continue;
+			HostMesh& m1 = *meshes[a];
+			HostMesh& m2 = *meshes[b];
+			float lo[3], hi[3];
+			bool hit = true;
+			for(int j = 0; j < 3; j++) {
+				lo[j] = fmaxf(m1.outline_min[j] - threshold, m2.outline_min[j] - threshold);
+				hi[j] = fminf(m1.outline_max[j] + threshold, m2.outline_max[j] + threshold);
+				if(lo[j] > hi[j]) { hit = false; break; }
+			}
+			if(!hit) continue;
+			gcm::CollPair pr;
+			memset(&pr, 0, sizeof pr);
+			pr.cand_off = (int)plan.cand_node.size();
+			for(size_t s = 0; s < m1.border_nodes.size(); s++) {
+				const float* c = &m1.coords[3*(size_t)m1.border_nodes[s]];
+				if(c[0] < lo[0] || c[0] > hi[0] || c[1] < lo[1] || c[1] > hi[1] || c[2] < lo[2] || c[2] > hi[2]) continue;
+				plan.cand_pair.push_back((int)plan.pairs.size());
+				plan.cand_node.push_back(m1.border_nodes[s]);
+				plan.cand_slot.push_back((int)s);
+				plan.cand_mesh.push_back(a);
+			}
+			pr.n_cand = (int)plan.cand_node.size() - pr.cand_off;
+			std::vector<int> fcs;
+			const int F = (int)(m2.faces.size() / 3);
+			for(int f = 0; f < F; f++) {
+				int out = 0;
+				for(int j = 0; j < 3; j++) {
+					const float* c = &m2.coords[3*(size_t)m2.faces[3*(size_t)f + j]];
+					if(c[0] < lo[0] || c[0] > hi[0] || c[1] < lo[1] || c[1] > hi[1] || c[2] < lo[2] || c[2] > hi[2]) out++;
+				}
+				if(out != 3) fcs.push_back(f);
+			}
+			pr.face_off = (int)plan.faces.size();
+			pr.n_faces = (int)fcs.size();
+			for(int f : fcs) {
+				gcm::CollFace cf;
+				cf.v0 = m2.faces[3*(size_t)f]; cf.v1 = m2.faces[3*(size_t)f + 1]; cf.v2 = m2.faces[3*(size_t)f + 2]; cf.face = f;
+				plan.faces.push_back(cf);
+				plan.face_mesh.push_back(b);
+			}
+			FaceGrid grid;
+			grid.build(m2, fcs);
+			pr.grid_ok = grid.ok ? 1 : 0;
+			pr.ax0 = grid.ax0; pr.ax1 = grid.ax1; pr.n0 = grid.n[0]; pr.n1 = grid.n[1];
+			pr.org0 = grid.org[0]; pr.org1 = grid.org[1]; pr.cell = grid.cell; pr.pad = grid.pad;
+			pr.ax2 = 3 - grid.ax0 - grid.ax1;
+			pr.lo2 = 1e300; pr.hi2 = -1e300;
+			for(int f : fcs)
+				for(int j = 0; j < 3; j++) {
+					const double c = m2.coords[3*(size_t)m2.faces[3*(size_t)f + j] + pr.ax2];
+					pr.lo2 = std::min(pr.lo2, c); pr.hi2 = std::max(pr.hi2, c);
+				}
+			pr.start_off = (int)plan.grid_start.size();
+			pr.items_off = (int)plan.grid_items.size();
+			if(grid.ok) {
+				plan.grid_start.insert(plan.grid_start.end(), grid.start.begin(), grid.start.end());
+				plan.grid_items.insert(plan.grid_items.end(), grid.items.begin(), grid.items.end());
+			}
+			pr.phase = b < a ? 1 : 0;      // partner earlier in local_meshes: already advanced when this mesh runs its stage
+			plan.pair_a.push_back(a); plan.pair_b.push_back(b);
+			plan.pairs.push_back(pr);
+		}
+		plan.mesh_cand_n[a] = (int)plan.cand_node.size() - plan.mesh_cand_off[a];
+	}
 }
 
 } // namespace gcmh

@@ -5,6 +5,7 @@
 // rand() stream they consume.  Nothing here does the per-node update: that is CUDA only.
 #pragma once
 #include <cstdint>
+#include "gcm_collide.cuh"
 #include <string>
 #include <vector>
 
@@ -133,6 +134,19 @@ struct VirtNodeHost {
 // InContact flag.  Throws HostError (the NaN checks of vector_intersects_triangle).
 void find_collisions(std::vector<HostMesh*>& meshes, float threshold, std::vector<VirtNodeHost>& virt,
                      std::vector<std::vector<int> >& axis_plus0);
+
+// The static half of collision discovery for the device detector (gcm_collide.cuh): zone-local node / slot / vertex
+// numbers, candidates in the reference's (mesh a, mesh b, node) loop order.
+struct CollisionPlan {
+	std::vector<gcm::CollPair> pairs;
+	std::vector<int> pair_a, pair_b;                       // positions in the meshes vector
+	std::vector<int> cand_pair, cand_node, cand_slot, cand_mesh;
+	std::vector<gcm::CollFace> faces;
+	std::vector<int> face_mesh;
+	std::vector<int> grid_start, grid_items;
+	std::vector<int> mesh_cand_off, mesh_cand_n;           // per mesh a: its contiguous candidate range
+};
+void build_collision_plan(std::vector<HostMesh*>& meshes, float threshold, CollisionPlan& plan);
 
 // ---- on-disk formats (gcm_io.cpp) ----------------------------------------------------------------
 struct MshData {           // what TetrMesh_1stOrder::load_msh_file leaves in nodes / tetrs

@@ -14,6 +14,7 @@ __device__ __forceinline__ void report_error(int* err, int code, int zone, int n
 } // namespace gcm
 #include "gcm_inner.cuh"
 #include "gcm_border.cuh"
+#include "gcm_collide.cuh"
 namespace gcm {
 
 // Writes one node's stage result: the 9 values into the next layer; with yield_plane != NULL the
@@ -32,11 +33,14 @@ __device__ __forceinline__ void store_node(float* __restrict__ un, size_t rs, in
 // is the caller's buffer swap.
 __global__ void __launch_bounds__(128)
 stage_generic_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list,
-                     int stage, float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane)
+                     int stage, float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane,
+                     const int* __restrict__ skip_contact = nullptr)
 {
 	int idx = blockIdx.x * blockDim.x + threadIdx.x;
 	if(idx >= n_list) return;
 	int node = list[idx];
+	// device-built contact state: a border node in contact on this axis belongs to the contact kernel
+	if(skip_contact && skip_contact[m.border_slot[node]] >= 0) return;
 	float out[9];
 	StageTap t;
 	int e = node_stage_nocontact(m, node, stage, out, tap ? &t : nullptr);
@@ -75,7 +79,8 @@ template<bool LU, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, LU ? (BLOCK > 64 ? 1 : 5) : 4)
 stage_border_fast_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
                          float* __restrict__ un, int* err, int zone, StageTap* tap, const float* __restrict__ yield_plane,
-                         const BndSlotStatic* __restrict__ bstat, const float4* __restrict__ cand, int* __restrict__ defer)
+                         const BndSlotStatic* __restrict__ bstat, const float4* __restrict__ cand, int* __restrict__ defer,
+                         const int* __restrict__ skip_contact = nullptr)
 {
 	// BLOCK <= 64: static array, 5 blocks per SM; BLOCK = 352: one block per SM on 228 096 bytes of dynamic shared
 	// memory (the whole SM: 352 instead of 320 systems resident)
@@ -85,6 +90,7 @@ stage_border_fast_kernel(const __grid_constant__ MeshView m, const int* __restri
 	const int idx = blockIdx.x * BLOCK + threadIdx.x;
 	if(idx >= n_list) return;
 	const int node = list[idx];
+	if(skip_contact && skip_contact[m.border_slot[node]] >= 0) return;     // in contact on this axis: the contact kernel's node
 	BndSlotStatic bs;
 	{
 		const uint4* q = reinterpret_cast<const uint4*>(bstat + m.border_slot[node]);
@@ -119,7 +125,8 @@ __global__ void __launch_bounds__(64)
 stage_contact_kernel(const __grid_constant__ MeshView m, const int* __restrict__ list, int n_list, int stage,
                      float* __restrict__ un, VirtNode* __restrict__ virt, const int* __restrict__ axis_plus0,
                      const float* __restrict__ normals, int calc_type, int partner_next, int first_step,
-                     int* err, int zone, StageTap* tap, int* deep, int deep_pass)
+                     int* err, int zone, StageTap* tap, int* deep, int deep_pass,
+                     const int* __restrict__ sel = nullptr, const int* __restrict__ sel_phase = nullptr, int want_phase = 0)
 {
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	const int n_work = deep_pass ? deep[0] : n_list;
@@ -128,6 +135,9 @@ stage_contact_kernel(const __grid_constant__ MeshView m, const int* __restrict__
 		const int node = deep_pass ? deep[1 + idx] : list[idx];
 		const int slot = m.border_slot[node];
 		const int vidx = axis_plus0[slot];
+		// device-built lists (gcm_collide.cuh): `list` holds every candidate of the collision pass; an entry runs if
+		// it hit a face, its virtual node is the one the real node ended up with, and its pair has the wanted phase
+		if(sel && !deep_pass && (sel[idx] < 0 || sel[idx] != vidx || sel_phase[idx] != want_phase)) continue;
 		MeshView mv = m;
 		if(partner_next) mv.u = un;
 		VirtNode vn = virt[vidx];
@@ -308,6 +318,23 @@ halo_push_kernel(const float* __restrict__ u, size_t rs, const int* __restrict__
 		__threadfence_system();
 		*reinterpret_cast<volatile int*>(flag + my_rank) = seq;
 		if(threadIdx.x == 0) *done_counter = 0;
+	}
+}
+
+// The exchange when the copy engines moved the records (contiguous halo layers, cudaMemcpyAsync on the same stream
+// in front of this kernel): thread k raises this process's flag at neighbour k, then waits for that neighbour's.
+__global__ void halo_flag_wait_kernel(const PeerTarget* __restrict__ targets, const int* __restrict__ flags, const int* __restrict__ peer_ranks,
+                                      int n_peers, int my_rank, int seq, int* err)
+{
+	const int k = threadIdx.x;
+	if(k >= n_peers) return;
+	__threadfence_system();
+	*reinterpret_cast<volatile int*>(targets[k].flag + my_rank) = seq;
+	const volatile int* f = flags + peer_ranks[k];
+	const long long t0 = clock64();
+	while(*f < seq) {
+		__nanosleep(100);
+		if(clock64() - t0 > 4000000000ll) { if(atomicCAS(&err[0], 0, ERR_PEER_TIMEOUT) == 0) { err[1] = -1; err[2] = peer_ranks[k]; err[3] = seq; } break; }
 	}
 }
 

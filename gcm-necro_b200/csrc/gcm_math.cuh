@@ -36,7 +36,8 @@ enum StepError {
 	ERR_BAD_Q = 10,           // "Bad vector q" ElasticMatrix3D.cpp:31-32
 	ERR_ZERO_VOLUME = 11,     // "Tetr volume is zero" / "Tri area is zero" TetrMesh_1stOrder.cpp:1010-1015
 	ERR_FOOT_PATTERN = 12,    // characteristic dedupe did not give the 5-point pattern (0,1,2,3,2,3,4,4,4)
-	ERR_PEER_TIMEOUT = 13     // a neighbour process never delivered its halo (direct peer-store exchange)
+	ERR_PEER_TIMEOUT = 13,    // a neighbour process never delivered its halo (direct peer-store exchange)
+	ERR_COLLISION_NAN = 14    // "NAN or INF in p1 / p2 / p3 / p0 / v / n / virt node coords"  TetrMesh_1stOrder.cpp:2196-2230,2297-2299
 };
 
 // x / y with the IEEE result, arranged so that a zero numerator never reaches the divider.

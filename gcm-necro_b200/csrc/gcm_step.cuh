@@ -1057,7 +1057,7 @@ GCM_HD int node_stage_border_lean(const MeshView& m, int node, int stage, float 
 struct VirtNode {
 	float pos[3];
 	float val[9];
-	float la, mu, rho;
+	float la, mu, rho, yield;
 	int base;      // merged index of the borrowed node (vert[0] of the face)
 	int real;      // merged index of the border node it belongs to
 	int phase;     // 0: partner zone comes later in local_meshes (reads the current layer);

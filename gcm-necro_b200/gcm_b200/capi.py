@@ -67,6 +67,7 @@ SIGNATURES = {
     "gcm_b200_zone_get_values": (_i, [_p, _i, _fp]),
     "gcm_b200_zone_upload_values_async": (_i, [_p, _i, _p]),
     "gcm_b200_zone_download_values_async": (_i, [_p, _i, _p]),
+    "gcm_b200_set_join_io": (_i, [_p]),
     "gcm_b200_set_add_border_condition": (_i, [_p, _i, _fp, _ip, _fp, _f, _f, _fp]),
     "gcm_b200_set_define_border_condition": (_i, [_p, _i, _fp, _ip, _fp, _f, _f, _ip]),
     "gcm_b200_zone_assign_border_conditions": (_i, [_p, _i, _ip]),
@@ -324,6 +325,10 @@ class TetrMeshSet:
 
     def end_step(self):
         self._ck(self.lib.gcm_b200_set_end_step(self.h))
+
+    def join_io(self):
+        """The set's stream waits for every download_values_async issued so far."""
+        self._ck(self.lib.gcm_b200_set_join_io(self.h))
 
     def track_destruction(self, on=True):
         """Keep the running maxima of calc_destruction_criterias (after pre_process_meshes)."""

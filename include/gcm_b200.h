@@ -83,6 +83,10 @@ int gcm_b200_zone_get_values(gcm_b200_set* s, int zone, float* values);
  * They return before the copy is done; gcm_b200_set_synchronize() waits. */
 int gcm_b200_zone_upload_values_async(gcm_b200_set* s, int zone, const float* host_values);
 int gcm_b200_zone_download_values_async(gcm_b200_set* s, int zone, float* host_values);
+/* The two calls above run their copies on streams of their own (H2D of the next input and D2H of the last result
+ * overlap each other and the step: PCIe is full duplex), hand-overs by events.  gcm_b200_set_join_io makes the set's
+ * stream (gcm_b200_set_stream) wait for every download issued so far, for callers that time or order work on it. */
+int gcm_b200_set_join_io(gcm_b200_set* s);
 /* A BorderCondition (calculator + StepPulseForm + BoxArea), TaskPreparator.cpp:388-441 and
  * gcm/methods/border/ (every .cpp there).  calc_type: 0 Free, 1 Fixed, 2 ExternalForce, 3 ExternalVelocity,
  * 4 ExternalValues.  params[5] = set_parameters(normal, tangential, dir x,y,z) for 2/3;

@@ -29,20 +29,20 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     else:
         dist.init_process_group("gloo")
-    if name == "mp16":
-        # 16^3 cube in 4 z-slab zones, 2 per rank; the golden reference is a single-process run of the
-        # product on this rank's GPU, compared after one step on nodes >= 4 cells away from the outer border (a
-        # step spreads information by 3 cells; the
+    if name == "mp24":
+        # 24^3 cube in 4 z-slab zones, 2 per rank; the golden reference is a single-process run of the
+        # product on this rank's GPU, compared after THREE steps (12 stage exchanges, both record layers in
+        # use) on nodes >= 10 cells away from the outer border (a step spreads information by 3 cells; the
         # border bases depend on the per-rank rand() stream, see tests/test_multiprocess.py)
         from gcm_b200 import meshgen
-        zs = meshgen.make_box_zones(16, 16, 16, 4, jitter=0.1, seed=2)
+        zs = meshgen.make_box_zones(24, 24, 24, 4, jitter=0.1, seed=2)
         case = dict(name=name, zones=zs, states=[meshgen.generic_state(z.coords, up.LA, up.MU, up.RHO, seed=6) for z in zs],
-                    material=(up.LA, up.MU, up.RHO, 1e16), steps=1, seed=5, borders=[], tap_step=-1)
+                    material=(up.LA, up.MU, up.RHO, 1e16), steps=3, seed=5, borders=[], tap_step=-1)
         one = up.run_product(case, device=lr)
         gold = []
         for z, r in zip(zs, one):
             c = np.rint(z.coords)
-            deep = np.all((c >= 4) & (c <= 11), axis=1) & (z.placement == 1)
+            deep = np.all((c >= 10) & (c <= 13), axis=1) & (z.placement == 1)
             fl = r["flags"].copy()
             fl[~deep] &= ~2          # compare() / local_mask() only look at Local nodes
             gold.append(dict(values=r["values"], flags=r["flags"], faces=r["faces"], cmp_flags=fl))

@@ -32,9 +32,20 @@ def test_two_ranks_host_half_gloo(built, name):
 
 
 @pytest.mark.gpu
-def test_two_ranks_nccl_halo_exchange(built):
+@pytest.mark.parametrize("p2p", ["1", "0"])
+def test_two_ranks_nccl_halo_exchange(built, p2p):
+    """Cross-process halo on the device against a single-process run, three steps: direct peer stores into the
+    neighbour's halo slots (p2p = 1, the default) and the pack -> ncclSend/ncclRecv -> unpack fallback (p2p = 0)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    r = _torchrun(2, ["gpu", "mp16"], 29532)
+    old = os.environ.get("GCM_B200_P2P")
+    os.environ["GCM_B200_P2P"] = p2p
+    try:
+        r = _torchrun(2, ["gpu", "mp24"], 29532 + int(p2p))
+    finally:
+        if old is None:
+            os.environ.pop("GCM_B200_P2P", None)
+        else:
+            os.environ["GCM_B200_P2P"] = old
     assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-1500:], r.stderr[-6000:])

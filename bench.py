@@ -432,8 +432,15 @@ def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
             traffic = t["bytes_per_launch"]
     except Exception:
         pass
+    avg_launch_s = in_ms * 1e-3 / max(in_launches, 1)
+    kb = 100       # what the cached inner kernel itself has to move per node-stage: record in 48 + record out 48 + pattern id 4
     roofline = {"bound": "hbm", "kernel": "inner-node axis stage", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                "note": "achieved/frac use SURVEY 8d's 292 algorithmic bytes per node-stage (CSR + tet table read every stage); the "
+                        "round-2 kernel caches owner and weights of inner nodes, so it beats that figure -- see kernel_bytes / traffic_frac",
+                "kernel_bytes_per_node_stage": kb,
+                "frac_kernel_bytes": (kb * in_units) / (in_ms * 1e-3) / 1e9 / peak if in_ms > 0 else None,
+                "traffic_frac": (traffic / avg_launch_s / 1e9 / peak) if (traffic and avg_launch_s > 0) else None,
                 "algorithmic_bytes_per_node_stage": B_STAGE, "avg_launch_ms": in_ms / max(in_launches, 1),
                 "nodes_per_launch": in_units / max(in_launches, 1),
                 "step_frac": value / world * B_STEP / 1e9 / peak,

@@ -448,6 +448,22 @@ def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
                 "kernel_ms_share": {k: v[0] for k, v in prof.items()},
                 "kernel_sha": kernel_source_hash(), "coverage": ms.kernel_stats()}
 
+    # ---- state digest: nodes >= 80 cells from the surface (rank-independent, see the module docstring) ----
+    ms.synchronize()
+    dig = np.zeros(2, np.int64)
+    for z in mine:
+        idx, gid = deep[z]
+        if len(idx):
+            v = ms.get_mesh_by_zone_num(z).get_values()[idx].view(np.uint32).astype(np.int64)
+            wts = (gid % 1000003 + 1)[:, None] * (np.arange(9, dtype=np.int64) + 1)[None, :]
+            dig[0] += int((v * wts % 2147483647).sum() % 2147483647)
+            dig[1] += len(idx)
+    digt = torch.from_numpy(dig).cuda()
+    if world > 1:
+        dist.all_reduce(digt)
+    state_digest = "%d:%d" % (int(digt[1].item()), int(digt[0].item()) % 2147483647)
+    steps_before_digest = int(round(ms.get_current_time() / 0.002))
+
     # ---- end to end through the C ABI with HOST buffers ---------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -480,21 +496,6 @@ def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
         if not np.array_equal(chk, host_out[mine[0]].numpy().reshape(chk.shape)):
             raise SystemExit("e2e: the downloaded state differs from the device state")
 
-    # ---- state digest: nodes >= 80 cells from the surface (rank-independent, see the module docstring) ----
-    ms.synchronize()
-    dig = np.zeros(2, np.int64)
-    for z in mine:
-        idx, gid = deep[z]
-        if len(idx):
-            v = ms.get_mesh_by_zone_num(z).get_values()[idx].view(np.uint32).astype(np.int64)
-            wts = (gid % 1000003 + 1)[:, None] * (np.arange(9, dtype=np.int64) + 1)[None, :]
-            dig[0] += int((v * wts % 2147483647).sum() % 2147483647)
-            dig[1] += len(idx)
-    digt = torch.from_numpy(dig).cuda()
-    if world > 1:
-        dist.all_reduce(digt)
-    state_digest = "%d:%d" % (int(digt[1].item()), int(digt[0].item()) % 2147483647)
-
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args)
@@ -512,7 +513,7 @@ def run_workload(args, rank, world, local_rank, size, nz, yield_limit, full):
                            "l2": "inputs larger than L2 (state %.0f MB + mesh > 126 MB per GPU)" % (n_total / world * 72 / 1e6),
                            "setup_s": t_setup},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue_ms, "clocks": clocks,
-                "state_digest": state_digest, "steps_total_before_digest": int(round(ms.get_current_time() / 0.002))}
+                "state_digest": state_digest, "steps_total_before_digest": steps_before_digest}
     ms.close()
     return line
 

@@ -111,6 +111,8 @@ struct DeviceMesh {
 	DevBuf<unsigned> ic_pat_idx;     // [3][N] pattern id per node or GCM_IC_NO_PATTERN
 	DevBuf<gcm::InnerCacheEntry> ic_patterns;   // [3][GCM_IC_MAX_PATTERNS]
 	bool pattern_ok[3] = {false, false, false};
+	DevBuf<int> shell;               // [1 + n]: inner nodes whose stencil touches another process's halo node (gcm_inner.cuh: GCM_IC_SHELL)
+	int n_shell = 0;
 	int n_patterns[3] = {0, 0, 0};
 	float icache_tau = -1.f;
 	bool icache_ready = false;
@@ -147,7 +149,8 @@ struct gcm_b200_set {
 	gcmh::MaterialRegistry materials;
 	DeviceMesh dm;
 	cudaStream_t stream = nullptr, aux = nullptr, aux2 = nullptr, rng_stream = nullptr, io_in = nullptr, io_out = nullptr;
-	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_rng_done = nullptr, ev_step_mark = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_rng_done = nullptr, ev_step_mark = nullptr, ev_halo = nullptr;
+	bool overlap = true;         // multi-process whole-step calls: the halo exchange beside the inner nodes that do not need it
 	bool bases_ahead = true;     // device generator: the NEXT step's bases are produced on rng_stream during this step
 	bool ahead_valid = false;    // dm.basis_next holds the bases of the coming step
 	int* d_err = nullptr;
@@ -664,13 +667,35 @@ void ensure_inner_cache(gcm_b200_set* s, float tau)
 			}
 		}
 	}
+	// shell nodes: flagged and listed when every axis runs from its pattern table and there are other processes
+	dm.n_shell = 0;
+	if(nf && !s->peers.empty() && dm.pattern_ok[0] && dm.pattern_ok[1] && dm.pattern_ok[2]) {
+		std::vector<unsigned char> mask(N, 0);
+		for(auto& kv : s->peers)
+			for(size_t k = 0; k < kv.second.recv_node.size(); k++)
+				mask[s->zones[kv.second.recv_zone[k]]->node_off + kv.second.recv_node[k]] = 1;
+		DevBuf<unsigned char> d_mask; d_mask.upload(mask, s->stream);
+		dm.shell.alloc((size_t)nf + 1);
+		CK(cudaMemsetAsync(dm.shell.p, 0, sizeof(int), s->stream));
+		gcm::ic_mark_shell_kernel<<<(nf + 255) / 256, 256, 0, s->stream>>>(dm.fast_list.p, nf, dm.ic_pat_idx.p, dm.ic_patterns.p, (int)N,
+			GCM_IC_MAX_PATTERNS, d_mask.p, dm.shell.p);
+		s->launches++;
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(s->h_err + 4, dm.shell.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+		CK(cudaStreamSynchronize(s->stream));
+		dm.n_shell = s->h_err[4];
+	}
 	dm.icache_tau = tau;
 	dm.icache_ready = true;
 }
 
 // One stage for the nodes of one zone (zone >= 0) or of every local zone (zone < 0).
 // fuse: stage 2 only -- fold the plastic stage into the writers (whole-step calls).
-void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = false)
+void comm_exchange(gcm_b200_set* s, cudaStream_t st);
+
+// exchange_here: the cross-process halo exchange of this stage has NOT been issued yet and is to run inside the
+// stage, on the border stream, beside the inner nodes that do not depend on it (whole-step calls of multi-process sets).
+void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = false, bool exchange_here = false)
 {
 	DeviceMesh& dm = s->dm;
 	Zone* z = zone >= 0 ? s->zones[zone].get() : nullptr;
@@ -702,8 +727,20 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 	}
 	cudaStream_t bst = s->stream;
 	const bool border_work = nb > 0;
+	// Overlapped stage: push + wait run on the border stream while the main stream already advances every inner node
+	// whose stencil stays clear of other processes' halo nodes; border nodes and the shell nodes follow the exchange.
+	const bool overlap = exchange_here && s->overlap && s->concurrent && cached && !contact && !tap && zone < 0
+		&& dm.pattern_ok[0] && dm.pattern_ok[1] && dm.pattern_ok[2] && s->fast_inner && dm.n_generic == 0;
+	if(exchange_here && !overlap) comm_exchange(s, s->stream);
+	if(overlap) {
+		bst = s->aux;
+		CK(cudaEventRecord(s->ev_fork, s->stream));
+		CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
+		comm_exchange(s, s->aux);
+		CK(cudaEventRecord(s->ev_halo, s->aux));
+	}
 	if(border_work) {
-		if(s->concurrent) {
+		if(s->concurrent && !overlap) {
 			bst = s->aux;
 			CK(cudaEventRecord(s->ev_fork, s->stream));
 			CK(cudaStreamWaitEvent(s->aux, s->ev_fork, 0));
@@ -756,8 +793,9 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 					const unsigned* pidx = dm.ic_pat_idx.p + (size_t)stage * dm.N;
 					const gcm::InnerCacheEntry* pats = dm.ic_patterns.p + (size_t)stage * GCM_IC_MAX_PATTERNS;
 					const bool pat = dm.pattern_ok[stage];
+					const int* shell_list = nullptr; int n_shell = 0;      // first launch: the node range, shell nodes left out
 #define GCM_LAUNCH_PATTERN(S_, P_, MB_) gcm::stage_inner_pattern_kernel<S_, P_, MB_><<<grid, block, 0, s->stream>>>(dm.ucur(), dm.rs, nbeg, nrange, dm.unext(), pidx, pats, tab, dm.n_mat, mid, yp, \
-						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N)
+						s->d_err, zone, tap, otap, dm.n2t_off.p, dm.n2t.p, (int)dm.N, shell_list, n_shell)
 #define GCM_LAUNCH_CACHED(S_, P_) do { if(pat) { if(s->inner_mb == 4) GCM_LAUNCH_PATTERN(S_, P_, 4); else if(s->inner_mb == 5) GCM_LAUNCH_PATTERN(S_, P_, 5); \
 						else if(s->inner_mb == 6) GCM_LAUNCH_PATTERN(S_, P_, 6); else GCM_LAUNCH_PATTERN(S_, P_, 1); } \
 					else gcm::stage_inner_cached_kernel<S_, P_><<<grid, block, 0, s->stream>>>(dm.ucur(), dm.rs, nbeg, nrange, dm.unext(), ce, tab, dm.n_mat, mid, yp, \
@@ -766,9 +804,21 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 					else if(stage == 1) GCM_LAUNCH_CACHED(1, false);
 					else if(yp) GCM_LAUNCH_CACHED(2, true);
 					else GCM_LAUNCH_CACHED(2, false);
+					s->launches++;
+					if(dm.n_shell && pat) {
+						// the shell nodes, once the halo exchange running beside the launch above has delivered (overlapped
+						// stage), or right behind it (everything else)
+						if(overlap) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));
+						shell_list = dm.shell.p + 1; n_shell = dm.n_shell;
+						const dim3 grid((unsigned)((n_shell + 255) / 256));
+						if(stage == 0) GCM_LAUNCH_CACHED(0, false);
+						else if(stage == 1) GCM_LAUNCH_CACHED(1, false);
+						else if(yp) GCM_LAUNCH_CACHED(2, true);
+						else GCM_LAUNCH_CACHED(2, false);
+						s->launches++;
+					} else if(overlap) CK(cudaStreamWaitEvent(s->stream, s->ev_halo, 0));   // the cold list below may touch the halo
 #undef GCM_LAUNCH_CACHED
 #undef GCM_LAUNCH_PATTERN
-					s->launches++;
 				}
 				if(dm.n_cold) {
 					// whatever the cache could not take: the literal routine, right behind (a per-zone call strides
@@ -792,7 +842,7 @@ void run_stage(gcm_b200_set* s, int zone, float tau, int stage, bool fuse = fals
 			}
 		}
 	}
-	if(border_work && s->concurrent) {
+	if((border_work && s->concurrent) || overlap) {
 		CK(cudaEventRecord(s->ev_join, s->aux));
 		CK(cudaStreamWaitEvent(s->stream, s->ev_join, 0));
 	}
@@ -1430,6 +1480,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 		CK(cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
 		CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&s->ev_halo, cudaEventDisableTiming));
 		CK(cudaStreamCreateWithFlags(&s->rng_stream, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&s->io_in, cudaStreamNonBlocking));
 		CK(cudaStreamCreateWithFlags(&s->io_out, cudaStreamNonBlocking));
@@ -1450,6 +1501,7 @@ int gcm_b200_set_create(gcm_b200_set** out, int device, int n_zones, const int* 
 	if(const char* e = getenv("GCM_B200_INNER_PATTERNS")) s->inner_patterns = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_P2P")) s->p2p = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_INNER_MB")) s->inner_mb = atoi(e);
+	if(const char* e = getenv("GCM_B200_OVERLAP")) s->overlap = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_DEVICE_COLLISIONS")) s->coll_device = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_P2P_DMA")) s->p2p_dma_wanted = atoi(e) != 0;
 	if(const char* e = getenv("GCM_B200_BORDER_LU_BLOCK")) s->border_lu_block = atoi(e);
@@ -1488,6 +1540,7 @@ int gcm_b200_set_destroy(gcm_b200_set* s)
 		for(int k = 0; k < 2; k++) { if(s->h_basis[k]) cudaFreeHost(s->h_basis[k]); if(s->basis_ev[k]) cudaEventDestroy(s->basis_ev[k]); }
 		if(s->ev_fork) cudaEventDestroy(s->ev_fork);
 		if(s->ev_join) cudaEventDestroy(s->ev_join);
+		if(s->ev_halo) cudaEventDestroy(s->ev_halo);
 		if(s->ev_rng_done) cudaEventDestroy(s->ev_rng_done);
 		if(s->ev_step_mark) cudaEventDestroy(s->ev_step_mark);
 		if(s->rng_stream) cudaStreamDestroy(s->rng_stream);
@@ -2050,10 +2103,10 @@ int gcm_b200_set_do_next_step(gcm_b200_set* s)
 	const bool fuse = s->fuse_plastic;
 	for(int stage = 0; stage < (fuse ? 3 : 4); stage++) {
 		if((rc = gcm_b200_set_sync_nodes(s))) return rc;
-		if(s->nccl_comm && (rc = gcm_b200_set_comm_sync_nodes(s))) return rc;
 		GUARD_BEGIN
 		NEED_DEVICE(s);
-		run_stage(s, -1, s->time_step, stage, fuse);
+		if(s->nccl_comm && stage == 3) comm_exchange(s, s->stream);     // only when stage 3 is its own pass (GCM_B200_FUSE_PLASTIC=0)
+		run_stage(s, -1, s->time_step, stage, fuse, s->nccl_comm != nullptr && stage < 3);
 		if(stage < 3) finish_axis_stage(s);
 		GUARD_END
 	}
@@ -2346,6 +2399,7 @@ int gcm_b200_set_kernel_stats(gcm_b200_set* s, long long* out16)
 	}
 	out16[11] = dm.exact_only;
 	out16[12] = s->p2p_ready ? 1 : 0;
+	out16[13] = dm.n_shell;
 	return 0;
 	GUARD_END
 }

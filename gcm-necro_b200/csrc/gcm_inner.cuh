@@ -549,6 +549,7 @@ GCM_HD void inner_cached_stage(const float* __restrict__ u, size_t rs, const Inn
 #define GCM_IC_WORDS 24
 #define GCM_IC_MAX_PATTERNS 32768
 #define GCM_IC_NO_PATTERN 0xffffffffu
+#define GCM_IC_SHELL 0x80000000u          // flag on a pattern id: the node's stencil touches another process's halo node
 
 // entry -> the 24 words of its pattern (ids relative to the node)
 GCM_HD void ic_relative(const InnerCacheEntry& e, int node, unsigned w[GCM_IC_WORDS])
@@ -738,6 +739,28 @@ ic_dedup_assign_kernel(const int* __restrict__ list, int n_list, const int* __re
 	pat_idx[node] = slot < 0 ? GCM_IC_NO_PATTERN : (unsigned)slot_pid[slot];
 }
 
+// Flags the nodes whose pattern (any axis) gathers a node of `peer_halo` (1 = halo node owned by another process)
+// and lists them: shell[0] = count, shell[1..] = nodes.
+__global__ void __launch_bounds__(256)
+ic_mark_shell_kernel(const int* __restrict__ list, int n_list, unsigned* __restrict__ pat_idx, const InnerCacheEntry* __restrict__ patterns,
+                     int n_nodes, int max_patterns, const unsigned char* __restrict__ peer_halo, int* __restrict__ shell)
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+	if(idx >= n_list) return;
+	const int node = list[idx];
+	bool touches = false;
+	for(int st = 0; st < 3; st++) {
+		const unsigned pid = pat_idx[(size_t)st * n_nodes + node];
+		if(pid == GCM_IC_NO_PATTERN) return;                 // not a node of the pattern path
+		const InnerCacheEntry& p = patterns[(size_t)st * max_patterns + pid];
+		touches = touches || peer_halo[p.a0 + node] || peer_halo[p.b0 + node] || peer_halo[p.c0 + node]
+		                  || peer_halo[p.a1 + node] || peer_halo[p.b1 + node] || peer_halo[p.c1 + node];
+	}
+	if(!touches) return;
+	for(int st = 0; st < 3; st++) pat_idx[(size_t)st * n_nodes + node] |= GCM_IC_SHELL;
+	shell[1 + atomicAdd(&shell[0], 1)] = node;
+}
+
 // The hot kernel over the pattern table: identical to stage_inner_cached_kernel but for where the
 // entry comes from (pattern id -> pattern -> absolute vertex ids).
 // MB = resident blocks per SM the register allocation aims at (1: unconstrained; occupancy against a few spilled words)
@@ -748,7 +771,8 @@ stage_inner_pattern_kernel(const float* __restrict__ u, size_t rs, int node_begi
                            const MatTab* __restrict__ tab, int n_mat,
                            const unsigned char* __restrict__ mat_id, const float* __restrict__ yield_plane,
                            int* err, int zone, StageTap* tap, const int* __restrict__ owner_tap,
-                           const int* __restrict__ n2t_off, const int* __restrict__ n2t, int n_nodes)
+                           const int* __restrict__ n2t_off, const int* __restrict__ n2t, int n_nodes,
+                           const int* __restrict__ shell_list, int n_shell)
 {
 	__shared__ float sU[GCM_MAX_MATERIALS][81];
 	__shared__ float sU1[GCM_MAX_MATERIALS][81];
@@ -758,11 +782,24 @@ stage_inner_pattern_kernel(const float* __restrict__ u, size_t rs, int node_begi
 		sU1[i / 81][i % 81] = mt.U1[i % 81];
 	}
 	__syncthreads();
+	// Two ways to be launched: over the contiguous node range [node_begin, node_begin + n_range) (shell_list == NULL:
+	// nodes flagged GCM_IC_SHELL are left to the other launch), or over shell_list (its first n_shell entries, those
+	// inside the range): the inner nodes whose stencil touches a halo node owned by another process, which have to
+	// wait for the exchange while everything else runs beside it (gcm_capi.cu: run_stage).
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if(idx >= n_range) return;
-	const int node = node_begin + idx;
-	const unsigned pid = __ldg(pat_idx + node);
-	if(pid == GCM_IC_NO_PATTERN) return;
+	int node;
+	unsigned pid;
+	if(shell_list) {
+		if(idx >= n_shell) return;
+		node = shell_list[idx];
+		if(node < node_begin || node >= node_begin + n_range) return;
+		pid = __ldg(pat_idx + node) & ~GCM_IC_SHELL;
+	} else {
+		if(idx >= n_range) return;
+		node = node_begin + idx;
+		pid = __ldg(pat_idx + node);
+		if(pid & GCM_IC_SHELL) return;          // GCM_IC_NO_PATTERN has the bit too
+	}
 	const float4 o0 = rec_quad(u, rs, node, 0), o1 = rec_quad(u, rs, node, 1), o2 = rec_quad(u, rs, node, 2);
 	InnerCacheEntry e;
 	{

@@ -365,7 +365,7 @@ class TetrMeshSet:
         a = (C.c_longlong * 16)()
         self._ck(self.lib.gcm_b200_set_kernel_stats(self.h, a))
         return dict(inner_cached=a[0], inner_cold=a[1], patterns=[a[2], a[3], a[4]], pattern_axes=[a[5], a[6], a[7]],
-                    border_flat=a[8], border_sharp=a[9], flat_deferred_last=a[10], exact_only=a[11], peer_stores=a[12])
+                    border_flat=a[8], border_sharp=a[9], flat_deferred_last=a[10], exact_only=a[11], peer_stores=a[12], inner_shell=a[13])
 
     def profile(self, on=True):
         self._ck(self.lib.gcm_b200_set_profile(self.h, int(on)))

@@ -192,7 +192,8 @@ int gcm_b200_set_profile_read(gcm_b200_set* s, int which, double* total_ms, long
  * [5..7] 1 where that axis runs from the pattern table, [8] flat border nodes, [9] sharp border nodes,
  * [10] flat border nodes the last border launch deferred to the literal routine, [11] 1 when the
  * conservative owner pre-filter is switched off for this mesh (huge coordinates), [12] 1 when the cross-process
- * halo exchange runs on direct peer stores (else NCCL send/recv, or none), [13..15] 0. */
+ * halo exchange runs on direct peer stores (else NCCL send/recv, or none), [13] inner nodes whose stencil touches another
+ * process's halo node (they wait for the exchange; the others run beside it), [14..15] 0. */
 int gcm_b200_set_kernel_stats(gcm_b200_set* s, long long* out16);
 /* Virtual (contact) nodes of the last collision pass: n and [16] floats each (coords, values). */
 int gcm_b200_set_virt_count(gcm_b200_set* s);

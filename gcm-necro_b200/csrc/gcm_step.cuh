@@ -111,6 +111,26 @@ GCM_HD Vec3 load_xyz(const MeshView& m, int i)
 
 struct TetGeom { int v[4]; Vec3 p[4]; float h, vol; };
 
+GCM_HD void load_tet_row(const MeshView& m, int t, int v[4])
+{
+#if defined(__CUDA_ARCH__)
+	const int4 q = reinterpret_cast<const int4*>(m.tets)[t];
+	v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+#else
+	for(int k = 0; k < 4; k++) v[k] = m.tets[4*(size_t)t + k];
+#endif
+}
+
+GCM_HD void load_tet_hv(const MeshView& m, int t, float& h, float& vol)
+{
+#if defined(__CUDA_ARCH__)
+	const float2 hv = reinterpret_cast<const float2*>(m.tet_hv)[t];
+	h = hv.x; vol = hv.y;
+#else
+	h = m.tet_hv[2*(size_t)t]; vol = m.tet_hv[2*(size_t)t + 1];
+#endif
+}
+
 GCM_HD void load_tet(const MeshView& m, int t, TetGeom& g)
 {
 #if defined(__CUDA_ARCH__)
@@ -239,26 +259,59 @@ GCM_HD int find_owner_second_ring(const MeshView& m, int base, const Vec3& node_
 	const int e0 = m.n2t_off[base], e1 = m.n2t_off[base + 1];
 	int best = 0x7fffffff;
 	bool inside_R = false;
+	// The search is a chain of dependent loads (tet id -> vertex ids -> coordinates -> predicate), ~400 candidates
+	// long for a virtual contact node: the ring-1 rows are read once, and the candidates of a vertex go through in
+	// groups of four whose loads are all issued before the first predicate -- same candidates, same order, same
+	// arithmetic, a quarter of the round trips.
+	const int R1_MAX = 32;
+	int r1[R1_MAX][4];
+	const int n1 = e1 - e0;
+	const bool have_r1 = n1 <= R1_MAX;
+	if(have_r1)
+		for(int a = 0; a < n1; a++) {
+			load_tet_row(m, m.n2t[e0 + a], r1[a]);
+		}
 	for(int a = e0; a < e1; a++) {
-		const int* tv1 = m.tets + 4*(size_t)m.n2t[a];
+		const int* tv1 = have_r1 ? r1[a - e0] : m.tets + 4*(size_t)m.n2t[a];
 		for(int j = 0; j < 4; j++) {
 			const int v = tv1[j];
 			if(v == base) continue;
 			bool seen = false;
-			for(int b = e0; b < a && !seen; b++) seen = tet_has_vertex(m, m.n2t[b], v);
+			if(have_r1) { for(int b = 0; b < a - e0 && !seen; b++) seen = r1[b][0] == v || r1[b][1] == v || r1[b][2] == v || r1[b][3] == v; }
+			else { for(int b = e0; b < a && !seen; b++) seen = tet_has_vertex(m, m.n2t[b], v); }
 			if(seen) continue;
-			for(int c = m.n2t_off[v]; c < m.n2t_off[v + 1]; c++) {
-				const int t2 = m.n2t[c];
-				if(t2 >= best || tet_has_vertex(m, t2, base)) continue;
-				TetGeom q;
-				load_tet(m, t2, q);
-				if(point_in_tetr(X, dx, dy, dz, delta, q.p[0], q.p[1], q.p[2], q.p[3], q.h, q.vol)) { best = t2; continue; }
-				for(int k = 0; k < 4; k++) {
-					const float lx = q.p[k].x, ly = q.p[k].y, lz = q.p[k].z;
-					if( ( (node_pos.x - lx) * (node_pos.x - lx)
-						+ (node_pos.y - ly) * (node_pos.y - ly)
-						+ (node_pos.z - lz) * (node_pos.z - lz) ) < R2 )
-						inside_R = true;
+			const int c1 = m.n2t_off[v + 1];
+			for(int c = m.n2t_off[v]; c < c1; c += 4) {
+				int tt[4], tv4[4][4];
+				bool take[4];
+				TetGeom q[4];
+				#pragma unroll
+				for(int u = 0; u < 4; u++) tt[u] = c + u < c1 ? m.n2t[c + u] : 0x7fffffff;
+				#pragma unroll
+				for(int u = 0; u < 4; u++) {
+					take[u] = tt[u] < best;
+					if(take[u]) {
+						load_tet_row(m, tt[u], tv4[u]);
+						take[u] = !(tv4[u][0] == base || tv4[u][1] == base || tv4[u][2] == base || tv4[u][3] == base);
+					}
+				}
+				#pragma unroll
+				for(int u = 0; u < 4; u++)
+					if(take[u]) {
+						for(int k = 0; k < 4; k++) { q[u].v[k] = tv4[u][k]; q[u].p[k] = load_xyz(m, tv4[u][k]); }
+						load_tet_hv(m, tt[u], q[u].h, q[u].vol);
+					}
+				#pragma unroll
+				for(int u = 0; u < 4; u++) {
+					if(!take[u] || tt[u] >= best) continue;      // an earlier one of the group may have lowered `best`
+					if(point_in_tetr(X, dx, dy, dz, delta, q[u].p[0], q[u].p[1], q[u].p[2], q[u].p[3], q[u].h, q[u].vol)) { best = tt[u]; continue; }
+					for(int k = 0; k < 4; k++) {
+						const float lx = q[u].p[k].x, ly = q[u].p[k].y, lz = q[u].p[k].z;
+						if( ( (node_pos.x - lx) * (node_pos.x - lx)
+							+ (node_pos.y - ly) * (node_pos.y - ly)
+							+ (node_pos.z - lz) * (node_pos.z - lz) ) < R2 )
+							inside_R = true;
+					}
 				}
 			}
 		}

@@ -32,6 +32,26 @@ def test_two_ranks_host_half_gloo(built, name):
 
 
 @pytest.mark.gpu
+def test_two_ranks_host_driven_stages(built):
+    """The stage-by-stage path a host drives itself (DataBus.sync_nodes through torch.distributed P2P ops +
+    gcm_b200_halo_pack / unpack, then gcm_b200_set_do_next_part_step): no overlapped stage, the shell nodes of
+    the pattern kernel run right behind the range launch.  Same 3-step comparison with the single-process run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    old = os.environ.get("GCM_B200_TORCH_HALO")
+    os.environ["GCM_B200_TORCH_HALO"] = "1"
+    try:
+        r = _torchrun(2, ["gpu", "mp24"], 29536)
+    finally:
+        if old is None:
+            os.environ.pop("GCM_B200_TORCH_HALO", None)
+        else:
+            os.environ["GCM_B200_TORCH_HALO"] = old
+    assert r.returncode == 0 and "MP_RESULT OK" in r.stdout, (r.stdout[-1500:], r.stderr[-6000:])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("p2p", ["1", "0"])
 def test_two_ranks_nccl_halo_exchange(built, p2p):
     """Cross-process halo on the device against a single-process run, three steps: direct peer stores into the

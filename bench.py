@@ -210,6 +210,10 @@ def main():
     ap.add_argument("--cpu-size", type=int, default=64, help="cube side of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="cube", choices=["cube", "contact"], help="contact: only the two-body configs[4] line")
+    ap.add_argument("--contact-side", type=int, default=126)
+    ap.add_argument("--contact-calc", default="adhesion", choices=["adhesion", "friction"])
+    ap.add_argument("--contact-every-step", action="store_true", help="run the collision detector every step instead of static")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the short configs[1] / configs[3] runs appended at 1 GPU")
     ap.add_argument("--yield-limit", type=float, default=YIELD, help="1e7 = BASELINE configs[3] (plastic corrector fires)")
     args = ap.parse_args()
@@ -233,6 +237,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if args.workload == "contact":
+        # BASELINE configs[4] alone (1 GPU): a short line of its own, for profiling the contact kernels
+        if rank == 0:
+            print(json.dumps({"metric": "tet node-updates/sec", "config": {"workload": "two %d^3 bodies in contact (BASELINE configs[4])" % args.contact_side},
+                              **run_contact(args, local_rank, args.contact_side, args.contact_calc, not args.contact_every_step)}))
+        return
     line = run_workload(args, rank, world, local_rank, args.size, args.zones, args.yield_limit, full=True)
     if rank == 0 and world == 1 and not args.no_extra_configs:
         # the other single-GPU configurations BASELINE.json names, as extra keys of the one line (short runs, device-timed)

@@ -527,11 +527,22 @@ GCM_HD void lu_solve(double* A, double* b)
 		}
 		double ajj = A[j*N+j];
 		if(ajj != 0.0) {
+			// The pivot row and the row being eliminated pass through registers, all N entries with compile-time
+			// indices (those at k <= j are carried along and not stored): the N loads of a row are in flight
+			// together instead of one dependent load-update-store per entry.  Each stored entry is the same
+			// product and difference as before.
+			double prow[N];
+			#pragma unroll
+			for(int k = 0; k < N; k++) prow[k] = A[j*N+k];
 			for(int i = j + 1; i < N; i++) {
+				double row[N];
+				#pragma unroll
+				for(int k = 0; k < N; k++) row[k] = A[i*N+k];
 				double aij = div_z(A[i*N+j], ajj);
 				A[i*N+j] = aij;
-				for(int k = j + 1; k < N; k++)
-					A[i*N+k] = A[i*N+k] - aij * A[j*N+k];
+				#pragma unroll
+				for(int k = 0; k < N; k++)
+					if(k > j) A[i*N+k] = row[k] - aij * prow[k];
 			}
 		}
 	}

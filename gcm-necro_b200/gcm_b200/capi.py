@@ -181,6 +181,12 @@ class TetrMesh_1stOrder:
         """VTKSnapshotWriter::dump_vtk for this zone."""
         self._ck(self.mesh_set.lib.gcm_b200_zone_dump_vtk(self.mesh_set.h, self.zone_num, str(path).encode()))
 
+    def assign_border_conditions(self, cond_of_node):
+        """nodes[i].border_condition = condition cond_of_node[i] (-1: the default Free border)."""
+        a = np.ascontiguousarray(cond_of_node, np.int32)
+        assert a.shape == (self._n_nodes,)
+        self._ck(self.mesh_set.lib.gcm_b200_zone_assign_border_conditions(self.mesh_set.h, self.zone_num, _iptr(a)))
+
     def translate(self, dx, dy, dz):
         self._ck(self.mesh_set.lib.gcm_b200_zone_translate(self.mesh_set.h, self.zone_num, dx, dy, dz))
 
@@ -303,6 +309,17 @@ class TetrMeshSet:
         vv = None if vals is None else np.ascontiguousarray(vals, np.float32)
         self._ck(self.lib.gcm_b200_set_add_border_condition(self.h, calc_type, _fptr(p), _iptr(vi), _fptr(vv),
                                                            start, duration, _fptr(b)))
+
+    def define_border_condition(self, calc_type, params=None, start=-1.0, duration=-1.0, vars=None, vals=None):
+        """A BorderCondition without its area (calculator + StepPulseForm); returns its id for
+        TetrMesh_1stOrder.assign_border_conditions."""
+        p = None if params is None else np.ascontiguousarray(params, np.float32)
+        vi = None if vars is None else np.ascontiguousarray(vars, np.int32)
+        vv = None if vals is None else np.ascontiguousarray(vals, np.float32)
+        cid = C.c_int(-1)
+        self._ck(self.lib.gcm_b200_set_define_border_condition(self.h, calc_type, _fptr(p), _iptr(vi), _fptr(vv),
+                                                              start, duration, C.byref(cid)))
+        return cid.value
 
     def do_next_step(self):
         self._ck(self.lib.gcm_b200_set_do_next_step(self.h))

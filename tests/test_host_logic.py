@@ -5,6 +5,7 @@ import subprocess
 import tempfile
 
 import numpy as np
+import pytest
 
 import util_parity as up
 from gcm_b200 import meshgen
@@ -137,3 +138,35 @@ def test_div6_fma_form_matches_ieee_division(tmp_path):
     assert out.returncode == 0, out.stdout
     assert "in exponents 2..254: 0" in out.stdout
     assert "0x3e2aaaab" in out.stdout
+
+
+def test_host_only_sets_refuse_device_work_and_accept_host_calls(built):
+    """A set created with device -1 does host work (load, preprocess, conditions, file formats) and refuses
+    everything that would need the GPU with CONFIG_EXCEPTION: there is no CPU execution path to fall back to."""
+    import gcm_b200
+    from gcm_b200 import meshgen
+    z = meshgen.make_cube(5)
+    ms = gcm_b200.TetrMeshSet(n_zones=1, device=-1)
+    m = ms.get_mesh_by_zone_num(0)
+    m.load(z, la=7e9, mu=1e9, rho=7.8e6)
+    ms.pre_process_meshes()
+    # per-node border conditions: ids from define, unknown ids refused
+    cid = ms.define_border_condition(gcm_b200.BC_EXT_FORCE, params=(-1e8, 3e7, 1.0, 0.5, 0.0), start=0.0, duration=0.003)
+    assert cid == 0
+    cid2 = ms.define_border_condition(gcm_b200.BC_FIXED)
+    assert cid2 == 1
+    ids = np.full(z.n_nodes, -1, np.int32)
+    ids[z.coords[:, 2] > 3.5] = cid
+    ids[z.coords[:, 2] < 0.5] = cid2
+    m.assign_border_conditions(ids)
+    ids[0] = 7
+    with pytest.raises(gcm_b200.GCMException) as e:
+        m.assign_border_conditions(ids)
+    assert e.value.code == gcm_b200.GCMException.CONFIG_EXCEPTION and "unknown border condition id" in e.value.message
+    for call in (ms.do_next_step, ms.begin_step, ms.join_io, lambda: ms.track_destruction(True), m.get_destruction_criterias,
+                 lambda: ms.do_next_part_step(0.002, 0), ms.synchronize):
+        with pytest.raises(gcm_b200.GCMException) as e:
+            call()
+        assert e.value.code == gcm_b200.GCMException.CONFIG_EXCEPTION
+        assert "no CPU execution path" in e.value.message or "host-only" in e.value.message
+    ms.close()

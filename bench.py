@@ -8,16 +8,20 @@ Workload (BASELINE.json configs[2], the one the metric is quoted on): elastic cu
 216^3 = 10 077 696 nodes / 59 630 250 tets (create_cube.c semantics, 6 tets per hex), split into
 8 z-slab zones with one halo layer, material la=7e9 mu=1e9 rho=7.8e6, plane P-wave initial state,
 tau = 0.002, srand(12345).  One *step* = TetrMeshSet::do_next_step = 3 axis stages + plastic
-stage on every local node, with the halo exchange before each stage.  Strong scaling: the 8 zones
+stage on every local node, with the halo exchange before each axis stage.  Strong scaling: the 8 zones
 are dealt to the N ranks (8/N zones per GPU); the cross-rank halo goes over NVLink (direct peer
-stores into the neighbour's halo slots, NCCL send/recv as the fallback).  The two end slabs carry a
-whole 216^2 face of border nodes each, and a border node costs several inner nodes, so by default
-the slabs are cut for equal work (--layers auto: 24,28,28,28,28,28,28,24 layers) instead of
-equal thickness (--layers equal); config.layers says which.
-One JSON line is printed by rank 0 (see the task contract for the keys).  state_digest = a checksum of
-the values of the nodes >= 80 cells away from the cube's surface after all the steps of the run: it
-does not depend on how the zones are dealt to ranks (the border bases do: every rank owns a rand()
-stream, as every MPI rank of the reference does), so runs at 1/2/4/8 GPUs must print the same one.
+stores into the neighbour's halo slots, issued beside the inner nodes that do not need them; NCCL
+send/recv as the fallback).  The two end slabs carry a whole 216^2 face of border nodes each, and a
+border node costs ~20 inner nodes, so by default the slabs are cut for equal work (--layers auto:
+12,32,32,32,32,32,32,12 layers) instead of equal thickness (--layers equal); config.layers says which.
+One JSON line is printed by rank 0 (see the task contract for the keys).  Extra keys: roofline.* next to the
+contract's figure (kernel_bytes_per_node_stage / frac_kernel_bytes: what the cached inner kernel itself has to
+move; traffic / traffic_frac: DRAM bytes ncu measured for these kernel sources), other_configs (1 GPU: the
+short lines of BASELINE configs[1], [3], [4]), host_issue_ms_per_step, and state_digest = a checksum of the
+values of the nodes >= 80 cells away from the cube's surface after the timed and the per-kernel steps (before
+the e2e phase): it does not depend on how the zones are dealt to ranks (the border bases do: every rank owns a
+rand() stream, as every MPI rank of the reference does), so runs at 1/2/4/8 GPUs with the same --steps and
+--warmup must print the same one.  --workload contact prints the configs[4] line alone.
 """
 from __future__ import annotations
 
